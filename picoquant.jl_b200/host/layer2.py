@@ -1,0 +1,202 @@
+"""Contraction drivers (host bookkeeping that walks a plan and issues backend
+calls).  Restates ``src/layer2.jl``: ``sort_indices`` (:209-216),
+``create_ncon_indices`` (:226-240), ``contract_pair!`` (:329-405),
+``contract_network!`` for edge plans (:250-284) and node-pair plans
+(:294-321), ``full_wavefunction_contraction!`` (:132-195) and
+``random_contraction_plan`` (:119-122).
+
+All of this is integer / label work and must be bit-exact with the reference:
+the emitted backend call stream (labels, ncon index lists, permutation and
+reshape arguments) is compared verbatim against hand-derived ``.tl`` streams in
+``tests/test_plan_stream.py``.
+"""
+from __future__ import annotations
+
+import random
+from typing import Dict, List, Optional, Sequence, Union
+
+from .backends import record_compute_costs
+from .layer3 import Node, TensorNetworkCircuit, new_label, _label_number
+
+
+def sort_indices(A: Node, B: Node):
+    """``src/layer2.jl:209-216``.  Julia's set operations on arrays keep
+    first-appearance order: common = A's shared indices in A order;
+    uncommon = A-open (A order) followed by B-open (B order)."""
+    b_set = set(B.indices)
+    common, seen = [], set()
+    for x in A.indices:
+        if x in b_set and x not in seen:
+            common.append(x)
+            seen.add(x)
+    common_set = set(common)
+    uncommon, seen = [], set()
+    for x in A.indices:
+        if x not in common_set and x not in seen:
+            uncommon.append(x)
+            seen.add(x)
+    for x in B.indices:
+        if x not in common_set and x not in seen:
+            uncommon.append(x)
+            seen.add(x)
+    return common, uncommon
+
+
+def create_ncon_indices(A: Node, B: Node, common_indices: Sequence[str],
+                        uncommon_indices: Sequence[str]):
+    """``src/layer2.jl:226-240``: contracted index k of ``common`` -> +k,
+    open index k of ``uncommon`` -> -k (both 1-based)."""
+    index_map: Dict[str, int] = {}
+    for k, x in enumerate(common_indices, start=1):
+        index_map[x] = k
+    for k, x in enumerate(uncommon_indices, start=1):
+        index_map[x] = -k
+    return [index_map[x] for x in A.indices], [index_map[x] for x in B.indices]
+
+
+def contract_pair(network: TensorNetworkCircuit, A_label: str,
+                  B_label: Optional[str] = None) -> Optional[str]:
+    """``contract_pair!``: with one label it is the edge form
+    (``src/layer2.jl:329-337``, silently skipping edges that are already gone);
+    with two labels it is the node form (``src/layer2.jl:346-405``)."""
+    if B_label is None:
+        edge = A_label
+        if edge in network.edges:
+            e = network.edges[edge]
+            return contract_pair(network, e.src, e.dst)
+        return None
+
+    if A_label == B_label:
+        return None
+
+    A = network.nodes[A_label]
+    B = network.nodes[B_label]
+    common_indices, remaining_indices = sort_indices(A, B)
+    A_ncon_indices, B_ncon_indices = create_ncon_indices(A, B, common_indices,
+                                                         remaining_indices)
+
+    # costs use the graph's dims (stale after slicing)
+    dims_map: Dict[str, int] = {}
+    for ind, d in zip(list(A.indices) + list(B.indices), list(A.dims) + list(B.dims)):
+        dims_map[ind] = d
+    contracted_dims = [dims_map[ind] for ind in common_indices]
+    C_dims = [dims_map[ind] for ind in remaining_indices]
+    record_compute_costs(network.backend, C_dims, contracted_dims)
+
+    C_label = new_label(network, "node")
+    network.nodes[C_label] = Node(remaining_indices, C_dims, C_label)
+
+    for index in common_indices:
+        del network.edges[index]
+
+    for index in remaining_indices:
+        e = network.edges[index]
+        if e.src in (A_label, B_label):
+            e.src = C_label
+        elif e.dst in (A_label, B_label):
+            e.dst = C_label
+
+    del network.nodes[A_label]
+    del network.nodes[B_label]
+
+    network.contract_tensors(A_label, A_ncon_indices, B_label, B_ncon_indices, C_label)
+    return C_label
+
+
+def random_contraction_plan(network: TensorNetworkCircuit, rng: Optional[random.Random] = None):
+    """``src/layer2.jl:119-122``: closed edges in random order.  (The
+    reference's ``shuffle`` draws from Julia's global RNG; the stream cannot be
+    matched here, so a ``random.Random`` may be supplied for determinism.)"""
+    closed = [k for k, v in network.edges.items() if v.src is not None and v.dst is not None]
+    (rng or random).shuffle(closed)
+    return closed
+
+
+def _finish(network: TensorNetworkCircuit, output_shape) -> str:
+    # common tail of both contract_network! methods (layer2.jl:266-283 / 303-320)
+    output_tensor = "node_%d" % network.counters["node"]
+    node = network.nodes[output_tensor]
+    if len(node.indices) != 0:
+        order = [node.indices.index(ind) + 1 for ind in network.output_qubits]
+        node.indices[:] = network.output_qubits[:]
+        network.permute_tensor(output_tensor, order)
+        if output_shape == "vector":
+            network.reshape_tensor(output_tensor, [list(range(1, len(node.indices) + 1))])
+        elif output_shape != "":
+            network.reshape_tensor(output_tensor, output_shape)
+    network.save_output(output_tensor)
+    return output_tensor
+
+
+def contract_network(network: TensorNetworkCircuit,
+                     plan: Union[Sequence[str], Sequence[Sequence[str]]],
+                     output_shape: Union[str, List[List[int]]] = "") -> str:
+    """``contract_network!``.  ``plan`` is either a list of edge labels
+    (``src/layer2.jl:250-284``; leftover disjoint pieces are then contracted
+    first-two-in-insertion-order) or a list of ``[A, B]`` node-label pairs
+    (``src/layer2.jl:294-321``)."""
+    plan = list(plan)
+    if plan and not isinstance(plan[0], str):
+        for A, B in plan:
+            contract_pair(network, A, B)
+        return _finish(network, output_shape)
+
+    for edge in plan:
+        contract_pair(network, edge)
+    while len(network.nodes) > 1:
+        it = iter(network.nodes)
+        n1 = next(it)
+        n2 = next(it)
+        contract_pair(network, n1, n2)
+    return _finish(network, output_shape)
+
+
+def _layer_nodes(network: TensorNetworkCircuit) -> Dict[int, List[str]]:
+    """``src/layer2.jl:149-156`` builds layer -> nodes by iterating an unordered
+    ``Dict`` (hash order in Julia).  The mirror fixes the
+    within-layer order to ascending node number, which for an SVD-split gate is
+    (first half, second half)."""
+    layer_nodes: Dict[int, List[str]] = {}
+    for k in sorted(network.node_layers, key=_label_number):
+        layer_nodes.setdefault(network.node_layers[k], []).append(k)
+    return layer_nodes
+
+
+def full_wavefunction_contraction(network: TensorNetworkCircuit,
+                                  output_shape: Union[str, List[List[int]]] = "") -> str:
+    """``full_wavefunction_contraction!`` (``src/layer2.jl:132-195``): outer
+    product of the input caps, then one ``contract_pair`` per gate layer in
+    circuit order, output caps (layer -1) last, final permute to
+    ``output_qubits[qubit_ordering]`` order, optional reshape, ``save_output``.
+    Returns the *label* of the final tensor (App. D.4)."""
+    input_nodes = [network.edges[e].src for e in network.input_qubits]
+    if any(n is None for n in input_nodes):
+        raise RuntimeError("Please create nodes for each input before using wavefunction contraction")
+
+    wf = input_nodes[0]
+    for wfi in input_nodes[1:]:
+        wf = contract_pair(network, wf, wfi)
+
+    layer_nodes = _layer_nodes(network)
+    gate_layers = [k for k in sorted(layer_nodes) if k > 0]
+    if -1 in layer_nodes:
+        gate_layers.append(-1)
+    for layer in gate_layers:
+        nodes = layer_nodes[layer]
+        n = nodes[0]
+        for n2 in nodes[1:]:
+            n = contract_pair(network, n, n2)
+        wf = contract_pair(network, wf, n)
+
+    node = network.nodes[wf]
+    if len(node.indices) != 0:
+        output_qubits = [network.output_qubits[q - 1] for q in network.qubit_ordering]
+        order = [node.indices.index(ind) + 1 for ind in output_qubits]
+        network.permute_tensor(wf, order)
+        if output_shape == "vector":
+            network.reshape_tensor(wf, [list(range(1, len(node.indices) + 1))])
+        elif output_shape != "":
+            network.reshape_tensor(wf, output_shape)
+
+    network.save_output(wf)
+    return wf
