@@ -1,0 +1,170 @@
+/*
+ * pq_b200.h -- C ABI of the B200-native tensor-contraction backend for PicoQuant.
+ *
+ * One `pq_handle` == one GPU == one CUDA stream == one device tensor store keyed
+ * by label, i.e. the device-side twin of PicoQuant's `InteractiveBackend{T}`
+ * (reference: src/backends/interactive.jl:10-23).  Every entry point below
+ * replaces one method of the reference's backend interface
+ * (src/backends.jl:62-66, forwarded at src/layer3.jl:124-134); the Julia-side
+ * `ccall` binding is shown in INTEGRATION.md.
+ *
+ * Conventions (same as the reference): labels are NUL-terminated strings (Julia
+ * Symbols), tensors are dense COLUMN-MAJOR, and every index / axis / range value
+ * crossing this interface is 1-BASED.  Functions return 0 on success or a negative
+ * `pq_status`; nothing throws across the ABI; `pq_last_error` gives the message.
+ * All device work is asynchronous on the handle's stream except `pq_load_tensor`
+ * and `pq_sync`.  A handle is not thread-safe.  There is no CPU fallback: creating
+ * a handle without a usable CUDA device fails.
+ */
+#ifndef PQ_B200_H
+#define PQ_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pq_handle pq_handle;
+typedef struct pq_program pq_program;
+
+typedef enum {
+  PQ_OK = 0,
+  PQ_ERR_INVALID = -1,   /* bad argument (rank, axis, permutation, label list ...) */
+  PQ_ERR_NOT_FOUND = -2, /* label absent (Julia: KeyError / `nothing`)             */
+  PQ_ERR_SHAPE = -3,     /* extent mismatch (Julia: DimensionMismatch)             */
+  PQ_ERR_CUDA = -4,      /* CUDA runtime / launch failure                          */
+  PQ_ERR_NCCL = -5,      /* NCCL unavailable or failed                             */
+  PQ_ERR_PARSE = -6,     /* malformed .tl command stream                           */
+  PQ_ERR_UNSUPPORTED = -7
+} pq_status;
+
+/* element type the backend computes and stores in (the `T` of InteractiveBackend{T}) */
+typedef enum { PQ_C64 = 0, PQ_C128 = 1 } pq_dtype;
+/* element type of a host buffer handed to save/load */
+typedef enum { PQ_HOST_F32 = 0, PQ_HOST_F64 = 1, PQ_HOST_C64 = 2, PQ_HOST_C128 = 3 } pq_host_dtype;
+
+#define PQ_MAX_RANK 64
+
+/* ---- lifetime -------------------------------------------------------------- */
+
+/* InteractiveBackend{T}() -- src/backends/interactive.jl:14-22. */
+int pq_create(int device, int dtype, pq_handle** out);
+int pq_destroy(pq_handle* h);
+const char* pq_last_error(const pq_handle* h);
+const char* pq_version(void);
+
+/* ---- the backend interface ---------------------------------------------------- */
+
+/* save_tensor_data(backend, label, data) -- interactive.jl:32-36.
+ * Copies `host` (column-major, `rank` extents in `dims`) to the device, converting to
+ * the backend dtype (`convert(T, data)`); replaces an existing tensor of that label. */
+int pq_save_tensor(pq_handle* h, const char* label, int rank, const int64_t* dims,
+                   const void* host, int host_dtype);
+
+/* size(load_tensor_data(...)) without the copy; PQ_ERR_NOT_FOUND mirrors `nothing`
+ * (interactive.jl:44-49).  `dims` must hold PQ_MAX_RANK entries. */
+int pq_tensor_info(pq_handle* h, const char* label, int* rank, int64_t* dims);
+
+/* load_tensor_data(backend, label) -- interactive.jl:44-49.  Synchronises the stream
+ * and copies the tensor into `host_out` (column-major) converted to `host_dtype`
+ * (PQ_HOST_C64 or PQ_HOST_C128). */
+int pq_load_tensor(pq_handle* h, const char* label, void* host_out, int host_dtype);
+
+/* contract_tensors(backend, A, A_ncon_indices, B, B_ncon_indices, C)
+ * -- interactive.jl:60-75 -> src/layer1.jl:85-92 (TensorOperations.tensorcontract).
+ * ncon labels: a value present in both lists is contracted, the rest are open;
+ * C's axes are A's open axes in A order followed by B's open axes in B order.
+ * Stores C, then deletes A and B. */
+int pq_contract(pq_handle* h, const char* A, const int32_t* a_idx, int na,
+                const char* B, const int32_t* b_idx, int nb, const char* C);
+
+/* permute_tensor(backend, tensor, axes) -- interactive.jl:111-115, layer1.jl:111-114
+ * (`permutedims`): size(out, k) == size(in, axes[k]); axes are 1-based. */
+int pq_permute(pq_handle* h, const char* label, const int32_t* axes, int n);
+
+/* reshape_tensor(backend, tensor, groups) -- interactive.jl:97-102: new extent k is
+ * the product of the old extents at the (1-based) axis positions of group k.
+ * `groups_flat` holds the concatenated groups, `group_sizes[k]` their lengths.
+ * Metadata only, no kernel. */
+int pq_reshape(pq_handle* h, const char* label, const int32_t* groups_flat,
+               const int32_t* group_sizes, int ngroups);
+
+/* view_tensor!(backend, view, node, bond_idx, bond_range) -- interactive.jl:169-172,
+ * layer1.jl:191-194: an independent COPY of `src` with axis `axis` (1-based)
+ * restricted to the 1-based positions idx[0..nidx); the axis is kept. */
+int pq_view(pq_handle* h, const char* view, const char* src, int axis,
+            const int32_t* idx, int nidx);
+
+/* delete_tensor!(backend, label) -- interactive.jl:159-161; a missing label is OK. */
+int pq_delete(pq_handle* h, const char* label);
+
+/* save_output(backend, node, name) -- interactive.jl:84-88: alias, no copy. */
+int pq_save_output(pq_handle* h, const char* node, const char* name);
+
+int pq_sync(pq_handle* h);
+
+/* ---- sliced contraction (examples/dist_slicing_example.jl:28-30) ------------------ */
+
+/* dst += src elementwise (dst is created as a copy of src when absent): the local
+ * accumulation of slice partials that precedes the single reduction. */
+int pq_accumulate(pq_handle* h, const char* dst, const char* src);
+
+/* NCCL communicator over the GPUs of one box; replaces MPI.Init / MPI.Reduce!
+ * (dist_slicing_example.jl:5-10,30).  `pq_comm_unique_id` fills 128 bytes on one rank;
+ * the caller broadcasts them (torch.distributed / MPI / files) and every rank calls
+ * `pq_comm_init`.  `pq_allreduce_sum` is one ncclAllReduce(sum) on the stream. */
+int pq_comm_unique_id(void* id128);
+int pq_comm_init(pq_handle* h, const void* id128, int rank, int nranks);
+int pq_allreduce_sum(pq_handle* h, const char* label);
+
+/* ---- .tl programs: execute_dsl_file on the device (src/layer1.jl:211-315) ---------- */
+
+/* Compiles a PicoQuant DSL command stream (grammar: src/backends/dsl.jl:65-214) against
+ * the tensors currently stored in the handle: `tensor <name> <key>` binds <name> to the
+ * stored tensor <key> (the handle's store stands in for the HDF5 file) without
+ * consuming it.  Shapes are propagated, every intermediate gets a fixed offset in one
+ * arena, and the launch sequence is captured into a CUDA graph on first run. */
+int pq_program_compile(pq_handle* h, const char* tl_text, pq_program** out);
+/* Number of `view` commands (slice parameters) in the program. */
+int pq_program_num_views(const pq_program* p);
+/* Runs the program.  `view_starts` (may be NULL) overrides, per `view` command in
+ * stream order, the 1-based start of its index range -- how one compiled plan is
+ * replayed for every slice.  `save <t> <file> <key>` stores <t> under <key> in the
+ * handle; when `accumulate_into` is non-NULL the saved tensor is also added to it. */
+int pq_program_run(pq_handle* h, pq_program* p, const int32_t* view_starts, int nviews,
+                   const char* accumulate_into);
+int pq_program_destroy(pq_handle* h, pq_program* p);
+/* arena bytes, number of kernel launches per run, complex MACs per run (data extents) */
+int pq_program_stats(const pq_program* p, int64_t* arena_bytes, int64_t* launches,
+                     int64_t* macs);
+
+/* ---- instrumentation ----------------------------------------------------------------- */
+
+/* Metrics measured on DATA extents (unlike the graph-side Metrics of backends.jl:8-57,
+ * which go stale after slicing): #contract calls, complex MACs, largest tensor. */
+int pq_get_counters(pq_handle* h, int64_t* n_contract, int64_t* macs, int64_t* max_elems,
+                    int64_t* kernel_launches);
+int pq_reset_counters(pq_handle* h);
+
+/* Per-kernel-class CUDA-event timing on the handle's stream (eager mode only).
+ * Classes: see pq_kernel_class_name.  Each record accumulates device time, launch
+ * count, algorithmic bytes and real flops. */
+#define PQ_NUM_KERNEL_CLASSES 12
+int pq_profile_enable(pq_handle* h, int on);
+int pq_profile_read(pq_handle* h, double* ms, int64_t* launches, double* bytes,
+                    double* flops); /* arrays of PQ_NUM_KERNEL_CLASSES */
+const char* pq_kernel_class_name(int cls);
+
+/* Behaviour knobs for A/B checks ("gemm": 0 auto, 1 SIMT, 2 DMMA/tensor;
+ * "permute": 0 auto, 1 generic, 2 tiled; "fused": 0 auto, 1 off; "graph": 0 auto, 1 off). */
+int pq_set_option(pq_handle* h, const char* key, int value);
+
+/* Stand-alone micro-benchmarks used by bench.py for roofline denominators measured on
+ * the same box: device-to-device copy GB/s and the FP64 DMMA / FP64 FMA issue peaks. */
+int pq_microbench(pq_handle* h, const char* what, double* result);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PQ_B200_H */

@@ -1,0 +1,197 @@
+// Shared host/device definitions for libpq_b200 (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <map>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/pq_b200.h"
+
+namespace pq {
+
+// ---------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------
+struct Error : std::runtime_error {
+  int code;
+  Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+#define PQ_CUDA(call)                                                              \
+  do {                                                                             \
+    cudaError_t e__ = (call);                                                      \
+    if (e__ != cudaSuccess)                                                        \
+      throw ::pq::Error(PQ_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__)); \
+  } while (0)
+
+#define PQ_REQUIRE(cond, code, msg)            \
+  do {                                         \
+    if (!(cond)) throw ::pq::Error((code), (msg)); \
+  } while (0)
+
+// ---------------------------------------------------------------------------
+// index maps: linear index over a list of fused dims -> element offset
+// ---------------------------------------------------------------------------
+constexpr int MAXF = 40;  // max fused dims (extent >= 2 each => 2^40 elements)
+
+struct IdxMap {
+  int nd;
+  int pow2;            // every extent is a power of two -> shifts instead of div/mod
+  int sh[MAXF];        // log2(ext) when pow2
+  int64_t ext[MAXF];
+  int64_t str[MAXF];   // element stride of each fused dim
+};
+
+__host__ __device__ inline int64_t map_offset(const IdxMap& m, int64_t i) {
+  int64_t off = 0;
+  if (m.pow2) {
+#pragma unroll 1
+    for (int d = 0; d < m.nd; ++d) {
+      off += (i & (m.ext[d] - 1)) * m.str[d];
+      i >>= m.sh[d];
+    }
+  } else {
+#pragma unroll 1
+    for (int d = 0; d < m.nd; ++d) {
+      int64_t q = i / m.ext[d];
+      off += (i - q * m.ext[d]) * m.str[d];
+      i = q;
+    }
+  }
+  return off;
+}
+
+// ---------------------------------------------------------------------------
+// tiled bit-permutation parameters (kernels_permute.cu)
+// ---------------------------------------------------------------------------
+constexpr int MAXTILEBITS = 12;
+struct TileParams {
+  int n;        // log2(total elements)
+  int t;        // tile bits
+  int a, b;     // low input / output bits that are contiguous inside the tile (>= 5)
+  int tin_pos[MAXTILEBITS];   // input bit position of tile bit u (input order)
+  int tout_pos[MAXTILEBITS];  // output bit position of tile bit v (output order)
+  int emap[MAXTILEBITS];      // tile bit (input order) feeding output-order tile bit v
+  int nrest;
+  int rest_in[48];   // input bit position of tile-counter bit w
+  int rest_out[48];  // output bit position of the same bit
+  int nswz;
+  int swz_src[4];    // smem swizzle: bit swz_src[k] of e is xor-ed into bit swz_dst[k]
+  int swz_dst[4];
+  long long ntiles;
+};
+
+// ---------------------------------------------------------------------------
+// kernel classes (profiling / roofline bookkeeping)
+// ---------------------------------------------------------------------------
+enum KClass {
+  KC_PERMUTE_TILED = 0,
+  KC_PERMUTE_GENERIC = 1,
+  KC_CONTRACT_SMALL = 2,
+  KC_CONTRACT_DIRECT = 3,
+  KC_CONTRACT_DOT = 4,
+  KC_GEMM_SIMT = 5,
+  KC_GEMM_TENSOR = 6,
+  KC_VIEW = 7,
+  KC_ACCUMULATE = 8,
+  KC_COPY = 9,
+  KC_ALLREDUCE = 10,
+  KC_OTHER = 11
+};
+static_assert(KC_OTHER + 1 == PQ_NUM_KERNEL_CLASSES, "class count");
+
+struct ProfRecord {
+  cudaEvent_t e0, e1;
+  int cls;
+  double bytes, flops;
+};
+
+struct Options {
+  int gemm = 0;     // 0 auto, 1 SIMT, 2 tensor (DMMA), 3 direct everywhere
+  int permute = 0;  // 0 auto, 1 generic, 2 tiled
+  int fused = 0;    // 0 auto, 1 disable the fused small-operand / dot kernels
+  int graph = 0;    // 0 auto (CUDA graph replay), 1 eager replay
+};
+
+// launch context handed to every kernel launcher
+struct Launch {
+  cudaStream_t stream = nullptr;
+  int elem_size = 16;   // 8 (c64) or 16 (c128)
+  int num_sms = 148;
+  int64_t* launch_counter = nullptr;
+  // profiling (eager only)
+  bool profile = false;
+  std::vector<ProfRecord>* prof = nullptr;
+  mutable ProfRecord cur{};
+  void begin(int cls, double bytes, double flops) const;
+  void end() const;
+  const Options* opt = nullptr;
+};
+
+// ---------------------------------------------------------------------------
+// lowering results
+// ---------------------------------------------------------------------------
+struct PermutePlan {
+  bool identity = true;
+  bool tiled = false;
+  int64_t total = 1;
+  IdxMap gmap{};     // output-order fused dims with input strides
+  TileParams tp{};
+};
+
+PermutePlan lower_permute(const std::vector<int64_t>& in_dims, const std::vector<int>& perm,
+                          int elem_size, const Options& opt);
+void run_permute(const Launch& L, const PermutePlan& p, const void* in, void* out);
+
+enum ContractKind { CK_SMALL_RIGHT, CK_SMALL_LEFT, CK_DIRECT, CK_DOT, CK_GEMM };
+
+struct ContractPlan {
+  ContractKind kind = CK_DIRECT;
+  int64_t M = 1, N = 1, K = 1;
+  std::vector<int64_t> cdims;          // logical dims of C (A-open then B-open)
+  IdxMap mA{}, kA{}, nB{}, kB{};       // fused index maps into A and B
+  // TTGT
+  PermutePlan permA, permB;            // A -> [M|K], B -> [N|K] canonical layouts
+  size_t tempA_bytes = 0, tempB_bytes = 0, ws_bytes = 0;
+  int dot_blocks = 0;
+};
+
+ContractPlan lower_contract(const std::vector<int64_t>& a_dims, const std::vector<int32_t>& a_idx,
+                            const std::vector<int64_t>& b_dims, const std::vector<int32_t>& b_idx,
+                            int elem_size, const Options& opt);
+// tempA/tempB/ws must hold the sizes the plan asks for (may be null when 0)
+void run_contract(const Launch& L, const ContractPlan& p, const void* A, const void* B, void* C,
+                  void* tempA, void* tempB, void* ws);
+
+void init_kernels();
+
+// misc kernels
+void run_view(const Launch& L, const void* in, void* out, int64_t inner, int64_t ext_in,
+              int64_t nsel, int64_t outer, int start0, const int32_t* start_dev);
+void run_accumulate(const Launch& L, void* dst, const void* src, int64_t n);
+double run_microbench(const Launch& L, const std::string& what);
+
+// gemm back ends on canonical layouts A'[m + M k], B''[n + N k], C[m + M n]
+void run_gemm_simt(const Launch& L, const void* A, const void* B, void* C, int64_t M, int64_t N,
+                   int64_t K);
+void run_zgemm_dmma(const Launch& L, const void* A, const void* B, void* C, int64_t M, int64_t N,
+                    int64_t K);
+
+inline int64_t prod(const std::vector<int64_t>& v) {
+  int64_t p = 1;
+  for (auto x : v) p *= x;
+  return p;
+}
+inline bool is_pow2(int64_t x) { return x > 0 && (x & (x - 1)) == 0; }
+inline int ilog2(int64_t x) {
+  int l = 0;
+  while ((int64_t(1) << l) < x) ++l;
+  return l;
+}
+
+}  // namespace pq

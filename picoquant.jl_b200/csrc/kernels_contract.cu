@@ -1,0 +1,410 @@
+// Contraction kernels that do not go through a GEMM launch:
+//
+//  * k_contract_small  (K4/K5) -- one operand is small (gate tensor, input cap, outer
+//    product factor): it is staged, already permuted, in shared memory; every thread
+//    owns one row of the big operand, gathers its K elements straight from the
+//    un-permuted tensor (no TTGT temporary), and writes NS outputs.  Reads the big
+//    operand once and writes C once => HBM-bound, algorithmic bytes
+//    (M*K + K*N + M*N) * sizeof(element).
+//  * k_contract_dot    (K6) -- tiny output, long contraction (the final inner product of
+//    a single-amplitude plan): split-K partial sums per CTA + a fixed-order second pass,
+//    so the result is deterministic.
+//  * k_contract_direct -- one thread per output element, gathers from both operands.
+//    Used for tiny problems and as the always-correct cross-check path.
+//  * k_gemm_simt       -- tiled SIMT complex GEMM on the canonical TTGT layouts; the
+//    c64 GEMM until the tcgen05 kernel lands and the cross-check for the DMMA kernel.
+//
+// Reference semantics: src/layer1.jl:85-92 (tensorcontract), C axes = A-open ++ B-open.
+#include "common.h"
+
+namespace pq {
+
+template <typename R> struct C2;
+template <> struct C2<float> { using type = float2; };
+template <> struct C2<double> { using type = double2; };
+
+template <typename V, typename R>
+__device__ __forceinline__ void cfma(V& acc, const V& a, const V& b) {
+  acc.x = fma(a.x, b.x, acc.x);
+  acc.x = fma(-a.y, b.y, acc.x);
+  acc.y = fma(a.x, b.y, acc.y);
+  acc.y = fma(a.y, b.x, acc.y);
+}
+
+// ---------------------------------------------------------------------------
+// small-operand fused kernel
+// ---------------------------------------------------------------------------
+struct SmallParams {
+  IdxMap rmap;    // row index r of the big operand -> element offset in it
+  IdxMap kbig;    // k -> element offset in the big operand
+  IdxMap ksmall;  // k -> element offset in the small operand
+  IdxMap ssmall;  // s (open index of the small operand) -> element offset in it
+  long long R;    // rows of the big operand
+  int K;
+  int S;          // open extent of the small operand (<= NS)
+  long long out_rs, out_ss;  // C offset = r * out_rs + s * out_ss
+};
+
+template <typename R, int NS>
+__global__ void __launch_bounds__(128)
+k_contract_small(const typename C2<R>::type* __restrict__ big,
+                 const typename C2<R>::type* __restrict__ small,
+                 typename C2<R>::type* __restrict__ out, const SmallParams p) {
+  using V = typename C2<R>::type;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  V* Q = reinterpret_cast<V*>(smem_raw);                       // [K][NS]
+  long long* koff = reinterpret_cast<long long*>(Q + (size_t)p.K * NS);  // [K]
+  for (int i = threadIdx.x; i < p.K * NS; i += blockDim.x) {
+    int k = i / NS, s = i - k * NS;
+    V v;
+    v.x = 0;
+    v.y = 0;
+    if (s < p.S) v = small[map_offset(p.ksmall, k) + map_offset(p.ssmall, s)];
+    Q[i] = v;
+  }
+  for (int k = threadIdx.x; k < p.K; k += blockDim.x) koff[k] = map_offset(p.kbig, k);
+  __syncthreads();
+
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < p.R; r += stride) {
+    const V* row = big + map_offset(p.rmap, r);
+    V acc[NS];
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+      acc[s].x = 0;
+      acc[s].y = 0;
+    }
+#pragma unroll 4
+    for (int k = 0; k < p.K; ++k) {
+      V a = row[koff[k]];
+#pragma unroll
+      for (int s = 0; s < NS; ++s) cfma<V, R>(acc[s], a, Q[k * NS + s]);
+    }
+    V* dst = out + r * p.out_rs;
+#pragma unroll
+    for (int s = 0; s < NS; ++s)
+      if (s < p.S) dst[s * p.out_ss] = acc[s];
+  }
+}
+
+template <typename R, int NS>
+static void launch_small_ns(const Launch& L, const SmallParams& p, const void* big,
+                            const void* small, void* out) {
+  using V = typename C2<R>::type;
+  size_t smem = (size_t)p.K * NS * sizeof(V) + (size_t)p.K * sizeof(long long);
+  long long blocks = (p.R + 127) / 128;
+  long long cap = (long long)L.num_sms * 32;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  k_contract_small<R, NS><<<(unsigned)blocks, 128, smem, L.stream>>>((const V*)big, (const V*)small,
+                                                                   (V*)out, p);
+}
+
+template <typename R>
+static void launch_small(const Launch& L, const SmallParams& p, const void* big, const void* small,
+                         void* out) {
+  if (p.S <= 1)
+    launch_small_ns<R, 1>(L, p, big, small, out);
+  else if (p.S <= 2)
+    launch_small_ns<R, 2>(L, p, big, small, out);
+  else if (p.S <= 4)
+    launch_small_ns<R, 4>(L, p, big, small, out);
+  else if (p.S <= 8)
+    launch_small_ns<R, 8>(L, p, big, small, out);
+  else
+    launch_small_ns<R, 16>(L, p, big, small, out);
+}
+
+// ---------------------------------------------------------------------------
+// direct kernel
+// ---------------------------------------------------------------------------
+struct DirectParams {
+  IdxMap mA, kA, nB, kB;
+  long long M, N, K;
+};
+
+template <typename R>
+__global__ void __launch_bounds__(128)
+k_contract_direct(const typename C2<R>::type* __restrict__ A,
+                  const typename C2<R>::type* __restrict__ B,
+                  typename C2<R>::type* __restrict__ C, const DirectParams p) {
+  using V = typename C2<R>::type;
+  const long long total = p.M * p.N;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < total; c += stride) {
+    long long n = c / p.M, m = c - n * p.M;
+    const V* a = A + map_offset(p.mA, m);
+    const V* b = B + map_offset(p.nB, n);
+    V acc;
+    acc.x = 0;
+    acc.y = 0;
+    for (long long k = 0; k < p.K; ++k)
+      cfma<V, R>(acc, a[map_offset(p.kA, k)], b[map_offset(p.kB, k)]);
+    C[c] = acc;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// dot kernel (M*N <= 16, long K)
+// ---------------------------------------------------------------------------
+struct DotParams {
+  IdxMap mA, kA, nB, kB;
+  int M, N;
+  long long K;
+};
+
+template <typename R>
+__global__ void __launch_bounds__(256)
+k_contract_dot(const typename C2<R>::type* __restrict__ A,
+               const typename C2<R>::type* __restrict__ B,
+               typename C2<R>::type* __restrict__ partial, const DotParams p) {
+  using V = typename C2<R>::type;
+  __shared__ long long offA[16], offB[16];
+  __shared__ V red[8][16];
+  const int MN = p.M * p.N;
+  if (threadIdx.x < MN) {
+    int n = threadIdx.x / p.M, m = threadIdx.x - n * p.M;
+    offA[threadIdx.x] = map_offset(p.mA, m);
+    offB[threadIdx.x] = map_offset(p.nB, n);
+  }
+  __syncthreads();
+  V acc[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    acc[j].x = 0;
+    acc[j].y = 0;
+  }
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < p.K; k += stride) {
+    const V* a = A + map_offset(p.kA, k);
+    const V* b = B + map_offset(p.kB, k);
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+      if (j < MN) cfma<V, R>(acc[j], a[offA[j]], b[offB[j]]);
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    if (j < MN) {
+      V v = acc[j];
+      for (int d = 16; d > 0; d >>= 1) {
+        v.x += __shfl_down_sync(0xffffffffu, v.x, d);
+        v.y += __shfl_down_sync(0xffffffffu, v.y, d);
+      }
+      if (lane == 0) red[warp][j] = v;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < MN) {
+    V v = red[0][threadIdx.x];
+    for (int w = 1; w < 8; ++w) {
+      v.x += red[w][threadIdx.x].x;
+      v.y += red[w][threadIdx.x].y;
+    }
+    partial[(long long)blockIdx.x * 16 + threadIdx.x] = v;
+  }
+}
+
+template <typename R>
+__global__ void k_dot_finish(const typename C2<R>::type* __restrict__ partial,
+                             typename C2<R>::type* __restrict__ C, int MN, int blocks) {
+  using V = typename C2<R>::type;
+  int j = threadIdx.x;
+  if (j < MN) {
+    V v;
+    v.x = 0;
+    v.y = 0;
+    for (int b = 0; b < blocks; ++b) {
+      v.x += partial[(long long)b * 16 + j].x;
+      v.y += partial[(long long)b * 16 + j].y;
+    }
+    C[j] = v;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// SIMT GEMM on canonical layouts: A[m + M k], B[n + N k], C[m + M n]
+// ---------------------------------------------------------------------------
+template <typename R>
+__global__ void __launch_bounds__(256)
+k_gemm_simt(const typename C2<R>::type* __restrict__ A, const typename C2<R>::type* __restrict__ B,
+            typename C2<R>::type* __restrict__ C, long long M, long long N, long long K) {
+  using V = typename C2<R>::type;
+  constexpr int BM = 64, BN = 64, BK = 8;
+  __shared__ V As[BK][BM];
+  __shared__ V Bs[BK][BN];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const long long m0 = (long long)blockIdx.x * BM, n0 = (long long)blockIdx.y * BN;
+  V acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      acc[i][j].x = 0;
+      acc[i][j].y = 0;
+    }
+  V zero;
+  zero.x = 0;
+  zero.y = 0;
+  for (long long k0 = 0; k0 < K; k0 += BK) {
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      int idx = threadIdx.x + q * 256;  // 0..511
+      int kk = idx >> 6, mm = idx & 63;
+      long long k = k0 + kk;
+      As[kk][mm] = (k < K && m0 + mm < M) ? A[(m0 + mm) + M * k] : zero;
+      Bs[kk][mm] = (k < K && n0 + mm < N) ? B[(n0 + mm) + N * k] : zero;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      V a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[kk][tx + 16 * i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = Bs[kk][ty + 16 * j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) cfma<V, R>(acc[i][j], a[i], b[j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    long long n = n0 + ty + 16 * j;
+    if (n >= N) continue;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      long long m = m0 + tx + 16 * i;
+      if (m < M) C[m + M * n] = acc[i][j];
+    }
+  }
+}
+
+void run_gemm_simt(const Launch& L, const void* A, const void* B, void* C, int64_t M, int64_t N,
+                   int64_t K) {
+  dim3 grid((unsigned)((M + 63) / 64), (unsigned)((N + 63) / 64));
+  PQ_REQUIRE(grid.y <= 65535, PQ_ERR_UNSUPPORTED, "N too large for the SIMT GEMM grid");
+  double bytes = double(M * K + N * K + M * N) * L.elem_size, flops = 8.0 * M * N * K;
+  L.begin(KC_GEMM_SIMT, bytes, flops);
+  if (L.elem_size == 16)
+    k_gemm_simt<double><<<grid, 256, 0, L.stream>>>((const double2*)A, (const double2*)B,
+                                                    (double2*)C, M, N, K);
+  else
+    k_gemm_simt<float><<<grid, 256, 0, L.stream>>>((const float2*)A, (const float2*)B, (float2*)C,
+                                                   M, N, K);
+  L.end();
+  PQ_CUDA(cudaGetLastError());
+}
+
+// ---------------------------------------------------------------------------
+// dispatcher
+// ---------------------------------------------------------------------------
+template <typename R>
+static void run_contract_t(const Launch& L, const ContractPlan& p, const void* A, const void* B,
+                           void* C, void* tempA, void* tempB, void* ws) {
+  using V = typename C2<R>::type;
+  const double bytes = double(p.M * p.K + p.K * p.N + p.M * p.N) * sizeof(V);
+  const double flops = 8.0 * double(p.M) * double(p.N) * double(p.K);
+  switch (p.kind) {
+    case CK_SMALL_RIGHT: {
+      SmallParams sp;
+      sp.rmap = p.mA;
+      sp.kbig = p.kA;
+      sp.ksmall = p.kB;
+      sp.ssmall = p.nB;
+      sp.R = p.M;
+      sp.K = (int)p.K;
+      sp.S = (int)p.N;
+      sp.out_rs = 1;
+      sp.out_ss = p.M;
+      L.begin(KC_CONTRACT_SMALL, bytes, flops);
+      launch_small<R>(L, sp, A, B, C);
+      L.end();
+      break;
+    }
+    case CK_SMALL_LEFT: {
+      SmallParams sp;
+      sp.rmap = p.nB;
+      sp.kbig = p.kB;
+      sp.ksmall = p.kA;
+      sp.ssmall = p.mA;
+      sp.R = p.N;
+      sp.K = (int)p.K;
+      sp.S = (int)p.M;
+      sp.out_rs = p.M;
+      sp.out_ss = 1;
+      L.begin(KC_CONTRACT_SMALL, bytes, flops);
+      launch_small<R>(L, sp, B, A, C);
+      L.end();
+      break;
+    }
+    case CK_DOT: {
+      DotParams dp;
+      dp.mA = p.mA;
+      dp.kA = p.kA;
+      dp.nB = p.nB;
+      dp.kB = p.kB;
+      dp.M = (int)p.M;
+      dp.N = (int)p.N;
+      dp.K = p.K;
+      L.begin(KC_CONTRACT_DOT, bytes, flops);
+      k_contract_dot<R><<<p.dot_blocks, 256, 0, L.stream>>>((const V*)A, (const V*)B, (V*)ws, dp);
+      L.end();
+      L.begin(KC_CONTRACT_DOT, 0, 0);
+      k_dot_finish<R><<<1, 32, 0, L.stream>>>((const V*)ws, (V*)C, (int)(p.M * p.N), p.dot_blocks);
+      L.end();
+      break;
+    }
+    case CK_DIRECT: {
+      DirectParams dp;
+      dp.mA = p.mA;
+      dp.kA = p.kA;
+      dp.nB = p.nB;
+      dp.kB = p.kB;
+      dp.M = p.M;
+      dp.N = p.N;
+      dp.K = p.K;
+      long long total = p.M * p.N;
+      long long blocks = (total + 127) / 128;
+      long long cap = (long long)L.num_sms * 32;
+      if (blocks > cap) blocks = cap;
+      if (blocks < 1) blocks = 1;
+      L.begin(KC_CONTRACT_DIRECT, bytes, flops);
+      k_contract_direct<R><<<(unsigned)blocks, 128, 0, L.stream>>>((const V*)A, (const V*)B, (V*)C,
+                                                                  dp);
+      L.end();
+      break;
+    }
+    case CK_GEMM: {
+      const void* Ap = A;
+      const void* Bp = B;
+      if (!p.permA.identity) {
+        run_permute(L, p.permA, A, tempA);
+        Ap = tempA;
+      }
+      if (!p.permB.identity) {
+        run_permute(L, p.permB, B, tempB);
+        Bp = tempB;
+      }
+      bool tensor = sizeof(R) == 8 && (L.opt == nullptr || L.opt->gemm != 1);
+      if (tensor)
+        run_zgemm_dmma(L, Ap, Bp, C, p.M, p.N, p.K);
+      else
+        run_gemm_simt(L, Ap, Bp, C, p.M, p.N, p.K);
+      break;
+    }
+  }
+  PQ_CUDA(cudaGetLastError());
+}
+
+void run_contract(const Launch& L, const ContractPlan& p, const void* A, const void* B, void* C,
+                  void* tempA, void* tempB, void* ws) {
+  if (L.elem_size == 16)
+    run_contract_t<double>(L, p, A, B, C, tempA, tempB, ws);
+  else
+    run_contract_t<float>(L, p, A, B, C, tempA, tempB, ws);
+}
+
+}  // namespace pq

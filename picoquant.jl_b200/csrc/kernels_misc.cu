@@ -1,0 +1,108 @@
+// Small data-movement kernels: K7 slice copy (view_tensor!, reference
+// src/layer1.jl:191-194), slice-partial accumulation, and the bandwidth probe.
+#include "common.h"
+
+namespace pq {
+
+double run_fp64_probe(const Launch& L, bool tensor);  // kernels_zgemm.cu
+
+// out[i + inner*(j + nsel*o)] = in[i + inner*((start-1+j) + ext_in*o)]
+// `start` (1-based) comes from device memory when start_dev != nullptr, so that one
+// captured launch can serve every slice of a sliced contraction.
+template <typename E>
+__global__ void __launch_bounds__(256)
+k_view(const E* __restrict__ in, E* __restrict__ out, long long inner, long long ext_in,
+       long long nsel, long long outer, int start0, const int* __restrict__ start_dev) {
+  const long long start = (start_dev ? (long long)(*start_dev) : (long long)start0) - 1;
+  const long long total = inner * nsel * outer;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
+    long long i = t % inner, rest = t / inner;
+    long long j = rest % nsel, o = rest / nsel;
+    out[t] = in[i + inner * ((start + j) + ext_in * o)];
+  }
+}
+
+void run_view(const Launch& L, const void* in, void* out, int64_t inner, int64_t ext_in,
+              int64_t nsel, int64_t outer, int start0, const int32_t* start_dev) {
+  long long total = inner * nsel * outer;
+  if (total <= 0) return;
+  long long blocks = (total + 255) / 256;
+  long long cap = (long long)L.num_sms * 32;
+  if (blocks > cap) blocks = cap;
+  L.begin(KC_VIEW, 2.0 * double(total) * L.elem_size, 0);
+  if (L.elem_size == 16)
+    k_view<double2><<<(unsigned)blocks, 256, 0, L.stream>>>((const double2*)in, (double2*)out, inner,
+                                                          ext_in, nsel, outer, start0, start_dev);
+  else
+    k_view<float2><<<(unsigned)blocks, 256, 0, L.stream>>>((const float2*)in, (float2*)out, inner,
+                                                         ext_in, nsel, outer, start0, start_dev);
+  L.end();
+  PQ_CUDA(cudaGetLastError());
+}
+
+template <typename R>
+__global__ void __launch_bounds__(256) k_accumulate(R* __restrict__ dst, const R* __restrict__ src,
+                                                    long long n) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    dst[i] += src[i];
+}
+
+void run_accumulate(const Launch& L, void* dst, const void* src, int64_t n) {
+  if (n <= 0) return;
+  long long reals = 2 * n;
+  long long blocks = (reals + 255) / 256;
+  long long cap = (long long)L.num_sms * 32;
+  if (blocks > cap) blocks = cap;
+  L.begin(KC_ACCUMULATE, 3.0 * double(n) * L.elem_size, 2.0 * n);
+  if (L.elem_size == 16)
+    k_accumulate<double><<<(unsigned)blocks, 256, 0, L.stream>>>((double*)dst, (const double*)src,
+                                                               reals);
+  else
+    k_accumulate<float><<<(unsigned)blocks, 256, 0, L.stream>>>((float*)dst, (const float*)src,
+                                                              reals);
+  L.end();
+  PQ_CUDA(cudaGetLastError());
+}
+
+__global__ void __launch_bounds__(256) k_copy16(const uint4* __restrict__ in, uint4* __restrict__ out,
+                                                long long n) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    out[i] = in[i];
+}
+
+double run_microbench(const Launch& L, const std::string& what) {
+  if (what == "dmma_tflops") return run_fp64_probe(L, true);
+  if (what == "dfma_tflops") return run_fp64_probe(L, false);
+  if (what == "copy_gbs") {
+    const long long n = 1LL << 26;  // 1 GiB in + 1 GiB out, larger than L2
+    uint4 *a = nullptr, *b = nullptr;
+    PQ_CUDA(cudaMalloc(&a, n * 16));
+    PQ_CUDA(cudaMalloc(&b, n * 16));
+    PQ_CUDA(cudaMemsetAsync(a, 1, n * 16, L.stream));
+    cudaEvent_t e0, e1;
+    PQ_CUDA(cudaEventCreate(&e0));
+    PQ_CUDA(cudaEventCreate(&e1));
+    float best = 1e30f;
+    for (int rep = 0; rep < 6; ++rep) {
+      PQ_CUDA(cudaEventRecord(e0, L.stream));
+      k_copy16<<<L.num_sms * 16, 256, 0, L.stream>>>(a, b, n);
+      PQ_CUDA(cudaEventRecord(e1, L.stream));
+      PQ_CUDA(cudaEventSynchronize(e1));
+      float ms = 0;
+      PQ_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+      if (rep > 0 && ms < best) best = ms;
+    }
+    PQ_CUDA(cudaGetLastError());
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(a);
+    cudaFree(b);
+    return 2.0 * double(n) * 16.0 / (best * 1e-3) / 1e9;
+  }
+  throw Error(PQ_ERR_INVALID, "unknown microbench: " + what);
+}
+
+}  // namespace pq

@@ -1,0 +1,509 @@
+// execute_dsl_file on the device (reference interpreter: src/layer1.jl:211-315; grammar
+// emitted by src/backends/dsl.jl:65-214).  A `.tl` command stream is compiled once:
+// shapes are propagated symbolically, every contraction is lowered to its kernel(s),
+// every intermediate (results, TTGT temporaries, split-K workspaces) gets a fixed
+// offset in one arena by replaying the alloc/free timeline through a best-fit
+// allocator, and the whole launch sequence is captured into a CUDA graph.  Replaying
+// the graph costs one host call per slice; `view` start indices live in device
+// memory so the same graph serves every slice of a sliced contraction
+// (reference flow: src/layer2/slicing.jl:100-110 + examples/dist_slicing_example.jl).
+#include <cstring>
+#include <sstream>
+
+#include "handle.h"
+
+using namespace pq;
+
+namespace {
+
+constexpr size_t ALIGN = 256;
+inline size_t round_up(size_t x) { return (x + ALIGN - 1) / ALIGN * ALIGN; }
+
+// offset allocator used at compile time only
+struct ArenaSim {
+  std::map<size_t, size_t> free_blocks;  // offset -> size
+  size_t top = 0;
+  size_t alloc(size_t bytes) {
+    bytes = round_up(bytes == 0 ? 1 : bytes);
+    auto best = free_blocks.end();
+    for (auto it = free_blocks.begin(); it != free_blocks.end(); ++it)
+      if (it->second >= bytes && (best == free_blocks.end() || it->second < best->second)) best = it;
+    if (best != free_blocks.end()) {
+      size_t off = best->first, sz = best->second;
+      free_blocks.erase(best);
+      if (sz > bytes) free_blocks[off + bytes] = sz - bytes;
+      return off;
+    }
+    // grow: extend a trailing free block if there is one
+    if (!free_blocks.empty()) {
+      auto last = std::prev(free_blocks.end());
+      if (last->first + last->second == top) {
+        size_t off = last->first;
+        top = off + bytes;
+        free_blocks.erase(last);
+        return off;
+      }
+    }
+    size_t off = top;
+    top += bytes;
+    return off;
+  }
+  void release(size_t off, size_t bytes) {
+    bytes = round_up(bytes == 0 ? 1 : bytes);
+    auto it = free_blocks.emplace(off, bytes).first;
+    auto nx = std::next(it);
+    if (nx != free_blocks.end() && it->first + it->second == nx->first) {
+      it->second += nx->second;
+      free_blocks.erase(nx);
+    }
+    if (it != free_blocks.begin()) {
+      auto pv = std::prev(it);
+      if (pv->first + pv->second == it->first) {
+        pv->second += it->second;
+        free_blocks.erase(it);
+      }
+    }
+  }
+};
+
+struct Sym {
+  bool leaf = false;
+  std::shared_ptr<Buffer> leafbuf;  // keeps a bound handle tensor alive
+  size_t offset = 0, bytes = 0;     // arena placement when !leaf
+  std::vector<int64_t> dims;
+};
+
+enum StepKind { ST_CONTRACT, ST_PERMUTE, ST_VIEW, ST_SAVE };
+
+struct Ref {  // pointer = leaf ? leafptr : arena + offset
+  void* leafptr = nullptr;
+  size_t offset = 0;
+  bool leaf = false;
+  bool null = true;
+};
+
+struct Step {
+  StepKind kind;
+  ContractPlan cp;
+  PermutePlan pp;
+  Ref a, b, c, ta, tb, ws;
+  // view
+  int64_t inner = 1, ext = 1, nsel = 1, outer = 1;
+  int start0 = 1, view_slot = -1;
+  // save
+  std::string key;
+  std::vector<int64_t> dims;
+  std::shared_ptr<Buffer> out;
+};
+
+std::vector<int32_t> parse_ints(const std::string& s) {
+  std::vector<int32_t> v;
+  std::stringstream ss(s);
+  std::string item;
+  while (std::getline(ss, item, ',')) {
+    if (item.empty()) continue;
+    v.push_back((int32_t)std::stol(item));
+  }
+  return v;
+}
+
+}  // namespace
+
+struct pq_program {
+  std::vector<Step> steps;
+  size_t arena_bytes = 0;
+  void* arena = nullptr;
+  int nviews = 0;
+  std::vector<int32_t> default_starts;
+  int32_t* d_starts = nullptr;
+  // pinned ring for asynchronous parameter uploads
+  static constexpr int RING = 32;
+  int32_t* h_ring = nullptr;
+  cudaEvent_t ring_ev[RING];
+  bool ring_used[RING];
+  int ring_pos = 0;
+  cudaGraphExec_t exec = nullptr;
+  int64_t launches = 0, macs = 0, ncontract = 0, max_elems = 0;
+  int device = 0;
+};
+
+static void* resolve(const pq_program* p, const Ref& r) {
+  if (r.null) return nullptr;
+  return r.leaf ? r.leafptr : (void*)((char*)p->arena + r.offset);
+}
+
+static void issue_steps(pq_handle* h, pq_program* p, Launch& L) {
+  for (Step& s : p->steps) {
+    switch (s.kind) {
+      case ST_CONTRACT:
+        run_contract(L, s.cp, resolve(p, s.a), resolve(p, s.b), resolve(p, s.c), resolve(p, s.ta),
+                     resolve(p, s.tb), resolve(p, s.ws));
+        break;
+      case ST_PERMUTE:
+        run_permute(L, s.pp, resolve(p, s.a), resolve(p, s.c));
+        break;
+      case ST_VIEW:
+        run_view(L, resolve(p, s.a), resolve(p, s.c), s.inner, s.ext, s.nsel, s.outer, s.start0,
+                 p->d_starts ? p->d_starts + s.view_slot : nullptr);
+        break;
+      case ST_SAVE: {
+        size_t bytes = size_t(prod(s.dims)) * h->elem_size;
+        L.begin(KC_COPY, 2.0 * bytes, 0);
+        PQ_CUDA(cudaMemcpyAsync(s.out->ptr, resolve(p, s.a), bytes, cudaMemcpyDeviceToDevice,
+                                L.stream));
+        L.end();
+        break;
+      }
+    }
+  }
+}
+
+extern "C" int pq_program_compile(pq_handle* h, const char* tl_text, pq_program** out) {
+  if (!h || !tl_text || !out) return PQ_ERR_INVALID;
+  *out = nullptr;
+  pq_program* p = new pq_program();
+  try {
+    PQ_CUDA(cudaSetDevice(h->device));
+    p->device = h->device;
+    std::map<std::string, Sym> syms;
+    ArenaSim sim;
+    const int es = h->elem_size;
+    auto ref_of = [&](const Sym& s) {
+      Ref r;
+      r.null = false;
+      r.leaf = s.leaf;
+      r.leafptr = s.leaf ? s.leafbuf->ptr : nullptr;
+      r.offset = s.offset;
+      return r;
+    };
+    auto temp_ref = [&](size_t off) {
+      Ref r;
+      r.null = false;
+      r.offset = off;
+      return r;
+    };
+    auto lookup = [&](const std::string& name) -> Sym& {
+      auto it = syms.find(name);
+      if (it == syms.end())
+        throw Error(PQ_ERR_NOT_FOUND, "KeyError: tensor '" + name + "' is not defined in the program");
+      return it->second;
+    };
+    auto drop = [&](const std::string& name) {
+      auto it = syms.find(name);
+      if (it == syms.end()) return;
+      if (!it->second.leaf) sim.release(it->second.offset, it->second.bytes);
+      syms.erase(it);
+    };
+
+    std::stringstream text(tl_text);
+    std::string line;
+    int lineno = 0;
+    while (std::getline(text, line)) {
+      ++lineno;
+      std::stringstream ls(line);
+      std::vector<std::string> tok;
+      std::string w;
+      while (ls >> w) tok.push_back(w);
+      if (tok.empty()) continue;
+      const std::string& cmd = tok[0];
+      auto need = [&](size_t n) {
+        if (tok.size() < n)
+          throw Error(PQ_ERR_PARSE, "line " + std::to_string(lineno) + ": too few arguments for '" +
+                                        cmd + "'");
+      };
+      if (cmd == "tensor") {
+        need(3);
+        Tensor& t = h->get(tok[2]);
+        Sym s;
+        s.leaf = true;
+        s.leafbuf = t.buf;
+        s.dims = t.dims;
+        s.bytes = t.buf->bytes;
+        drop(tok[1]);
+        syms[tok[1]] = s;
+      } else if (cmd == "del") {
+        need(2);
+        drop(tok[1]);
+      } else if (cmd == "ncon") {
+        need(4);
+        size_t pos = 1;
+        std::string C = tok[pos++], A = tok[pos++];
+        Sym sa = lookup(A);
+        std::vector<int32_t> ai, bi;
+        if (!sa.dims.empty()) {
+          need(pos + 1);
+          ai = parse_ints(tok[pos++]);
+        }
+        need(pos + 1);
+        std::string B = tok[pos++];
+        Sym sb = lookup(B);
+        if (!sb.dims.empty()) {
+          need(pos + 1);
+          bi = parse_ints(tok[pos++]);
+        }
+        Step st;
+        st.kind = ST_CONTRACT;
+        st.cp = lower_contract(sa.dims, ai, sb.dims, bi, es, h->opt);
+        st.a = ref_of(sa);
+        st.b = ref_of(sb);
+        Sym sc;
+        sc.dims = st.cp.cdims;
+        sc.bytes = size_t(st.cp.M * st.cp.N) * es;
+        sc.offset = sim.alloc(sc.bytes);
+        st.c = ref_of(sc);
+        size_t oa = 0, ob = 0, ow = 0;
+        if (st.cp.tempA_bytes) st.ta = temp_ref(oa = sim.alloc(st.cp.tempA_bytes));
+        if (st.cp.tempB_bytes) st.tb = temp_ref(ob = sim.alloc(st.cp.tempB_bytes));
+        if (st.cp.ws_bytes) st.ws = temp_ref(ow = sim.alloc(st.cp.ws_bytes));
+        if (st.cp.tempA_bytes) sim.release(oa, st.cp.tempA_bytes);
+        if (st.cp.tempB_bytes) sim.release(ob, st.cp.tempB_bytes);
+        if (st.cp.ws_bytes) sim.release(ow, st.cp.ws_bytes);
+        p->macs += st.cp.M * st.cp.N * st.cp.K;
+        p->ncontract += 1;
+        if (st.cp.M * st.cp.N > p->max_elems) p->max_elems = st.cp.M * st.cp.N;
+        p->steps.push_back(std::move(st));
+        drop(C);
+        syms[C] = sc;  // the DSL's own `del A` / `del B` lines release the operands
+      } else if (cmd == "permute") {
+        need(3);
+        Sym& s = lookup(tok[1]);
+        std::vector<int32_t> axes = parse_ints(tok[2]);
+        PQ_REQUIRE(axes.size() == s.dims.size(), PQ_ERR_INVALID, "permute: axes length != rank");
+        std::vector<int> perm(axes.size());
+        for (size_t k = 0; k < axes.size(); ++k) perm[k] = axes[k] - 1;
+        PermutePlan pp = lower_permute(s.dims, perm, es, h->opt);
+        std::vector<int64_t> nd(axes.size());
+        for (size_t k = 0; k < axes.size(); ++k) nd[k] = s.dims[perm[k]];
+        if (!pp.identity) {
+          Step st;
+          st.kind = ST_PERMUTE;
+          st.pp = pp;
+          st.a = ref_of(s);
+          Sym ns;
+          ns.dims = nd;
+          ns.bytes = size_t(pp.total) * es;
+          ns.offset = sim.alloc(ns.bytes);
+          st.c = ref_of(ns);
+          p->steps.push_back(std::move(st));
+          std::string name = tok[1];
+          drop(name);
+          syms[name] = ns;
+        } else {
+          s.dims = nd;
+        }
+      } else if (cmd == "reshape") {
+        need(3);
+        Sym& s = lookup(tok[1]);
+        std::vector<int64_t> nd;
+        std::stringstream gs(tok[2]);
+        std::string g;
+        while (std::getline(gs, g, ';')) {
+          int64_t d = 1;
+          for (int32_t ax : parse_ints(g)) {
+            PQ_REQUIRE(ax >= 1 && ax <= (int)s.dims.size(), PQ_ERR_INVALID, "reshape: axis out of range");
+            d *= s.dims[ax - 1];
+          }
+          nd.push_back(d);
+        }
+        PQ_REQUIRE(prod(nd) == prod(s.dims), PQ_ERR_SHAPE, "reshape changes the number of elements");
+        s.dims = nd;
+      } else if (cmd == "view") {
+        need(5);
+        Sym src = lookup(tok[2]);
+        int axis = std::stoi(tok[3]);
+        std::vector<int32_t> idx = parse_ints(tok[4]);
+        PQ_REQUIRE(axis >= 1 && axis <= (int)src.dims.size(), PQ_ERR_INVALID, "view: axis out of range");
+        PQ_REQUIRE(!idx.empty(), PQ_ERR_INVALID, "view: empty index list");
+        for (size_t j = 1; j < idx.size(); ++j)
+          PQ_REQUIRE(idx[j] == idx[j - 1] + 1, PQ_ERR_UNSUPPORTED,
+                     "view: programs support contiguous index ranges only");
+        const int64_t ext = src.dims[axis - 1];
+        PQ_REQUIRE(idx.front() >= 1 && idx.back() <= ext, PQ_ERR_INVALID, "view: index out of range");
+        Step st;
+        st.kind = ST_VIEW;
+        for (int d = 0; d < axis - 1; ++d) st.inner *= src.dims[d];
+        for (size_t d = axis; d < src.dims.size(); ++d) st.outer *= src.dims[d];
+        st.ext = ext;
+        st.nsel = (int64_t)idx.size();
+        st.start0 = idx.front();
+        st.view_slot = p->nviews++;
+        p->default_starts.push_back(idx.front());
+        st.a = ref_of(src);
+        Sym v;
+        v.dims = src.dims;
+        v.dims[axis - 1] = st.nsel;
+        v.bytes = size_t(prod(v.dims)) * es;
+        v.offset = sim.alloc(v.bytes);
+        st.c = ref_of(v);
+        p->steps.push_back(std::move(st));
+        drop(tok[1]);
+        syms[tok[1]] = v;
+      } else if (cmd == "save") {
+        need(4);
+        Sym& s = lookup(tok[1]);
+        Step st;
+        st.kind = ST_SAVE;
+        st.a = ref_of(s);
+        st.key = tok[3];
+        st.dims = s.dims;
+        st.out = std::make_shared<Buffer>(size_t(prod(s.dims)) * es, h->stream);
+        p->steps.push_back(std::move(st));
+      } else if (cmd == "decompose") {
+        throw Error(PQ_ERR_UNSUPPORTED, "decompose (SVD) is outside the contraction hot path");
+      }
+      // unknown commands are ignored, like the reference interpreter does
+    }
+
+    p->arena_bytes = sim.top;
+    PQ_CUDA(cudaMalloc(&p->arena, p->arena_bytes ? p->arena_bytes : ALIGN));
+    if (p->nviews > 0) {
+      PQ_CUDA(cudaMalloc(&p->d_starts, sizeof(int32_t) * p->nviews));
+      PQ_CUDA(cudaMemcpy(p->d_starts, p->default_starts.data(), sizeof(int32_t) * p->nviews,
+                         cudaMemcpyHostToDevice));
+      PQ_CUDA(cudaMallocHost(&p->h_ring, sizeof(int32_t) * p->nviews * pq_program::RING));
+      for (int i = 0; i < pq_program::RING; ++i) {
+        PQ_CUDA(cudaEventCreateWithFlags(&p->ring_ev[i], cudaEventDisableTiming));
+        p->ring_used[i] = false;
+      }
+    }
+    // count launches with a dry bookkeeping pass (no device work)
+    {
+      int64_t n = 0;
+      for (const Step& s : p->steps) {
+        if (s.kind == ST_CONTRACT) {
+          if (s.cp.kind == CK_GEMM)
+            n += 1 + (s.cp.permA.identity ? 0 : 1) + (s.cp.permB.identity ? 0 : 1);
+          else if (s.cp.kind == CK_DOT)
+            n += 2;
+          else
+            n += 1;
+        } else {
+          n += 1;
+        }
+      }
+      p->launches = n;
+    }
+  } catch (const Error& e) {
+    h->last_error = e.what();
+    if (p->arena) cudaFree(p->arena);
+    delete p;
+    return e.code;
+  } catch (const std::exception& e) {
+    h->last_error = e.what();
+    delete p;
+    return PQ_ERR_PARSE;
+  }
+  *out = p;
+  return PQ_OK;
+}
+
+extern "C" int pq_program_num_views(const pq_program* p) { return p ? p->nviews : PQ_ERR_INVALID; }
+
+extern "C" int pq_program_stats(const pq_program* p, int64_t* arena_bytes, int64_t* launches,
+                                int64_t* macs) {
+  if (!p) return PQ_ERR_INVALID;
+  if (arena_bytes) *arena_bytes = (int64_t)p->arena_bytes;
+  if (launches) *launches = p->launches;
+  if (macs) *macs = p->macs;
+  return PQ_OK;
+}
+
+extern "C" int pq_program_run(pq_handle* h, pq_program* p, const int32_t* view_starts, int nviews,
+                              const char* accumulate_into) {
+  if (!h || !p) return PQ_ERR_INVALID;
+  try {
+    PQ_CUDA(cudaSetDevice(h->device));
+    PQ_REQUIRE(p->device == h->device, PQ_ERR_INVALID, "program belongs to another device");
+    if (view_starts) {
+      PQ_REQUIRE(nviews == p->nviews, PQ_ERR_INVALID, "pq_program_run: wrong number of view starts");
+      if (p->nviews > 0) {
+        int slot = p->ring_pos;
+        p->ring_pos = (p->ring_pos + 1) % pq_program::RING;
+        if (p->ring_used[slot]) PQ_CUDA(cudaEventSynchronize(p->ring_ev[slot]));
+        int32_t* src = p->h_ring + size_t(slot) * p->nviews;
+        memcpy(src, view_starts, sizeof(int32_t) * p->nviews);
+        PQ_CUDA(cudaMemcpyAsync(p->d_starts, src, sizeof(int32_t) * p->nviews,
+                                cudaMemcpyHostToDevice, h->stream));
+        PQ_CUDA(cudaEventRecord(p->ring_ev[slot], h->stream));
+        p->ring_used[slot] = true;
+      }
+    }
+    Launch L = h->launch_ctx();
+    const bool eager = h->profile || h->opt.graph == 1;
+    if (eager) {
+      issue_steps(h, p, L);
+    } else {
+      if (!p->exec) {
+        Launch LC = L;
+        LC.launch_counter = nullptr;
+        LC.profile = false;
+        cudaGraph_t graph = nullptr;
+        PQ_CUDA(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+        try {
+          issue_steps(h, p, LC);
+        } catch (...) {
+          cudaStreamEndCapture(h->stream, &graph);
+          if (graph) cudaGraphDestroy(graph);
+          throw;
+        }
+        PQ_CUDA(cudaStreamEndCapture(h->stream, &graph));
+        cudaError_t e = cudaGraphInstantiate(&p->exec, graph, 0);
+        cudaGraphDestroy(graph);
+        PQ_CUDA(e);
+      }
+      PQ_CUDA(cudaGraphLaunch(p->exec, h->stream));
+      h->launches += p->launches;
+    }
+    h->n_contract += p->ncontract;
+    h->macs += p->macs;
+    h->note_tensor(p->max_elems);
+    for (Step& s : p->steps) {
+      if (s.kind != ST_SAVE) continue;
+      Tensor t;
+      t.dims = s.dims;
+      t.buf = s.out;
+      h->tensors[s.key] = t;
+      if (accumulate_into) {
+        auto it = h->tensors.find(accumulate_into);
+        int64_t n = prod(s.dims);
+        if (it == h->tensors.end()) {
+          Tensor d;
+          d.dims = s.dims;
+          d.buf = std::make_shared<Buffer>(size_t(n) * h->elem_size, h->stream);
+          L.begin(KC_COPY, 2.0 * n * h->elem_size, 0);
+          PQ_CUDA(cudaMemcpyAsync(d.buf->ptr, s.out->ptr, size_t(n) * h->elem_size,
+                                  cudaMemcpyDeviceToDevice, h->stream));
+          L.end();
+          h->tensors[accumulate_into] = d;
+        } else {
+          PQ_REQUIRE(it->second.numel() == n, PQ_ERR_SHAPE, "accumulate: size mismatch");
+          run_accumulate(L, it->second.buf->ptr, s.out->ptr, n);
+        }
+      }
+    }
+  } catch (const Error& e) {
+    h->last_error = e.what();
+    return e.code;
+  } catch (const std::exception& e) {
+    h->last_error = e.what();
+    return PQ_ERR_INVALID;
+  }
+  return PQ_OK;
+}
+
+extern "C" int pq_program_destroy(pq_handle* h, pq_program* p) {
+  if (!p) return PQ_OK;
+  if (h) {
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+  }
+  if (p->exec) cudaGraphExecDestroy(p->exec);
+  if (p->arena) cudaFree(p->arena);
+  if (p->d_starts) cudaFree(p->d_starts);
+  if (p->h_ring) {
+    cudaFreeHost(p->h_ring);
+    for (int i = 0; i < pq_program::RING; ++i) cudaEventDestroy(p->ring_ev[i]);
+  }
+  delete p;
+  return PQ_OK;
+}

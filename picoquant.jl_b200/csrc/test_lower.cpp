@@ -1,0 +1,298 @@
+// CPU harness for the integer half of the CUDA path: emulates the tiled
+// bit-permutation kernel and the gather maps of the contraction kernels on the host,
+// using the very same index functions the kernels call (tile_math.h, map_offset), and
+// compares them with brute-force multi-index arithmetic.  Run by tests/test_lowering.py.
+#include <algorithm>
+#include <complex>
+#include <cstdio>
+#include <cstdlib>
+#include <numeric>
+#include <random>
+
+#include "common.h"
+#include "tile_math.h"
+
+using namespace pq;
+typedef std::complex<double> cd;
+
+static int failures = 0;
+#define CHECK(cond, ...)            \
+  do {                              \
+    if (!(cond)) {                  \
+      ++failures;                   \
+      std::printf("FAIL: " __VA_ARGS__); \
+      std::printf("\n");            \
+    }                               \
+  } while (0)
+
+// brute force: out[o] = in[i] where the multi-index of o over out dims maps to perm
+static std::vector<int64_t> ref_permute_sources(const std::vector<int64_t>& dims,
+                                                const std::vector<int>& perm) {
+  int r = (int)dims.size();
+  int64_t total = prod(dims);
+  std::vector<int64_t> istr(r);
+  int64_t acc = 1;
+  for (int i = 0; i < r; ++i) {
+    istr[i] = acc;
+    acc *= dims[i];
+  }
+  std::vector<int64_t> src(total);
+  for (int64_t o = 0; o < total; ++o) {
+    int64_t rem = o, off = 0;
+    for (int k = 0; k < r; ++k) {
+      int64_t e = dims[perm[k]];
+      off += (rem % e) * istr[perm[k]];
+      rem /= e;
+    }
+    src[o] = off;
+  }
+  return src;
+}
+
+static void emulate_tiled(const TileParams& tp, std::vector<int64_t>& out_src, int elem_size) {
+  // out_src[o] = input offset that lands at output offset o
+  const int T = 1 << tp.t;
+  std::vector<int64_t> tile(T);
+  const int c = elem_size == 16 ? 3 : 4;
+  for (long long r = 0; r < tp.ntiles; ++r) {
+    long long ib, ob;
+    tile_bases(tp, r, ib, ob);
+    std::vector<char> used(T, 0);
+    for (int e = 0; e < T; ++e) {
+      int s = tile_swizzle(tp, e);
+      CHECK(s >= 0 && s < T && !used[s], "swizzle not a bijection (e=%d s=%d)", e, s);
+      used[s] = 1;
+      tile[s] = ib + ((long long)(e & 31) | tile_in_hi(tp, e >> TILE_LO));
+    }
+    for (int o = 0; o < T; ++o) {
+      int e = tile_e_lo(tp, o & 31) | tile_e_hi(tp, o >> TILE_LO);
+      long long dst = ob + ((long long)(o & 31) | tile_out_hi(tp, o >> TILE_LO));
+      out_src[dst] = tile[tile_swizzle(tp, e)];
+    }
+    // bank-conflict freedom of both phases for the first tile
+    if (r == 0) {
+      const int group = 1 << c;
+      for (int base = 0; base < T; base += group) {
+        unsigned seen_w = 0, seen_r = 0;
+        for (int q = 0; q < group; ++q) {
+          int sw = tile_swizzle(tp, base + q) & (group - 1);
+          int o = base + q;
+          int e = tile_e_lo(tp, o & 31) | tile_e_hi(tp, o >> TILE_LO);
+          int sr = tile_swizzle(tp, e) & (group - 1);
+          seen_w |= 1u << sw;
+          seen_r |= 1u << sr;
+        }
+        CHECK(seen_w == (1u << group) - 1, "smem write conflict at e-base %d", base);
+        CHECK(seen_r == (1u << group) - 1, "smem read conflict at o-base %d", base);
+      }
+    }
+  }
+}
+
+static void test_permutations(std::mt19937& rng) {
+  Options opt;
+  int tiled_cases = 0, generic_cases = 0;
+  for (int iter = 0; iter < 300; ++iter) {
+    int elem = (iter & 1) ? 16 : 8;
+    std::vector<int64_t> dims;
+    int64_t total = 1;
+    bool pow2 = (iter % 3) != 0;
+    int target_bits = 4 + (int)(rng() % 13);  // up to 2^16 elements
+    while (true) {
+      int64_t e = pow2 ? (int64_t(1) << (rng() % 3)) : (int64_t)(1 + rng() % 5);
+      if (total * e > (int64_t(1) << target_bits)) break;
+      dims.push_back(e);
+      total *= e;
+      if (dims.size() >= 20) break;
+    }
+    if (dims.empty()) dims.push_back(1);
+    std::vector<int> perm(dims.size());
+    std::iota(perm.begin(), perm.end(), 0);
+    if (iter % 7 == 0) {
+      // a "gate application" style permutation: move one axis to the end
+      int a = (int)(rng() % perm.size());
+      std::rotate(perm.begin() + a, perm.begin() + a + 1, perm.end());
+    } else if (iter % 11 != 0) {
+      std::shuffle(perm.begin(), perm.end(), rng);
+    }
+    PermutePlan P = lower_permute(dims, perm, elem, opt);
+    std::vector<int64_t> ref = ref_permute_sources(dims, perm);
+    if (P.identity) {
+      for (int64_t o = 0; o < total; ++o) CHECK(ref[o] == o, "identity plan for a non-identity permutation");
+      continue;
+    }
+    for (int64_t o = 0; o < total; ++o) {
+      int64_t got = map_offset(P.gmap, o);
+      if (got != ref[o]) {
+        CHECK(false, "generic map mismatch at %lld (iter %d)", (long long)o, iter);
+        break;
+      }
+    }
+    ++generic_cases;
+    if (P.tiled) {
+      ++tiled_cases;
+      CHECK(P.tp.a >= 5 && P.tp.b >= 5, "tile runs too short");
+      std::vector<int64_t> got(total, -1);
+      emulate_tiled(P.tp, got, elem);
+      for (int64_t o = 0; o < total; ++o)
+        if (got[o] != ref[o]) {
+          CHECK(false, "tiled permute mismatch at %lld (iter %d, n=%d t=%d)", (long long)o, iter,
+                P.tp.n, P.tp.t);
+          break;
+        }
+    }
+  }
+  std::printf("permutations: %d generic, %d tiled cases\n", generic_cases, tiled_cases);
+  CHECK(tiled_cases > 20, "too few tiled cases exercised");
+}
+
+static void test_contractions(std::mt19937& rng) {
+  int kinds[5] = {0, 0, 0, 0, 0};
+  for (int iter = 0; iter < 600; ++iter) {
+    Options opt;
+    if (iter % 5 == 1) opt.fused = 1;
+    if (iter % 5 == 2) opt.gemm = 3;
+    // random label assignment: each label goes to A only, B only, or both
+    int nlab = 1 + (int)(rng() % (iter % 3 == 0 ? 12 : 7));
+    std::vector<int64_t> ad, bd;
+    std::vector<int32_t> ai, bi;
+    int nopen = 0, ncon = 0;
+    for (int l = 0; l < nlab; ++l) {
+      int64_t e = (iter % 4 == 0) ? (int64_t)(1 + rng() % 4) : (int64_t(1) << (rng() % 3));
+      int where = (int)(rng() % 3);
+      if (where == 0) { ad.push_back(e); ai.push_back(-(++nopen)); }
+      else if (where == 1) { bd.push_back(e); bi.push_back(-(++nopen)); }
+      else { ++ncon; ad.push_back(e); ai.push_back(ncon); bd.push_back(e); bi.push_back(ncon); }
+    }
+    // shuffle axis order of each operand independently
+    auto shuffle_axes = [&](std::vector<int64_t>& d, std::vector<int32_t>& ix) {
+      std::vector<int> p(d.size());
+      std::iota(p.begin(), p.end(), 0);
+      std::shuffle(p.begin(), p.end(), rng);
+      std::vector<int64_t> d2(d.size());
+      std::vector<int32_t> i2(d.size());
+      for (size_t k = 0; k < p.size(); ++k) { d2[k] = d[p[k]]; i2[k] = ix[p[k]]; }
+      d = d2; ix = i2;
+    };
+    shuffle_axes(ad, ai);
+    shuffle_axes(bd, bi);
+    ContractPlan P = lower_contract(ad, ai, bd, bi, 16, opt);
+    kinds[P.kind]++;
+    int64_t na = prod(ad), nb = prod(bd);
+    std::vector<cd> A(na), B(nb);
+    for (auto& x : A) x = cd((double)(rng() % 17) - 8, (double)(rng() % 13) - 6);
+    for (auto& x : B) x = cd((double)(rng() % 11) - 5, (double)(rng() % 7) - 3);
+    // brute force over all labels
+    std::vector<int64_t> astr(ad.size()), bstr(bd.size());
+    { int64_t s = 1; for (size_t i = 0; i < ad.size(); ++i) { astr[i] = s; s *= ad[i]; } }
+    { int64_t s = 1; for (size_t i = 0; i < bd.size(); ++i) { bstr[i] = s; s *= bd[i]; } }
+    // C axes: A-open (A order) then B-open (B order)
+    std::vector<int> a_open, b_open, a_con, b_con;
+    for (size_t i = 0; i < ai.size(); ++i) {
+      auto it = std::find(bi.begin(), bi.end(), ai[i]);
+      if (it == bi.end()) a_open.push_back((int)i);
+      else { a_con.push_back((int)i); b_con.push_back((int)(it - bi.begin())); }
+    }
+    for (size_t i = 0; i < bi.size(); ++i)
+      if (std::find(ai.begin(), ai.end(), bi[i]) == ai.end()) b_open.push_back((int)i);
+    int64_t M = 1, N = 1, K = 1;
+    for (int i : a_open) M *= ad[i];
+    for (int i : b_open) N *= bd[i];
+    for (int i : a_con) K *= ad[i];
+    CHECK(M == P.M && N == P.N && K == P.K, "M/N/K mismatch");
+    CHECK(prod(P.cdims) == M * N, "cdims product mismatch");
+    std::vector<cd> Cref(M * N), Cgot(M * N);
+    for (int64_t m = 0; m < M; ++m)
+      for (int64_t n = 0; n < N; ++n) {
+        int64_t oa = 0, ob = 0, r = m;
+        for (int i : a_open) { oa += (r % ad[i]) * astr[i]; r /= ad[i]; }
+        r = n;
+        for (int i : b_open) { ob += (r % bd[i]) * bstr[i]; r /= bd[i]; }
+        cd acc = 0;
+        for (int64_t k = 0; k < K; ++k) {
+          int64_t ka = 0, kb = 0, rk = k;
+          for (size_t q = 0; q < a_con.size(); ++q) {
+            int64_t e = ad[a_con[q]];
+            ka += (rk % e) * astr[a_con[q]];
+            kb += (rk % e) * bstr[b_con[q]];
+            rk /= e;
+          }
+          acc += A[oa + ka] * B[ob + kb];
+        }
+        Cref[m + M * n] = acc;
+      }
+    // the maps the kernels use
+    for (int64_t m = 0; m < M; ++m)
+      for (int64_t n = 0; n < N; ++n) {
+        cd acc = 0;
+        for (int64_t k = 0; k < K; ++k)
+          acc += A[map_offset(P.mA, m) + map_offset(P.kA, k)] *
+                 B[map_offset(P.nB, n) + map_offset(P.kB, k)];
+        Cgot[m + M * n] = acc;
+      }
+    for (int64_t i = 0; i < M * N; ++i)
+      if (Cgot[i] != Cref[i]) {
+        CHECK(false, "contraction map mismatch (iter %d)", iter);
+        break;
+      }
+    // canonical TTGT layouts: A' = [M|K], B' = [N|K]
+    if (P.kind == CK_GEMM) {
+      std::vector<cd> Ap(M * K), Bp(N * K);
+      if (P.permA.identity) Ap = A;
+      else for (int64_t i = 0; i < M * K; ++i) Ap[i] = A[map_offset(P.permA.gmap, i)];
+      if (P.permB.identity) Bp = B;
+      else for (int64_t i = 0; i < N * K; ++i) Bp[i] = B[map_offset(P.permB.gmap, i)];
+      for (int64_t m = 0; m < M; ++m)
+        for (int64_t n = 0; n < N; ++n) {
+          cd acc = 0;
+          for (int64_t k = 0; k < K; ++k) acc += Ap[m + M * k] * Bp[n + N * k];
+          if (acc != Cref[m + M * n]) {
+            CHECK(false, "TTGT layout mismatch (iter %d)", iter);
+            m = M; break;
+          }
+        }
+    }
+  }
+  std::printf("contractions: small_right %d small_left %d direct %d dot %d gemm %d\n", kinds[0],
+              kinds[1], kinds[2], kinds[3], kinds[4]);
+}
+
+static void test_big_shapes() {
+  // QFT-26 style gate application and an RQC sweep step: only check plan selection
+  Options opt;
+  std::vector<int64_t> ad(26, 2), bd(4, 2);
+  std::vector<int32_t> ai(26), bi = {1, 2, -25, -26};
+  int o = 0;
+  for (int i = 0; i < 26; ++i) ai[i] = (i == 7) ? 1 : (i == 19) ? 2 : -(++o);
+  ContractPlan P = lower_contract(ad, ai, bd, bi, 16, opt);
+  CHECK(P.kind == CK_SMALL_RIGHT && P.M == (1 << 24) && P.N == 4 && P.K == 4, "QFT gate plan");
+  CHECK(P.mA.nd == 3 && P.kA.nd == 2, "QFT gate fusion: got %d m-groups %d k-groups", P.mA.nd, P.kA.nd);
+  std::vector<int64_t> ad2(24, 2), bd2(12, 2);
+  std::vector<int32_t> ai2(24), bi2(12);
+  o = 0;
+  for (int i = 0; i < 24; ++i) ai2[i] = (i % 4 == 1) ? (i / 4 + 1) : -(++o);
+  for (int i = 0; i < 12; ++i) bi2[i] = (i < 6) ? (6 - i) : -(++o);
+  P = lower_contract(ad2, ai2, bd2, bi2, 16, opt);
+  CHECK(P.kind == CK_GEMM && P.M == (1 << 18) && P.N == 64 && P.K == 64, "sweep step plan");
+  CHECK(!P.permA.identity && P.permA.tiled, "sweep step A permute should be tiled");
+  std::printf("big shapes: ok (sweep A-permute tile t=%d a=%d b=%d)\n", P.permA.tp.t, P.permA.tp.a,
+              P.permA.tp.b);
+}
+
+int main() {
+  std::mt19937 rng(12345);
+  try {
+    test_permutations(rng);
+    test_contractions(rng);
+    test_big_shapes();
+  } catch (const Error& e) {
+    std::printf("FAIL: exception %d %s\n", e.code, e.what());
+    return 2;
+  }
+  if (failures) {
+    std::printf("FAILED %d checks\n", failures);
+    return 1;
+  }
+  std::printf("ALL OK\n");
+  return 0;
+}

@@ -1,0 +1,312 @@
+"""``B200Backend``: PicoQuant's backend interface on top of ``libpq_b200.so``.
+
+The Python twin of ``InteractiveBackend{T}`` (``src/backends/interactive.jl``)
+whose tensor store lives in B200 HBM behind the C ABI declared in
+``include/pq_b200.h``.  The nine backend functions keep the reference's names,
+argument meaning (1-based, column-major) and error behaviour (missing label ->
+``KeyError``; ``load_tensor_data`` of a missing label -> ``None``;
+``delete_tensor`` of a missing label is fine).
+
+There is **no CPU fallback**: if the shared library is missing, cannot be
+loaded, or no CUDA device is usable, construction raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import (POINTER, byref, c_char_p, c_double, c_int, c_int32, c_int64, c_void_p)
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from .backends import AbstractBackend, Metrics
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), "csrc", "libpq_b200.so")
+
+PQ_C64, PQ_C128 = 0, 1
+PQ_HOST_F32, PQ_HOST_F64, PQ_HOST_C64, PQ_HOST_C128 = 0, 1, 2, 3
+PQ_MAX_RANK = 64
+PQ_NUM_KERNEL_CLASSES = 12
+
+_STATUS = {-1: "PQ_ERR_INVALID", -2: "PQ_ERR_NOT_FOUND", -3: "PQ_ERR_SHAPE", -4: "PQ_ERR_CUDA",
+           -5: "PQ_ERR_NCCL", -6: "PQ_ERR_PARSE", -7: "PQ_ERR_UNSUPPORTED"}
+
+# every symbol include/pq_b200.h declares (checked by tests/test_abi.py)
+ABI_SYMBOLS = [
+    "pq_create", "pq_destroy", "pq_last_error", "pq_version", "pq_save_tensor",
+    "pq_tensor_info", "pq_load_tensor", "pq_contract", "pq_permute", "pq_reshape", "pq_view",
+    "pq_delete", "pq_save_output", "pq_sync", "pq_accumulate", "pq_comm_unique_id",
+    "pq_comm_init", "pq_allreduce_sum", "pq_program_compile", "pq_program_num_views",
+    "pq_program_run", "pq_program_destroy", "pq_program_stats", "pq_get_counters",
+    "pq_reset_counters", "pq_profile_enable", "pq_profile_read", "pq_kernel_class_name",
+    "pq_set_option", "pq_microbench",
+]
+
+_lib = None
+
+
+class B200Error(RuntimeError):
+    pass
+
+
+def load_library(path: Optional[str] = None) -> ctypes.CDLL:
+    """Loads ``libpq_b200.so`` (built in-tree by ``__graft_entry__.build()``) and
+    declares the prototypes.  Raises if the library is absent."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    p = path or LIB_PATH
+    if not os.path.isfile(p):
+        raise B200Error("libpq_b200.so not found at %s -- run __graft_entry__.build() "
+                        "(there is no CPU fallback)" % p)
+    lib = ctypes.CDLL(p)
+    i32p, i64p = POINTER(c_int32), POINTER(c_int64)
+    lib.pq_version.restype = c_char_p
+    lib.pq_last_error.restype = c_char_p
+    lib.pq_last_error.argtypes = [c_void_p]
+    lib.pq_kernel_class_name.restype = c_char_p
+    lib.pq_kernel_class_name.argtypes = [c_int]
+    lib.pq_create.argtypes = [c_int, c_int, POINTER(c_void_p)]
+    lib.pq_destroy.argtypes = [c_void_p]
+    lib.pq_save_tensor.argtypes = [c_void_p, c_char_p, c_int, i64p, c_void_p, c_int]
+    lib.pq_tensor_info.argtypes = [c_void_p, c_char_p, POINTER(c_int), i64p]
+    lib.pq_load_tensor.argtypes = [c_void_p, c_char_p, c_void_p, c_int]
+    lib.pq_contract.argtypes = [c_void_p, c_char_p, i32p, c_int, c_char_p, i32p, c_int, c_char_p]
+    lib.pq_permute.argtypes = [c_void_p, c_char_p, i32p, c_int]
+    lib.pq_reshape.argtypes = [c_void_p, c_char_p, i32p, i32p, c_int]
+    lib.pq_view.argtypes = [c_void_p, c_char_p, c_char_p, c_int, i32p, c_int]
+    lib.pq_delete.argtypes = [c_void_p, c_char_p]
+    lib.pq_save_output.argtypes = [c_void_p, c_char_p, c_char_p]
+    lib.pq_sync.argtypes = [c_void_p]
+    lib.pq_accumulate.argtypes = [c_void_p, c_char_p, c_char_p]
+    lib.pq_comm_unique_id.argtypes = [c_void_p]
+    lib.pq_comm_init.argtypes = [c_void_p, c_void_p, c_int, c_int]
+    lib.pq_allreduce_sum.argtypes = [c_void_p, c_char_p]
+    lib.pq_program_compile.argtypes = [c_void_p, c_char_p, POINTER(c_void_p)]
+    lib.pq_program_num_views.argtypes = [c_void_p]
+    lib.pq_program_run.argtypes = [c_void_p, c_void_p, i32p, c_int, c_char_p]
+    lib.pq_program_destroy.argtypes = [c_void_p, c_void_p]
+    lib.pq_program_stats.argtypes = [c_void_p, i64p, i64p, i64p]
+    lib.pq_get_counters.argtypes = [c_void_p, i64p, i64p, i64p, i64p]
+    lib.pq_reset_counters.argtypes = [c_void_p]
+    lib.pq_profile_enable.argtypes = [c_void_p, c_int]
+    lib.pq_profile_read.argtypes = [c_void_p, POINTER(c_double), i64p, POINTER(c_double),
+                                    POINTER(c_double)]
+    lib.pq_set_option.argtypes = [c_void_p, c_char_p, c_int]
+    lib.pq_microbench.argtypes = [c_void_p, c_char_p, POINTER(c_double)]
+    for name in ABI_SYMBOLS:
+        fn = getattr(lib, name)
+        if fn.restype is not c_char_p:
+            fn.restype = c_int
+    if path is None:
+        _lib = lib
+    return lib
+
+
+def _i32(values: Sequence[int]):
+    arr = (c_int32 * max(1, len(values)))(*[int(v) for v in values])
+    return arr
+
+
+_HOST_DTYPES = {np.dtype(np.float32): PQ_HOST_F32, np.dtype(np.float64): PQ_HOST_F64,
+                np.dtype(np.complex64): PQ_HOST_C64, np.dtype(np.complex128): PQ_HOST_C128}
+
+
+class Program:
+    """A compiled ``.tl`` command stream (``pq_program``)."""
+
+    def __init__(self, backend: "B200Backend", text: str) -> None:
+        self.backend = backend
+        self._p = c_void_p()
+        backend._check(backend.lib.pq_program_compile(backend._h, text.encode(), byref(self._p)))
+        self.num_views = backend.lib.pq_program_num_views(self._p)
+        a, l, m = c_int64(), c_int64(), c_int64()
+        backend.lib.pq_program_stats(self._p, byref(a), byref(l), byref(m))
+        self.arena_bytes, self.launches, self.macs = a.value, l.value, m.value
+
+    def run(self, view_starts: Optional[Sequence[int]] = None,
+            accumulate_into: Optional[str] = None) -> None:
+        b = self.backend
+        if view_starts is None:
+            vs, n = None, 0
+        else:
+            vs, n = _i32(view_starts), len(view_starts)
+        acc = accumulate_into.encode() if accumulate_into else None
+        b._check(b.lib.pq_program_run(b._h, self._p, vs, n, acc))
+
+    def close(self) -> None:
+        if self._p:
+            self.backend.lib.pq_program_destroy(self.backend._h, self._p)
+            self._p = c_void_p()
+
+    def __del__(self):
+        try:
+            if self.backend._h:
+                self.close()
+        except Exception:
+            pass
+
+
+class B200Backend(AbstractBackend):
+    """``InteractiveBackend{CuArray{T}}`` re-thought: labels -> tensors in HBM.
+
+    ``dtype`` is the backend element type (``np.complex64`` default, like the
+    reference's default constructor, or ``np.complex128``)."""
+
+    def __init__(self, dtype=np.complex64, device: int = 0) -> None:
+        self.lib = load_library()
+        self.dtype = np.dtype(dtype)
+        if self.dtype not in (np.dtype(np.complex64), np.dtype(np.complex128)):
+            raise ValueError("backend dtype must be complex64 or complex128")
+        self.metrics = Metrics()
+        self._h = c_void_p()
+        rc = self.lib.pq_create(int(device), PQ_C128 if self.dtype == np.complex128 else PQ_C64,
+                                byref(self._h))
+        if rc != 0 or not self._h:
+            self._h = c_void_p()
+            raise B200Error("pq_create failed (%s): a CUDA device is required, there is no CPU "
+                            "fallback" % _STATUS.get(rc, rc))
+        self.device = device
+
+    # -- plumbing -----------------------------------------------------------
+    def _check(self, rc: int) -> None:
+        if rc == 0:
+            return
+        msg = self.lib.pq_last_error(self._h).decode(errors="replace")
+        if rc == -2:
+            raise KeyError(msg)
+        if rc == -3:
+            raise ValueError("DimensionMismatch: " + msg)
+        raise B200Error("%s: %s" % (_STATUS.get(rc, rc), msg))
+
+    def close(self) -> None:
+        if self._h:
+            self.lib.pq_destroy(self._h)
+            self._h = c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- the nine backend functions -----------------------------------------
+    def save_tensor_data(self, tensor_label, tensor_data):
+        arr = np.asarray(tensor_data)
+        if arr.dtype not in _HOST_DTYPES:
+            arr = arr.astype(np.complex128 if np.iscomplexobj(arr) else np.float64)
+        arr = np.asarray(arr, order="F")
+        if not arr.flags.f_contiguous:
+            arr = np.array(arr, order="F")
+        dims = (c_int64 * max(1, arr.ndim))(*arr.shape)
+        self._check(self.lib.pq_save_tensor(self._h, tensor_label.encode(), arr.ndim, dims,
+                                            arr.ctypes.data_as(c_void_p), _HOST_DTYPES[arr.dtype]))
+
+    def tensor_shape(self, tensor_label):
+        rank = c_int()
+        dims = (c_int64 * PQ_MAX_RANK)()
+        rc = self.lib.pq_tensor_info(self._h, tensor_label.encode(), byref(rank), dims)
+        if rc == -2:
+            return None
+        self._check(rc)
+        return tuple(dims[i] for i in range(rank.value))
+
+    def load_tensor_data(self, tensor_label):
+        shape = self.tensor_shape(tensor_label)
+        if shape is None:
+            return None
+        out = np.empty(shape, dtype=self.dtype, order="F")
+        code = PQ_HOST_C128 if self.dtype == np.complex128 else PQ_HOST_C64
+        self._check(self.lib.pq_load_tensor(self._h, tensor_label.encode(),
+                                            out.ctypes.data_as(c_void_p), code))
+        return out
+
+    def contract_tensors(self, A_label, A_ncon_indices, B_label, B_ncon_indices, C_label):
+        self._check(self.lib.pq_contract(self._h, A_label.encode(), _i32(A_ncon_indices),
+                                         len(A_ncon_indices), B_label.encode(),
+                                         _i32(B_ncon_indices), len(B_ncon_indices),
+                                         C_label.encode()))
+
+    def save_output(self, node, name="result"):
+        self._check(self.lib.pq_save_output(self._h, node.encode(), name.encode()))
+
+    def reshape_tensor(self, tensor, groups):
+        flat: List[int] = [int(x) for g in groups for x in g]
+        sizes = [len(g) for g in groups]
+        self._check(self.lib.pq_reshape(self._h, tensor.encode(), _i32(flat), _i32(sizes),
+                                        len(sizes)))
+
+    def permute_tensor(self, tensor, axes):
+        self._check(self.lib.pq_permute(self._h, tensor.encode(), _i32(axes), len(axes)))
+
+    def decompose_tensor(self, tensor, left_positions, right_positions, *, threshold=1e-13,
+                         max_rank=0, left_label, right_label):
+        raise NotImplementedError("decompose_tensor! (SVD) is outside the contraction hot path "
+                                  "(SURVEY §8f)")
+
+    def delete_tensor(self, tensor_label):
+        self.lib.pq_delete(self._h, tensor_label.encode())
+
+    def view_tensor(self, view_node, node, bond_idx, bond_range):
+        idx = list(bond_range)
+        self._check(self.lib.pq_view(self._h, view_node.encode(), node.encode(), int(bond_idx),
+                                     _i32(idx), len(idx)))
+
+    # -- beyond the nine: sliced accumulation, programs, instrumentation ------
+    def sync(self):
+        self._check(self.lib.pq_sync(self._h))
+
+    def accumulate(self, dst, src):
+        self._check(self.lib.pq_accumulate(self._h, dst.encode(), src.encode()))
+
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        lib = load_library()
+        buf = ctypes.create_string_buffer(128)
+        rc = lib.pq_comm_unique_id(buf)
+        if rc != 0:
+            raise B200Error("pq_comm_unique_id failed: %s" % _STATUS.get(rc, rc))
+        return buf.raw
+
+    def comm_init(self, unique_id: bytes, rank: int, nranks: int):
+        buf = ctypes.create_string_buffer(unique_id, 128)
+        self._check(self.lib.pq_comm_init(self._h, buf, rank, nranks))
+
+    def allreduce_sum(self, label):
+        self._check(self.lib.pq_allreduce_sum(self._h, label.encode()))
+
+    def compile_program(self, tl_text: str) -> Program:
+        return Program(self, tl_text)
+
+    def counters(self):
+        a, b, c, d = c_int64(), c_int64(), c_int64(), c_int64()
+        self._check(self.lib.pq_get_counters(self._h, byref(a), byref(b), byref(c), byref(d)))
+        return {"n_contract": a.value, "macs": b.value, "max_elems": c.value,
+                "kernel_launches": d.value}
+
+    def reset_counters(self):
+        self.lib.pq_reset_counters(self._h)
+
+    def profile_enable(self, on: bool):
+        self._check(self.lib.pq_profile_enable(self._h, 1 if on else 0))
+
+    def profile_read(self):
+        n = PQ_NUM_KERNEL_CLASSES
+        ms, la = (c_double * n)(), (c_int64 * n)()
+        by, fl = (c_double * n)(), (c_double * n)()
+        self._check(self.lib.pq_profile_read(self._h, ms, la, by, fl))
+        out = {}
+        for i in range(n):
+            if la[i]:
+                out[self.lib.pq_kernel_class_name(i).decode()] = {
+                    "ms": ms[i], "launches": la[i], "bytes": by[i], "flops": fl[i]}
+        return out
+
+    def set_option(self, key: str, value: int):
+        self._check(self.lib.pq_set_option(self._h, key.encode(), int(value)))
+
+    def microbench(self, what: str) -> float:
+        r = c_double()
+        self._check(self.lib.pq_microbench(self._h, what.encode(), byref(r)))
+        return r.value

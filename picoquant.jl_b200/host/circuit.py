@@ -191,6 +191,25 @@ class Circuit:
                 lines.append("%s %s;" % (name, args))
         return "\n".join(lines) + "\n"
 
+    def simulate(self, input_config: str = None) -> np.ndarray:
+        """Dense little-endian state-vector simulation (known-answer tests only;
+        stands in for qiskit Aer in test/algorithms_tests.jl).  Input caps follow
+        ``add_input!`` ('0', '1', '+', '-')."""
+        n = self.n_qubits
+        caps = {"0": [1, 0], "1": [0, 1], "+": [2 ** -0.5, 2 ** -0.5], "-": [2 ** -0.5, -2 ** -0.5]}
+        cfg = input_config or "0" * n
+        psi = np.ones(1, dtype=np.complex128)
+        for ch in cfg:            # qubit 0 is the fastest (least significant) axis
+            psi = np.kron(np.array(caps[ch], dtype=np.complex128), psi)
+        psi = psi.reshape((2,) * n)   # C-order: axis 0 <-> qubit n-1, axis n-1 <-> qubit 0
+        for name, params, qubits in self.gates():
+            k = len(qubits)
+            g = gate_matrix(name, params).reshape((2,) * (2 * k))  # [out_{k-1}..out_0, in_{k-1}..in_0]
+            axes = [n - 1 - q for q in reversed(qubits)]           # state axes of q_{k-1}..q_0
+            psi = np.tensordot(g, psi, axes=(list(range(k, 2 * k)), axes))
+            psi = np.moveaxis(psi, list(range(k)), axes)
+        return psi.reshape(-1)
+
     def to_matrix(self) -> np.ndarray:
         """Dense unitary (little-endian), for tiny known-answer tests only."""
         n = self.n_qubits

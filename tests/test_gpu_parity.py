@@ -1,0 +1,475 @@
+"""GPU parity tests: the CUDA path behind the C ABI (B200Backend) against the CPU
+oracle on the same seeded inputs, plus the reference's own known-answer tests and
+size-independent properties at BASELINE sizes.  Tolerances are the north-star's:
+rel-L2 <= 1e-10 for ComplexF64 and <= 1e-5 for ComplexF32 (checked against the
+F64 oracle downcast); pure data movement (permute / view) must be bit-exact."""
+import random
+
+import numpy as np
+import pytest
+
+from helpers import TOL, golden_qasm, load_golden_json, rel_l2, statevector, switch_endianness
+from oracle import layer1
+from oracle.interactive import OracleBackend, execute_dsl
+from picoquant_jl_b200.host import (Circuit, DSLBackend, TensorNetworkCircuit, add_gate,
+                                    add_input, add_output, contract_network, contract_pair,
+                                    convert_circuit_to_network, create_ghz_preparation_circuit,
+                                    create_qft_circuit, create_RQC,
+                                    create_simple_preparation_circuit,
+                                    full_wavefunction_contraction, load_qasm_as_circuit,
+                                    network_from_dict, partition_network_on_virtual_bonds,
+                                    random_contraction_plan, slice_tensor_network)
+from picoquant_jl_b200.host.backends import TensorStore
+from picoquant_jl_b200.host.planner import greedy_plan, sweep_plan
+from picoquant_jl_b200.host.sliced import SlicedContraction, record_sliced_contraction
+
+pytestmark = pytest.mark.gpu
+
+DTYPES = [np.complex128, np.complex64]
+
+
+def B200(dtype, **opts):
+    from picoquant_jl_b200.host.b200_backend import B200Backend
+    b = B200Backend(dtype)
+    for k, v in opts.items():
+        b.set_option(k, v)
+    return b
+
+
+def rand_tensor(rng, shape, dtype):
+    a = rng.standard_normal(shape) + 1j * rng.standard_normal(shape)
+    return np.asarray(a.astype(dtype), order="F")
+
+
+# ---------------------------------------------------------------------------
+# kernel level
+# ---------------------------------------------------------------------------
+PERMUTE_CASES = [
+    ((2,) * 12, "reverse"), ((2,) * 14, "random"), ((2,) * 16, "rotate3"), ((2,) * 18, "random"),
+    ((2,) * 20, "qft"), ((4, 2, 2, 8, 2, 4, 2, 2, 2, 2, 2), "random"), ((3, 5, 2, 7, 4), "random"),
+    ((2, 3), "reverse"), ((1, 2, 1, 2), "random"), ((64, 64), "reverse"), ((2,) * 22, "random"),
+    ((6, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2), "random"), ((2,) * 13, "identity"), ((7,), "identity"),
+]
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("mode", [0, 1])
+def test_permute_bit_exact(dtype, mode):
+    rng = np.random.default_rng(3)
+    prng = random.Random(5)
+    b = B200(dtype, permute=mode)
+    for shape, kind in PERMUTE_CASES:
+        r = len(shape)
+        if kind == "reverse":
+            perm = list(range(r, 0, -1))
+        elif kind == "identity":
+            perm = list(range(1, r + 1))
+        elif kind == "rotate3":
+            perm = list(range(4, r + 1)) + [1, 2, 3]
+        elif kind == "qft":  # the final permute of full-wf QFT: [1,3,5,...,6,4,2]
+            perm = list(range(1, r + 1, 2)) + list(range(r - (r % 2), 0, -2))
+        else:
+            perm = list(range(1, r + 1))
+            prng.shuffle(perm)
+        a = rand_tensor(rng, shape, dtype)
+        b.save_tensor_data("t", a)
+        b.permute_tensor("t", perm)
+        got = b.load_tensor_data("t")
+        ref = layer1.permute_tensor(a, perm)
+        assert got.shape == ref.shape, (shape, perm)
+        assert np.array_equal(got, ref), (shape, perm, kind)
+
+
+def _random_contraction(rng, prng, max_labels, max_elems, extents):
+    while True:
+        nlab = prng.randint(1, max_labels)
+        ad, ai, bd, bi = [], [], [], []
+        nopen = ncon = 0
+        for _ in range(nlab):
+            e = prng.choice(extents)
+            where = prng.choice("ABK")
+            if where == "A":
+                nopen += 1
+                ad.append(e)
+                ai.append(-nopen)
+            elif where == "B":
+                nopen += 1
+                bd.append(e)
+                bi.append(-nopen)
+            else:
+                ncon += 1
+                ad.append(e)
+                ai.append(ncon)
+                bd.append(e)
+                bi.append(ncon)
+        pa = list(range(len(ad)))
+        pb = list(range(len(bd)))
+        prng.shuffle(pa)
+        prng.shuffle(pb)
+        ad, ai = [ad[i] for i in pa], [ai[i] for i in pa]
+        bd, bi = [bd[i] for i in pb], [bi[i] for i in pb]
+        if int(np.prod(ad or [1])) <= max_elems and int(np.prod(bd or [1])) <= max_elems:
+            return ad, ai, bd, bi
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("opts", [dict(), dict(fused=1), dict(gemm=1), dict(gemm=3),
+                                  dict(fused=1, gemm=1, permute=1)])
+def test_random_contractions_match_oracle(dtype, opts):
+    rng = np.random.default_rng(11)
+    prng = random.Random(13)
+    b = B200(dtype, **opts)
+    tol = TOL[np.dtype(dtype)]
+    n_done = 0
+    for it in range(120):
+        extents = [2] if it % 3 == 0 else ([1, 2, 4] if it % 3 == 1 else [1, 2, 3, 5])
+        ad, ai, bd, bi = _random_contraction(rng, prng, 14 if it % 3 == 0 else 8, 1 << 14, extents)
+        A = rand_tensor(rng, tuple(ad), dtype)
+        B = rand_tensor(rng, tuple(bd), dtype)
+        b.save_tensor_data("A", A)
+        b.save_tensor_data("B", B)
+        b.contract_tensors("A", ai, "B", bi, "C")
+        got = b.load_tensor_data("C")
+        ref = layer1.contract_tensors((A.astype(np.complex128), B.astype(np.complex128)), (ai, bi))
+        assert got.shape == ref.shape, (ad, ai, bd, bi)
+        assert rel_l2(got, ref) < tol, (ad, ai, bd, bi, rel_l2(got, ref))
+        assert b.load_tensor_data("A") is None and b.load_tensor_data("B") is None
+        n_done += 1
+    assert n_done == 120
+
+
+GEMM_SHAPES = [
+    # (A dims, a_idx, B dims, b_idx): TTGT with both permutes, ragged tiles, K tails
+    ((64, 8, 32), [-1, 1, -2], (16, 8, 48), [-3, 1, -4]),          # M=2048 N=768 K=8
+    ((30, 7, 20), [-1, 1, -2], (7, 50), [1, -3]),                    # non-pow2, K=7
+    ((2,) * 16, [-1, 1, -2, 2, -3, 3, -4, 4, -5, 5, -6, 6, -7, -8, -9, -10],
+     (2,) * 12, [6, 5, 4, 3, 2, 1, -11, -12, -13, -14, -15, -16]),  # sweep-step shape M=1024 N=64 K=64
+    ((128, 96), [-1, 1], (96, 80), [1, -2]),                        # plain matrix product, no permute of A
+    ((96, 128), [1, -1], (80, 96), [-2, 1]),                        # both transposed
+    ((4096, 2, 4), [-1, 1, 2], (4, 2, 33), [2, 1, -2]),             # N=33 ragged
+    ((1, 257, 1, 19), [-1, -2, -3, 1], (19, 1, 65), [1, -4, -5]),    # extent-1 axes kept in C
+]
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("gemm", [0, 1])
+def test_gemm_path_shapes(dtype, gemm):
+    rng = np.random.default_rng(17)
+    b = B200(dtype, gemm=gemm, fused=1)
+    tol = TOL[np.dtype(dtype)]
+    for ad, ai, bd, bi in GEMM_SHAPES:
+        A = rand_tensor(rng, tuple(ad), dtype)
+        B = rand_tensor(rng, tuple(bd), dtype)
+        b.save_tensor_data("A", A)
+        b.save_tensor_data("B", B)
+        b.contract_tensors("A", ai, "B", bi, "C")
+        got = b.load_tensor_data("C")
+        ref = layer1.contract_tensors((A.astype(np.complex128), B.astype(np.complex128)), (ai, bi))
+        assert got.shape == ref.shape
+        assert rel_l2(got, ref) < tol, (ad, ai, rel_l2(got, ref))
+    prof_names = None
+    b.profile_enable(True)
+    ad, ai, bd, bi = GEMM_SHAPES[0]
+    b.save_tensor_data("A", rand_tensor(rng, tuple(ad), dtype))
+    b.save_tensor_data("B", rand_tensor(rng, tuple(bd), dtype))
+    b.contract_tensors("A", ai, "B", bi, "C")
+    prof_names = set(b.profile_read())
+    expected = "gemm_tensor" if (gemm == 0 and np.dtype(dtype) == np.complex128) else "gemm_simt"
+    assert expected in prof_names, prof_names
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_fused_kernel_classes_and_dot(dtype):
+    """Gate application (small right), cap contraction (small left) and the final
+    inner product (dot) must run as single fused launches, and match the oracle."""
+    rng = np.random.default_rng(19)
+    b = B200(dtype)
+    tol = TOL[np.dtype(dtype)]
+    cases = [
+        ((2,) * 18, [-(i + 1) if i not in (4, 11) else (1 if i == 4 else 2) for i in range(18)],
+         (2, 2, 2, 2), [2, 1, -30, -31], "contract_small"),
+        ((2, 2), [-1, 1], (2,) * 16, [-(i + 2) if i != 7 else 1 for i in range(16)], "contract_small"),
+        ((2,) * 17, list(range(1, 18)), (2,) * 17, list(range(17, 0, -1)), "contract_dot"),
+        ((2,) * 15 + (2,), list(range(1, 16)) + [-1], (2,) * 15, list(range(15, 0, -1)), "contract_dot"),
+    ]
+    for ad, ai, bd, bi, cls in cases:
+        # renumber open labels to be distinct negatives
+        A = rand_tensor(rng, tuple(ad), dtype)
+        B = rand_tensor(rng, tuple(bd), dtype)
+        b.save_tensor_data("A", A)
+        b.save_tensor_data("B", B)
+        b.profile_enable(True)
+        b.contract_tensors("A", ai, "B", bi, "C")
+        prof = b.profile_read()
+        b.profile_enable(False)
+        assert set(prof) == {cls}, prof
+        got = b.load_tensor_data("C")
+        ref = layer1.contract_tensors((A.astype(np.complex128), B.astype(np.complex128)), (ai, bi))
+        assert got.shape == ref.shape
+        assert rel_l2(got, ref) < tol, (cls, rel_l2(got, ref))
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_backend_semantics(dtype):
+    """interactive.jl semantics: conversion on save, None for missing labels,
+    KeyError on missing operands, alias on save_output, view keeps the axis,
+    reshape groups, delete of a missing label is fine."""
+    rng = np.random.default_rng(23)
+    b = B200(dtype)
+    assert b.load_tensor_data("nope") is None
+    b.delete_tensor("nope")
+    with pytest.raises(KeyError):
+        b.contract_tensors("x", [1], "y", [1], "z")
+    # real float64 input is converted to the backend's complex type
+    b.save_tensor_data("cap", np.array([1.0, 0.0]))
+    got = b.load_tensor_data("cap")
+    assert got.dtype == np.dtype(dtype) and np.array_equal(got, np.array([1, 0], dtype=dtype))
+    a = rand_tensor(rng, (2, 3, 4, 5), np.complex128)
+    b.save_tensor_data("a", a)
+    assert rel_l2(b.load_tensor_data("a"), a.astype(dtype)) == 0.0
+    b.view_tensor("v", "a", 3, range(2, 4))
+    assert np.array_equal(b.load_tensor_data("v"), a.astype(dtype)[:, :, 1:3, :])
+    b.view_tensor("v1", "a", 1, range(2, 3))
+    assert b.load_tensor_data("v1").shape == (1, 3, 4, 5)
+    b.view_tensor("v2", "a", 4, [1, 3, 4])
+    assert np.array_equal(b.load_tensor_data("v2"), a.astype(dtype)[:, :, :, [0, 2, 3]])
+    b.save_output("a", "result")
+    b.permute_tensor("a", [2, 1, 3, 4])                     # rebinding must not touch the alias
+    assert np.array_equal(b.load_tensor_data("result"), a.astype(dtype))
+    assert b.load_tensor_data("a").shape == (3, 2, 4, 5)
+    b.reshape_tensor("a", [[1, 2], [3], [4]])
+    assert b.load_tensor_data("a").shape == (6, 4, 5)
+    b.reshape_tensor("a", [[1, 2, 3]])
+    assert b.load_tensor_data("a").shape == (120,)
+    with pytest.raises(ValueError):
+        b.save_tensor_data("p", rand_tensor(rng, (2, 3), dtype))
+        b.save_tensor_data("q", rand_tensor(rng, (4, 2), dtype))
+        b.contract_tensors("p", [-1, 1], "q", [1, -2], "r")
+    # scalars: rank-0 result and rank-0 operand
+    b.save_tensor_data("s1", rand_tensor(rng, (2,), dtype))
+    b.save_tensor_data("s2", rand_tensor(rng, (2,), dtype))
+    s1, s2 = b.load_tensor_data("s1"), b.load_tensor_data("s2")
+    b.contract_tensors("s1", [1], "s2", [1], "s")
+    assert b.load_tensor_data("s").shape == ()
+    assert abs(b.load_tensor_data("s") - np.sum(s1.astype(np.complex128) * s2)) < 1e-5
+    b.save_tensor_data("w", rand_tensor(rng, (3,), dtype))
+    w = b.load_tensor_data("w")
+    sval = b.load_tensor_data("s")
+    b.contract_tensors("s", [], "w", [-1], "sw")
+    assert rel_l2(b.load_tensor_data("sw"), sval * w) < TOL[np.dtype(dtype)]
+    b.accumulate("acc", "sw")
+    b.accumulate("acc", "sw")
+    assert rel_l2(b.load_tensor_data("acc"), 2 * sval * w) < TOL[np.dtype(dtype)]
+
+
+# ---------------------------------------------------------------------------
+# the reference's own tests, on the device backend
+# ---------------------------------------------------------------------------
+def test_reference_stored_contraction_golden_on_gpu():
+    d = load_golden_json("ghz_3.json")
+    g = load_golden_json("ghz_3_contracted.json")
+    b = B200(np.complex128)
+    tn = network_from_dict(d, b)
+    for k, v in d["nodes"].items():
+        data = np.array(v["data_re"]) + 1j * np.array(v["data_im"])
+        b.save_tensor_data(k, np.reshape(data, v["data_dims"], order="F"))
+    for edge in load_golden_json("ghz_3_plan.json"):
+        contract_pair(tn, edge)
+    (label, gnode), = g["nodes"].items()
+    out = b.load_tensor_data(label)
+    ref = np.array(gnode["data_re"]) + 1j * np.array(gnode["data_im"])
+    assert list(out.shape) == gnode["data_dims"]
+    assert rel_l2(out.ravel(order="F"), ref) < 1e-15
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_reference_known_answers_on_gpu(dtype):
+    tol = TOL[np.dtype(dtype)]
+    # metrics golden + GHZ-3 (test/layer2_tests.jl:106-143, layer1_tests.jl:11-46)
+    b = B200(dtype)
+    c = Circuit(3).h(0).cx(0, 1).cx(0, 1).cx(0, 2)
+    tn = convert_circuit_to_network(c, b)
+    add_input(tn, "000")
+    full_wavefunction_contraction(tn, "vector")
+    assert b.metrics.as_tuple() == (8, 44, 124)
+    cnt = b.counters()
+    assert cnt["n_contract"] == 6 and cnt["macs"] == 124 and cnt["kernel_launches"] >= 6
+    ghz = load_qasm_as_circuit(golden_qasm("ghz_3.qasm"))
+    for seed in range(3):
+        bb = B200(dtype)
+        tn = convert_circuit_to_network(ghz, bb)
+        add_input(tn, "000")
+        add_output(tn, "000")
+        contract_network(tn, random_contraction_plan(tn, random.Random(seed)))
+        res = bb.load_tensor_data("result")
+        assert res.shape == () and abs(res - 1 / np.sqrt(2)) < 10 * tol
+    # disjoint pieces (layer2_tests.jl:69-103)
+    bb = B200(dtype)
+    tn = convert_circuit_to_network(Circuit(2).h(0).h(1), bb)
+    add_input(tn, "00")
+    contract_network(tn, random_contraction_plan(tn, random.Random(1)), "vector")
+    res = bb.load_tensor_data("result")
+    assert res.ndim == 1 and abs(res.real[0] - 0.5) < 10 * tol
+    # GHZ-5 (layer2_tests.jl:308-328)
+    psi = statevector(create_ghz_preparation_circuit(5), B200(dtype))
+    ref = np.zeros(32, dtype=np.complex128)
+    ref[[0, -1]] = 1 / np.sqrt(2)
+    assert rel_l2(psi, ref) < tol
+    # decomposed gate re-contraction (layer3_tests.jl:57-71)
+    rng = np.random.default_rng(7)
+    gate = rand_tensor(rng, (2, 2, 2, 2), np.complex128)
+    bb = B200(dtype)
+    tn = TensorNetworkCircuit(2, bb)
+    out = contract_pair(tn, *add_gate(tn, gate, [1, 2], decompose=True))
+    assert rel_l2(np.transpose(bb.load_tensor_data(out), (0, 2, 1, 3)), gate) < 10 * tol
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("name,n", [("qft_3.qasm", 3), ("qft_5.qasm", 5), ("qft_10.qasm", 10)])
+def test_qft_fixtures_on_gpu(dtype, name, n):
+    """configs 1-2: closed form for |0..0> and parity with the oracle for a
+    non-trivial input ('1', '+', '-' caps)."""
+    tol = TOL[np.dtype(dtype)]
+    circ = load_qasm_as_circuit(golden_qasm(name))
+    psi = statevector(circ, B200(dtype))
+    assert rel_l2(psi, np.full(2 ** n, 2 ** (-n / 2))) < tol
+    cfg = ("1+-0" * n)[:n]
+    got = statevector(circ, B200(dtype), input_config=cfg)
+    ref = statevector(circ, OracleBackend(np.complex128), input_config=cfg)
+    assert rel_l2(got, ref) < tol
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_qft_against_inverse_fft_on_gpu(dtype):
+    """test/algorithms_tests.jl:39-82 with n = 8 and 14."""
+    tol = TOL[np.dtype(dtype)]
+    for n in (8, 14):
+        prep = create_simple_preparation_circuit(n, 3, 43)
+        full = prep.compose(create_qft_circuit(n))
+        psi_in = statevector(prep, OracleBackend(np.complex128))
+        ref = np.fft.ifft(switch_endianness(psi_in))
+        ref /= np.linalg.norm(ref)
+        psi = switch_endianness(statevector(full, B200(dtype)))
+        assert abs(abs(np.vdot(psi, ref)) - 1.0) < 10 * tol
+        oracle = statevector(full, OracleBackend(np.complex128))
+        assert rel_l2(switch_endianness(psi), oracle) < tol
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_slicing_identity_on_gpu(dtype):
+    """test/layer2_tests.jl:419-455 through the backend calls (view_tensor!)."""
+    tol = TOL[np.dtype(dtype)]
+    n = 4
+    circ = create_simple_preparation_circuit(n, 2, 5).compose(create_qft_circuit(n))
+    wf = statevector(circ, OracleBackend(np.complex128), decompose=True)
+    for P in (4, 8):
+        total = np.zeros(2 ** n, dtype=np.complex128)
+        for p in range(1, P + 1):
+            b = B200(dtype)
+            tn = convert_circuit_to_network(circ, b, decompose=True)
+            add_input(tn, "0" * n)
+            labels, values = partition_network_on_virtual_bonds(tn, P, p)
+            slice_tensor_network(tn, labels, values)
+            full_wavefunction_contraction(tn, "vector")
+            total += b.load_tensor_data("result")
+        assert rel_l2(total, wf) < tol
+
+
+# ---------------------------------------------------------------------------
+# .tl programs (execute_dsl_file on the device) and sliced replay
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("graph", [0, 1])
+def test_program_matches_dsl_interpreter(dtype, graph):
+    tol = TOL[np.dtype(dtype)]
+    circ = create_RQC(3, 3, 8, seed=4)
+    dsl = DSLBackend()
+    tn = convert_circuit_to_network(circ, dsl, decompose=True)
+    add_input(tn, "0" * 9)
+    full_wavefunction_contraction(tn, "vector")
+    out = TensorStore()
+    execute_dsl(dsl.text(), dsl.store, np.complex128, output_store=out)
+    ref = out.read("result")
+    assert rel_l2(ref, circ.simulate()) < 1e-12
+    b = B200(dtype, graph=graph)
+    for key, arr in dsl.store.data.items():
+        b.save_tensor_data(key, arr)
+    prog = b.compile_program(dsl.text())
+    assert prog.num_views == 0 and prog.launches > 0 and prog.arena_bytes > 0
+    for _ in range(3):  # replays must be idempotent (leaves are not consumed)
+        prog.run()
+        assert rel_l2(b.load_tensor_data("result"), ref) < tol
+    assert b.counters()["kernel_launches"] >= 3 * prog.launches
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_sliced_program_replay(dtype):
+    """One compiled plan replayed for every partition; the stream for partition p
+    equals the one the host mirror emits for p (only view indices differ)."""
+    tol = TOL[np.dtype(dtype)]
+    circ = create_RQC(3, 4, 10, seed=2)
+    n = circ.n_qubits
+
+    def plan_fn(tn, sliced):
+        return sweep_plan(tn, 3, 4, sliced_bonds=sliced)
+
+    for P in (4, 16):
+        rec = record_sliced_contraction(circ, P, 1, plan_fn=plan_fn, output_config="0" * n)
+        other = record_sliced_contraction(circ, P, P, plan_fn=plan_fn, output_config="0" * n)
+        assert rec.text_for(P) == other.text and rec.text_for(1) == rec.text
+        b = B200(dtype)
+        sc = SlicedContraction(b, rec)
+        sc.run(range(1, P + 1))
+        got = sc.result()
+        ref = circ.simulate()[0]
+        assert got.shape == ()
+        assert abs(got - ref) / abs(ref) < 20 * tol, (P, got, ref)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_rqc_amplitude_plans(dtype):
+    """config-4 shape at test size: single amplitude of a 4x4 depth-16 RQC with the
+    greedy plan (undecomposed network, GEMM-heavy) and the sweep plan (decomposed)."""
+    tol = TOL[np.dtype(dtype)]
+    circ = create_RQC(4, 4, 16, seed=9)
+    ref = circ.simulate()[0]
+    for decompose in (False, True):
+        b = B200(dtype)
+        tn = convert_circuit_to_network(circ, b, decompose=decompose)
+        add_input(tn, "0" * 16)
+        add_output(tn, "0" * 16)
+        plan = sweep_plan(tn, 4, 4) if decompose else greedy_plan(tn)
+        contract_network(tn, plan)
+        got = b.load_tensor_data("result")
+        assert abs(got - ref) / abs(ref) < 50 * tol, (decompose, got, ref)
+
+
+# ---------------------------------------------------------------------------
+# BASELINE sizes through size-independent properties
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_qft_20_closed_form(dtype):
+    """Closed form of the reference's QFT circuit for a basis input: in big-endian
+    indexing the circuit is the normalised inverse DFT (test/algorithms_tests.jl:39-82),
+    so amp_BE[k] = 2^{-n/2} exp(2 pi i x_BE k / 2^n)."""
+    n = 20
+    tol = TOL[np.dtype(dtype)]
+    circ = create_qft_circuit(n)
+    x_le = 0b10110011100011110001
+    cfg = "".join("1" if (x_le >> q) & 1 else "0" for q in range(n))
+    x_be = int(cfg, 2)  # qubit 0 becomes the most significant bit
+    psi = statevector(circ, B200(dtype), input_config=cfg)
+    k = np.arange(2 ** n, dtype=np.int64)
+    ref_be = np.exp(2j * np.pi * ((x_be * k) % (2 ** n)) / 2 ** n) * 2 ** (-n / 2)
+    assert rel_l2(switch_endianness(psi), ref_be) < 4 * tol
+
+
+def test_qft_26_uniform_c64():
+    """config 3 at full size (2^26 amplitudes, ComplexF32): uniform superposition."""
+    n = 26
+    b = B200(np.complex64)
+    psi = statevector(create_qft_circuit(n), b)
+    assert psi.shape == (2 ** n,)
+    assert abs(np.linalg.norm(psi.astype(np.complex128)) - 1.0) < 1e-4
+    assert np.max(np.abs(psi - 2 ** (-n / 2))) < 1e-5 * 2 ** (-n / 2) * 50
+    assert b.counters()["n_contract"] == 389
