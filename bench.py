@@ -1,0 +1,425 @@
+#!/usr/bin/env python
+"""bench.py -- sliced random-quantum-circuit single-amplitude contraction on B200.
+
+Workload (BASELINE.json config 5, the one the metric is quoted on): Google-style
+RQC on a 7x7 grid, depth 24 (``create_RQC`` gate sequence, numpy seed 0), input
+|0..0>, output bitstring 0..0, two-qubit gates SVD-split (``decompose=true``), network
+sliced on the first k=6 virtual bonds in edge order (``slicing.jl:41-56``) into P=64
+slices, each slice contracted with the harness's deterministic sweep plan through
+``contract_network!``'s command stream.  A "step" is one full amplitude: all P slices
+(sharded contiguously over the N GPUs), device-side accumulation, one NCCL all-reduce.
+
+    python bench.py --gpus N --steps K --warmup W            # this framework
+    python bench.py --impl reference --gpus N --steps K ...  # CPU oracle arm
+
+Prints ONE JSON line (rank 0).  ``value`` = whole-job real TFLOP/s of contraction
+(8 flops per complex MAC, MACs counted on data extents) with inputs resident in HBM;
+``e2e`` = the same metric through the backend API from host buffers (H2D of every
+gate tensor + compile-free replay + D2H of the amplitude inside the timed region).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import picoquant_jl_b200  # noqa: E402,F401
+from picoquant_jl_b200.host import create_RQC  # noqa: E402
+from picoquant_jl_b200.host.backends import TensorStore, parse_dsl  # noqa: E402
+from picoquant_jl_b200.host.planner import sweep_plan  # noqa: E402
+from picoquant_jl_b200.host.sliced import (SlicedContraction, partitions_of_rank,  # noqa: E402
+                                           record_sliced_contraction)
+
+METRIC = "rqc_amplitude_contraction_tflops"
+UNIT = "TFLOP/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--dtype", default="c128", choices=["c128", "c64"])
+    ap.add_argument("--rows", type=int, default=7)
+    ap.add_argument("--cols", type=int, default=7)
+    ap.add_argument("--depth", type=int, default=24)
+    ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--slices", type=int, default=64)
+    ap.add_argument("--cpu-sample-slices", type=int, default=2)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-profile", action="store_true")
+    return ap.parse_args()
+
+
+def build_workload(a):
+    circ = create_RQC(a.rows, a.cols, a.depth, seed=a.seed)
+    n = circ.n_qubits
+
+    def plan_fn(tn, sliced):
+        return sweep_plan(tn, a.rows, a.cols, sliced_bonds=sliced)
+
+    rec = record_sliced_contraction(circ, a.slices, 1, plan_fn=plan_fn, output_config="0" * n)
+    name = "rqc_%dx%d_d%d_seed%d_amplitude_sliced_P%d" % (a.rows, a.cols, a.depth, a.seed, a.slices)
+    return circ, rec, name
+
+
+def slice_macs(rec):
+    """Complex MACs of one slice on DATA extents (sliced bonds have extent 1)."""
+    shapes, macs = {}, 0
+    for cmd, x in parse_dsl(rec.text):
+        if cmd == "tensor":
+            shapes[x["t"]] = list(rec.store.read(x["key"]).shape)
+        elif cmd == "view":
+            s = list(shapes[x["t"]])
+            s[x["axis"] - 1] = len(x["idx"])
+            shapes[x["v"]] = s
+        elif cmd == "ncon":
+            sa, sb = shapes[x["A"]], shapes[x["B"]]
+            bset = set(x["b_idx"])
+            k = 1
+            for d, lab in zip(sa, x["a_idx"]):
+                if lab in bset:
+                    k *= d
+            m = int(np.prod(sa)) // k
+            nn = int(np.prod(sb)) // k
+            macs += m * nn * k
+            aset = set(x["a_idx"])
+            shapes[x["C"]] = [d for d, lab in zip(sa, x["a_idx"]) if lab not in bset] + \
+                             [d for d, lab in zip(sb, x["b_idx"]) if lab not in aset]
+        elif cmd == "del":
+            shapes.pop(x["t"], None)
+    return macs
+
+
+# ---------------------------------------------------------------------------
+# CPU arm: the oracle (NumPy/OpenBLAS restatement of the reference's CPU path)
+# ---------------------------------------------------------------------------
+def run_cpu_slices(rec, dtype, partitions):
+    from oracle.interactive import execute_dsl
+    total = 0
+    for p in partitions:
+        out = TensorStore()
+        execute_dsl(rec.text_for(p), rec.store, dtype, output_store=out)
+        total = total + out.read("result")
+    return total
+
+
+def cpu_threads():
+    try:
+        from threadpoolctl import threadpool_info
+        return max([i.get("num_threads", 1) for i in threadpool_info()] + [1])
+    except Exception:  # noqa: BLE001
+        return os.cpu_count() or 1
+
+
+def reference_arm(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    circ, rec, name = build_workload(a)
+    dtype = np.complex128 if a.dtype == "c128" else np.complex64
+    macs = slice_macs(rec)
+    per_step = 1  # one slice per step keeps K+W steps within minutes
+    for w in range(a.warmup):
+        run_cpu_slices(rec, dtype, [1 + (w % a.slices)])
+    t0 = time.perf_counter()
+    for s in range(a.steps):
+        run_cpu_slices(rec, dtype, [1 + (s % a.slices)])
+    dt = (time.perf_counter() - t0) / max(1, a.steps)
+    value = 8.0 * macs * per_step / dt / 1e12
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus,
+        "steps": a.steps, "warmup": a.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": a.dtype, "data": "synthetic",
+        "config": {"workload": name, "slices": a.slices, "plan": "sweep",
+                   "note": "reference CPU path restated in NumPy/OpenBLAS (the Julia reference "
+                           "cannot run here); each step contracts ONE of the %d slices; a full "
+                           "amplitude costs %d x this" % (a.slices, a.slices)},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cpu_threads(), "kind": "port",
+                         "sample": "1 slice of %d per step" % a.slices},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "amplitude_wall_ms_extrapolated": dt * 1e3 * a.slices,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------
+# clocks sampler (nvidia-smi, during the timed region)
+# ---------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device = device
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:  # noqa: BLE001
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": max(mx) if mx else None, "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------
+def main():
+    a = parse_args()
+    if a.impl == "reference":
+        reference_arm(a)
+        return
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    from picoquant_jl_b200.host.b200_backend import B200Backend
+    dtype = np.complex128 if a.dtype == "c128" else np.complex64
+    circ, rec, name = build_workload(a)
+    macs = slice_macs(rec)
+    mine = partitions_of_rank(a.slices, rank, world)
+
+    b = B200Backend(dtype, device=local_rank)
+    if world > 1:
+        ids = [B200Backend.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        b.comm_init(ids[0], rank, world)
+    sc = SlicedContraction(b, rec)          # uploads the gate tensors, compiles the plan
+    assert sc.program.macs == macs, (sc.program.macs, macs)
+
+    def barrier():
+        b.sync()
+        if world > 1:
+            dist.barrier()
+
+    def amplitude_step():
+        b.delete_tensor("partial_sum")
+        sc.run(mine, "partial_sum")
+        if world > 1:
+            b.allreduce_sum("partial_sum")
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    for _ in range(a.warmup):
+        amplitude_step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    b.reset_counters()
+    b.timer_begin()
+    for _ in range(a.steps):
+        amplitude_step()
+    ms = b.timer_end()
+    barrier()
+    launches = b.counters()["kernel_launches"]
+    clocks = sampler.stop() if rank == 0 else None
+    ms = max_over_ranks(ms)
+    ms_per_step = ms / a.steps
+    total_flops = 8.0 * macs * a.slices
+    value = total_flops / (ms_per_step * 1e-3) / 1e12
+    amplitude = b.load_tensor_data("partial_sum")
+
+    # ---- end to end through the backend API, from host buffers ------------------
+    h2d = 0
+    e2e_times = []
+    for it in range(max(2, min(a.steps, 3)) + 1):
+        barrier()
+        t0 = time.perf_counter()
+        h2d = sc.upload()                      # H2D of every gate tensor (host arrays)
+        amplitude_step()
+        amp_e2e = b.load_tensor_data("partial_sum")   # D2H of the amplitude (syncs)
+        dt = time.perf_counter() - t0
+        if it > 0:
+            e2e_times.append(max_over_ranks(dt))
+    e2e_s = float(np.mean(e2e_times))
+    e2e_value = total_flops / e2e_s / 1e12
+    d2h = int(np.asarray(amp_e2e).size * np.dtype(dtype).itemsize)
+
+    # ---- per-kernel roofline: one eager, event-timed pass over one slice ---------
+    kernels, roofline = {}, None
+    peaks = {}
+    if rank == 0 and not a.no_profile:
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                mp = json.load(f)
+            peaks["hbm_gbs"] = float(mp["hbm_gbs"])
+            peaks["hbm_source"] = "MEASURED_PEAKS.json (driver-written, of measured)"
+        except Exception:  # noqa: BLE001
+            peaks["hbm_gbs"] = 6650.0
+            peaks["hbm_source"] = "fallback 6.65 TB/s (B200_PROFILING.md)"
+        peaks["fp64_dmma_probe_tflops"] = b.microbench("dmma_tflops")
+        try:
+            n = 4096
+            x = torch.randn(n, n, dtype=torch.complex128, device="cuda")
+            y = torch.randn(n, n, dtype=torch.complex128, device="cuda")
+            torch.matmul(x, y)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            best = 1e30
+            for _ in range(3):
+                e0.record()
+                torch.matmul(x, y)
+                e1.record()
+                torch.cuda.synchronize()
+                best = min(best, e0.elapsed_time(e1))
+            peaks["cublas_zgemm_tflops"] = 8.0 * n ** 3 / (best * 1e-3) / 1e12
+            del x, y
+        except Exception as e:  # noqa: BLE001
+            peaks["cublas_zgemm_tflops"] = None
+            peaks["cublas_error"] = repr(e)
+        b.profile_enable(True)
+        reps = 3
+        for r in range(reps):
+            sc.program.run(rec.view_starts(mine[r % len(mine)]) if rec.bond_labels else None, None)
+        prof = b.profile_read()
+        b.profile_enable(False)
+        total_ms = sum(v["ms"] for v in prof.values())
+        for cls, v in prof.items():
+            k = {"launches_per_slice": v["launches"] // reps, "ms_per_slice": v["ms"] / reps,
+                 "share_of_slice": v["ms"] / total_ms if total_ms else None,
+                 "avg_launch_us": 1e3 * v["ms"] / v["launches"]}
+            if v["flops"] and cls in ("gemm_tensor", "gemm_simt"):
+                k["achieved_tflops"] = v["flops"] / (v["ms"] * 1e-3) / 1e12
+            if v["bytes"]:
+                k["achieved_gbs"] = v["bytes"] / (v["ms"] * 1e-3) / 1e9
+            kernels[cls] = k
+        dom = max(prof, key=lambda c: prof[c]["ms"])
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+                traffic = json.load(f).get(dom)
+        except Exception:  # noqa: BLE001
+            pass
+        if dom in ("gemm_tensor", "gemm_simt"):
+            peak = peaks.get("cublas_zgemm_tflops") or peaks["fp64_dmma_probe_tflops"]
+            ach = kernels[dom]["achieved_tflops"]
+            roofline = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": peak,
+                        "unit": "TFLOP/s", "frac": ach / peak, "traffic": traffic,
+                        "peak_source": "cuBLAS ZGEMM 4096^3 measured in this run (FP64 tensor "
+                                       "pipe; MEASURED_PEAKS.json has no FP64 figure)"}
+        else:
+            ach = kernels[dom]["achieved_gbs"]
+            roofline = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"],
+                        "unit": "GB/s", "frac": ach / peaks["hbm_gbs"], "traffic": traffic,
+                        "peak_source": peaks["hbm_source"]}
+        if "permute_tiled" in kernels:
+            kernels["permute_tiled"]["frac_of_hbm"] = kernels["permute_tiled"]["achieved_gbs"] / peaks["hbm_gbs"]
+        if "gemm_tensor" in kernels and peaks.get("cublas_zgemm_tflops"):
+            kernels["gemm_tensor"]["frac_of_cublas_zgemm"] = (kernels["gemm_tensor"]["achieved_tflops"]
+                                                              / peaks["cublas_zgemm_tflops"])
+
+    # ---- CPU baseline on this box's host cores (rank 0, N=1 only) -----------------
+    cpu = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        sample = list(range(1, a.cpu_sample_slices + 1))
+        run_cpu_slices(rec, dtype, [1])  # warm-up (BLAS threads, page faults)
+        t0 = time.perf_counter()
+        part = run_cpu_slices(rec, dtype, sample)
+        dt = time.perf_counter() - t0
+        cpu = {"value": 8.0 * macs * len(sample) / dt / 1e12, "unit": UNIT, "cores": cpu_threads(),
+               "kind": "port", "sample": "%d of %d slices (%.1f s), NumPy/OpenBLAS oracle"
+                                         % (len(sample), a.slices, dt),
+               "amplitude_wall_s_extrapolated": dt / len(sample) * a.slices}
+        # cheap parity guard: device partial sum of the same slices vs the oracle
+        b.delete_tensor("check_sum")
+        sc.run(sample, "check_sum")
+        dev = b.load_tensor_data("check_sum")
+        err = abs(dev - part) / abs(part)
+        cpu["parity_rel_err_vs_device"] = float(err)
+        tol = 1e-10 if a.dtype == "c128" else 1e-5
+        if not err < 50 * tol:
+            raise SystemExit("parity failure: device %r vs oracle %r" % (dev, part))
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps,
+            "warmup": a.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": a.dtype, "data": "synthetic",
+            "config": {"workload": name, "slices": a.slices, "slices_per_gpu": len(mine),
+                       "plan": "sweep (harness planner)", "complex_macs_per_slice": macs,
+                       "contract_calls_per_slice": sum(1 for c, _ in parse_dsl(rec.text)
+                                                       if c == "ncon"),
+                       "kernel_launches_per_slice": sc.program.launches,
+                       "arena_bytes": sc.program.arena_bytes, "parallelism": "slices/%d" % world,
+                       "l2": "inputs larger than L2: per-step intermediates of 2^24 elements "
+                             "(256 MiB c128) stream through the 126 MB L2"},
+            "amplitude_wall_ms": ms_per_step,
+            "amplitude": [float(np.real(amplitude)), float(np.imag(amplitude))],
+            "complex_mac_per_s": macs * a.slices / (ms_per_step * 1e-3),
+            "tflops_per_gpu": value / world,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+                    "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s * 1e3},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": roofline,
+            "kernels": kernels,
+            "peaks": peaks,
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    barrier()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

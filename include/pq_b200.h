@@ -156,6 +156,12 @@ int pq_profile_read(pq_handle* h, double* ms, int64_t* launches, double* bytes,
                     double* flops); /* arrays of PQ_NUM_KERNEL_CLASSES */
 const char* pq_kernel_class_name(int cls);
 
+/* Device-side stopwatch on the handle's stream (CUDA events): `pq_timer_begin` records
+ * the start event; `pq_timer_end` records the stop event, waits for it and returns the
+ * elapsed milliseconds.  This is how bench.py times the stream the kernels run on. */
+int pq_timer_begin(pq_handle* h);
+int pq_timer_end(pq_handle* h, double* ms);
+
 /* Behaviour knobs for A/B checks ("gemm": 0 auto, 1 SIMT, 2 DMMA/tensor;
  * "permute": 0 auto, 1 generic, 2 tiled; "fused": 0 auto, 1 off; "graph": 0 auto, 1 off). */
 int pq_set_option(pq_handle* h, const char* key, int value);

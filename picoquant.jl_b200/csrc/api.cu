@@ -133,6 +133,10 @@ extern "C" int pq_destroy(pq_handle* h) {
   h->drain_profile();
   h->tensors.clear();
   if (h->comm) comm_destroy(h->comm);
+  if (h->timer0) {
+    cudaEventDestroy(h->timer0);
+    cudaEventDestroy(h->timer1);
+  }
   cudaStreamSynchronize(h->stream);
   cudaStreamDestroy(h->stream);
   delete h;
@@ -184,7 +188,17 @@ extern "C" int pq_save_tensor(pq_handle* h, const char* label, int rank, const i
   t.dims.assign(dims, dims + rank);
   for (auto d : t.dims) PQ_REQUIRE(d >= 1, PQ_ERR_INVALID, "extents must be >= 1");
   int64_t n = t.numel();
-  t.buf = std::make_shared<Buffer>(size_t(n) * h->elem_size, h->stream);
+  // Re-saving a tensor of the same size whose buffer is referenced only by this label
+  // (and by compiled programs bound to it) updates the data in place, so programs see
+  // the new values -- like execute_dsl_file re-reading the HDF5 file.  Otherwise the
+  // label is rebound to a fresh buffer and aliases keep the old array.
+  auto old = h->tensors.find(label);
+  if (old != h->tensors.end() && old->second.buf && !old->second.buf->external &&
+      old->second.buf->bytes == size_t(n) * h->elem_size &&
+      old->second.buf.use_count() - old->second.buf->pins == 1)
+    t.buf = old->second.buf;
+  else
+    t.buf = std::make_shared<Buffer>(size_t(n) * h->elem_size, h->stream);
   bool direct = (h->dtype == PQ_C128 && host_dtype == PQ_HOST_C128) ||
                 (h->dtype == PQ_C64 && host_dtype == PQ_HOST_C64);
   if (direct) {
@@ -477,6 +491,31 @@ extern "C" const char* pq_kernel_class_name(int cls) {
       "gemm_simt",     "gemm_tensor",     "view",           "accumulate",      "copy",
       "allreduce",     "other"};
   return (cls >= 0 && cls < PQ_NUM_KERNEL_CLASSES) ? names[cls] : "?";
+}
+
+extern "C" int pq_timer_begin(pq_handle* h) {
+  if (!h) return PQ_ERR_INVALID;
+  PQ_TRY(h)
+  set_device(h);
+  if (!h->timer0) {
+    PQ_CUDA(cudaEventCreate(&h->timer0));
+    PQ_CUDA(cudaEventCreate(&h->timer1));
+  }
+  PQ_CUDA(cudaEventRecord(h->timer0, h->stream));
+  PQ_CATCH(h)
+}
+
+extern "C" int pq_timer_end(pq_handle* h, double* ms) {
+  if (!h) return PQ_ERR_INVALID;
+  PQ_TRY(h)
+  PQ_REQUIRE(ms && h->timer0, PQ_ERR_INVALID, "pq_timer_end without pq_timer_begin");
+  set_device(h);
+  PQ_CUDA(cudaEventRecord(h->timer1, h->stream));
+  PQ_CUDA(cudaEventSynchronize(h->timer1));
+  float f = 0;
+  PQ_CUDA(cudaEventElapsedTime(&f, h->timer0, h->timer1));
+  *ms = f;
+  PQ_CATCH(h)
 }
 
 extern "C" int pq_set_option(pq_handle* h, const char* key, int value) {

@@ -12,6 +12,7 @@ struct Buffer {
   size_t bytes = 0;
   cudaStream_t stream = nullptr;
   bool external = false;  // memory owned by somebody else (program arenas)
+  int pins = 0;           // compiled programs bound to this buffer (leaf tensors)
   Buffer(size_t n, cudaStream_t s);
   Buffer(void* p, size_t n) : ptr(p), bytes(n), external(true) {}
   ~Buffer();
@@ -49,6 +50,7 @@ struct pq_handle {
   double prof_bytes[PQ_NUM_KERNEL_CLASSES] = {0};
   double prof_flops[PQ_NUM_KERNEL_CLASSES] = {0};
   pq::Comm* comm = nullptr;
+  cudaEvent_t timer0 = nullptr, timer1 = nullptr;
 
   pq::Launch launch_ctx();
   pq::Tensor& get(const std::string& label);

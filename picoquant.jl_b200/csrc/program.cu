@@ -125,6 +125,8 @@ struct pq_program {
   cudaGraphExec_t exec = nullptr;
   int64_t launches = 0, macs = 0, ncontract = 0, max_elems = 0;
   int device = 0;
+  // leaf tensors the program is bound to: (store key, pinned buffer)
+  std::vector<std::pair<std::string, std::shared_ptr<Buffer>>> leaves;
 };
 
 static void* resolve(const pq_program* p, const Ref& r) {
@@ -219,6 +221,8 @@ extern "C" int pq_program_compile(pq_handle* h, const char* tl_text, pq_program*
         s.leafbuf = t.buf;
         s.dims = t.dims;
         s.bytes = t.buf->bytes;
+        t.buf->pins += 1;
+        p->leaves.emplace_back(tok[2], t.buf);
         drop(tok[1]);
         syms[tok[1]] = s;
       } else if (cmd == "del") {
@@ -386,10 +390,13 @@ extern "C" int pq_program_compile(pq_handle* h, const char* tl_text, pq_program*
   } catch (const Error& e) {
     h->last_error = e.what();
     if (p->arena) cudaFree(p->arena);
+    for (auto& l : p->leaves) l.second->pins -= 1;
     delete p;
     return e.code;
   } catch (const std::exception& e) {
     h->last_error = e.what();
+    if (p->arena) cudaFree(p->arena);
+    for (auto& l : p->leaves) l.second->pins -= 1;
     delete p;
     return PQ_ERR_PARSE;
   }
@@ -414,6 +421,12 @@ extern "C" int pq_program_run(pq_handle* h, pq_program* p, const int32_t* view_s
   try {
     PQ_CUDA(cudaSetDevice(h->device));
     PQ_REQUIRE(p->device == h->device, PQ_ERR_INVALID, "program belongs to another device");
+    for (auto& l : p->leaves) {
+      auto it = h->tensors.find(l.first);
+      PQ_REQUIRE(it != h->tensors.end() && it->second.buf.get() == l.second.get(), PQ_ERR_INVALID,
+                 "tensor '" + l.first + "' was deleted or rebound since the program was compiled; "
+                 "recompile the program");
+    }
     if (view_starts) {
       PQ_REQUIRE(nviews == p->nviews, PQ_ERR_INVALID, "pq_program_run: wrong number of view starts");
       if (p->nviews > 0) {
@@ -498,6 +511,7 @@ extern "C" int pq_program_destroy(pq_handle* h, pq_program* p) {
     cudaStreamSynchronize(h->stream);
   }
   if (p->exec) cudaGraphExecDestroy(p->exec);
+  for (auto& l : p->leaves) l.second->pins -= 1;
   if (p->arena) cudaFree(p->arena);
   if (p->d_starts) cudaFree(p->d_starts);
   if (p->h_ring) {

@@ -40,7 +40,7 @@ ABI_SYMBOLS = [
     "pq_comm_init", "pq_allreduce_sum", "pq_program_compile", "pq_program_num_views",
     "pq_program_run", "pq_program_destroy", "pq_program_stats", "pq_get_counters",
     "pq_reset_counters", "pq_profile_enable", "pq_profile_read", "pq_kernel_class_name",
-    "pq_set_option", "pq_microbench",
+    "pq_set_option", "pq_microbench", "pq_timer_begin", "pq_timer_end",
 ]
 
 _lib = None
@@ -95,6 +95,8 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
                                     POINTER(c_double)]
     lib.pq_set_option.argtypes = [c_void_p, c_char_p, c_int]
     lib.pq_microbench.argtypes = [c_void_p, c_char_p, POINTER(c_double)]
+    lib.pq_timer_begin.argtypes = [c_void_p]
+    lib.pq_timer_end.argtypes = [c_void_p, POINTER(c_double)]
     for name in ABI_SYMBOLS:
         fn = getattr(lib, name)
         if fn.restype is not c_char_p:
@@ -168,6 +170,11 @@ class B200Backend(AbstractBackend):
             raise B200Error("pq_create failed (%s): a CUDA device is required, there is no CPU "
                             "fallback" % _STATUS.get(rc, rc))
         self.device = device
+        # A/B knobs from the environment (profiling runs): PQ_B200_OPTS="graph=1,gemm=1"
+        for item in os.environ.get("PQ_B200_OPTS", "").split(","):
+            if "=" in item:
+                k, v = item.split("=", 1)
+                self.set_option(k.strip(), int(v))
 
     # -- plumbing -----------------------------------------------------------
     def _check(self, rc: int) -> None:
@@ -302,6 +309,15 @@ class B200Backend(AbstractBackend):
                 out[self.lib.pq_kernel_class_name(i).decode()] = {
                     "ms": ms[i], "launches": la[i], "bytes": by[i], "flops": fl[i]}
         return out
+
+    def timer_begin(self):
+        self._check(self.lib.pq_timer_begin(self._h))
+
+    def timer_end(self) -> float:
+        """Milliseconds of device time on the handle's stream since ``timer_begin``."""
+        ms = c_double()
+        self._check(self.lib.pq_timer_end(self._h, byref(ms)))
+        return ms.value
 
     def set_option(self, key: str, value: int):
         self._check(self.lib.pq_set_option(self._h, key.encode(), int(value)))

@@ -424,6 +424,17 @@ def test_sliced_program_replay(dtype):
         ref = circ.simulate()[0]
         assert got.shape == ()
         assert abs(got - ref) / abs(ref) < 20 * tol, (P, got, ref)
+        # re-uploading the gate tensors (same shapes) updates the bound buffers in place
+        sc.upload()
+        b.delete_tensor("partial_sum")
+        sc.run(range(1, P + 1))
+        assert abs(sc.result() - ref) / abs(ref) < 20 * tol
+    # rebinding a leaf to a different shape invalidates the program (no stale reads)
+    from picoquant_jl_b200.host.b200_backend import B200Error
+    first_leaf = rec.text.split()[2]
+    b.save_tensor_data(first_leaf, np.zeros((3, 3), dtype=dtype))
+    with pytest.raises(B200Error):
+        sc.program.run(rec.view_starts(1), None)
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
