@@ -115,7 +115,7 @@ struct Options {
   int gemm = 0;     // 0 auto, 1 SIMT, 2 tensor (DMMA), 3 direct everywhere
   int permute = 0;  // 0 auto, 1 generic, 2 tiled
   int fused = 0;    // 0 auto, 1 disable the fused small-operand / dot kernels
-  int graph = 0;    // 0 auto (CUDA graph replay), 1 eager replay
+  int graph = 0;    // 0 CUDA graph with parallel branches, 1 eager replay, 2 single-chain graph
 };
 
 // launch context handed to every kernel launcher
@@ -158,6 +158,7 @@ struct ContractPlan {
   // TTGT
   PermutePlan permA, permB;            // A -> [M|K], B -> [N|K] canonical layouts
   size_t tempA_bytes = 0, tempB_bytes = 0, ws_bytes = 0;
+  bool fused_gemm = false;             // gather straight from A and B inside the GEMM
   int dot_blocks = 0;
 };
 
@@ -181,6 +182,7 @@ void run_gemm_simt(const Launch& L, const void* A, const void* B, void* C, int64
                    int64_t K);
 void run_zgemm_dmma(const Launch& L, const void* A, const void* B, void* C, int64_t M, int64_t N,
                     int64_t K);
+void run_zgemm_fused(const Launch& L, const ContractPlan& cp, const void* A, const void* B, void* C);
 
 inline int64_t prod(const std::vector<int64_t>& v) {
   int64_t p = 1;

@@ -378,6 +378,10 @@ static void run_contract_t(const Launch& L, const ContractPlan& p, const void* A
       break;
     }
     case CK_GEMM: {
+      if (p.fused_gemm) {
+        run_zgemm_fused(L, p, A, B, C);
+        break;
+      }
       const void* Ap = A;
       const void* Bp = B;
       if (!p.permA.identity) {

@@ -265,7 +265,17 @@ ContractPlan lower_contract(const std::vector<int64_t>& a_dims, const std::vecto
     P.dot_blocks = (int)blocks;
     P.ws_bytes = size_t(blocks) * 16 * elem_size;
   }
-  if (P.kind == CK_GEMM) {
+  if (P.kind == CK_GEMM && elem_size == 16 && opt.fused == 0 && (opt.gemm == 0 || opt.gemm == 2) &&
+      K <= 1024) {
+    // fused TTGT: k offsets are tabulated as 32-bit element offsets
+    int64_t ka = 0, kb = 0;
+    for (int d = 0; d < P.kA.nd; ++d) {
+      ka += (P.kA.ext[d] - 1) * P.kA.str[d];
+      kb += (P.kB.ext[d] - 1) * P.kB.str[d];
+    }
+    P.fused_gemm = ka < (int64_t(1) << 31) && kb < (int64_t(1) << 31);
+  }
+  if (P.kind == CK_GEMM && !P.fused_gemm) {
     std::vector<int> pa = a_open, pb = b_open;
     pa.insert(pa.end(), a_con.begin(), a_con.end());
     pb.insert(pb.end(), b_con.begin(), b_con.end());

@@ -7,6 +7,9 @@
 // the graph costs one host call per slice; `view` start indices live in device
 // memory so the same graph serves every slice of a sliced contraction
 // (reference flow: src/layer2/slicing.jl:100-110 + examples/dist_slicing_example.jl).
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <sstream>
 
@@ -70,17 +73,24 @@ struct Sym {
   bool leaf = false;
   std::shared_ptr<Buffer> leafbuf;  // keeps a bound handle tensor alive
   size_t offset = 0, bytes = 0;     // arena placement when !leaf
+  bool small = false;               // lives in the no-reuse arena for small tensors
   std::vector<int64_t> dims;
 };
 
 enum StepKind { ST_CONTRACT, ST_PERMUTE, ST_VIEW, ST_SAVE };
 
-struct Ref {  // pointer = leaf ? leafptr : arena + offset
+struct Ref {  // pointer = leaf ? leafptr : (small ? arena_small : arena) + offset
   void* leafptr = nullptr;
   size_t offset = 0;
   bool leaf = false;
+  bool small = false;
   bool null = true;
 };
+
+// Tensors up to this size are bump-allocated and never recycled within a program, so
+// that the only hazards between the ~10^3 tiny contractions of a slice are true data
+// dependencies and independent world-lines can run on parallel graph branches.
+constexpr size_t SMALL_TENSOR_BYTES = 64 * 1024;
 
 struct Step {
   StepKind kind;
@@ -111,8 +121,9 @@ std::vector<int32_t> parse_ints(const std::string& s) {
 
 struct pq_program {
   std::vector<Step> steps;
-  size_t arena_bytes = 0;
+  size_t arena_bytes = 0, arena_small_bytes = 0;
   void* arena = nullptr;
+  void* arena_small = nullptr;
   int nviews = 0;
   std::vector<int32_t> default_starts;
   int32_t* d_starts = nullptr;
@@ -127,15 +138,147 @@ struct pq_program {
   int device = 0;
   // leaf tensors the program is bound to: (store key, pinned buffer)
   std::vector<std::pair<std::string, std::shared_ptr<Buffer>>> leaves;
+  // dependency DAG for multi-stream capture: deps[j] = earlier steps j must wait for
+  std::vector<std::vector<int>> deps;
+  static constexpr int NSTREAMS = 8;
+  cudaStream_t side[NSTREAMS] = {nullptr};
+  std::vector<cudaEvent_t> step_ev;
+  cudaEvent_t fork_ev = nullptr;
 };
+
+namespace {
+struct Range {
+  const char* lo;
+  const char* hi;
+};
+inline bool overlap(const Range& a, const Range& b) { return a.lo < b.hi && b.lo < a.hi; }
+}  // namespace
 
 static void* resolve(const pq_program* p, const Ref& r) {
   if (r.null) return nullptr;
-  return r.leaf ? r.leafptr : (void*)((char*)p->arena + r.offset);
+  if (r.leaf) return r.leafptr;
+  return (void*)((char*)(r.small ? p->arena_small : p->arena) + r.offset);
 }
 
+static void issue_step(pq_handle* h, pq_program* p, Step& s, Launch& L);
+
 static void issue_steps(pq_handle* h, pq_program* p, Launch& L) {
-  for (Step& s : p->steps) {
+  for (Step& s : p->steps) issue_step(h, p, s, L);
+}
+
+// read / write address ranges of a step (after the arena has been allocated)
+static void step_ranges(pq_handle* h, const pq_program* p, const Step& s, std::vector<Range>& rd,
+                        std::vector<Range>& wr) {
+  const size_t es = h->elem_size;
+  auto rng = [&](const Ref& r, size_t bytes) {
+    const char* b = (const char*)resolve(p, r);
+    return Range{b, b + (bytes ? bytes : 1)};
+  };
+  switch (s.kind) {
+    case ST_CONTRACT:
+      rd.push_back(rng(s.a, size_t(s.cp.M * s.cp.K) * es));
+      rd.push_back(rng(s.b, size_t(s.cp.N * s.cp.K) * es));
+      wr.push_back(rng(s.c, size_t(s.cp.M * s.cp.N) * es));
+      if (!s.ta.null) wr.push_back(rng(s.ta, s.cp.tempA_bytes));
+      if (!s.tb.null) wr.push_back(rng(s.tb, s.cp.tempB_bytes));
+      if (!s.ws.null) wr.push_back(rng(s.ws, s.cp.ws_bytes));
+      break;
+    case ST_PERMUTE:
+      rd.push_back(rng(s.a, size_t(s.pp.total) * es));
+      wr.push_back(rng(s.c, size_t(s.pp.total) * es));
+      break;
+    case ST_VIEW:
+      rd.push_back(rng(s.a, size_t(s.inner * s.ext * s.outer) * es));
+      wr.push_back(rng(s.c, size_t(s.inner * s.nsel * s.outer) * es));
+      break;
+    case ST_SAVE: {
+      size_t bytes = size_t(prod(s.dims)) * es;
+      rd.push_back(rng(s.a, bytes));
+      wr.push_back(Range{(const char*)s.out->ptr, (const char*)s.out->ptr + (bytes ? bytes : 1)});
+      break;
+    }
+  }
+}
+
+// RAW / WAR / WAW hazards between steps, including those created by arena reuse
+static void build_dag(pq_handle* h, pq_program* p) {
+  const int n = (int)p->steps.size();
+  std::vector<std::vector<Range>> rd(n), wr(n);
+  for (int j = 0; j < n; ++j) step_ranges(h, p, p->steps[j], rd[j], wr[j]);
+  p->deps.assign(n, {});
+  for (int j = 0; j < n; ++j) {
+    for (int i = j - 1; i >= 0; --i) {
+      bool hit = false;
+      for (const Range& w : wr[j]) {
+        for (const Range& r : rd[i]) hit = hit || overlap(w, r);
+        for (const Range& r : wr[i]) hit = hit || overlap(w, r);
+      }
+      for (const Range& r : rd[j])
+        for (const Range& w : wr[i]) hit = hit || overlap(r, w);
+      if (hit) p->deps[j].push_back(i);
+    }
+  }
+  if (getenv("PQ_B200_DEBUG")) {
+    std::vector<int> depth(n, 1);
+    int maxd = 0;
+    size_t nd = 0;
+    for (int j = 0; j < n; ++j) {
+      for (int d : p->deps[j]) depth[j] = std::max(depth[j], depth[d] + 1);
+      maxd = std::max(maxd, depth[j]);
+      nd += p->deps[j].size();
+    }
+    fprintf(stderr, "[pq_b200] program DAG: %d steps, %zu hazard edges, critical path %d steps\n", n,
+            nd, maxd);
+  }
+}
+
+// Issues every step during stream capture, spreading independent steps over several
+// capture streams joined by events, so the instantiated graph is a DAG rather than a
+// chain: the ~10^3 tiny world-line contractions of a slice run concurrently.
+static void issue_steps_dag(pq_handle* h, pq_program* p, Launch& L0) {
+  const int n = (int)p->steps.size();
+  const int S = pq_program::NSTREAMS;
+  cudaStream_t streams[pq_program::NSTREAMS + 1];
+  streams[0] = L0.stream;
+  for (int s = 0; s < S; ++s) streams[s + 1] = p->side[s];
+  const int NS = S + 1;
+  PQ_CUDA(cudaEventRecord(p->fork_ev, streams[0]));
+  for (int s = 1; s < NS; ++s) PQ_CUDA(cudaStreamWaitEvent(streams[s], p->fork_ev, 0));
+  std::vector<int> tail(NS, -1);            // last step issued on each stream
+  std::vector<int> where(n, 0);             // stream of each step
+  std::vector<std::vector<int>> synced(NS, std::vector<int>(NS, -1));
+  for (int j = 0; j < n; ++j) {
+    const std::vector<int>& deps = p->deps[j];  // descending order
+    int best = -1;
+    for (int d : deps)
+      for (int s = 0; s < NS; ++s)
+        if (tail[s] == d && (best < 0 || tail[s] > tail[best])) best = s;
+    if (best < 0) {
+      best = 0;
+      for (int s = 1; s < NS; ++s)
+        if (tail[s] < tail[best]) best = s;
+    }
+    for (int d : deps) {
+      int sd = where[d];
+      if (sd == best || synced[best][sd] >= d) continue;
+      PQ_CUDA(cudaStreamWaitEvent(streams[best], p->step_ev[d], 0));
+      synced[best][sd] = d;
+    }
+    Launch L = L0;
+    L.stream = streams[best];
+    issue_step(h, p, p->steps[j], L);
+    PQ_CUDA(cudaEventRecord(p->step_ev[j], streams[best]));
+    tail[best] = j;
+    where[j] = best;
+  }
+  for (int s = 1; s < NS; ++s) {  // join every side stream back into the origin
+    PQ_CUDA(cudaEventRecord(p->fork_ev, streams[s]));
+    PQ_CUDA(cudaStreamWaitEvent(streams[0], p->fork_ev, 0));
+  }
+}
+
+static void issue_step(pq_handle* h, pq_program* p, Step& s, Launch& L) {
+  {
     switch (s.kind) {
       case ST_CONTRACT:
         run_contract(L, s.cp, resolve(p, s.a), resolve(p, s.b), resolve(p, s.c), resolve(p, s.ta),
@@ -170,12 +313,24 @@ extern "C" int pq_program_compile(pq_handle* h, const char* tl_text, pq_program*
     std::map<std::string, Sym> syms;
     ArenaSim sim;
     const int es = h->elem_size;
+    size_t small_top = 0;
+    auto place = [&](Sym& s) {  // assigns an arena slot to a freshly created tensor
+      if (s.bytes <= SMALL_TENSOR_BYTES) {
+        s.small = true;
+        s.offset = small_top;
+        small_top += round_up(s.bytes ? s.bytes : 1);
+      } else {
+        s.small = false;
+        s.offset = sim.alloc(s.bytes);
+      }
+    };
     auto ref_of = [&](const Sym& s) {
       Ref r;
       r.null = false;
       r.leaf = s.leaf;
       r.leafptr = s.leaf ? s.leafbuf->ptr : nullptr;
       r.offset = s.offset;
+      r.small = s.small;
       return r;
     };
     auto temp_ref = [&](size_t off) {
@@ -193,7 +348,7 @@ extern "C" int pq_program_compile(pq_handle* h, const char* tl_text, pq_program*
     auto drop = [&](const std::string& name) {
       auto it = syms.find(name);
       if (it == syms.end()) return;
-      if (!it->second.leaf) sim.release(it->second.offset, it->second.bytes);
+      if (!it->second.leaf && !it->second.small) sim.release(it->second.offset, it->second.bytes);
       syms.erase(it);
     };
 
@@ -253,7 +408,7 @@ extern "C" int pq_program_compile(pq_handle* h, const char* tl_text, pq_program*
         Sym sc;
         sc.dims = st.cp.cdims;
         sc.bytes = size_t(st.cp.M * st.cp.N) * es;
-        sc.offset = sim.alloc(sc.bytes);
+        place(sc);
         st.c = ref_of(sc);
         size_t oa = 0, ob = 0, ow = 0;
         if (st.cp.tempA_bytes) st.ta = temp_ref(oa = sim.alloc(st.cp.tempA_bytes));
@@ -286,7 +441,7 @@ extern "C" int pq_program_compile(pq_handle* h, const char* tl_text, pq_program*
           Sym ns;
           ns.dims = nd;
           ns.bytes = size_t(pp.total) * es;
-          ns.offset = sim.alloc(ns.bytes);
+          place(ns);
           st.c = ref_of(ns);
           p->steps.push_back(std::move(st));
           std::string name = tok[1];
@@ -337,7 +492,7 @@ extern "C" int pq_program_compile(pq_handle* h, const char* tl_text, pq_program*
         v.dims = src.dims;
         v.dims[axis - 1] = st.nsel;
         v.bytes = size_t(prod(v.dims)) * es;
-        v.offset = sim.alloc(v.bytes);
+        place(v);
         st.c = ref_of(v);
         p->steps.push_back(std::move(st));
         drop(tok[1]);
@@ -359,7 +514,9 @@ extern "C" int pq_program_compile(pq_handle* h, const char* tl_text, pq_program*
     }
 
     p->arena_bytes = sim.top;
+    p->arena_small_bytes = small_top;
     PQ_CUDA(cudaMalloc(&p->arena, p->arena_bytes ? p->arena_bytes : ALIGN));
+    PQ_CUDA(cudaMalloc(&p->arena_small, small_top ? small_top : ALIGN));
     if (p->nviews > 0) {
       PQ_CUDA(cudaMalloc(&p->d_starts, sizeof(int32_t) * p->nviews));
       PQ_CUDA(cudaMemcpy(p->d_starts, p->default_starts.data(), sizeof(int32_t) * p->nviews,
@@ -370,12 +527,20 @@ extern "C" int pq_program_compile(pq_handle* h, const char* tl_text, pq_program*
         p->ring_used[i] = false;
       }
     }
+    build_dag(h, p);
+    for (int i = 0; i < pq_program::NSTREAMS; ++i)
+      PQ_CUDA(cudaStreamCreateWithFlags(&p->side[i], cudaStreamNonBlocking));
+    PQ_CUDA(cudaEventCreateWithFlags(&p->fork_ev, cudaEventDisableTiming));
+    p->step_ev.resize(p->steps.size());
+    for (auto& e : p->step_ev) PQ_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     // count launches with a dry bookkeeping pass (no device work)
     {
       int64_t n = 0;
       for (const Step& s : p->steps) {
         if (s.kind == ST_CONTRACT) {
-          if (s.cp.kind == CK_GEMM)
+          if (s.cp.kind == CK_GEMM && s.cp.fused_gemm)
+            n += 1;
+          else if (s.cp.kind == CK_GEMM)
             n += 1 + (s.cp.permA.identity ? 0 : 1) + (s.cp.permB.identity ? 0 : 1);
           else if (s.cp.kind == CK_DOT)
             n += 2;
@@ -390,12 +555,14 @@ extern "C" int pq_program_compile(pq_handle* h, const char* tl_text, pq_program*
   } catch (const Error& e) {
     h->last_error = e.what();
     if (p->arena) cudaFree(p->arena);
+    if (p->arena_small) cudaFree(p->arena_small);
     for (auto& l : p->leaves) l.second->pins -= 1;
     delete p;
     return e.code;
   } catch (const std::exception& e) {
     h->last_error = e.what();
     if (p->arena) cudaFree(p->arena);
+    if (p->arena_small) cudaFree(p->arena_small);
     for (auto& l : p->leaves) l.second->pins -= 1;
     delete p;
     return PQ_ERR_PARSE;
@@ -409,7 +576,7 @@ extern "C" int pq_program_num_views(const pq_program* p) { return p ? p->nviews 
 extern "C" int pq_program_stats(const pq_program* p, int64_t* arena_bytes, int64_t* launches,
                                 int64_t* macs) {
   if (!p) return PQ_ERR_INVALID;
-  if (arena_bytes) *arena_bytes = (int64_t)p->arena_bytes;
+  if (arena_bytes) *arena_bytes = (int64_t)(p->arena_bytes + p->arena_small_bytes);
   if (launches) *launches = p->launches;
   if (macs) *macs = p->macs;
   return PQ_OK;
@@ -453,7 +620,10 @@ extern "C" int pq_program_run(pq_handle* h, pq_program* p, const int32_t* view_s
         cudaGraph_t graph = nullptr;
         PQ_CUDA(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
         try {
-          issue_steps(h, p, LC);
+          if (h->opt.graph == 2)
+            issue_steps(h, p, LC);       // single-stream chain (A/B against the DAG)
+          else
+            issue_steps_dag(h, p, LC);   // independent steps on parallel branches
         } catch (...) {
           cudaStreamEndCapture(h->stream, &graph);
           if (graph) cudaGraphDestroy(graph);
@@ -511,8 +681,13 @@ extern "C" int pq_program_destroy(pq_handle* h, pq_program* p) {
     cudaStreamSynchronize(h->stream);
   }
   if (p->exec) cudaGraphExecDestroy(p->exec);
+  for (auto& e : p->step_ev) cudaEventDestroy(e);
+  if (p->fork_ev) cudaEventDestroy(p->fork_ev);
+  for (int i = 0; i < pq_program::NSTREAMS; ++i)
+    if (p->side[i]) cudaStreamDestroy(p->side[i]);
   for (auto& l : p->leaves) l.second->pins -= 1;
   if (p->arena) cudaFree(p->arena);
+  if (p->arena_small) cudaFree(p->arena_small);
   if (p->d_starts) cudaFree(p->d_starts);
   if (p->h_ring) {
     cudaFreeHost(p->h_ring);

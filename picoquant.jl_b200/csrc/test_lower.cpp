@@ -274,6 +274,10 @@ static void test_big_shapes() {
   for (int i = 0; i < 12; ++i) bi2[i] = (i < 6) ? (6 - i) : -(++o);
   P = lower_contract(ad2, ai2, bd2, bi2, 16, opt);
   CHECK(P.kind == CK_GEMM && P.M == (1 << 18) && P.N == 64 && P.K == 64, "sweep step plan");
+  CHECK(P.fused_gemm && P.tempA_bytes == 0 && P.tempB_bytes == 0, "sweep step should be fused TTGT");
+  opt.fused = 1;  // materialised TTGT
+  P = lower_contract(ad2, ai2, bd2, bi2, 16, opt);
+  CHECK(P.kind == CK_GEMM && !P.fused_gemm, "unfused sweep step plan");
   CHECK(!P.permA.identity && P.permA.tiled, "sweep step A permute should be tiled");
   std::printf("big shapes: ok (sweep A-permute tile t=%d a=%d b=%d)\n", P.permA.tp.t, P.permA.tp.a,
               P.permA.tp.b);

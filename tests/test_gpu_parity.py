@@ -178,6 +178,34 @@ def test_gemm_path_shapes(dtype, gemm):
     assert expected in prof_names, prof_names
 
 
+def test_fused_ttgt_zgemm_shapes():
+    """The persistent fused-TTGT ZGEMM (operands gathered inside the GEMM, no permuted
+    temporaries): ragged tiles, K tails, several tiles per CTA, low-address contracted axes."""
+    rng = np.random.default_rng(29)
+    b = B200(np.complex128)
+    shapes = list(GEMM_SHAPES) + [
+        ((2,) * 20, [1, 2, 3] + [-(i + 1) for i in range(14)] + [4, 5, 6],
+         (2,) * 12, [6, 5, 4, 3, 2, 1] + [-(20 + i) for i in range(6)]),       # M=2^14 N=64 K=64
+        ((8, 2 ** 16, 8), [1, -1, 2], (8, 8, 40), [2, 1, -2]),                   # many tiles per CTA
+        ((2 ** 17, 9), [-1, 1], (9, 70), [1, -2]),                               # KT = 1, N ragged
+        ((3, 700, 5), [1, -1, 2], (5, 3, 130), [2, 1, -2]),                      # non-pow2 everything
+    ]
+    for ad, ai, bd, bi in shapes:
+        A = rand_tensor(rng, tuple(ad), np.complex128)
+        B = rand_tensor(rng, tuple(bd), np.complex128)
+        b.save_tensor_data("A", A)
+        b.save_tensor_data("B", B)
+        b.profile_enable(True)
+        b.contract_tensors("A", ai, "B", bi, "C")
+        prof = b.profile_read()
+        b.profile_enable(False)
+        assert set(prof) == {"gemm_tensor"}, (ad, prof)   # one launch, no permute kernels
+        got = b.load_tensor_data("C")
+        ref = layer1.contract_tensors((A, B), (ai, bi))
+        assert got.shape == ref.shape
+        assert rel_l2(got, ref) < 1e-10, (ad, ai, rel_l2(got, ref))
+
+
 @pytest.mark.parametrize("dtype", DTYPES)
 def test_fused_kernel_classes_and_dot(dtype):
     """Gate application (small right), cap contraction (small left) and the final
@@ -379,7 +407,7 @@ def test_slicing_identity_on_gpu(dtype):
 # .tl programs (execute_dsl_file on the device) and sliced replay
 # ---------------------------------------------------------------------------
 @pytest.mark.parametrize("dtype", DTYPES)
-@pytest.mark.parametrize("graph", [0, 1])
+@pytest.mark.parametrize("graph", [0, 1, 2])
 def test_program_matches_dsl_interpreter(dtype, graph):
     tol = TOL[np.dtype(dtype)]
     circ = create_RQC(3, 3, 8, seed=4)
@@ -400,6 +428,33 @@ def test_program_matches_dsl_interpreter(dtype, graph):
         prog.run()
         assert rel_l2(b.load_tensor_data("result"), ref) < tol
     assert b.counters()["kernel_launches"] >= 3 * prog.launches
+
+
+@pytest.mark.parametrize("graph", [0, 2])
+def test_large_program_dag_vs_chain(graph):
+    """A 5x5 depth-16 sliced amplitude (GEMM steps, arena reuse, ~500 launches): the
+    multi-stream DAG capture must give the same amplitude as the single-chain graph and
+    as the oracle's interpreter."""
+    circ = create_RQC(5, 5, 16, seed=3)
+    n = circ.n_qubits
+
+    def plan_fn(tn, sliced):
+        return sweep_plan(tn, 5, 5, sliced_bonds=sliced)
+
+    P = 8
+    rec = record_sliced_contraction(circ, P, 1, plan_fn=plan_fn, output_config="0" * n)
+    ref = 0
+    for p in range(1, P + 1):
+        out = TensorStore()
+        execute_dsl(rec.text_for(p), rec.store, np.complex128, output_store=out)
+        ref = ref + out.read("result")
+    b = B200(np.complex128, graph=graph)
+    sc = SlicedContraction(b, rec)
+    for _ in range(2):
+        b.delete_tensor("partial_sum")
+        sc.run(range(1, P + 1))
+        got = sc.result()
+        assert abs(got - ref) / abs(ref) < 1e-10, (graph, got, ref)
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
