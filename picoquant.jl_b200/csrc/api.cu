@@ -212,8 +212,9 @@ extern "C" int pq_save_tensor(pq_handle* h, const char* label, int rank, const i
       convert_host<double>(host, host_dtype, (double*)tmp.data(), n);
     else
       convert_host<float>(host, host_dtype, (float*)tmp.data(), n);
+    // pageable source: the runtime copies it to its staging buffer before returning, so
+    // `tmp` may be released right away and the host does not have to wait for the GPU
     PQ_CUDA(cudaMemcpyAsync(t.buf->ptr, tmp.data(), tmp.size(), cudaMemcpyHostToDevice, h->stream));
-    PQ_CUDA(cudaStreamSynchronize(h->stream));
   }
   h->note_tensor(n);
   h->tensors[label] = std::move(t);

@@ -139,6 +139,7 @@ struct Launch {
 struct PermutePlan {
   bool identity = true;
   bool tiled = false;
+  bool paired = false;   // c64 only: lowest axis untouched, pairs move as 16-byte elements
   int64_t total = 1;
   IdxMap gmap{};     // output-order fused dims with input strides
   TileParams tp{};

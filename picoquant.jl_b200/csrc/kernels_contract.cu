@@ -87,6 +87,66 @@ k_contract_small(const typename C2<R>::type* __restrict__ big,
   }
 }
 
+// ComplexF32, small operand on the right, lowest axis of the big operand open with even
+// extent: every thread owns TWO adjacent rows, so all global traffic is 16-byte
+// (LDG.128 of (re,im,re,im), STG.128 of two results).
+template <int NS>
+__global__ void __launch_bounds__(128)
+k_contract_small_c64x2(const float2* __restrict__ big, const float2* __restrict__ small,
+                       float2* __restrict__ out, const SmallParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float2* Q = reinterpret_cast<float2*>(smem_raw);                           // [K][NS]
+  long long* koff = reinterpret_cast<long long*>(Q + (size_t)p.K * NS);      // [K]
+  for (int i = threadIdx.x; i < p.K * NS; i += blockDim.x) {
+    int k = i / NS, s = i - k * NS;
+    float2 v = make_float2(0.f, 0.f);
+    if (s < p.S) v = small[map_offset(p.ksmall, k) + map_offset(p.ssmall, s)];
+    Q[i] = v;
+  }
+  for (int k = threadIdx.x; k < p.K; k += blockDim.x) koff[k] = map_offset(p.kbig, k);
+  __syncthreads();
+  const long long pairs = p.R >> 1;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < pairs; t += stride) {
+    const float2* row = big + map_offset(p.rmap, 2 * t);
+    float2 acc0[NS], acc1[NS];
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+      acc0[s] = make_float2(0.f, 0.f);
+      acc1[s] = make_float2(0.f, 0.f);
+    }
+#pragma unroll 4
+    for (int k = 0; k < p.K; ++k) {
+      const float4 a = *reinterpret_cast<const float4*>(row + koff[k]);
+      const float2 a0 = make_float2(a.x, a.y), a1 = make_float2(a.z, a.w);
+#pragma unroll
+      for (int s = 0; s < NS; ++s) {
+        const float2 q = Q[k * NS + s];
+        cfma<float2, float>(acc0[s], a0, q);
+        cfma<float2, float>(acc1[s], a1, q);
+      }
+    }
+    float2* dst = out + 2 * t;  // out_rs == 1
+#pragma unroll
+    for (int s = 0; s < NS; ++s)
+      if (s < p.S)
+        *reinterpret_cast<float4*>(dst + s * p.out_ss) =
+            make_float4(acc0[s].x, acc0[s].y, acc1[s].x, acc1[s].y);
+  }
+}
+
+template <int NS>
+static void launch_small_c64x2(const Launch& L, const SmallParams& p, const void* big,
+                               const void* small, void* out) {
+  size_t smem = (size_t)p.K * NS * sizeof(float2) + (size_t)p.K * sizeof(long long);
+  long long blocks = (p.R / 2 + 127) / 128;
+  long long cap = (long long)L.num_sms * 32;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  k_contract_small_c64x2<NS><<<(unsigned)blocks, 128, smem, L.stream>>>(
+      (const float2*)big, (const float2*)small, (float2*)out, p);
+}
+
 template <typename R, int NS>
 static void launch_small_ns(const Launch& L, const SmallParams& p, const void* big,
                             const void* small, void* out) {
@@ -100,9 +160,36 @@ static void launch_small_ns(const Launch& L, const SmallParams& p, const void* b
                                                                    (V*)out, p);
 }
 
+// 16-byte path condition: c64, result rows contiguous (small operand on the right), the
+// fastest axis of the big operand is an open axis of even extent (then every other stride
+// of that tensor, the k offsets included, is even and all accesses are 16-byte aligned)
+static bool small_vec2_ok(const SmallParams& p) {
+  if (p.out_rs != 1 || (p.R & 1) || (p.out_ss & 1) || p.rmap.nd < 1) return false;
+  if (p.rmap.str[0] != 1 || (p.rmap.ext[0] & 1)) return false;
+  for (int d = 1; d < p.rmap.nd; ++d)
+    if (p.rmap.str[d] & 1) return false;
+  for (int d = 0; d < p.kbig.nd; ++d)
+    if (p.kbig.str[d] & 1) return false;
+  return true;
+}
+
 template <typename R>
 static void launch_small(const Launch& L, const SmallParams& p, const void* big, const void* small,
                          void* out) {
+  if (sizeof(R) == 4 && small_vec2_ok(p) && ((uintptr_t)big % 16 == 0) &&
+      ((uintptr_t)out % 16 == 0)) {
+    if (p.S <= 1)
+      launch_small_c64x2<1>(L, p, big, small, out);
+    else if (p.S <= 2)
+      launch_small_c64x2<2>(L, p, big, small, out);
+    else if (p.S <= 4)
+      launch_small_c64x2<4>(L, p, big, small, out);
+    else if (p.S <= 8)
+      launch_small_c64x2<8>(L, p, big, small, out);
+    else
+      launch_small_c64x2<16>(L, p, big, small, out);
+    return;
+  }
   if (p.S <= 1)
     launch_small_ns<R, 1>(L, p, big, small, out);
   else if (p.S <= 2)

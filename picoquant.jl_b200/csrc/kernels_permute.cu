@@ -7,7 +7,7 @@
 //    tile holds the >=5 lowest input bits and the >=5 lowest output bits, so both the
 //    global reads (input order) and the global writes (output order) are runs of >=32
 //    consecutive elements (512 B for c128).  An xor swizzle keeps both shared-memory
-//    phases bank-conflict free.
+//    phases bank-conflict free.  Tiles are double-buffered with cp.async.
 //  * k_permute_generic -- any extents: one thread per output element, coalesced
 //    writes, gathered reads.  Fallback and cross-check.
 #include "common.h"
@@ -23,14 +23,26 @@ k_permute_generic(const E* __restrict__ in, E* __restrict__ out, IdxMap map, lon
     out[i] = in[map_offset(map, i)];
 }
 
+template <int BYTES>
+__device__ __forceinline__ void cp_async_elem(void* smem, const void* gmem) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  if (BYTES == 16)
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+  else
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(s), "l"(gmem));
+}
+
+// Two tile buffers: the cp.async gather of tile r+1 (global -> swizzled shared memory,
+// no register staging) is in flight while tile r is being written out, so every CTA keeps
+// reads and writes outstanding at the same time.
 template <typename E>
 __global__ void __launch_bounds__(256)
 k_permute_tiled(const E* __restrict__ in, E* __restrict__ out, const TileParams tp) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int tile_elems = 1 << tp.t;
   const int nhi = 1 << (tp.t - TILE_LO);
-  E* tile = reinterpret_cast<E*>(smem_raw);
-  long long* in_hi = reinterpret_cast<long long*>(smem_raw + sizeof(E) * tile_elems);
+  E* tile0 = reinterpret_cast<E*>(smem_raw);
+  long long* in_hi = reinterpret_cast<long long*>(smem_raw + 2 * sizeof(E) * tile_elems);
   long long* out_hi = in_hi + nhi;
   int* e_hi = reinterpret_cast<int*>(out_hi + nhi);
   int* e_lo = e_hi + nhi;
@@ -43,47 +55,63 @@ k_permute_tiled(const E* __restrict__ in, E* __restrict__ out, const TileParams 
   if (threadIdx.x < 32) e_lo[threadIdx.x] = tile_e_lo(tp, threadIdx.x);
   __syncthreads();
 
-  for (long long r = blockIdx.x; r < tp.ntiles; r += gridDim.x) {
+  auto gather = [&](long long r, E* tile) {
     long long in_base, out_base;
     tile_bases(tp, r, in_base, out_base);
     const E* src = in + in_base;
-    E* dst = out + out_base;
 #pragma unroll 4
-    for (int e = threadIdx.x; e < tile_elems; e += 256) {
-      E v = src[(long long)(e & 31) | in_hi[e >> TILE_LO]];
-      tile[tile_swizzle(tp, e)] = v;
-    }
+    for (int e = threadIdx.x; e < tile_elems; e += 256)
+      cp_async_elem<sizeof(E)>(tile + tile_swizzle(tp, e),
+                               src + ((long long)(e & 31) | in_hi[e >> TILE_LO]));
+  };
+
+  long long r = blockIdx.x;
+  if (r < tp.ntiles) gather(r, tile0);
+  asm volatile("cp.async.commit_group;\n" ::);
+  int buf = 0;
+  for (; r < tp.ntiles; r += gridDim.x) {
+    const long long rn = r + gridDim.x;
+    if (rn < tp.ntiles) gather(rn, tile0 + (buf ^ 1) * tile_elems);
+    asm volatile("cp.async.commit_group;\n" ::);
+    asm volatile("cp.async.wait_group 1;\n" ::);
     __syncthreads();
+    long long in_base, out_base;
+    tile_bases(tp, r, in_base, out_base);
+    E* dst = out + out_base;
+    const E* tile = tile0 + buf * tile_elems;
 #pragma unroll 4
     for (int o = threadIdx.x; o < tile_elems; o += 256) {
       int e = e_lo[o & 31] | e_hi[o >> TILE_LO];
       dst[(long long)(o & 31) | out_hi[o >> TILE_LO]] = tile[tile_swizzle(tp, e)];
     }
-    __syncthreads();
+    __syncthreads();  // the buffer just drained is the prefetch target of the next iteration
+    buf ^= 1;
   }
+  asm volatile("cp.async.wait_group 0;\n" ::);
 }
 
 template <typename E>
 static void launch_permute(const Launch& L, const PermutePlan& p, const void* in, void* out) {
-  const double bytes = 2.0 * double(p.total) * sizeof(E);
+  const long long total = p.paired ? p.total / 2 : p.total;
+  const double bytes = 2.0 * double(total) * sizeof(E);
   if (p.tiled && (L.opt == nullptr || L.opt->permute != 1)) {
     const TileParams& tp = p.tp;
     const int nhi = 1 << (tp.t - TILE_LO);
-    size_t smem = sizeof(E) * (size_t(1) << tp.t) + size_t(nhi) * (8 + 8 + 4) + 32 * 4;
+    size_t smem = 2 * sizeof(E) * (size_t(1) << tp.t) + size_t(nhi) * (8 + 8 + 4) + 32 * 4;
     long long grid = tp.ntiles;
-    long long cap = (long long)L.num_sms * 16;
+    long long cap = (long long)L.num_sms * 6;  // ~6 resident CTAs per SM, several tiles each
     if (grid > cap) grid = cap;
     L.begin(KC_PERMUTE_TILED, bytes, 0);
     k_permute_tiled<E><<<(unsigned)grid, 256, smem, L.stream>>>((const E*)in, (E*)out, tp);
     L.end();
   } else {
-    long long blocks = (p.total + 255) / 256;
+    long long blocks = (total + 255) / 256;
     long long cap = (long long)L.num_sms * 32;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
     L.begin(KC_PERMUTE_GENERIC, bytes, 0);
     k_permute_generic<E><<<(unsigned)blocks, 256, 0, L.stream>>>((const E*)in, (E*)out, p.gmap,
-                                                               p.total);
+                                                               total);
     L.end();
   }
   PQ_CUDA(cudaGetLastError());
@@ -98,8 +126,8 @@ void run_permute(const Launch& L, const PermutePlan& p, const void* in, void* ou
     L.end();
     return;
   }
-  if (L.elem_size == 16)
-    launch_permute<double2>(L, p, in, out);
+  if (L.elem_size == 16 || p.paired)
+    launch_permute<double2>(L, p, in, out);  // c64 pairs travel as 16-byte elements
   else
     launch_permute<float2>(L, p, in, out);
 }

@@ -121,6 +121,17 @@ static void test_permutations(std::mt19937& rng) {
       for (int64_t o = 0; o < total; ++o) CHECK(ref[o] == o, "identity plan for a non-identity permutation");
       continue;
     }
+    // a paired plan moves 16-byte pairs: unit u of the plan covers elements 2u, 2u+1
+    const int64_t units = P.paired ? total / 2 : total;
+    const int64_t w = P.paired ? 2 : 1;
+    CHECK(!P.paired || elem == 8, "pairing is a c64-only trick");
+    std::vector<int64_t> uref(units);
+    for (int64_t u = 0; u < units; ++u) {
+      uref[u] = ref[u * w] / w;
+      if (P.paired) CHECK(ref[2 * u] % 2 == 0 && ref[2 * u + 1] == ref[2 * u] + 1, "pair split");
+    }
+    ref = uref;
+    total = units;
     for (int64_t o = 0; o < total; ++o) {
       int64_t got = map_offset(P.gmap, o);
       if (got != ref[o]) {
@@ -133,7 +144,7 @@ static void test_permutations(std::mt19937& rng) {
       ++tiled_cases;
       CHECK(P.tp.a >= 5 && P.tp.b >= 5, "tile runs too short");
       std::vector<int64_t> got(total, -1);
-      emulate_tiled(P.tp, got, elem);
+      emulate_tiled(P.tp, got, P.paired ? 16 : elem);
       for (int64_t o = 0; o < total; ++o)
         if (got[o] != ref[o]) {
           CHECK(false, "tiled permute mismatch at %lld (iter %d, n=%d t=%d)", (long long)o, iter,
