@@ -118,6 +118,7 @@ extern "C" int pq_create(int device, int dtype, pq_handle** out) {
     uint64_t threshold = UINT64_MAX;
     PQ_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold));
     init_kernels();
+    init_kernels_cgemm();
   } catch (const std::exception&) {
     delete h;
     return PQ_ERR_CUDA;

@@ -171,6 +171,7 @@ void run_contract(const Launch& L, const ContractPlan& p, const void* A, const v
                   void* tempA, void* tempB, void* ws);
 
 void init_kernels();
+void init_kernels_cgemm();
 
 // misc kernels
 void run_view(const Launch& L, const void* in, void* out, int64_t inner, int64_t ext_in,
@@ -184,6 +185,8 @@ void run_gemm_simt(const Launch& L, const void* A, const void* B, void* C, int64
 void run_zgemm_dmma(const Launch& L, const void* A, const void* B, void* C, int64_t M, int64_t N,
                     int64_t K);
 void run_zgemm_fused(const Launch& L, const ContractPlan& cp, const void* A, const void* B, void* C);
+void run_cgemm_tcgen05(const Launch& L, const void* A, const void* B, void* C, int64_t M, int64_t N,
+                       int64_t K);
 
 inline int64_t prod(const std::vector<int64_t>& v) {
   int64_t p = 1;

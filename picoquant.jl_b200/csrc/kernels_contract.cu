@@ -479,9 +479,11 @@ static void run_contract_t(const Launch& L, const ContractPlan& p, const void* A
         run_permute(L, p.permB, B, tempB);
         Bp = tempB;
       }
-      bool tensor = sizeof(R) == 8 && (L.opt == nullptr || L.opt->gemm != 1);
-      if (tensor)
-        run_zgemm_dmma(L, Ap, Bp, C, p.M, p.N, p.K);
+      const bool tensor = (L.opt == nullptr || L.opt->gemm != 1);
+      if (tensor && sizeof(R) == 8)
+        run_zgemm_dmma(L, Ap, Bp, C, p.M, p.N, p.K);      // FP64 DMMA
+      else if (tensor)
+        run_cgemm_tcgen05(L, Ap, Bp, C, p.M, p.N, p.K);   // tcgen05, 3xTF32
       else
         run_gemm_simt(L, Ap, Bp, C, p.M, p.N, p.K);
       break;
