@@ -13,8 +13,6 @@
 // {0,32,64,96} + {0,16} mod 128 -> conflict-free LDS.128.  A complex product is four
 // real DMMAs (ar*br, -ai*bi -> re; ar*bi, ai*br -> im).
 // Roofline: 8*M*N*K real flops against the FP64 pipe; operands are re-read from L2.
-#include <cstdlib>
-
 #include "common.h"
 
 namespace pq {
@@ -156,155 +154,145 @@ struct FusedParams {
   long long M, N, K;
 };
 
-// Persistent: each CTA walks tiles t = blockIdx.x, +gridDim.x, ... (m-tiles fastest) and the
-// cp.async ring runs ahead ACROSS tile boundaries, so the fill of tile i+1 overlaps the
-// last k-blocks and the epilogue of tile i (the skinny K=64 steps of an RQC sweep only have
-// 4 k-blocks per tile; without this the pipeline would drain on every tile).
-constexpr int ROW_RING = 4;
-
-__global__ void __launch_bounds__(256, 2)
-k_zgemm_fused(const double2* __restrict__ A, const double2* __restrict__ B, double2* __restrict__ C,
-              const FusedParams p) {
+// One output tile per CTA (a persistent variant with a cross-tile cp.async ring was
+// measured ~7 % slower on B200: the hardware CTA scheduler de-phases resident CTAs better).
+// Two tile configurations:
+//   <64,64, 2x4 warps, 3 stages, 2 CTAs/SM>  warp tile 32x16 -- large N and K
+//   <64,32, 4x2 warps, 2 stages, 4 CTAs/SM>  warp tile 16x16 -- the skinny K<=128 sweep steps:
+//     64 registers and 51 KB of shared memory per CTA put four independent CTAs (32 warps)
+//     on every SM, which hides the per-tile fill latency that dominates when a tile has only
+//     four k-blocks (27.4 -> 30.7 TFLOP/s on M=2^18, N=K=64; cuBLAS ZGEMM on pre-permuted
+//     operands: 30.7-31.7).  A Gauss-3M variant (3 DMMAs per complex product) was tried and
+//     gave no gain: these steps are bound by tile fill latency, not by the DMMA pipe.
+template <int TBM, int TBN, int WGM, int WGN, int NST, int MINB>
+__global__ void __launch_bounds__(256, MINB)
+k_zgemm_fused_t(const double2* __restrict__ A, const double2* __restrict__ B,
+                double2* __restrict__ C, const FusedParams p) {
+  constexpr int PA = TBM + 2, PB = TBN + 2;              // smem pitches (double2)
+  constexpr int XT = TBM / WGM / 8, YT = TBN / WGN / 8;  // 8x8 sub-tiles per warp
+  constexpr int A_ELEMS = BK * PA, B_ELEMS = BK * PB;
+  constexpr int A_STEP = 256 / TBM, A_CNT = BK / A_STEP;  // k-rows per pass / passes
+  constexpr int B_STEP = 256 / TBN, B_CNT = BK / B_STEP;
+  static_assert(WGM * WGN == 8, "eight warps");
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double2* sA = reinterpret_cast<double2*>(smem_raw);
-  double2* sB = sA + STAGES * STAGE_ELEMS;
-  long long* rowA = reinterpret_cast<long long*>(sB + STAGES * STAGE_ELEMS);  // [ROW_RING][BM]
-  long long* rowB = rowA + ROW_RING * BM;                                      // [ROW_RING][BN]
-  int* koffA = reinterpret_cast<int*>(rowB + ROW_RING * BN);                   // [K]
-  int* koffB = koffA + p.K;                                                    // [K]
+  double2* sB = sA + NST * A_ELEMS;
+  long long* rowA = reinterpret_cast<long long*>(sB + NST * B_ELEMS);  // [TBM]
+  long long* rowB = rowA + TBM;                                        // [TBN]
+  int* koffA = reinterpret_cast<int*>(rowB + TBN);                     // [K]
+  int* koffB = koffA + p.K;                                            // [K]
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int wm = warp & 1, wn = warp >> 1;
+  const int wm = warp % WGM, wn = warp / WGM;
   const long long M = p.M, N = p.N;
   const int K = (int)p.K;
-  const long long tiles_m = (M + BM - 1) / BM, tiles_n = (N + BN - 1) / BN;
-  const long long ntiles = tiles_m * tiles_n;
+  const long long tiles_n = (N + TBN - 1) / TBN;
+  // n-tiles fastest: CTAs that share the same rows of A are scheduled back to back (L2 reuse)
+  const long long tm = (long long)blockIdx.x / tiles_n, tn = (long long)blockIdx.x - tm * tiles_n;
+  const long long m0 = tm * TBM, n0 = tn * TBN;
   const int KT = (K + BK - 1) / BK;
-  if ((long long)blockIdx.x >= ntiles) return;
-  const int my_count = (int)((ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
-
-  auto tile_origin = [&](int i, long long& m0, long long& n0) {
-    long long t = (long long)blockIdx.x + (long long)i * gridDim.x;
-    long long tn = t / tiles_m, tm = t - tn * tiles_m;
-    m0 = tm * BM;
-    n0 = tn * BN;
-  };
-  auto compute_rows = [&](int i) {  // tables of tile i into ring slot i % ROW_RING
-    if (tid >= BM + BN) return;
-    long long m0, n0;
-    tile_origin(i, m0, n0);
-    const int slot = i & (ROW_RING - 1);
-    if (tid < BM)
-      rowA[slot * BM + tid] = (m0 + tid < M) ? map_offset(p.mA, m0 + tid) : -1;
-    else
-      rowB[slot * BN + (tid - BM)] =
-          (n0 + (tid - BM) < N) ? map_offset(p.nB, n0 + (tid - BM)) : -1;
-  };
-
-  // ---- prefetch stream: (pf_i, pf_kt) walks this CTA's flattened (tile, k-block) list ----
-  const int mm = tid & 63, kk0 = tid >> 6;          // this thread's column and first k-row
-  int pf_i = 0, pf_kt = 0, pf_ring = 0;
-  long long pf_ra = -1, pf_rb = -1;
-  auto prefetch = [&]() {
-    if (pf_i < my_count) {
-      if (pf_kt == 0) {
-        const int slot = pf_i & (ROW_RING - 1);
-        pf_ra = rowA[slot * BM + mm];
-        pf_rb = rowB[slot * BN + mm];
-      }
-      double2* dA = sA + pf_ring * STAGE_ELEMS + kk0 * PITCH + mm;
-      double2* dB = sB + pf_ring * STAGE_ELEMS + kk0 * PITCH + mm;
-      const int kbase = pf_kt * BK + kk0;
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int k = kbase + 4 * q;
-        const bool kin = k < K;
-        const bool va = kin && (pf_ra >= 0), vb = kin && (pf_rb >= 0);
-        const int ka = kin ? koffA[k] : 0, kb = kin ? koffB[k] : 0;
-        cp_async16(dA + 4 * q * PITCH, va ? (A + pf_ra + ka) : A, va);
-        cp_async16(dB + 4 * q * PITCH, vb ? (B + pf_rb + kb) : B, vb);
-      }
-      if (++pf_kt == KT) {
-        pf_kt = 0;
-        ++pf_i;
-      }
-      pf_ring = (pf_ring + 1 == STAGES) ? 0 : pf_ring + 1;
-    }
-    cp_async_commit();
-  };
 
   for (int k = tid; k < K; k += 256) {
     koffA[k] = (int)map_offset(p.kA, k);
     koffB[k] = (int)map_offset(p.kB, k);
   }
-  for (int i = 0; i < ROW_RING - 1 && i < my_count; ++i) compute_rows(i);
+  if (tid < TBM)
+    rowA[tid] = (m0 + tid < M) ? map_offset(p.mA, m0 + tid) : -1;
+  else if (tid < TBM + TBN)
+    rowB[tid - TBM] = (n0 + (tid - TBM) < N) ? map_offset(p.nB, n0 + (tid - TBM)) : -1;
   __syncthreads();
 
+  const int ma = tid % TBM, ka0 = tid / TBM, mb = tid % TBN, kb0 = tid / TBN;
+  const long long ra = rowA[ma], rb = rowB[mb];
+  auto load_stage = [&](int stage, int kt) {
+    double2* dA = sA + stage * A_ELEMS + ka0 * PA + ma;
+    double2* dB = sB + stage * B_ELEMS + kb0 * PB + mb;
+    const int k0 = kt * BK;
 #pragma unroll
-  for (int s = 0; s < STAGES - 1; ++s) prefetch();
-
-  double cr[4][2][2], ci[4][2][2];
-  const int frow = lane >> 2, fk = lane & 3;
-  int ring = 0;
-  for (int i = 0; i < my_count; ++i) {
-#pragma unroll
-    for (int a = 0; a < 4; ++a)
-#pragma unroll
-      for (int b = 0; b < 2; ++b) {
-        cr[a][b][0] = cr[a][b][1] = 0.0;
-        ci[a][b][0] = ci[a][b][1] = 0.0;
-      }
-    for (int kt = 0; kt < KT; ++kt) {
-      cp_async_wait<STAGES - 2>();
-      __syncthreads();
-      // ring slot of tile i-1 is free: all of its stages were issued before tile i began
-      if (kt == 0 && i + ROW_RING - 1 < my_count) compute_rows(i + ROW_RING - 1);
-      prefetch();
-      const double2* tA = sA + ring * STAGE_ELEMS + wm * 32 + frow;
-      const double2* tB = sB + ring * STAGE_ELEMS + wn * 16 + frow;
-#pragma unroll
-      for (int ks = 0; ks < BK; ks += 4) {
-        double2 a[4], b[2];
-#pragma unroll
-        for (int x = 0; x < 4; ++x) a[x] = tA[(ks + fk) * PITCH + x * 8];
-#pragma unroll
-        for (int y = 0; y < 2; ++y) b[y] = tB[(ks + fk) * PITCH + y * 8];
-#pragma unroll
-        for (int x = 0; x < 4; ++x)
-#pragma unroll
-          for (int y = 0; y < 2; ++y) {
-            dmma(cr[x][y][0], cr[x][y][1], a[x].x, b[y].x);
-            dmma(ci[x][y][0], ci[x][y][1], a[x].x, b[y].y);
-          }
-#pragma unroll
-        for (int x = 0; x < 4; ++x) {
-          const double nai = -a[x].y;
-#pragma unroll
-          for (int y = 0; y < 2; ++y) {
-            dmma(cr[x][y][0], cr[x][y][1], nai, b[y].y);
-            dmma(ci[x][y][0], ci[x][y][1], a[x].y, b[y].x);
-          }
-        }
-      }
-      ring = (ring + 1 == STAGES) ? 0 : ring + 1;
+    for (int q = 0; q < A_CNT; ++q) {
+      const int k = k0 + ka0 + q * A_STEP;
+      const bool v = (k < K) && (ra >= 0);
+      cp_async16(dA + q * A_STEP * PA, v ? (A + ra + koffA[k]) : A, v);
     }
-    // epilogue of tile i; the loads of the next tile are already in flight
-    long long m0, n0;
-    tile_origin(i, m0, n0);
 #pragma unroll
-    for (int y = 0; y < 2; ++y)
+    for (int q = 0; q < B_CNT; ++q) {
+      const int k = k0 + kb0 + q * B_STEP;
+      const bool v = (k < K) && (rb >= 0);
+      cp_async16(dB + q * B_STEP * PB, v ? (B + rb + koffB[k]) : B, v);
+    }
+  };
+
+  double cr[XT][YT][2], ci[XT][YT][2];
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        long long n = n0 + wn * 16 + y * 8 + 2 * fk + c;
-        if (n >= N) continue;
+  for (int x = 0; x < XT; ++x)
 #pragma unroll
-        for (int x = 0; x < 4; ++x) {
-          long long m = m0 + wm * 32 + x * 8 + frow;
-          if (m < M) C[m + M * n] = make_double2(cr[x][y][c], ci[x][y][c]);
+    for (int y = 0; y < YT; ++y) {
+      cr[x][y][0] = cr[x][y][1] = 0.0;
+      ci[x][y][0] = ci[x][y][1] = 0.0;
+    }
+
+#pragma unroll
+  for (int s = 0; s < NST - 1; ++s) {
+    if (s < KT) load_stage(s, s);
+    cp_async_commit();
+  }
+
+  const int frow = lane >> 2, fk = lane & 3;
+  int ring = 0, pring = NST - 1;
+  for (int kt = 0; kt < KT; ++kt) {
+    cp_async_wait<NST - 2>();
+    __syncthreads();
+    if (kt + NST - 1 < KT) load_stage(pring, kt + NST - 1);
+    cp_async_commit();
+    const double2* tA = sA + ring * A_ELEMS + wm * (XT * 8) + frow;
+    const double2* tB = sB + ring * B_ELEMS + wn * (YT * 8) + frow;
+#pragma unroll
+    for (int ks = 0; ks < BK; ks += 4) {
+      double2 a[XT], b[YT];
+#pragma unroll
+      for (int x = 0; x < XT; ++x) a[x] = tA[(ks + fk) * PA + x * 8];
+#pragma unroll
+      for (int y = 0; y < YT; ++y) b[y] = tB[(ks + fk) * PB + y * 8];
+#pragma unroll
+      for (int x = 0; x < XT; ++x)
+#pragma unroll
+        for (int y = 0; y < YT; ++y) {
+          dmma(cr[x][y][0], cr[x][y][1], a[x].x, b[y].x);
+          dmma(ci[x][y][0], ci[x][y][1], a[x].x, b[y].y);
+        }
+#pragma unroll
+      for (int x = 0; x < XT; ++x) {
+        const double nai = -a[x].y;
+#pragma unroll
+        for (int y = 0; y < YT; ++y) {
+          dmma(cr[x][y][0], cr[x][y][1], nai, b[y].y);
+          dmma(ci[x][y][0], ci[x][y][1], a[x].y, b[y].x);
         }
       }
+    }
+    ring = (ring + 1 == NST) ? 0 : ring + 1;
+    pring = (pring + 1 == NST) ? 0 : pring + 1;
   }
   cp_async_wait<0>();
+
+#pragma unroll
+  for (int y = 0; y < YT; ++y)
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      const long long n = n0 + wn * (YT * 8) + y * 8 + 2 * fk + c;
+      if (n >= N) continue;
+#pragma unroll
+      for (int x = 0; x < XT; ++x) {
+        const long long m = m0 + wm * (XT * 8) + x * 8 + frow;
+        if (m < M) C[m + M * n] = make_double2(cr[x][y][c], ci[x][y][c]);
+      }
+    }
+}
+
+template <int TBM, int TBN, int NST>
+constexpr size_t fused_smem(int K) {
+  return size_t(NST) * BK * ((TBM + 2) + (TBN + 2)) * sizeof(double2) + size_t(TBM + TBN) * 8 +
+         size_t(K) * 8;
 }
 
 // FP64 issue-rate probes for the roofline denominators (dependent chains per warp are
@@ -343,14 +331,28 @@ __global__ void __launch_bounds__(256) k_probe_dfma(double* out, int iters) {
 
 // per-device one-time kernel attributes (called from pq_create, outside any capture)
 constexpr int FUSED_MAX_K = 1024;
-constexpr size_t FUSED_SMEM_MAX =
-    SMEM_BYTES + size_t(ROW_RING) * (BM + BN) * 8 + size_t(FUSED_MAX_K) * 8;
 
 void init_kernels() {
   PQ_CUDA(cudaFuncSetAttribute(k_zgemm_dmma, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)SMEM_BYTES));
-  PQ_CUDA(cudaFuncSetAttribute(k_zgemm_fused, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               (int)FUSED_SMEM_MAX));
+  PQ_CUDA(cudaFuncSetAttribute(k_zgemm_fused_t<64, 64, 2, 4, 3, 2>,
+                               cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)fused_smem<64, 64, 3>(FUSED_MAX_K)));
+  PQ_CUDA(cudaFuncSetAttribute(k_zgemm_fused_t<64, 32, 4, 2, 2, 4>,
+                               cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)fused_smem<64, 32, 2>(FUSED_MAX_K)));
+}
+
+void run_zgemm_dmma(const Launch& L, const void* A, const void* B, void* C, int64_t M, int64_t N,
+                    int64_t K) {
+  dim3 grid((unsigned)((M + BM - 1) / BM), (unsigned)((N + BN - 1) / BN));
+  PQ_REQUIRE(grid.y <= 65535, PQ_ERR_UNSUPPORTED, "N too large for the ZGEMM grid");
+  double bytes = double(M * K + N * K + M * N) * 16.0, flops = 8.0 * M * N * K;
+  L.begin(KC_GEMM_TENSOR, bytes, flops);
+  k_zgemm_dmma<<<grid, 256, SMEM_BYTES, L.stream>>>((const double2*)A, (const double2*)B,
+                                                    (double2*)C, M, N, K);
+  L.end();
+  PQ_CUDA(cudaGetLastError());
 }
 
 // fused TTGT ZGEMM straight from the un-permuted operands (K <= 1024, 32-bit k offsets)
@@ -364,34 +366,27 @@ void run_zgemm_fused(const Launch& L, const ContractPlan& cp, const void* A, con
   fp.M = cp.M;
   fp.N = cp.N;
   fp.K = cp.K;
-  long long ntiles = ((cp.M + BM - 1) / BM) * ((cp.N + BN - 1) / BN);
-  // One tile per CTA by default: on B200 the hardware CTA scheduler (2 resident CTAs per SM,
-  // naturally de-phased) beat a persistent 2-CTA/SM grid by ~7% on the skinny sweep steps
-  // (measured, profiles/); PQ_ZGEMM_CTAS_PER_SM=k caps the grid at k*SMs persistent CTAs.
-  static const long long per_sm =
-      getenv("PQ_ZGEMM_CTAS_PER_SM") ? atoll(getenv("PQ_ZGEMM_CTAS_PER_SM")) : (1LL << 40);
-  long long cap = per_sm <= 0 ? (1LL << 40) : per_sm * L.num_sms;
-  if (cap > 0x7fffffffLL) cap = 0x7fffffffLL;
-  unsigned grid = (unsigned)(ntiles < cap ? ntiles : cap);
   PQ_REQUIRE(cp.K <= FUSED_MAX_K, PQ_ERR_INVALID, "fused ZGEMM: K too large");
-  size_t smem = SMEM_BYTES + size_t(ROW_RING) * (BM + BN) * 8 + size_t(cp.K) * 8;
   double bytes = double(cp.M * cp.K + cp.N * cp.K + cp.M * cp.N) * 16.0;
   double flops = 8.0 * double(cp.M) * double(cp.N) * double(cp.K);
+  // short contractions (few k-blocks per tile) are fill-latency bound: use the small-CTA
+  // configuration with four resident CTAs per SM; option "zgemm_cfg" forces 1 (64x64) / 2 (64x32)
+  int cfg = L.opt ? L.opt->zgemm_cfg : 0;
+  if (cfg == 0) cfg = (cp.K <= 128) ? 2 : 1;
   L.begin(KC_GEMM_TENSOR, bytes, flops);
-  k_zgemm_fused<<<grid, 256, smem, L.stream>>>((const double2*)A, (const double2*)B, (double2*)C,
-                                               fp);
-  L.end();
-  PQ_CUDA(cudaGetLastError());
-}
-
-void run_zgemm_dmma(const Launch& L, const void* A, const void* B, void* C, int64_t M, int64_t N,
-                    int64_t K) {
-  dim3 grid((unsigned)((M + BM - 1) / BM), (unsigned)((N + BN - 1) / BN));
-  PQ_REQUIRE(grid.y <= 65535, PQ_ERR_UNSUPPORTED, "N too large for the ZGEMM grid");
-  double bytes = double(M * K + N * K + M * N) * 16.0, flops = 8.0 * M * N * K;
-  L.begin(KC_GEMM_TENSOR, bytes, flops);
-  k_zgemm_dmma<<<grid, 256, SMEM_BYTES, L.stream>>>((const double2*)A, (const double2*)B,
-                                                    (double2*)C, M, N, K);
+  if (cfg == 2) {
+    long long tiles = ((cp.M + 63) / 64) * ((cp.N + 31) / 32);
+    PQ_REQUIRE(tiles <= 0x7fffffffLL, PQ_ERR_UNSUPPORTED, "too many tiles");
+    k_zgemm_fused_t<64, 32, 4, 2, 2, 4><<<(unsigned)tiles, 256, fused_smem<64, 32, 2>((int)cp.K),
+                                          L.stream>>>((const double2*)A, (const double2*)B,
+                                                      (double2*)C, fp);
+  } else {
+    long long tiles = ((cp.M + 63) / 64) * ((cp.N + 63) / 64);
+    PQ_REQUIRE(tiles <= 0x7fffffffLL, PQ_ERR_UNSUPPORTED, "too many tiles");
+    k_zgemm_fused_t<64, 64, 2, 4, 3, 2><<<(unsigned)tiles, 256, fused_smem<64, 64, 3>((int)cp.K),
+                                          L.stream>>>((const double2*)A, (const double2*)B,
+                                                      (double2*)C, fp);
+  }
   L.end();
   PQ_CUDA(cudaGetLastError());
 }

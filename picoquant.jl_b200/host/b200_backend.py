@@ -210,6 +210,23 @@ class B200Backend(AbstractBackend):
         self._check(self.lib.pq_save_tensor(self._h, tensor_label.encode(), arr.ndim, dims,
                                             arr.ctypes.data_as(c_void_p), _HOST_DTYPES[arr.dtype]))
 
+    def prepare_save(self, tensor_label, tensor_data):
+        """Pre-marshals the arguments of ``pq_save_tensor`` for a host array that
+        will be uploaded repeatedly (the array is kept alive by the tuple)."""
+        arr = np.asarray(tensor_data)
+        if arr.dtype not in _HOST_DTYPES:
+            arr = arr.astype(np.complex128 if np.iscomplexobj(arr) else np.float64)
+        arr = np.array(arr, order="F", copy=True) if not arr.flags.f_contiguous else arr
+        dims = (c_int64 * max(1, arr.ndim))(*arr.shape)
+        args = (self._h, tensor_label.encode(), arr.ndim, dims, arr.ctypes.data_as(c_void_p),
+                _HOST_DTYPES[arr.dtype], arr)
+        return args, arr.size * self.dtype.itemsize
+
+    def save_prepared(self, args):
+        rc = self.lib.pq_save_tensor(*args[:6])
+        if rc != 0:
+            self._check(rc)
+
     def tensor_shape(self, tensor_label):
         rank = c_int()
         dims = (c_int64 * PQ_MAX_RANK)()

@@ -119,6 +119,7 @@ class SlicedContraction:
     def __init__(self, backend, recording: SlicedRecording, upload: bool = True) -> None:
         self.backend = backend
         self.rec = recording
+        self._upload_args = None
         if upload:
             self.upload()
         self.program = backend.compile_program(recording.text)
@@ -126,13 +127,20 @@ class SlicedContraction:
 
     def upload(self) -> int:
         """Host -> device copy of every leaf tensor named by a ``tensor``
-        command (the HDF5 file of the reference DSL flow).  Returns the bytes."""
+        command (the HDF5 file of the reference DSL flow), one ``pq_save_tensor``
+        per tensor from the host arrays.  Returns the bytes copied.  The ctypes
+        argument tuples are prepared once; the copies themselves happen on
+        every call."""
+        if self._upload_args is None:
+            self._upload_args = []
+            for cmd, a in parse_dsl(self.rec.text):
+                if cmd == "tensor":
+                    self._upload_args.append(self.backend.prepare_save(
+                        a["key"], self.rec.store.read(a["key"])))
         nbytes = 0
-        for cmd, a in parse_dsl(self.rec.text):
-            if cmd == "tensor":
-                data = self.rec.store.read(a["key"])
-                self.backend.save_tensor_data(a["key"], data)
-                nbytes += data.size * self.backend.dtype.itemsize
+        for args, n in self._upload_args:
+            self.backend.save_prepared(args)
+            nbytes += n
         return nbytes
 
     def run(self, partitions: Sequence[int], accumulate_into: str = "partial_sum") -> None:

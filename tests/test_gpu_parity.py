@@ -178,11 +178,12 @@ def test_gemm_path_shapes(dtype, gemm):
     assert expected in prof_names, prof_names
 
 
-def test_fused_ttgt_zgemm_shapes():
+@pytest.mark.parametrize("cfg", [0, 1, 2])
+def test_fused_ttgt_zgemm_shapes(cfg):
     """The persistent fused-TTGT ZGEMM (operands gathered inside the GEMM, no permuted
     temporaries): ragged tiles, K tails, several tiles per CTA, low-address contracted axes."""
     rng = np.random.default_rng(29)
-    b = B200(np.complex128)
+    b = B200(np.complex128, zgemm_cfg=cfg)
     shapes = list(GEMM_SHAPES) + [
         ((2,) * 20, [1, 2, 3] + [-(i + 1) for i in range(14)] + [4, 5, 6],
          (2,) * 12, [6, 5, 4, 3, 2, 1] + [-(20 + i) for i in range(6)]),       # M=2^14 N=64 K=64
@@ -204,6 +205,50 @@ def test_fused_ttgt_zgemm_shapes():
         ref = layer1.contract_tensors((A, B), (ai, bi))
         assert got.shape == ref.shape
         assert rel_l2(got, ref) < 1e-10, (ad, ai, rel_l2(got, ref))
+
+
+@pytest.mark.parametrize("K", [8, 40, 255, 256, 257, 513, 4096])
+def test_tcgen05_cgemm_accuracy_over_k(K):
+    """ComplexF32 GEMM on tcgen05 with 3xTF32 splitting and K-chunked fp32 folding: the
+    rel-L2 error against the ComplexF64 oracle must stay below 1e-5 for short and long
+    contractions, including the chunk boundaries (KCHUNK = 256)."""
+    rng = np.random.default_rng(31 + K)
+    b = B200(np.complex64, fused=1)
+    M, N = 384 + 5, 96 + 3
+    A = rand_tensor(rng, (M, K), np.complex64)
+    B = rand_tensor(rng, (K, N), np.complex64)
+    b.save_tensor_data("A", A)
+    b.save_tensor_data("B", B)
+    b.profile_enable(True)
+    b.contract_tensors("A", [-1, 1], "B", [1, -2], "C")
+    prof = b.profile_read()
+    b.profile_enable(False)
+    assert "gemm_tensor" in prof and "gemm_simt" not in prof
+    got = b.load_tensor_data("C")
+    ref = A.astype(np.complex128) @ B.astype(np.complex128)
+    assert rel_l2(got, ref) < 1e-5, (K, rel_l2(got, ref))
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_plan_independence_rqc_4x5(dtype):
+    """Size-independent property for the RQC amplitude configs: two different contraction
+    plans (greedy on the undecomposed network -- GEMM heavy, K up to 2^10 -- and the sweep
+    plan on the decomposed one) and the sliced replay must agree on the amplitude."""
+    tol = TOL[np.dtype(dtype)]
+    circ = create_RQC(4, 5, 16, seed=21)
+    n = circ.n_qubits
+    vals = []
+    for decompose in (False, True):
+        b = B200(dtype)
+        tn = convert_circuit_to_network(circ, b, decompose=decompose)
+        add_input(tn, "0" * n)
+        add_output(tn, "0" * n)
+        plan = sweep_plan(tn, 4, 5) if decompose else greedy_plan(tn)
+        contract_network(tn, plan)
+        vals.append(complex(b.load_tensor_data("result")))
+    ref = circ.simulate()[0]
+    for v in vals:
+        assert abs(v - ref) / abs(ref) < 100 * tol, (vals, ref)
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
