@@ -297,6 +297,37 @@ def main():
     value = total_flops / (ms_per_step * 1e-3) / 1e12
     amplitude = b.load_tensor_data("partial_sum")
 
+    # ---- the same amplitude with slice-invariant hoisting (reported separately) -----
+    # pq_program_prepare executes the steps that do not depend on the slice once per
+    # amplitude; only the slice-dependent steps are replayed per slice.  Not the headline:
+    # `value` above executes the full stream for every slice, like the reference flow.
+    def amplitude_step_hoisted():
+        b.delete_tensor("partial_sum")
+        sc.run(mine, "partial_sum", hoist=True)
+        if world > 1:
+            b.allreduce_sum("partial_sum")
+
+    for _ in range(a.warmup):
+        amplitude_step_hoisted()
+    barrier()
+    b.timer_begin()
+    for _ in range(a.steps):
+        amplitude_step_hoisted()
+    ms_h = max_over_ranks(b.timer_end()) / a.steps
+    barrier()
+    amp_h = b.load_tensor_data("partial_sum")
+    executed_h = 8.0 * world * (sc.program.macs_invariant + len(mine) * sc.program.macs_dependent)
+    hoisted = {
+        "ms_per_step": ms_h,
+        "effective_tflops": total_flops / (ms_h * 1e-3) / 1e12,
+        "executed_tflops": executed_h / (ms_h * 1e-3) / 1e12,
+        "invariant_mac_share": sc.program.macs_invariant / max(1, sc.program.macs),
+        "amplitude_rel_diff_vs_full_replay": float(abs(amp_h - amplitude) / abs(amplitude)),
+        "note": "slice-invariant steps executed once per amplitude (per GPU), slice-dependent "
+                "steps per slice; effective = reference-equivalent flops / time",
+    }
+    sc.program.set_hoist(False)
+
     # ---- end to end through the backend API, from host buffers ------------------
     h2d = 0
     e2e_times = []
@@ -465,6 +496,7 @@ def main():
             "tflops_per_gpu": value / world,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s * 1e3},
+            "hoisted": hoisted,
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": roofline,

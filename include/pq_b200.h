@@ -135,6 +135,16 @@ int pq_program_num_views(const pq_program* p);
 int pq_program_run(pq_handle* h, pq_program* p, const int32_t* view_starts, int nviews,
                    const char* accumulate_into);
 int pq_program_destroy(pq_handle* h, pq_program* p);
+/* Slice-invariant hoisting.  Steps of a program whose inputs do not depend on any `view`
+ * (slice) parameter compute the same tensors for every slice of a sliced contraction.  With
+ * hoisting enabled, `pq_program_prepare` executes that invariant part once (call it once per
+ * amplitude, and again whenever the bound tensors are re-saved) and `pq_program_run` replays
+ * only the slice-dependent part.  Off by default: every run then executes the whole stream,
+ * exactly like one execute_dsl_file call per slice in the reference flow. */
+int pq_program_set_hoist(pq_program* p, int on);
+int pq_program_prepare(pq_handle* h, pq_program* p);
+int pq_program_hoist_stats(const pq_program* p, int64_t* macs_invariant, int64_t* macs_dependent,
+                           int64_t* launches_invariant, int64_t* launches_dependent);
 /* arena bytes, number of kernel launches per run, complex MACs per run (data extents) */
 int pq_program_stats(const pq_program* p, int64_t* arena_bytes, int64_t* launches,
                      int64_t* macs);

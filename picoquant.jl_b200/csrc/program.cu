@@ -74,6 +74,8 @@ struct Sym {
   std::shared_ptr<Buffer> leafbuf;  // keeps a bound handle tensor alive
   size_t offset = 0, bytes = 0;     // arena placement when !leaf
   bool small = false;               // lives in the no-reuse arena for small tensors
+  bool dep = false;                 // depends on a `view` (slice) parameter
+  bool used_by_dep = false;         // slice-invariant tensor read by a slice-dependent step
   std::vector<int64_t> dims;
 };
 
@@ -84,6 +86,7 @@ struct Ref {  // pointer = leaf ? leafptr : (small ? arena_small : arena) + offs
   size_t offset = 0;
   bool leaf = false;
   bool small = false;
+  bool dep = false;   // which of the two big arenas (slice-invariant / slice-dependent)
   bool null = true;
 };
 
@@ -94,6 +97,7 @@ constexpr size_t SMALL_TENSOR_BYTES = 64 * 1024;
 
 struct Step {
   StepKind kind;
+  bool dep = false;  // slice-dependent (must run for every slice) vs slice-invariant
   ContractPlan cp;
   PermutePlan pp;
   Ref a, b, c, ta, tb, ws;
@@ -121,9 +125,15 @@ std::vector<int32_t> parse_ints(const std::string& s) {
 
 struct pq_program {
   std::vector<Step> steps;
+  // [0]: slice-invariant steps, [1]: slice-dependent steps (disjoint arenas, so that the
+  // invariant part can be executed once per amplitude and the dependent part per slice)
+  size_t arena_bytes2[2] = {0, 0};
   size_t arena_bytes = 0, arena_small_bytes = 0;
-  void* arena = nullptr;
+  void* arena2[2] = {nullptr, nullptr};
   void* arena_small = nullptr;
+  bool hoist = false;      // run() executes only the slice-dependent part
+  bool prepared = false;   // the invariant part has been executed since hoisting was enabled
+  int64_t macs2[2] = {0, 0}, launches2[2] = {0, 0}, ncontract2[2] = {0, 0};
   int nviews = 0;
   std::vector<int32_t> default_starts;
   int32_t* d_starts = nullptr;
@@ -133,7 +143,7 @@ struct pq_program {
   cudaEvent_t ring_ev[RING];
   bool ring_used[RING];
   int ring_pos = 0;
-  cudaGraphExec_t exec = nullptr;
+  cudaGraphExec_t exec2[3] = {nullptr, nullptr, nullptr};  // invariant, dependent, whole stream
   int64_t launches = 0, macs = 0, ncontract = 0, max_elems = 0;
   int device = 0;
   // leaf tensors the program is bound to: (store key, pinned buffer)
@@ -157,13 +167,15 @@ inline bool overlap(const Range& a, const Range& b) { return a.lo < b.hi && b.lo
 static void* resolve(const pq_program* p, const Ref& r) {
   if (r.null) return nullptr;
   if (r.leaf) return r.leafptr;
-  return (void*)((char*)(r.small ? p->arena_small : p->arena) + r.offset);
+  return (void*)((char*)(r.small ? p->arena_small : p->arena2[r.dep ? 1 : 0]) + r.offset);
 }
 
 static void issue_step(pq_handle* h, pq_program* p, Step& s, Launch& L);
 
-static void issue_steps(pq_handle* h, pq_program* p, Launch& L) {
-  for (Step& s : p->steps) issue_step(h, p, s, L);
+// phase 0: slice-invariant steps, phase 1: slice-dependent steps (stream order within a phase)
+static void issue_steps(pq_handle* h, pq_program* p, Launch& L, int phase) {
+  for (Step& s : p->steps)
+    if (phase < 0 || (s.dep ? 1 : 0) == phase) issue_step(h, p, s, L);
 }
 
 // read / write address ranges of a step (after the arena has been allocated)
@@ -235,7 +247,7 @@ static void build_dag(pq_handle* h, pq_program* p) {
 // Issues every step during stream capture, spreading independent steps over several
 // capture streams joined by events, so the instantiated graph is a DAG rather than a
 // chain: the ~10^3 tiny world-line contractions of a slice run concurrently.
-static void issue_steps_dag(pq_handle* h, pq_program* p, Launch& L0) {
+static void issue_steps_dag(pq_handle* h, pq_program* p, Launch& L0, int phase) {
   const int n = (int)p->steps.size();
   const int S = pq_program::NSTREAMS;
   cudaStream_t streams[pq_program::NSTREAMS + 1];
@@ -248,7 +260,11 @@ static void issue_steps_dag(pq_handle* h, pq_program* p, Launch& L0) {
   std::vector<int> where(n, 0);             // stream of each step
   std::vector<std::vector<int>> synced(NS, std::vector<int>(NS, -1));
   for (int j = 0; j < n; ++j) {
-    const std::vector<int>& deps = p->deps[j];  // descending order
+    if (phase >= 0 && (p->steps[j].dep ? 1 : 0) != phase) continue;
+    // hazards towards the other phase are ordered by the graph launches themselves
+    std::vector<int> deps;
+    for (int d : p->deps[j])  // descending order
+      if (phase < 0 || (p->steps[d].dep ? 1 : 0) == phase) deps.push_back(d);
     int best = -1;
     for (int d : deps)
       for (int s = 0; s < NS; ++s)
@@ -303,6 +319,46 @@ static void issue_step(pq_handle* h, pq_program* p, Step& s, Launch& L) {
   }
 }
 
+// Executes one phase of the program on the handle's stream: eagerly (profiling / option
+// graph=1) or by launching its CUDA graph, captured on first use.
+static void run_phase(pq_handle* h, pq_program* p, Launch& L, int phase) {
+  // phase -1 = the whole stream as ONE graph (no hoisting): invariant and dependent chains
+  // then share the parallel branches
+  const int slot = phase < 0 ? 2 : phase;
+  const int64_t nl = phase < 0 ? p->launches : p->launches2[phase];
+  if (nl == 0) return;
+  const bool eager = h->profile || h->opt.graph == 1;
+  if (eager) {
+    issue_steps(h, p, L, phase);
+  } else {
+    if (!p->exec2[slot]) {
+      Launch LC = L;
+      LC.launch_counter = nullptr;
+      LC.profile = false;
+      cudaGraph_t graph = nullptr;
+      PQ_CUDA(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+      try {
+        if (h->opt.graph == 2)
+          issue_steps(h, p, LC, phase);       // single-stream chain (A/B against the DAG)
+        else
+          issue_steps_dag(h, p, LC, phase);   // independent steps on parallel branches
+      } catch (...) {
+        cudaStreamEndCapture(h->stream, &graph);
+        if (graph) cudaGraphDestroy(graph);
+        throw;
+      }
+      PQ_CUDA(cudaStreamEndCapture(h->stream, &graph));
+      cudaError_t e = cudaGraphInstantiate(&p->exec2[slot], graph, 0);
+      cudaGraphDestroy(graph);
+      PQ_CUDA(e);
+    }
+    PQ_CUDA(cudaGraphLaunch(p->exec2[slot], h->stream));
+    h->launches += nl;
+  }
+  h->n_contract += phase < 0 ? p->ncontract : p->ncontract2[phase];
+  h->macs += phase < 0 ? p->macs : p->macs2[phase];
+}
+
 extern "C" int pq_program_compile(pq_handle* h, const char* tl_text, pq_program** out) {
   if (!h || !tl_text || !out) return PQ_ERR_INVALID;
   *out = nullptr;
@@ -311,7 +367,7 @@ extern "C" int pq_program_compile(pq_handle* h, const char* tl_text, pq_program*
     PQ_CUDA(cudaSetDevice(h->device));
     p->device = h->device;
     std::map<std::string, Sym> syms;
-    ArenaSim sim;
+    ArenaSim sims[2];  // [0] slice-invariant, [1] slice-dependent
     const int es = h->elem_size;
     size_t small_top = 0;
     auto place = [&](Sym& s) {  // assigns an arena slot to a freshly created tensor
@@ -321,7 +377,7 @@ extern "C" int pq_program_compile(pq_handle* h, const char* tl_text, pq_program*
         small_top += round_up(s.bytes ? s.bytes : 1);
       } else {
         s.small = false;
-        s.offset = sim.alloc(s.bytes);
+        s.offset = sims[s.dep ? 1 : 0].alloc(s.bytes);
       }
     };
     auto ref_of = [&](const Sym& s) {
@@ -331,12 +387,14 @@ extern "C" int pq_program_compile(pq_handle* h, const char* tl_text, pq_program*
       r.leafptr = s.leaf ? s.leafbuf->ptr : nullptr;
       r.offset = s.offset;
       r.small = s.small;
+      r.dep = s.dep;
       return r;
     };
-    auto temp_ref = [&](size_t off) {
+    auto temp_ref = [&](size_t off, bool dep) {
       Ref r;
       r.null = false;
       r.offset = off;
+      r.dep = dep;
       return r;
     };
     auto lookup = [&](const std::string& name) -> Sym& {
@@ -348,7 +406,10 @@ extern "C" int pq_program_compile(pq_handle* h, const char* tl_text, pq_program*
     auto drop = [&](const std::string& name) {
       auto it = syms.find(name);
       if (it == syms.end()) return;
-      if (!it->second.leaf && !it->second.small) sim.release(it->second.offset, it->second.bytes);
+      // an invariant tensor that a slice-dependent step reads must survive every replay
+      const Sym& y = it->second;
+      if (!y.leaf && !y.small && !(!y.dep && y.used_by_dep))
+        sims[y.dep ? 1 : 0].release(y.offset, y.bytes);
       syms.erase(it);
     };
 
@@ -402,22 +463,31 @@ extern "C" int pq_program_compile(pq_handle* h, const char* tl_text, pq_program*
         }
         Step st;
         st.kind = ST_CONTRACT;
+        st.dep = sa.dep || sb.dep;
+        if (st.dep) {
+          if (!sa.dep) lookup(A).used_by_dep = true;
+          if (!sb.dep) lookup(B).used_by_dep = true;
+        }
         st.cp = lower_contract(sa.dims, ai, sb.dims, bi, es, h->opt);
         st.a = ref_of(sa);
         st.b = ref_of(sb);
         Sym sc;
+        sc.dep = st.dep;
         sc.dims = st.cp.cdims;
         sc.bytes = size_t(st.cp.M * st.cp.N) * es;
         place(sc);
         st.c = ref_of(sc);
+        ArenaSim& sim = sims[st.dep ? 1 : 0];
         size_t oa = 0, ob = 0, ow = 0;
-        if (st.cp.tempA_bytes) st.ta = temp_ref(oa = sim.alloc(st.cp.tempA_bytes));
-        if (st.cp.tempB_bytes) st.tb = temp_ref(ob = sim.alloc(st.cp.tempB_bytes));
-        if (st.cp.ws_bytes) st.ws = temp_ref(ow = sim.alloc(st.cp.ws_bytes));
+        if (st.cp.tempA_bytes) st.ta = temp_ref(oa = sim.alloc(st.cp.tempA_bytes), st.dep);
+        if (st.cp.tempB_bytes) st.tb = temp_ref(ob = sim.alloc(st.cp.tempB_bytes), st.dep);
+        if (st.cp.ws_bytes) st.ws = temp_ref(ow = sim.alloc(st.cp.ws_bytes), st.dep);
         if (st.cp.tempA_bytes) sim.release(oa, st.cp.tempA_bytes);
         if (st.cp.tempB_bytes) sim.release(ob, st.cp.tempB_bytes);
         if (st.cp.ws_bytes) sim.release(ow, st.cp.ws_bytes);
         p->macs += st.cp.M * st.cp.N * st.cp.K;
+        p->macs2[st.dep ? 1 : 0] += st.cp.M * st.cp.N * st.cp.K;
+        p->ncontract2[st.dep ? 1 : 0] += 1;
         p->ncontract += 1;
         if (st.cp.M * st.cp.N > p->max_elems) p->max_elems = st.cp.M * st.cp.N;
         p->steps.push_back(std::move(st));
@@ -436,9 +506,11 @@ extern "C" int pq_program_compile(pq_handle* h, const char* tl_text, pq_program*
         if (!pp.identity) {
           Step st;
           st.kind = ST_PERMUTE;
+          st.dep = s.dep;
           st.pp = pp;
           st.a = ref_of(s);
           Sym ns;
+          ns.dep = s.dep;
           ns.dims = nd;
           ns.bytes = size_t(pp.total) * es;
           place(ns);
@@ -480,6 +552,8 @@ extern "C" int pq_program_compile(pq_handle* h, const char* tl_text, pq_program*
         PQ_REQUIRE(idx.front() >= 1 && idx.back() <= ext, PQ_ERR_INVALID, "view: index out of range");
         Step st;
         st.kind = ST_VIEW;
+        st.dep = true;  // its start index is a per-slice parameter
+        if (!src.dep) lookup(tok[2]).used_by_dep = true;
         for (int d = 0; d < axis - 1; ++d) st.inner *= src.dims[d];
         for (size_t d = axis; d < src.dims.size(); ++d) st.outer *= src.dims[d];
         st.ext = ext;
@@ -489,6 +563,7 @@ extern "C" int pq_program_compile(pq_handle* h, const char* tl_text, pq_program*
         p->default_starts.push_back(idx.front());
         st.a = ref_of(src);
         Sym v;
+        v.dep = true;
         v.dims = src.dims;
         v.dims[axis - 1] = st.nsel;
         v.bytes = size_t(prod(v.dims)) * es;
@@ -502,6 +577,7 @@ extern "C" int pq_program_compile(pq_handle* h, const char* tl_text, pq_program*
         Sym& s = lookup(tok[1]);
         Step st;
         st.kind = ST_SAVE;
+        st.dep = s.dep;
         st.a = ref_of(s);
         st.key = tok[3];
         st.dims = s.dims;
@@ -513,9 +589,12 @@ extern "C" int pq_program_compile(pq_handle* h, const char* tl_text, pq_program*
       // unknown commands are ignored, like the reference interpreter does
     }
 
-    p->arena_bytes = sim.top;
     p->arena_small_bytes = small_top;
-    PQ_CUDA(cudaMalloc(&p->arena, p->arena_bytes ? p->arena_bytes : ALIGN));
+    for (int a = 0; a < 2; ++a) {
+      p->arena_bytes2[a] = sims[a].top;
+      PQ_CUDA(cudaMalloc(&p->arena2[a], sims[a].top ? sims[a].top : ALIGN));
+    }
+    p->arena_bytes = sims[0].top + sims[1].top;
     PQ_CUDA(cudaMalloc(&p->arena_small, small_top ? small_top : ALIGN));
     if (p->nviews > 0) {
       PQ_CUDA(cudaMalloc(&p->d_starts, sizeof(int32_t) * p->nviews));
@@ -535,33 +614,30 @@ extern "C" int pq_program_compile(pq_handle* h, const char* tl_text, pq_program*
     for (auto& e : p->step_ev) PQ_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     // count launches with a dry bookkeeping pass (no device work)
     {
-      int64_t n = 0;
       for (const Step& s : p->steps) {
+        int64_t n = 1;
         if (s.kind == ST_CONTRACT) {
-          if (s.cp.kind == CK_GEMM && s.cp.fused_gemm)
-            n += 1;
-          else if (s.cp.kind == CK_GEMM)
-            n += 1 + (s.cp.permA.identity ? 0 : 1) + (s.cp.permB.identity ? 0 : 1);
+          if (s.cp.kind == CK_GEMM && !s.cp.fused_gemm)
+            n = 1 + (s.cp.permA.identity ? 0 : 1) + (s.cp.permB.identity ? 0 : 1);
           else if (s.cp.kind == CK_DOT)
-            n += 2;
-          else
-            n += 1;
-        } else {
-          n += 1;
+            n = 2;
         }
+        p->launches2[s.dep ? 1 : 0] += n;
       }
-      p->launches = n;
+      p->launches = p->launches2[0] + p->launches2[1];
     }
   } catch (const Error& e) {
     h->last_error = e.what();
-    if (p->arena) cudaFree(p->arena);
+    for (int a = 0; a < 2; ++a)
+      if (p->arena2[a]) cudaFree(p->arena2[a]);
     if (p->arena_small) cudaFree(p->arena_small);
     for (auto& l : p->leaves) l.second->pins -= 1;
     delete p;
     return e.code;
   } catch (const std::exception& e) {
     h->last_error = e.what();
-    if (p->arena) cudaFree(p->arena);
+    for (int a = 0; a < 2; ++a)
+      if (p->arena2[a]) cudaFree(p->arena2[a]);
     if (p->arena_small) cudaFree(p->arena_small);
     for (auto& l : p->leaves) l.second->pins -= 1;
     delete p;
@@ -582,18 +658,58 @@ extern "C" int pq_program_stats(const pq_program* p, int64_t* arena_bytes, int64
   return PQ_OK;
 }
 
+extern "C" int pq_program_set_hoist(pq_program* p, int on) {
+  if (!p) return PQ_ERR_INVALID;
+  p->hoist = on != 0;
+  p->prepared = false;
+  return PQ_OK;
+}
+
+extern "C" int pq_program_hoist_stats(const pq_program* p, int64_t* macs_invariant,
+                                      int64_t* macs_dependent, int64_t* launches_invariant,
+                                      int64_t* launches_dependent) {
+  if (!p) return PQ_ERR_INVALID;
+  if (macs_invariant) *macs_invariant = p->macs2[0];
+  if (macs_dependent) *macs_dependent = p->macs2[1];
+  if (launches_invariant) *launches_invariant = p->launches2[0];
+  if (launches_dependent) *launches_dependent = p->launches2[1];
+  return PQ_OK;
+}
+
+static void check_leaves(pq_handle* h, pq_program* p) {
+  PQ_REQUIRE(p->device == h->device, PQ_ERR_INVALID, "program belongs to another device");
+  for (auto& l : p->leaves) {
+    auto it = h->tensors.find(l.first);
+    PQ_REQUIRE(it != h->tensors.end() && it->second.buf.get() == l.second.get(), PQ_ERR_INVALID,
+               "tensor '" + l.first + "' was deleted or rebound since the program was compiled; "
+               "recompile the program");
+  }
+}
+
+extern "C" int pq_program_prepare(pq_handle* h, pq_program* p) {
+  if (!h || !p) return PQ_ERR_INVALID;
+  try {
+    PQ_CUDA(cudaSetDevice(h->device));
+    check_leaves(h, p);
+    Launch L = h->launch_ctx();
+    run_phase(h, p, L, 0);
+    p->prepared = p->hoist;
+  } catch (const Error& e) {
+    h->last_error = e.what();
+    return e.code;
+  } catch (const std::exception& e) {
+    h->last_error = e.what();
+    return PQ_ERR_INVALID;
+  }
+  return PQ_OK;
+}
+
 extern "C" int pq_program_run(pq_handle* h, pq_program* p, const int32_t* view_starts, int nviews,
                               const char* accumulate_into) {
   if (!h || !p) return PQ_ERR_INVALID;
   try {
     PQ_CUDA(cudaSetDevice(h->device));
-    PQ_REQUIRE(p->device == h->device, PQ_ERR_INVALID, "program belongs to another device");
-    for (auto& l : p->leaves) {
-      auto it = h->tensors.find(l.first);
-      PQ_REQUIRE(it != h->tensors.end() && it->second.buf.get() == l.second.get(), PQ_ERR_INVALID,
-                 "tensor '" + l.first + "' was deleted or rebound since the program was compiled; "
-                 "recompile the program");
-    }
+    check_leaves(h, p);
     if (view_starts) {
       PQ_REQUIRE(nviews == p->nviews, PQ_ERR_INVALID, "pq_program_run: wrong number of view starts");
       if (p->nviews > 0) {
@@ -609,36 +725,17 @@ extern "C" int pq_program_run(pq_handle* h, pq_program* p, const int32_t* view_s
       }
     }
     Launch L = h->launch_ctx();
-    const bool eager = h->profile || h->opt.graph == 1;
-    if (eager) {
-      issue_steps(h, p, L);
+    // hoisting: the slice-invariant part runs once (pq_program_prepare), only the
+    // slice-dependent part is replayed per slice
+    if (!p->hoist) {
+      run_phase(h, p, L, -1);
     } else {
-      if (!p->exec) {
-        Launch LC = L;
-        LC.launch_counter = nullptr;
-        LC.profile = false;
-        cudaGraph_t graph = nullptr;
-        PQ_CUDA(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
-        try {
-          if (h->opt.graph == 2)
-            issue_steps(h, p, LC);       // single-stream chain (A/B against the DAG)
-          else
-            issue_steps_dag(h, p, LC);   // independent steps on parallel branches
-        } catch (...) {
-          cudaStreamEndCapture(h->stream, &graph);
-          if (graph) cudaGraphDestroy(graph);
-          throw;
-        }
-        PQ_CUDA(cudaStreamEndCapture(h->stream, &graph));
-        cudaError_t e = cudaGraphInstantiate(&p->exec, graph, 0);
-        cudaGraphDestroy(graph);
-        PQ_CUDA(e);
+      if (!p->prepared) {
+        run_phase(h, p, L, 0);
+        p->prepared = true;
       }
-      PQ_CUDA(cudaGraphLaunch(p->exec, h->stream));
-      h->launches += p->launches;
+      run_phase(h, p, L, 1);
     }
-    h->n_contract += p->ncontract;
-    h->macs += p->macs;
     h->note_tensor(p->max_elems);
     for (Step& s : p->steps) {
       if (s.kind != ST_SAVE) continue;
@@ -680,13 +777,15 @@ extern "C" int pq_program_destroy(pq_handle* h, pq_program* p) {
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
   }
-  if (p->exec) cudaGraphExecDestroy(p->exec);
+  for (int a = 0; a < 3; ++a)
+    if (p->exec2[a]) cudaGraphExecDestroy(p->exec2[a]);
   for (auto& e : p->step_ev) cudaEventDestroy(e);
   if (p->fork_ev) cudaEventDestroy(p->fork_ev);
   for (int i = 0; i < pq_program::NSTREAMS; ++i)
     if (p->side[i]) cudaStreamDestroy(p->side[i]);
   for (auto& l : p->leaves) l.second->pins -= 1;
-  if (p->arena) cudaFree(p->arena);
+  for (int a = 0; a < 2; ++a)
+    if (p->arena2[a]) cudaFree(p->arena2[a]);
   if (p->arena_small) cudaFree(p->arena_small);
   if (p->d_starts) cudaFree(p->d_starts);
   if (p->h_ring) {

@@ -41,6 +41,7 @@ ABI_SYMBOLS = [
     "pq_program_run", "pq_program_destroy", "pq_program_stats", "pq_get_counters",
     "pq_reset_counters", "pq_profile_enable", "pq_profile_read", "pq_kernel_class_name",
     "pq_set_option", "pq_microbench", "pq_timer_begin", "pq_timer_end",
+    "pq_program_set_hoist", "pq_program_prepare", "pq_program_hoist_stats",
 ]
 
 _lib = None
@@ -88,6 +89,9 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
     lib.pq_program_run.argtypes = [c_void_p, c_void_p, i32p, c_int, c_char_p]
     lib.pq_program_destroy.argtypes = [c_void_p, c_void_p]
     lib.pq_program_stats.argtypes = [c_void_p, i64p, i64p, i64p]
+    lib.pq_program_set_hoist.argtypes = [c_void_p, c_int]
+    lib.pq_program_prepare.argtypes = [c_void_p, c_void_p]
+    lib.pq_program_hoist_stats.argtypes = [c_void_p, i64p, i64p, i64p, i64p]
     lib.pq_get_counters.argtypes = [c_void_p, i64p, i64p, i64p, i64p]
     lib.pq_reset_counters.argtypes = [c_void_p]
     lib.pq_profile_enable.argtypes = [c_void_p, c_int]
@@ -126,6 +130,18 @@ class Program:
         a, l, m = c_int64(), c_int64(), c_int64()
         backend.lib.pq_program_stats(self._p, byref(a), byref(l), byref(m))
         self.arena_bytes, self.launches, self.macs = a.value, l.value, m.value
+        mi, md, li, ld = c_int64(), c_int64(), c_int64(), c_int64()
+        backend.lib.pq_program_hoist_stats(self._p, byref(mi), byref(md), byref(li), byref(ld))
+        self.macs_invariant, self.macs_dependent = mi.value, md.value
+        self.launches_invariant, self.launches_dependent = li.value, ld.value
+
+    def set_hoist(self, on: bool) -> None:
+        """Slice-invariant hoisting: ``prepare()`` runs the part of the stream that does not
+        depend on any ``view`` index once; ``run()`` then replays only the rest."""
+        self.backend._check(self.backend.lib.pq_program_set_hoist(self._p, 1 if on else 0))
+
+    def prepare(self) -> None:
+        self.backend._check(self.backend.lib.pq_program_prepare(self.backend._h, self._p))
 
     def run(self, view_starts: Optional[Sequence[int]] = None,
             accumulate_into: Optional[str] = None) -> None:

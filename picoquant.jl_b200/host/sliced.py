@@ -143,7 +143,17 @@ class SlicedContraction:
             nbytes += n
         return nbytes
 
-    def run(self, partitions: Sequence[int], accumulate_into: str = "partial_sum") -> None:
+    def run(self, partitions: Sequence[int], accumulate_into: str = "partial_sum",
+            hoist: bool = False) -> None:
+        """Contracts the given partitions and accumulates their results on the device.
+
+        ``hoist=False`` (default) replays the whole command stream for every partition,
+        like the reference flow does.  ``hoist=True`` executes the slice-invariant part of
+        the stream once per call (``pq_program_prepare``) and only the slice-dependent part
+        per partition -- same result, less work."""
+        self.program.set_hoist(hoist)
+        if hoist:
+            self.program.prepare()
         for p in partitions:
             self.program.run(self.rec.view_starts(p) if self.rec.bond_labels else None,
                              accumulate_into)

@@ -495,11 +495,19 @@ def test_large_program_dag_vs_chain(graph):
         ref = ref + out.read("result")
     b = B200(np.complex128, graph=graph)
     sc = SlicedContraction(b, rec)
-    for _ in range(2):
+    assert sc.program.macs_invariant + sc.program.macs_dependent == sc.program.macs
+    assert sc.program.macs_invariant > 0 and sc.program.macs_dependent > 0
+    for hoist in (False, True, True, False):
+        # hoisting runs the slice-invariant steps once per call instead of once per slice
         b.delete_tensor("partial_sum")
-        sc.run(range(1, P + 1))
+        b.reset_counters()
+        sc.run(range(1, P + 1), hoist=hoist)
         got = sc.result()
-        assert abs(got - ref) / abs(ref) < 1e-10, (graph, got, ref)
+        assert abs(got - ref) / abs(ref) < 1e-10, (graph, hoist, got, ref)
+        macs = b.counters()["macs"]
+        expect = (sc.program.macs_invariant + P * sc.program.macs_dependent) if hoist \
+            else P * sc.program.macs
+        assert macs == expect, (hoist, macs, expect)
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
