@@ -112,6 +112,18 @@ def run_cpu_slices(rec, dtype, partitions):
     return total
 
 
+def use_all_host_threads():
+    """The CPU arm uses every host core (torchrun exports OMP_NUM_THREADS=1, which would
+    silently make OpenBLAS single-threaded).  Returns the BLAS thread count in effect."""
+    n = os.cpu_count() or 1
+    try:
+        from threadpoolctl import threadpool_info, threadpool_limits
+        threadpool_limits(limits=n)
+        return max([i.get("num_threads", 1) for i in threadpool_info()] + [1])
+    except Exception:  # noqa: BLE001
+        return n
+
+
 def cpu_threads():
     try:
         from threadpoolctl import threadpool_info
@@ -124,6 +136,7 @@ def reference_arm(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    use_all_host_threads()
     circ, rec, name = build_workload(a)
     dtype = np.complex128 if a.dtype == "c128" else np.complex64
     macs = slice_macs(rec)
@@ -456,6 +469,7 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         sample = list(range(1, a.cpu_sample_slices + 1))
+        use_all_host_threads()
         run_cpu_slices(rec, dtype, [1])  # warm-up (BLAS threads, page faults)
         t0 = time.perf_counter()
         part = run_cpu_slices(rec, dtype, sample)

@@ -94,10 +94,12 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
                : "memory");
 }
 
+// hi part of the split: x rounded to TF32 (10 explicit mantissa bits), done with one integer
+// add and one mask.  cvt.rna.tf32.f32 compiles to a ~10-instruction emulation on sm_100a
+// (ncu source view: FSETP/SEL/LOP3 chains were a third of all issued instructions); the
+// integer form differs only for NaN/Inf inputs, which the tensor core would propagate anyway.
 __device__ __forceinline__ float tf32_hi(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;\n" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
+  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
 }
 
 // byte offset of (row, k) inside one plane of an operand tile with `rows` rows
@@ -117,37 +119,67 @@ struct Cfg {
 };
 
 // One loader work item = (row, 16-byte K chunk) = 4 consecutive k of one row of a
-// ROWS x TK complex tile stored as src[row + ld*k].  Items are strided over the CTA's
-// threads; NITEMS = per-thread item count.  `fetch` only issues the global loads (into
-// registers), `split_store` converts and writes the four planes: the loads of stage kt+1
-// are in flight while stage kt is converted, synchronised and fed to the tensor core.
+// ROWS x TK complex tile stored as src[row + ld*k].  Items are strided over the loader
+// threads.  LoadMap holds what does not change from stage to stage (global base pointer,
+// shared-memory offset); LoadRegs is one register set of fetched values.  `fetch` only
+// issues the global loads, `split_store` converts and writes the four planes, so loads of
+// later stages are in flight while the current one is converted and fed to the tensor core.
 template <int ROWS>
-struct Loader {
+struct LoadMap {
   static constexpr int ITEMS = ROWS * (TK / 4);
   static constexpr int NITEMS = (ITEMS + NTHREADS - 1) / NTHREADS;
-  float2 v[NITEMS][4];
+  const float2* base[NITEMS];  // element (row, k = 4*chunk) of stage 0; nullptr: row out of range
+  uint32_t off[NITEMS];        // byte offset inside a plane
+  int kfirst[NITEMS];          // 4*chunk
+  long long ld;
 
-  __device__ __forceinline__ void fetch(const float2* __restrict__ src, long long ld,
-                                        long long row0, long long nrows, long long k0,
-                                        long long K, int tid) {
+  __device__ __forceinline__ void init(const float2* __restrict__ src, long long ld_, long long row0,
+                                       long long nrows, int tid) {
+    ld = ld_;
 #pragma unroll
     for (int i = 0; i < NITEMS; ++i) {
       const int it = tid + i * NTHREADS;
       const int row = it % ROWS, chunk = it / ROWS;
+      const bool ok = (it < ITEMS) && (row0 + row < nrows);
+      kfirst[i] = chunk * 4;
+      base[i] = ok ? src + (row0 + row) + ld * (chunk * 4) : nullptr;
+      off[i] = (it < ITEMS) ? plane_off(ROWS, row, chunk * 4) : 0xffffffffu;
+    }
+  }
+};
+
+template <int ROWS>
+struct LoadRegs {
+  static constexpr int NITEMS = LoadMap<ROWS>::NITEMS;
+  float2 v[NITEMS][4];
+
+  __device__ __forceinline__ void fetch(const LoadMap<ROWS>& m, long long kt, long long K) {
+    const long long k0 = kt * TK;
+    const bool full = k0 + TK <= K;  // uniform: only the last stage can be ragged
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const long long k = k0 + chunk * 4 + j;
-        const bool ok = (it < ITEMS) && (row0 + row < nrows) && (k < K);
-        v[i][j] = ok ? src[(row0 + row) + ld * k] : make_float2(0.f, 0.f);
+    for (int i = 0; i < NITEMS; ++i) {
+      const float2* p = m.base[i];
+      if (p != nullptr) {
+        p += k0 * m.ld;
+        if (full) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) v[i][j] = p[j * m.ld];
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            v[i][j] = (k0 + m.kfirst[i] + j < K) ? p[j * m.ld] : make_float2(0.f, 0.f);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[i][j] = make_float2(0.f, 0.f);
       }
     }
   }
-  __device__ __forceinline__ void split_store(unsigned char* planes, int plane_bytes, int tid) {
+  __device__ __forceinline__ void split_store(const LoadMap<ROWS>& m, unsigned char* planes,
+                                              int plane_bytes) {
 #pragma unroll
     for (int i = 0; i < NITEMS; ++i) {
-      const int it = tid + i * NTHREADS;
-      if (it >= ITEMS) break;
-      const int row = it % ROWS, chunk = it / ROWS;
+      if (m.off[i] == 0xffffffffu) continue;
       float4 rh, rl, ih, il;
       rh.x = tf32_hi(v[i][0].x); rh.y = tf32_hi(v[i][1].x);
       rh.z = tf32_hi(v[i][2].x); rh.w = tf32_hi(v[i][3].x);
@@ -157,11 +189,11 @@ struct Loader {
       rl.z = v[i][2].x - rh.z; rl.w = v[i][3].x - rh.w;
       il.x = v[i][0].y - ih.x; il.y = v[i][1].y - ih.y;
       il.z = v[i][2].y - ih.z; il.w = v[i][3].y - ih.w;
-      const uint32_t off = plane_off(ROWS, row, chunk * 4);
-      *reinterpret_cast<float4*>(planes + 0 * plane_bytes + off) = rh;
-      *reinterpret_cast<float4*>(planes + 1 * plane_bytes + off) = rl;
-      *reinterpret_cast<float4*>(planes + 2 * plane_bytes + off) = ih;
-      *reinterpret_cast<float4*>(planes + 3 * plane_bytes + off) = il;
+      unsigned char* dst = planes + m.off[i];
+      *reinterpret_cast<float4*>(dst + 0 * plane_bytes) = rh;
+      *reinterpret_cast<float4*>(dst + 1 * plane_bytes) = rl;
+      *reinterpret_cast<float4*>(dst + 2 * plane_bytes) = ih;
+      *reinterpret_cast<float4*>(dst + 3 * plane_bytes) = il;
     }
   }
 };
@@ -209,12 +241,21 @@ k_cgemm_tcgen05(const float2* __restrict__ A, const float2* __restrict__ B, floa
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(drained + 2);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const long long m0 = (long long)blockIdx.x * TM, n0 = (long long)blockIdx.y * BN;
+  // Rasterisation: consecutive CTAs walk GROUP_M m-tiles x all n-tiles, so one wave of CTAs
+  // re-uses a band of A (GROUP_M*128 rows) and a few column tiles of B out of L2 instead of
+  // streaming all of A once per wave (2.16 GB -> ~0.5 GB of DRAM traffic at 4096^3).
+  constexpr long long GROUP_M = 16;
+  const long long tiles_m = (M + TM - 1) / TM, tiles_n = (N + BN - 1) / BN;
+  const long long bid = blockIdx.x;
+  const long long group = bid / (GROUP_M * tiles_n);
+  const long long gm = (tiles_m - group * GROUP_M) < GROUP_M ? (tiles_m - group * GROUP_M) : GROUP_M;
+  const long long rem = bid - group * GROUP_M * tiles_n;
+  const long long m0 = (group * GROUP_M + rem % gm) * TM, n0 = (rem / gm) * BN;
   const long long KT = (K + TK - 1) / TK;
 
   if (tid == 0) {
     for (int s = 0; s < NSTAGE; ++s) {
-      mbar_init(&full[s], NLOAD);
+      mbar_init(&full[s], NLOAD / 32);   // one arrival per loader warp
       mbar_init(&empty[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
@@ -332,27 +373,43 @@ k_cgemm_tcgen05(const float2* __restrict__ A, const float2* __restrict__ B, floa
       }
     };
 
-    Loader<TM> la;
-    Loader<BN> lb;
-    la.fetch(A, M, m0, M, 0, K, tid);
-    lb.fetch(B, N, n0, N, 0, K, tid);
-    for (long long kt = 0; kt < KT; ++kt) {
+    // two register sets: the global loads of stages kt+1 and kt+2 are both in flight while
+    // stage kt is converted (the loaders are latency-bound, so bytes in flight = throughput)
+    LoadMap<TM> ma;
+    LoadMap<BN> mb;
+    ma.init(A, M, m0, M, tid);
+    mb.init(B, N, n0, N, tid);
+    LoadRegs<TM> la0, la1;
+    LoadRegs<BN> lb0, lb1;
+    la0.fetch(ma, 0, K);
+    lb0.fetch(mb, 0, K);
+    if (KT > 1) {
+      la1.fetch(ma, 1, K);
+      lb1.fetch(mb, 1, K);
+    }
+    auto stage_body = [&](LoadRegs<TM>& la, LoadRegs<BN>& lb, long long kt) {
       const int s = (int)(kt % NSTAGE);
       const long long chunk = kt / STAGES_PER_CHUNK;
       const int kin = (int)(kt - chunk * STAGES_PER_CHUNK);
       unsigned char* stage = smem + s * cfg::STAGE;
       if (kt >= NSTAGE) mbar_wait(&empty[s], (uint32_t)(((kt / NSTAGE) - 1) & 1));
-      la.split_store(stage, cfg::A_PLANE, tid);
-      lb.split_store(stage + 4 * cfg::A_PLANE, cfg::B_PLANE, tid);
-      if (kt + 1 < KT) {  // loads of the next stage fly while this one is consumed
-        la.fetch(A, M, m0, M, (kt + 1) * TK, K, tid);
-        lb.fetch(B, N, n0, N, (kt + 1) * TK, K, tid);
+      la.split_store(ma, stage, cfg::A_PLANE);
+      lb.split_store(mb, stage + 4 * cfg::A_PLANE, cfg::B_PLANE);
+      if (kt + 2 < KT) {  // refill this register set with the stage after next
+        la.fetch(ma, kt + 2, K);
+        lb.fetch(mb, kt + 2, K);
       }
+      // generic-proxy writes -> visible to the tensor core; one arrival per warp
       asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
-      mbar_arrive(&full[s]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full[s]);
       // the previous chunk is complete (or about to be): fold it while the tensor core
       // works on this chunk in the other TMEM set
       if (kin == 0 && chunk >= 1 && warp < 4) fold(chunk - 1, false);
+    };
+    for (long long kt = 0; kt < KT; kt += 2) {
+      stage_body(la0, lb0, kt);
+      if (kt + 1 < KT) stage_body(la1, lb1, kt + 1);
     }
     if (warp < 4) fold((KT - 1) / STAGES_PER_CHUNK, true);
   }
@@ -369,8 +426,9 @@ template <int BN>
 void launch(const Launch& L, const void* A, const void* B, void* C, int64_t M, int64_t N,
             int64_t K) {
   using cfg = Cfg<BN>;
-  dim3 grid((unsigned)((M + TM - 1) / TM), (unsigned)((N + BN - 1) / BN));
-  PQ_REQUIRE(grid.y <= 65535, PQ_ERR_UNSUPPORTED, "N too large for the tcgen05 CGEMM grid");
+  long long tiles = ((M + TM - 1) / TM) * ((N + BN - 1) / BN);
+  PQ_REQUIRE(tiles <= 0x7fffffffLL, PQ_ERR_UNSUPPORTED, "too many tiles for the tcgen05 CGEMM grid");
+  unsigned grid = (unsigned)tiles;
   k_cgemm_tcgen05<BN><<<grid, NALL, cfg::SMEM, L.stream>>>((const float2*)A, (const float2*)B,
                                                               (float2*)C, M, N, K);
 }
