@@ -528,6 +528,7 @@ extern "C" int pq_set_option(pq_handle* h, const char* key, int value) {
   else if (k == "fused") h->opt.fused = value;
   else if (k == "graph") h->opt.graph = value;
   else if (k == "zgemm_cfg") h->opt.zgemm_cfg = value;
+  else if (k == "zgemm_kfirst") h->opt.zgemm_kfirst = value;
   else {
     h->last_error = "unknown option: " + k;
     return PQ_ERR_INVALID;

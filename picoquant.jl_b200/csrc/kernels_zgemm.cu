@@ -164,7 +164,12 @@ struct FusedParams {
 //     four k-blocks (27.4 -> 30.7 TFLOP/s on M=2^18, N=K=64; cuBLAS ZGEMM on pre-permuted
 //     operands: 30.7-31.7).  A Gauss-3M variant (3 DMMAs per complex product) was tried and
 //     gave no gain: these steps are bound by tile fill latency, not by the DMMA pipe.
-template <int TBM, int TBN, int WGM, int WGN, int NST, int MINB>
+// AKF / BKF ("k first"): gather order of the A / B tile loads.  false: consecutive threads
+// walk the rows of the tile (m or n), true: they walk k first.  The host picks, per operand,
+// the order in which consecutive threads touch consecutive addresses (k first when the
+// fastest axis of that tensor is a contracted one); otherwise every 16-byte cp.async of a
+// warp would land in a different 128-byte line.
+template <int TBM, int TBN, int WGM, int WGN, int NST, int MINB, bool AKF, bool BKF>
 __global__ void __launch_bounds__(256, MINB)
 k_zgemm_fused_t(const double2* __restrict__ A, const double2* __restrict__ B,
                 double2* __restrict__ C, const FusedParams p) {
@@ -202,23 +207,51 @@ k_zgemm_fused_t(const double2* __restrict__ A, const double2* __restrict__ B,
     rowB[tid - TBM] = (n0 + (tid - TBM) < N) ? map_offset(p.nB, n0 + (tid - TBM)) : -1;
   __syncthreads();
 
+  // row-first: thread -> (row = tid % R, k-row = tid / R + q * (256 / R))
+  // k-first:   thread -> (k-row = tid % BK, row = tid / BK + q * (256 / BK))
+  constexpr int KF_STEP = 256 / BK, A_KF_CNT = TBM / KF_STEP, B_KF_CNT = TBN / KF_STEP;
   const int ma = tid % TBM, ka0 = tid / TBM, mb = tid % TBN, kb0 = tid / TBN;
-  const long long ra = rowA[ma], rb = rowB[mb];
+  const int kf_k = tid % BK, kf_r = tid / BK;
+  const long long ra = AKF ? 0 : rowA[ma], rb = BKF ? 0 : rowB[mb];
   auto load_stage = [&](int stage, int kt) {
-    double2* dA = sA + stage * A_ELEMS + ka0 * PA + ma;
-    double2* dB = sB + stage * B_ELEMS + kb0 * PB + mb;
     const int k0 = kt * BK;
+    if (!AKF) {
+      double2* dA = sA + stage * A_ELEMS + ka0 * PA + ma;
 #pragma unroll
-    for (int q = 0; q < A_CNT; ++q) {
-      const int k = k0 + ka0 + q * A_STEP;
-      const bool v = (k < K) && (ra >= 0);
-      cp_async16(dA + q * A_STEP * PA, v ? (A + ra + koffA[k]) : A, v);
+      for (int q = 0; q < A_CNT; ++q) {
+        const int k = k0 + ka0 + q * A_STEP;
+        const bool v = (k < K) && (ra >= 0);
+        cp_async16(dA + q * A_STEP * PA, v ? (A + ra + koffA[k]) : A, v);
+      }
+    } else {
+      double2* dA = sA + stage * A_ELEMS + kf_k * PA + kf_r;
+      const int k = k0 + kf_k;
+      const int ko = (k < K) ? koffA[k] : 0;
+#pragma unroll
+      for (int q = 0; q < A_KF_CNT; ++q) {
+        const long long r = rowA[kf_r + q * KF_STEP];
+        const bool v = (k < K) && (r >= 0);
+        cp_async16(dA + q * KF_STEP, v ? (A + r + ko) : A, v);
+      }
     }
+    if (!BKF) {
+      double2* dB = sB + stage * B_ELEMS + kb0 * PB + mb;
 #pragma unroll
-    for (int q = 0; q < B_CNT; ++q) {
-      const int k = k0 + kb0 + q * B_STEP;
-      const bool v = (k < K) && (rb >= 0);
-      cp_async16(dB + q * B_STEP * PB, v ? (B + rb + koffB[k]) : B, v);
+      for (int q = 0; q < B_CNT; ++q) {
+        const int k = k0 + kb0 + q * B_STEP;
+        const bool v = (k < K) && (rb >= 0);
+        cp_async16(dB + q * B_STEP * PB, v ? (B + rb + koffB[k]) : B, v);
+      }
+    } else {
+      double2* dB = sB + stage * B_ELEMS + kf_k * PB + kf_r;
+      const int k = k0 + kf_k;
+      const int ko = (k < K) ? koffB[k] : 0;
+#pragma unroll
+      for (int q = 0; q < B_KF_CNT; ++q) {
+        const long long r = rowB[kf_r + q * KF_STEP];
+        const bool v = (k < K) && (r >= 0);
+        cp_async16(dB + q * KF_STEP, v ? (B + r + ko) : B, v);
+      }
     }
   };
 
@@ -332,15 +365,41 @@ __global__ void __launch_bounds__(256) k_probe_dfma(double* out, int iters) {
 // per-device one-time kernel attributes (called from pq_create, outside any capture)
 constexpr int FUSED_MAX_K = 1024;
 
+template <bool AKF, bool BKF>
+static void init_fused() {
+  PQ_CUDA(cudaFuncSetAttribute(k_zgemm_fused_t<64, 64, 2, 4, 3, 2, AKF, BKF>,
+                               cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)fused_smem<64, 64, 3>(FUSED_MAX_K)));
+  PQ_CUDA(cudaFuncSetAttribute(k_zgemm_fused_t<64, 32, 4, 2, 2, 4, AKF, BKF>,
+                               cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)fused_smem<64, 32, 2>(FUSED_MAX_K)));
+}
+
+template <bool AKF, bool BKF>
+static void launch_fused(int cfg, const Launch& L, const FusedParams& fp, const void* A,
+                         const void* B, void* C) {
+  if (cfg == 2) {
+    long long tiles = ((fp.M + 63) / 64) * ((fp.N + 31) / 32);
+    PQ_REQUIRE(tiles <= 0x7fffffffLL, PQ_ERR_UNSUPPORTED, "too many tiles");
+    k_zgemm_fused_t<64, 32, 4, 2, 2, 4, AKF, BKF>
+        <<<(unsigned)tiles, 256, fused_smem<64, 32, 2>((int)fp.K), L.stream>>>(
+            (const double2*)A, (const double2*)B, (double2*)C, fp);
+  } else {
+    long long tiles = ((fp.M + 63) / 64) * ((fp.N + 63) / 64);
+    PQ_REQUIRE(tiles <= 0x7fffffffLL, PQ_ERR_UNSUPPORTED, "too many tiles");
+    k_zgemm_fused_t<64, 64, 2, 4, 3, 2, AKF, BKF>
+        <<<(unsigned)tiles, 256, fused_smem<64, 64, 3>((int)fp.K), L.stream>>>(
+            (const double2*)A, (const double2*)B, (double2*)C, fp);
+  }
+}
+
 void init_kernels() {
   PQ_CUDA(cudaFuncSetAttribute(k_zgemm_dmma, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)SMEM_BYTES));
-  PQ_CUDA(cudaFuncSetAttribute(k_zgemm_fused_t<64, 64, 2, 4, 3, 2>,
-                               cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               (int)fused_smem<64, 64, 3>(FUSED_MAX_K)));
-  PQ_CUDA(cudaFuncSetAttribute(k_zgemm_fused_t<64, 32, 4, 2, 2, 4>,
-                               cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               (int)fused_smem<64, 32, 2>(FUSED_MAX_K)));
+  init_fused<false, false>();
+  init_fused<false, true>();
+  init_fused<true, false>();
+  init_fused<true, true>();
 }
 
 void run_zgemm_dmma(const Launch& L, const void* A, const void* B, void* C, int64_t M, int64_t N,
@@ -373,20 +432,22 @@ void run_zgemm_fused(const Launch& L, const ContractPlan& cp, const void* A, con
   // configuration with four resident CTAs per SM; option "zgemm_cfg" forces 1 (64x64) / 2 (64x32)
   int cfg = L.opt ? L.opt->zgemm_cfg : 0;
   if (cfg == 0) cfg = (cp.K <= 128) ? 2 : 1;
+  auto min_stride = [](const IdxMap& m) {
+    int64_t best = INT64_MAX;
+    for (int d = 0; d < m.nd; ++d) best = m.str[d] < best ? m.str[d] : best;
+    return best;
+  };
+  bool akf = min_stride(cp.kA) < min_stride(cp.mA), bkf = min_stride(cp.kB) < min_stride(cp.nB);
+  if (L.opt && L.opt->zgemm_kfirst == 1) akf = bkf = false;  // A/B check knob
   L.begin(KC_GEMM_TENSOR, bytes, flops);
-  if (cfg == 2) {
-    long long tiles = ((cp.M + 63) / 64) * ((cp.N + 31) / 32);
-    PQ_REQUIRE(tiles <= 0x7fffffffLL, PQ_ERR_UNSUPPORTED, "too many tiles");
-    k_zgemm_fused_t<64, 32, 4, 2, 2, 4><<<(unsigned)tiles, 256, fused_smem<64, 32, 2>((int)cp.K),
-                                          L.stream>>>((const double2*)A, (const double2*)B,
-                                                      (double2*)C, fp);
-  } else {
-    long long tiles = ((cp.M + 63) / 64) * ((cp.N + 63) / 64);
-    PQ_REQUIRE(tiles <= 0x7fffffffLL, PQ_ERR_UNSUPPORTED, "too many tiles");
-    k_zgemm_fused_t<64, 64, 2, 4, 3, 2><<<(unsigned)tiles, 256, fused_smem<64, 64, 3>((int)cp.K),
-                                          L.stream>>>((const double2*)A, (const double2*)B,
-                                                      (double2*)C, fp);
-  }
+  if (akf && bkf)
+    launch_fused<true, true>(cfg, L, fp, A, B, C);
+  else if (akf)
+    launch_fused<true, false>(cfg, L, fp, A, B, C);
+  else if (bkf)
+    launch_fused<false, true>(cfg, L, fp, A, B, C);
+  else
+    launch_fused<false, false>(cfg, L, fp, A, B, C);
   L.end();
   PQ_CUDA(cudaGetLastError());
 }

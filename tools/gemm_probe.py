@@ -28,7 +28,7 @@ cases = {
     "M18_K3_N6": case(21, [18, 19, 20]),
 }
 out = {}
-for mode, opts in (("fused", {}), ("ttgt", {"fused": 1})):
+for mode, opts in (("fused", {}), ("fused_rowfirst", {"zgemm_kfirst": 1}), ("ttgt", {"fused": 1})):
     b = B200Backend(np.complex128)
     for k, v in opts.items():
         b.set_option(k, v)
