@@ -53,6 +53,8 @@ def parse_args():
     ap.add_argument("--depth", type=int, default=24)
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--slices", type=int, default=64)
+    ap.add_argument("--lanes", type=int, default=2,
+                    help="slices kept in flight per GPU (pq_program_run_slices)")
     ap.add_argument("--cpu-sample-slices", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
@@ -279,7 +281,7 @@ def main():
 
     def amplitude_step():
         b.delete_tensor("partial_sum")
-        sc.run(mine, "partial_sum")
+        sc.run(mine, "partial_sum", lanes=a.lanes)
         if world > 1:
             b.allreduce_sum("partial_sum")
 
@@ -316,7 +318,7 @@ def main():
     # `value` above executes the full stream for every slice, like the reference flow.
     def amplitude_step_hoisted():
         b.delete_tensor("partial_sum")
-        sc.run(mine, "partial_sum", hoist=True)
+        sc.run(mine, "partial_sum", hoist=True, lanes=a.lanes)
         if world > 1:
             b.allreduce_sum("partial_sum")
 
@@ -502,6 +504,7 @@ def main():
                                                        if c == "ncon"),
                        "kernel_launches_per_slice": sc.program.launches,
                        "arena_bytes": sc.program.arena_bytes, "parallelism": "slices/%d" % world,
+                       "slices_in_flight_per_gpu": a.lanes,
                        "l2": "inputs larger than L2: per-step intermediates of 2^24 elements "
                              "(256 MiB c128) stream through the 126 MB L2"},
             "amplitude_wall_ms": ms_per_step,

@@ -134,6 +134,13 @@ int pq_program_num_views(const pq_program* p);
  * handle; when `accumulate_into` is non-NULL the saved tensor is also added to it. */
 int pq_program_run(pq_handle* h, pq_program* p, const int32_t* view_starts, int nviews,
                    const char* accumulate_into);
+/* The slice loop of examples/dist_slicing_example.jl:14-28 (one rank's share of it) in one
+ * call: for s in [0, nslices) run the program with view_starts[s * nviews ...] and add the
+ * saved result to `accumulate_into`, in slice order -- the sum is bit-identical to nslices
+ * pq_program_run calls.  Up to `nlanes` (1..8) slices are kept in flight on private
+ * arenas / streams / graph instances; accumulations are ordered on the handle's stream. */
+int pq_program_run_slices(pq_handle* h, pq_program* p, const int32_t* view_starts, int nslices,
+                          int nviews, const char* accumulate_into, int nlanes);
 int pq_program_destroy(pq_handle* h, pq_program* p);
 /* Slice-invariant hoisting.  Steps of a program whose inputs do not depend on any `view`
  * (slice) parameter compute the same tensors for every slice of a sliced contraction.  With

@@ -527,6 +527,7 @@ extern "C" int pq_set_option(pq_handle* h, const char* key, int value) {
   else if (k == "permute") h->opt.permute = value;
   else if (k == "fused") h->opt.fused = value;
   else if (k == "graph") h->opt.graph = value;
+  else if (k == "prio") h->opt.prio = value;
   else if (k == "zgemm_cfg") h->opt.zgemm_cfg = value;
   else if (k == "zgemm_kfirst") h->opt.zgemm_kfirst = value;
   else {

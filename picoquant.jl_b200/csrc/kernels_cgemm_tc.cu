@@ -16,9 +16,13 @@
 // 16-byte K chunks).  The split therefore costs no extra pass over HBM.
 //
 // Math per K = 8 step (tf32 UMMA K):  12 MMAs
-//     Cr += ArH*BrH + ArH*BrL + ArL*BrH - (AiH*BiH + AiH*BiL + AiL*BiH)   (a_negate)
-//     Ci += ArH*BiH + ArH*BiL + ArL*BiH +  AiH*BrH + AiH*BrL + AiL*BrH
-// i.e. hi*hi + hi*lo + lo*hi per real product (the lo*lo term, ~2^-22 relative, is dropped).
+//     Cr += ArH*BrH - AiH*BiH                    Xr += ArH*BrL + ArL*BrH - (AiH*BiL + AiL*BiH)
+//     Ci += ArH*BiH + AiH*BrH                    Xi += ArH*BiL + ArL*BiH +  AiH*BrL + AiL*BrH
+// i.e. hi*hi + hi*lo + lo*hi per real product (the lo*lo term, ~2^-22 relative, is dropped;
+// `a_negate` gives the minus sign).  The cross terms go to their OWN accumulators (Xr, Xi):
+// every MMA truncates when it adds into its accumulator, an error relative to the
+// accumulator's magnitude.  Kept apart, the 8 cross-term MMAs only disturb sums that are
+// 2^-11 of the result, and the main accumulators see 2 instead of 6 truncations per K-step.
 //
 // Pipeline: two shared-memory stages; all 8 warps load+split stage s while the tensor core
 // works on stage s^1; one elected thread issues the MMAs and tcgen05.commit signals an
@@ -113,9 +117,11 @@ struct Cfg {
   static constexpr int B_PLANE = BN * TK * 4;
   static constexpr int STAGE = 4 * A_PLANE + 4 * B_PLANE;
   static constexpr int SMEM = NSTAGE * STAGE + 128;
-  // two accumulator sets (ping-pong over K chunks) + the running sums, 2*BN fp32 columns each
-  static constexpr int TMEM_COLS = (6 * BN <= 32) ? 32 : (6 * BN <= 64) ? 64 : (6 * BN <= 128) ? 128
-                                   : (6 * BN <= 256) ? 256 : 512;
+  // two hi*hi accumulator sets (ping-pong over K chunks) + the running sums + the
+  // cross-term accumulators, 2*BN fp32 columns each
+  static constexpr int TMEM_COLS = (8 * BN <= 32) ? 32 : (8 * BN <= 64) ? 64 : (8 * BN <= 128) ? 128
+                                   : (8 * BN <= 256) ? 256 : 512;
+  static_assert(8 * BN <= 512, "TMEM has 512 columns");
 };
 
 // One loader work item = (row, 16-byte K chunk) = 4 consecutive k of one row of a
@@ -185,10 +191,12 @@ struct LoadRegs {
       rh.z = tf32_hi(v[i][2].x); rh.w = tf32_hi(v[i][3].x);
       ih.x = tf32_hi(v[i][0].y); ih.y = tf32_hi(v[i][1].y);
       ih.z = tf32_hi(v[i][2].y); ih.w = tf32_hi(v[i][3].y);
-      rl.x = v[i][0].x - rh.x; rl.y = v[i][1].x - rh.y;
-      rl.z = v[i][2].x - rh.z; rl.w = v[i][3].x - rh.w;
-      il.x = v[i][0].y - ih.x; il.y = v[i][1].y - ih.y;
-      il.z = v[i][2].y - ih.z; il.w = v[i][3].y - ih.w;
+      // the tensor core TRUNCATES fp32 inputs to tf32: round the lo parts to nearest here, or
+      // their (one-sided) truncation error accumulates as a bias over K and over the plan
+      rl.x = tf32_hi(v[i][0].x - rh.x); rl.y = tf32_hi(v[i][1].x - rh.y);
+      rl.z = tf32_hi(v[i][2].x - rh.z); rl.w = tf32_hi(v[i][3].x - rh.w);
+      il.x = tf32_hi(v[i][0].y - ih.x); il.y = tf32_hi(v[i][1].y - ih.y);
+      il.z = tf32_hi(v[i][2].y - ih.z); il.w = tf32_hi(v[i][3].y - ih.w);
       unsigned char* dst = planes + m.off[i];
       *reinterpret_cast<float4*>(dst + 0 * plane_bytes) = rh;
       *reinterpret_cast<float4*>(dst + 1 * plane_bytes) = rl;
@@ -276,6 +284,7 @@ k_cgemm_tcgen05(const float2* __restrict__ A, const float2* __restrict__ B, floa
   asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_sum = tmem_base + 4 * BN;   // running sums: re in [0,BN), im in [BN,2BN)
+  const uint32_t tmem_x = tmem_base + 6 * BN;     // cross terms (hi*lo + lo*hi), never folded
 
   constexpr uint32_t IDESC = make_idesc(TM, BN, false);
   constexpr uint32_t IDESC_NEG = make_idesc(TM, BN, true);
@@ -308,18 +317,20 @@ k_cgemm_tcgen05(const float2* __restrict__ A, const float2* __restrict__ B, floa
           const uint64_t bih = make_desc(bo + 2 * cfg::B_PLANE, B_LBO, SBO);
           const uint64_t bil = make_desc(bo + 3 * cfg::B_PLANE, B_LBO, SBO);
           const uint32_t acc = (kin > 0 || ks > 0) ? 1u : 0u;   // a chunk starts from zero
+          const uint32_t accx = (kt > 0 || ks > 0) ? 1u : 0u;   // cross terms: whole K
+          const uint32_t tmem_xr = tmem_x, tmem_xi = tmem_x + BN;
           umma_tf32(tmem_cr, arh, brh, IDESC, acc);
-          umma_tf32(tmem_cr, arh, brl, IDESC, 1u);
-          umma_tf32(tmem_cr, arl, brh, IDESC, 1u);
-          umma_tf32(tmem_cr, aih, bih, IDESC_NEG, 1u);
-          umma_tf32(tmem_cr, aih, bil, IDESC_NEG, 1u);
-          umma_tf32(tmem_cr, ail, bih, IDESC_NEG, 1u);
           umma_tf32(tmem_ci, arh, bih, IDESC, acc);
-          umma_tf32(tmem_ci, arh, bil, IDESC, 1u);
-          umma_tf32(tmem_ci, arl, bih, IDESC, 1u);
+          umma_tf32(tmem_xr, arh, brl, IDESC, accx);
+          umma_tf32(tmem_xi, arh, bil, IDESC, accx);
+          umma_tf32(tmem_cr, aih, bih, IDESC_NEG, 1u);
           umma_tf32(tmem_ci, aih, brh, IDESC, 1u);
-          umma_tf32(tmem_ci, aih, brl, IDESC, 1u);
-          umma_tf32(tmem_ci, ail, brh, IDESC, 1u);
+          umma_tf32(tmem_xr, arl, brh, IDESC, 1u);
+          umma_tf32(tmem_xi, arl, bih, IDESC, 1u);
+          umma_tf32(tmem_xr, aih, bil, IDESC_NEG, 1u);
+          umma_tf32(tmem_xi, aih, brl, IDESC, 1u);
+          umma_tf32(tmem_xr, ail, bih, IDESC_NEG, 1u);
+          umma_tf32(tmem_xi, ail, brh, IDESC, 1u);
         }
         umma_commit(&empty[s]);   // the stage may be refilled once these MMAs have completed
         if (kin == STAGES_PER_CHUNK - 1 || kt == KT - 1) umma_commit(&chunk_done[set]);
@@ -354,6 +365,16 @@ k_cgemm_tcgen05(const float2* __restrict__ A, const float2* __restrict__ B, floa
           }
         }
         if (final) {
+          // + the cross terms of the whole contraction (their last MMA precedes the commit
+          // this fold waited for)
+          PQ_TMEM_LD8(ar, tmem_x + lane_base + c0);
+          PQ_TMEM_LD8(aq, tmem_x + lane_base + BN + c0);
+          asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(ar[j]));
+            q[j] = __float_as_uint(__uint_as_float(q[j]) + __uint_as_float(aq[j]));
+          }
           if (m < M) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) {

@@ -240,7 +240,12 @@ struct DotParams {
   long long K;
 };
 
-template <typename R>
+// MNT = compile-time bound on M*N (1, 4 or 16), U = independent k-iterations in flight per
+// thread (the loads of one operand are usually scattered, so memory-level parallelism, not
+// arithmetic, sets the speed).  The partial sums are combined in a fixed order
+// (thread-strided k, shuffle tree, warp order, then k_dot_finish), so the result does not
+// depend on scheduling.
+template <typename R, int MNT, int U>
 __global__ void __launch_bounds__(256)
 k_contract_dot(const typename C2<R>::type* __restrict__ A,
                const typename C2<R>::type* __restrict__ B,
@@ -255,23 +260,37 @@ k_contract_dot(const typename C2<R>::type* __restrict__ A,
     offB[threadIdx.x] = map_offset(p.nB, n);
   }
   __syncthreads();
-  V acc[16];
+  V acc[MNT];
 #pragma unroll
-  for (int j = 0; j < 16; ++j) {
+  for (int j = 0; j < MNT; ++j) {
     acc[j].x = 0;
     acc[j].y = 0;
   }
   const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < p.K; k += stride) {
+  long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (MNT == 1) {
+    const long long oa = offA[0], ob = offB[0];
+    for (; k + (U - 1) * stride < p.K; k += U * stride) {
+      V a[U], b[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        a[u] = A[map_offset(p.kA, k + u * stride) + oa];
+        b[u] = B[map_offset(p.kB, k + u * stride) + ob];
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) cfma<V, R>(acc[0], a[u], b[u]);
+    }
+  }
+  for (; k < p.K; k += stride) {
     const V* a = A + map_offset(p.kA, k);
     const V* b = B + map_offset(p.kB, k);
 #pragma unroll
-    for (int j = 0; j < 16; ++j)
+    for (int j = 0; j < MNT; ++j)
       if (j < MN) cfma<V, R>(acc[j], a[offA[j]], b[offB[j]]);
   }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
-  for (int j = 0; j < 16; ++j) {
+  for (int j = 0; j < MNT; ++j) {
     if (j < MN) {
       V v = acc[j];
       for (int d = 16; d > 0; d >>= 1) {
@@ -292,20 +311,35 @@ k_contract_dot(const typename C2<R>::type* __restrict__ A,
   }
 }
 
+// 64 groups of 16 threads: group g sums the partials of blocks g, g+64, ... for output j,
+// then a fixed-order pass over the 64 group sums.
 template <typename R>
-__global__ void k_dot_finish(const typename C2<R>::type* __restrict__ partial,
-                             typename C2<R>::type* __restrict__ C, int MN, int blocks) {
+__global__ void __launch_bounds__(1024)
+k_dot_finish(const typename C2<R>::type* __restrict__ partial,
+             typename C2<R>::type* __restrict__ C, int MN, int blocks) {
   using V = typename C2<R>::type;
-  int j = threadIdx.x;
+  __shared__ V part[64][16];
+  const int j = threadIdx.x & 15, g = threadIdx.x >> 4;
+  V v;
+  v.x = 0;
+  v.y = 0;
   if (j < MN) {
-    V v;
-    v.x = 0;
-    v.y = 0;
-    for (int b = 0; b < blocks; ++b) {
-      v.x += partial[(long long)b * 16 + j].x;
-      v.y += partial[(long long)b * 16 + j].y;
+#pragma unroll 4
+    for (int b = g; b < blocks; b += 64) {
+      const V q = partial[(long long)b * 16 + j];
+      v.x += q.x;
+      v.y += q.y;
     }
-    C[j] = v;
+  }
+  part[g][j] = v;
+  __syncthreads();
+  if (threadIdx.x < MN) {
+    V t = part[0][threadIdx.x];
+    for (int q = 1; q < 64; ++q) {
+      t.x += part[q][threadIdx.x].x;
+      t.y += part[q][threadIdx.x].y;
+    }
+    C[threadIdx.x] = t;
   }
 }
 
@@ -437,10 +471,15 @@ static void run_contract_t(const Launch& L, const ContractPlan& p, const void* A
       dp.N = (int)p.N;
       dp.K = p.K;
       L.begin(KC_CONTRACT_DOT, bytes, flops);
-      k_contract_dot<R><<<p.dot_blocks, 256, 0, L.stream>>>((const V*)A, (const V*)B, (V*)ws, dp);
+      if (p.M * p.N == 1)
+        k_contract_dot<R, 1, 4><<<p.dot_blocks, 256, 0, L.stream>>>((const V*)A, (const V*)B, (V*)ws, dp);
+      else if (p.M * p.N <= 4)
+        k_contract_dot<R, 4, 1><<<p.dot_blocks, 256, 0, L.stream>>>((const V*)A, (const V*)B, (V*)ws, dp);
+      else
+        k_contract_dot<R, 16, 1><<<p.dot_blocks, 256, 0, L.stream>>>((const V*)A, (const V*)B, (V*)ws, dp);
       L.end();
       L.begin(KC_CONTRACT_DOT, 0, 0);
-      k_dot_finish<R><<<1, 32, 0, L.stream>>>((const V*)ws, (V*)C, (int)(p.M * p.N), p.dot_blocks);
+      k_dot_finish<R><<<1, 1024, 0, L.stream>>>((const V*)ws, (V*)C, (int)(p.M * p.N), p.dot_blocks);
       L.end();
       break;
     }

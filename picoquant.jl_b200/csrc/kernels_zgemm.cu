@@ -164,6 +164,9 @@ struct FusedParams {
 //     four k-blocks (27.4 -> 30.7 TFLOP/s on M=2^18, N=K=64; cuBLAS ZGEMM on pre-permuted
 //     operands: 30.7-31.7).  A Gauss-3M variant (3 DMMAs per complex product) was tried and
 //     gave no gain: these steps are bound by tile fill latency, not by the DMMA pipe.
+//   <128,8, 8x1 warps, 2 stages, 3 CTAs/SM>  warp tile 16x8 -- N <= 16 with K >= 32 (a site
+//     tensor with one open bond of 8 absorbed into the boundary): one m8n8k4 DMMA column
+//     covers all of N, so no tensor-pipe work is wasted on padding; HBM-bound.
 // AKF / BKF ("k first"): gather order of the A / B tile loads.  false: consecutive threads
 // walk the rows of the tile (m or n), true: they walk k first.  The host picks, per operand,
 // the order in which consecutive threads touch consecutive addresses (k first when the
@@ -177,7 +180,8 @@ k_zgemm_fused_t(const double2* __restrict__ A, const double2* __restrict__ B,
   constexpr int XT = TBM / WGM / 8, YT = TBN / WGN / 8;  // 8x8 sub-tiles per warp
   constexpr int A_ELEMS = BK * PA, B_ELEMS = BK * PB;
   constexpr int A_STEP = 256 / TBM, A_CNT = BK / A_STEP;  // k-rows per pass / passes
-  constexpr int B_STEP = 256 / TBN, B_CNT = BK / B_STEP;
+  // a B tile narrower than 256 / BK columns is loaded by the first TBN * BK threads only
+  constexpr int B_STEP = (256 / TBN < BK) ? 256 / TBN : BK, B_CNT = BK / B_STEP;
   static_assert(WGM * WGN == 8, "eight warps");
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double2* sA = reinterpret_cast<double2*>(smem_raw);
@@ -209,7 +213,8 @@ k_zgemm_fused_t(const double2* __restrict__ A, const double2* __restrict__ B,
 
   // row-first: thread -> (row = tid % R, k-row = tid / R + q * (256 / R))
   // k-first:   thread -> (k-row = tid % BK, row = tid / BK + q * (256 / BK))
-  constexpr int KF_STEP = 256 / BK, A_KF_CNT = TBM / KF_STEP, B_KF_CNT = TBN / KF_STEP;
+  constexpr int KF_STEP = 256 / BK, A_KF_CNT = TBM / KF_STEP;
+  constexpr int B_KF_CNT = TBN >= KF_STEP ? TBN / KF_STEP : 1;
   const int ma = tid % TBM, ka0 = tid / TBM, mb = tid % TBN, kb0 = tid / TBN;
   const int kf_k = tid % BK, kf_r = tid / BK;
   const long long ra = AKF ? 0 : rowA[ma], rb = BKF ? 0 : rowB[mb];
@@ -235,22 +240,26 @@ k_zgemm_fused_t(const double2* __restrict__ A, const double2* __restrict__ B,
       }
     }
     if (!BKF) {
-      double2* dB = sB + stage * B_ELEMS + kb0 * PB + mb;
+      if (TBN * BK >= 256 || kb0 < BK) {
+        double2* dB = sB + stage * B_ELEMS + kb0 * PB + mb;
 #pragma unroll
-      for (int q = 0; q < B_CNT; ++q) {
-        const int k = k0 + kb0 + q * B_STEP;
-        const bool v = (k < K) && (rb >= 0);
-        cp_async16(dB + q * B_STEP * PB, v ? (B + rb + koffB[k]) : B, v);
+        for (int q = 0; q < B_CNT; ++q) {
+          const int k = k0 + kb0 + q * B_STEP;
+          const bool v = (k < K) && (rb >= 0);
+          cp_async16(dB + q * B_STEP * PB, v ? (B + rb + koffB[k]) : B, v);
+        }
       }
     } else {
-      double2* dB = sB + stage * B_ELEMS + kf_k * PB + kf_r;
-      const int k = k0 + kf_k;
-      const int ko = (k < K) ? koffB[k] : 0;
+      if (TBN >= KF_STEP || kf_r < TBN) {
+        double2* dB = sB + stage * B_ELEMS + kf_k * PB + kf_r;
+        const int k = k0 + kf_k;
+        const int ko = (k < K) ? koffB[k] : 0;
 #pragma unroll
-      for (int q = 0; q < B_KF_CNT; ++q) {
-        const long long r = rowB[kf_r + q * KF_STEP];
-        const bool v = (k < K) && (r >= 0);
-        cp_async16(dB + q * KF_STEP, v ? (B + r + ko) : B, v);
+        for (int q = 0; q < B_KF_CNT; ++q) {
+          const long long r = rowB[kf_r + q * KF_STEP];
+          const bool v = (k < K) && (r >= 0);
+          cp_async16(dB + q * KF_STEP, v ? (B + r + ko) : B, v);
+        }
       }
     }
   };
@@ -373,12 +382,21 @@ static void init_fused() {
   PQ_CUDA(cudaFuncSetAttribute(k_zgemm_fused_t<64, 32, 4, 2, 2, 4, AKF, BKF>,
                                cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)fused_smem<64, 32, 2>(FUSED_MAX_K)));
+  PQ_CUDA(cudaFuncSetAttribute(k_zgemm_fused_t<128, 8, 8, 1, 2, 3, AKF, BKF>,
+                               cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)fused_smem<128, 8, 2>(FUSED_MAX_K)));
 }
 
 template <bool AKF, bool BKF>
 static void launch_fused(int cfg, const Launch& L, const FusedParams& fp, const void* A,
                          const void* B, void* C) {
-  if (cfg == 2) {
+  if (cfg == 3) {
+    long long tiles = ((fp.M + 127) / 128) * ((fp.N + 7) / 8);
+    PQ_REQUIRE(tiles <= 0x7fffffffLL, PQ_ERR_UNSUPPORTED, "too many tiles");
+    k_zgemm_fused_t<128, 8, 8, 1, 2, 3, AKF, BKF>
+        <<<(unsigned)tiles, 256, fused_smem<128, 8, 2>((int)fp.K), L.stream>>>(
+            (const double2*)A, (const double2*)B, (double2*)C, fp);
+  } else if (cfg == 2) {
     long long tiles = ((fp.M + 63) / 64) * ((fp.N + 31) / 32);
     PQ_REQUIRE(tiles <= 0x7fffffffLL, PQ_ERR_UNSUPPORTED, "too many tiles");
     k_zgemm_fused_t<64, 32, 4, 2, 2, 4, AKF, BKF>
@@ -431,7 +449,7 @@ void run_zgemm_fused(const Launch& L, const ContractPlan& cp, const void* A, con
   // short contractions (few k-blocks per tile) are fill-latency bound: use the small-CTA
   // configuration with four resident CTAs per SM; option "zgemm_cfg" forces 1 (64x64) / 2 (64x32)
   int cfg = L.opt ? L.opt->zgemm_cfg : 0;
-  if (cfg == 0) cfg = (cp.K <= 128) ? 2 : 1;
+  if (cfg == 0) cfg = (cp.N <= 16) ? 3 : (cp.K <= 128) ? 2 : 1;
   auto min_stride = [](const IdxMap& m) {
     int64_t best = INT64_MAX;
     for (int d = 0; d < m.nd; ++d) best = m.str[d] < best ? m.str[d] : best;
@@ -439,6 +457,7 @@ void run_zgemm_fused(const Launch& L, const ContractPlan& cp, const void* A, con
   };
   bool akf = min_stride(cp.kA) < min_stride(cp.mA), bkf = min_stride(cp.kB) < min_stride(cp.nB);
   if (L.opt && L.opt->zgemm_kfirst == 1) akf = bkf = false;  // A/B check knob
+  if (cfg == 3) akf = bkf = false;  // measured: no gain for the narrow tiles (HBM-bound)
   L.begin(KC_GEMM_TENSOR, bytes, flops);
   if (akf && bkf)
     launch_fused<true, true>(cfg, L, fp, A, B, C);

@@ -255,8 +255,16 @@ ContractPlan lower_contract(const std::vector<int64_t>& a_dims, const std::vecto
   const int64_t M = P.M, N = P.N, K = P.K;
   const bool fused_ok = opt.fused == 0 && opt.gemm != 3;
   const int64_t SMALL_Q = 1024;  // elements of the small operand kept in shared memory
+  // c128, one open bond of 8-16 on the small side, K >= 32: the per-row FP64 FMA work of the
+  // small-operand kernel (2 N K per row) exceeds what HBM delivers; the narrow-tile DMMA
+  // GEMM (128x8 tiles) is HBM-bound instead
+  const bool narrow_gemm = elem_size == 16 && opt.fused == 0 && (opt.gemm == 0 || opt.gemm == 2) &&
+                           N >= 8 && N <= 16 && K >= 32 && K <= 1024 && M >= 4096 &&
+                           (opt.zgemm_cfg == 0 || opt.zgemm_cfg == 3);
   if (opt.gemm == 3) {
     P.kind = CK_DIRECT;
+  } else if (narrow_gemm) {
+    P.kind = CK_GEMM;
   } else if (fused_ok && N <= 16 && K <= 256 && N * K <= SMALL_Q && M >= N) {
     P.kind = CK_SMALL_RIGHT;
   } else if (fused_ok && M <= 16 && K <= 256 && M * K <= SMALL_Q) {
@@ -270,8 +278,38 @@ ContractPlan lower_contract(const std::vector<int64_t>& a_dims, const std::vecto
   }
 
   if (P.kind == CK_DOT) {
-    int64_t blocks = (K + 2047) / 2048;
-    if (blocks > 592) blocks = 592;
+    // A sum over k may visit k in any order: enumerate the contracted bits so that the five
+    // lowest (= the lanes of a warp) alternate between the lowest-address bits of A and of B.
+    // Both operands are then read in runs of >= 4 consecutive elements (whole 32-byte
+    // sectors) instead of one of them being a 16-byte gather.
+    bool pow2 = true;
+    for (const D3& d : kd) pow2 = pow2 && is_pow2(d.ext);
+    if (pow2 && kd.size() > 1) {
+      std::vector<D3> bits;
+      for (const D3& d : kd)
+        for (int q = 0; q < ilog2(d.ext); ++q) bits.push_back({2, d.sa << q, d.sb << q});
+      std::vector<D3> order;
+      std::vector<char> used(bits.size(), 0);
+      for (int pick = 0; pick < 6 && order.size() < bits.size(); ++pick) {
+        int best = -1;
+        for (int i = 0; i < (int)bits.size(); ++i) {
+          if (used[i]) continue;
+          const int64_t key = (pick & 1) ? bits[i].sb : bits[i].sa;
+          if (best < 0 || key < ((pick & 1) ? bits[best].sb : bits[best].sa)) best = i;
+        }
+        used[best] = 1;
+        order.push_back(bits[best]);
+      }
+      for (size_t i = 0; i < bits.size(); ++i)
+        if (!used[i]) order.push_back(bits[i]);
+      order = fuse(order, true);
+      if ((int)order.size() <= MAXF) {
+        fill_map(P.kA, order, false);
+        fill_map(P.kB, order, true);
+      }
+    }
+    int64_t blocks = (K + 1023) / 1024;   // >= 4 k per thread
+    if (blocks > 1184) blocks = 1184;     // 8 resident CTAs on each of the 148 SMs
     if (blocks < 1) blocks = 1;
     P.dot_blocks = (int)blocks;
     P.ws_bytes = size_t(blocks) * 16 * elem_size;

@@ -107,7 +107,7 @@ struct Step {
   // save
   std::string key;
   std::vector<int64_t> dims;
-  std::shared_ptr<Buffer> out;
+  int save_slot = -1;  // index into LaneMem::outs
 };
 
 std::vector<int32_t> parse_ints(const std::string& s) {
@@ -123,27 +123,46 @@ std::vector<int32_t> parse_ints(const std::string& s) {
 
 }  // namespace
 
+// Per-lane memory of a program.  Lane 0 is the program's own memory; further lanes are
+// private copies (arenas, view parameters, `save` buffers, graph instances) that let
+// pq_program_run_slices keep several slices in flight on separate streams.
+struct LaneMem {
+  void* arena2[2] = {nullptr, nullptr};  // [0] slice-invariant, [1] slice-dependent
+  void* arena_small = nullptr;
+  int32_t* d_starts = nullptr;
+  // graph instances: invariant part (lane 0 only), dependent part, whole stream
+  cudaGraphExec_t exec2[3] = {nullptr, nullptr, nullptr};
+  std::vector<std::shared_ptr<Buffer>> outs;  // one per `save` step
+  cudaStream_t stream = nullptr;              // run_slices: the lane's own stream
+  cudaEvent_t done_ev = nullptr, acc_ev = nullptr;
+};
+
 struct pq_program {
   std::vector<Step> steps;
   // [0]: slice-invariant steps, [1]: slice-dependent steps (disjoint arenas, so that the
   // invariant part can be executed once per amplitude and the dependent part per slice)
   size_t arena_bytes2[2] = {0, 0};
   size_t arena_bytes = 0, arena_small_bytes = 0;
-  void* arena2[2] = {nullptr, nullptr};
-  void* arena_small = nullptr;
+  static constexpr int MAX_LANES = 8;
+  std::vector<LaneMem> lanes;  // lanes[0] always exists
+  int nsaves = 0;
   bool hoist = false;      // run() executes only the slice-dependent part
   bool prepared = false;   // the invariant part has been executed since hoisting was enabled
   int64_t macs2[2] = {0, 0}, launches2[2] = {0, 0}, ncontract2[2] = {0, 0};
   int nviews = 0;
   std::vector<int32_t> default_starts;
-  int32_t* d_starts = nullptr;
   // pinned ring for asynchronous parameter uploads
   static constexpr int RING = 32;
   int32_t* h_ring = nullptr;
   cudaEvent_t ring_ev[RING];
   bool ring_used[RING];
   int ring_pos = 0;
-  cudaGraphExec_t exec2[3] = {nullptr, nullptr, nullptr};  // invariant, dependent, whole stream
+  // run_slices: view parameters of a whole batch of slices (pinned staging + device table)
+  int32_t* h_table = nullptr;
+  int32_t* d_table = nullptr;
+  size_t table_cap = 0;
+  cudaEvent_t table_ev = nullptr, batch_ev = nullptr;
+  bool table_used = false;
   int64_t launches = 0, macs = 0, ncontract = 0, max_elems = 0;
   int device = 0;
   // leaf tensors the program is bound to: (store key, pinned buffer)
@@ -164,18 +183,26 @@ struct Range {
 inline bool overlap(const Range& a, const Range& b) { return a.lo < b.hi && b.lo < a.hi; }
 }  // namespace
 
-static void* resolve(const pq_program* p, const Ref& r) {
+// Where a step's operands live for a given lane.  `split` = the invariant part runs on its
+// own (hoisting): slice-invariant tensors then exist once, in lane 0, for every lane.
+struct Where {
+  int lane = 0;
+  bool split = false;
+};
+
+static void* resolve(const pq_program* p, const Ref& r, Where w = Where()) {
   if (r.null) return nullptr;
   if (r.leaf) return r.leafptr;
-  return (void*)((char*)(r.small ? p->arena_small : p->arena2[r.dep ? 1 : 0]) + r.offset);
+  const LaneMem& m = p->lanes[(w.split && !r.dep) ? 0 : w.lane];
+  return (void*)((char*)(r.small ? m.arena_small : m.arena2[r.dep ? 1 : 0]) + r.offset);
 }
 
-static void issue_step(pq_handle* h, pq_program* p, Step& s, Launch& L);
+static void issue_step(pq_handle* h, pq_program* p, Step& s, Launch& L, Where w);
 
 // phase 0: slice-invariant steps, phase 1: slice-dependent steps (stream order within a phase)
-static void issue_steps(pq_handle* h, pq_program* p, Launch& L, int phase) {
+static void issue_steps(pq_handle* h, pq_program* p, Launch& L, int phase, Where w) {
   for (Step& s : p->steps)
-    if (phase < 0 || (s.dep ? 1 : 0) == phase) issue_step(h, p, s, L);
+    if (phase < 0 || (s.dep ? 1 : 0) == phase) issue_step(h, p, s, L, w);
 }
 
 // read / write address ranges of a step (after the arena has been allocated)
@@ -206,7 +233,8 @@ static void step_ranges(pq_handle* h, const pq_program* p, const Step& s, std::v
     case ST_SAVE: {
       size_t bytes = size_t(prod(s.dims)) * es;
       rd.push_back(rng(s.a, bytes));
-      wr.push_back(Range{(const char*)s.out->ptr, (const char*)s.out->ptr + (bytes ? bytes : 1)});
+      const char* o = (const char*)p->lanes[0].outs[s.save_slot]->ptr;
+      wr.push_back(Range{o, o + (bytes ? bytes : 1)});
       break;
     }
   }
@@ -247,7 +275,7 @@ static void build_dag(pq_handle* h, pq_program* p) {
 // Issues every step during stream capture, spreading independent steps over several
 // capture streams joined by events, so the instantiated graph is a DAG rather than a
 // chain: the ~10^3 tiny world-line contractions of a slice run concurrently.
-static void issue_steps_dag(pq_handle* h, pq_program* p, Launch& L0, int phase) {
+static void issue_steps_dag(pq_handle* h, pq_program* p, Launch& L0, int phase, Where w) {
   const int n = (int)p->steps.size();
   const int S = pq_program::NSTREAMS;
   cudaStream_t streams[pq_program::NSTREAMS + 1];
@@ -282,7 +310,7 @@ static void issue_steps_dag(pq_handle* h, pq_program* p, Launch& L0, int phase) 
     }
     Launch L = L0;
     L.stream = streams[best];
-    issue_step(h, p, p->steps[j], L);
+    issue_step(h, p, p->steps[j], L, w);
     PQ_CUDA(cudaEventRecord(p->step_ev[j], streams[best]));
     tail[best] = j;
     where[j] = best;
@@ -293,76 +321,158 @@ static void issue_steps_dag(pq_handle* h, pq_program* p, Launch& L0, int phase) 
   }
 }
 
-static void issue_step(pq_handle* h, pq_program* p, Step& s, Launch& L) {
-  {
-    switch (s.kind) {
-      case ST_CONTRACT:
-        run_contract(L, s.cp, resolve(p, s.a), resolve(p, s.b), resolve(p, s.c), resolve(p, s.ta),
-                     resolve(p, s.tb), resolve(p, s.ws));
-        break;
-      case ST_PERMUTE:
-        run_permute(L, s.pp, resolve(p, s.a), resolve(p, s.c));
-        break;
-      case ST_VIEW:
-        run_view(L, resolve(p, s.a), resolve(p, s.c), s.inner, s.ext, s.nsel, s.outer, s.start0,
-                 p->d_starts ? p->d_starts + s.view_slot : nullptr);
-        break;
-      case ST_SAVE: {
-        size_t bytes = size_t(prod(s.dims)) * h->elem_size;
-        L.begin(KC_COPY, 2.0 * bytes, 0);
-        PQ_CUDA(cudaMemcpyAsync(s.out->ptr, resolve(p, s.a), bytes, cudaMemcpyDeviceToDevice,
-                                L.stream));
-        L.end();
-        break;
-      }
+static void issue_step(pq_handle* h, pq_program* p, Step& s, Launch& L, Where w) {
+  switch (s.kind) {
+    case ST_CONTRACT:
+      run_contract(L, s.cp, resolve(p, s.a, w), resolve(p, s.b, w), resolve(p, s.c, w),
+                   resolve(p, s.ta, w), resolve(p, s.tb, w), resolve(p, s.ws, w));
+      break;
+    case ST_PERMUTE:
+      run_permute(L, s.pp, resolve(p, s.a, w), resolve(p, s.c, w));
+      break;
+    case ST_VIEW: {
+      int32_t* starts = p->lanes[w.lane].d_starts;
+      run_view(L, resolve(p, s.a, w), resolve(p, s.c, w), s.inner, s.ext, s.nsel, s.outer, s.start0,
+               starts ? starts + s.view_slot : nullptr);
+      break;
+    }
+    case ST_SAVE: {
+      size_t bytes = size_t(prod(s.dims)) * h->elem_size;
+      L.begin(KC_COPY, 2.0 * bytes, 0);
+      PQ_CUDA(cudaMemcpyAsync(p->lanes[w.lane].outs[s.save_slot]->ptr, resolve(p, s.a, w), bytes,
+                              cudaMemcpyDeviceToDevice, L.stream));
+      L.end();
+      break;
     }
   }
 }
 
+// Kernel nodes with small grids get the highest launch priority, nodes with large grids
+// (GEMM-shaped steps, state-sized permutes) the lowest.  The block scheduler otherwise
+// drains a large grid completely before it dispatches the first CTA of a later kernel, so
+// the latency-bound chains of tiny contractions -- of this slice or of another slice in
+// flight on a different lane -- would sit behind every GEMM instead of slipping into the
+// SM slots its retiring CTAs free.
+static void prioritise_small_nodes(cudaGraph_t graph, int num_sms) {
+  int least = 0, greatest = 0;
+  if (cudaDeviceGetStreamPriorityRange(&least, &greatest) != cudaSuccess || least == greatest) return;
+  size_t n = 0;
+  if (cudaGraphGetNodes(graph, nullptr, &n) != cudaSuccess || n == 0) return;
+  std::vector<cudaGraphNode_t> nodes(n);
+  if (cudaGraphGetNodes(graph, nodes.data(), &n) != cudaSuccess) return;
+  for (cudaGraphNode_t nd : nodes) {
+    cudaGraphNodeType t;
+    if (cudaGraphNodeGetType(nd, &t) != cudaSuccess || t != cudaGraphNodeTypeKernel) continue;
+    cudaKernelNodeParams kp;
+    if (cudaGraphKernelNodeGetParams(nd, &kp) != cudaSuccess) continue;
+    const long long ctas = (long long)kp.gridDim.x * kp.gridDim.y * kp.gridDim.z;
+    cudaLaunchAttributeValue v;
+    memset(&v, 0, sizeof(v));
+    v.priority = ctas > 2LL * num_sms ? least : greatest;
+    cudaGraphKernelNodeSetAttribute(nd, cudaLaunchAttributePriority, &v);
+  }
+  cudaGetLastError();
+}
+
 // Executes one phase of the program on the handle's stream: eagerly (profiling / option
 // graph=1) or by launching its CUDA graph, captured on first use.
-static void run_phase(pq_handle* h, pq_program* p, Launch& L, int phase) {
+static void run_phase(pq_handle* h, pq_program* p, Launch& L, int phase, int lane = 0,
+                      cudaStream_t on = nullptr) {
   // phase -1 = the whole stream as ONE graph (no hoisting): invariant and dependent chains
   // then share the parallel branches
   const int slot = phase < 0 ? 2 : phase;
   const int64_t nl = phase < 0 ? p->launches : p->launches2[phase];
   if (nl == 0) return;
+  Where w;
+  w.lane = lane;
+  w.split = phase >= 0;
+  LaneMem& m = p->lanes[lane];
   const bool eager = h->profile || h->opt.graph == 1;
   if (eager) {
-    issue_steps(h, p, L, phase);
+    issue_steps(h, p, L, phase, w);
   } else {
-    if (!p->exec2[slot]) {
+    if (!m.exec2[slot]) {
+      // graphs are captured on the handle's stream (nothing executes) and may be launched
+      // on any stream
       Launch LC = L;
+      LC.stream = h->stream;
       LC.launch_counter = nullptr;
       LC.profile = false;
       cudaGraph_t graph = nullptr;
       PQ_CUDA(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
       try {
         if (h->opt.graph == 2)
-          issue_steps(h, p, LC, phase);       // single-stream chain (A/B against the DAG)
+          issue_steps(h, p, LC, phase, w);       // single-stream chain (A/B against the DAG)
         else
-          issue_steps_dag(h, p, LC, phase);   // independent steps on parallel branches
+          issue_steps_dag(h, p, LC, phase, w);   // independent steps on parallel branches
       } catch (...) {
         cudaStreamEndCapture(h->stream, &graph);
         if (graph) cudaGraphDestroy(graph);
         throw;
       }
       PQ_CUDA(cudaStreamEndCapture(h->stream, &graph));
-      cudaError_t e = cudaGraphInstantiate(&p->exec2[slot], graph, 0);
+      if (h->opt.prio == 0) prioritise_small_nodes(graph, h->num_sms);
+      cudaError_t e = cudaGraphInstantiate(&m.exec2[slot], graph, 0);
       cudaGraphDestroy(graph);
       PQ_CUDA(e);
     }
-    PQ_CUDA(cudaGraphLaunch(p->exec2[slot], h->stream));
+    PQ_CUDA(cudaGraphLaunch(m.exec2[slot], on ? on : h->stream));
     h->launches += nl;
   }
   h->n_contract += phase < 0 ? p->ncontract : p->ncontract2[phase];
   h->macs += phase < 0 ? p->macs : p->macs2[phase];
 }
 
+// Allocates the memory of lanes [1, n) (lane 0 is allocated by pq_program_compile).
+static void ensure_lanes(pq_handle* h, pq_program* p, int n) {
+  while ((int)p->lanes.size() < n) {
+    LaneMem m;
+    for (int a = 0; a < 2; ++a)
+      PQ_CUDA(cudaMalloc(&m.arena2[a], p->arena_bytes2[a] ? p->arena_bytes2[a] : ALIGN));
+    PQ_CUDA(cudaMalloc(&m.arena_small, p->arena_small_bytes ? p->arena_small_bytes : ALIGN));
+    if (p->nviews > 0) {
+      PQ_CUDA(cudaMalloc(&m.d_starts, sizeof(int32_t) * p->nviews));
+      PQ_CUDA(cudaMemcpy(m.d_starts, p->default_starts.data(), sizeof(int32_t) * p->nviews,
+                         cudaMemcpyHostToDevice));
+    }
+    for (const Step& s : p->steps)
+      if (s.kind == ST_SAVE)
+        m.outs.push_back(std::make_shared<Buffer>(size_t(prod(s.dims)) * h->elem_size, h->stream));
+    p->lanes.push_back(std::move(m));
+  }
+  for (int l = 0; l < n; ++l) {
+    LaneMem& m = p->lanes[l];
+    if (m.stream) continue;
+    PQ_CUDA(cudaStreamCreateWithFlags(&m.stream, cudaStreamNonBlocking));
+    PQ_CUDA(cudaEventCreateWithFlags(&m.done_ev, cudaEventDisableTiming));
+    PQ_CUDA(cudaEventCreateWithFlags(&m.acc_ev, cudaEventDisableTiming));
+  }
+  if (!p->batch_ev) {
+    PQ_CUDA(cudaEventCreateWithFlags(&p->batch_ev, cudaEventDisableTiming));
+    PQ_CUDA(cudaEventCreateWithFlags(&p->table_ev, cudaEventDisableTiming));
+  }
+}
+
+static void free_lanes(pq_program* p) {
+  for (LaneMem& m : p->lanes) {
+    for (int a = 0; a < 3; ++a)
+      if (m.exec2[a]) cudaGraphExecDestroy(m.exec2[a]);
+    for (int a = 0; a < 2; ++a)
+      if (m.arena2[a]) cudaFree(m.arena2[a]);
+    if (m.arena_small) cudaFree(m.arena_small);
+    if (m.d_starts) cudaFree(m.d_starts);
+    if (m.stream) cudaStreamDestroy(m.stream);
+    if (m.done_ev) cudaEventDestroy(m.done_ev);
+    if (m.acc_ev) cudaEventDestroy(m.acc_ev);
+  }
+  p->lanes.clear();
+}
+
 extern "C" int pq_program_compile(pq_handle* h, const char* tl_text, pq_program** out) {
   if (!h || !tl_text || !out) return PQ_ERR_INVALID;
   *out = nullptr;
   pq_program* p = new pq_program();
+  p->lanes.emplace_back();
   try {
     PQ_CUDA(cudaSetDevice(h->device));
     p->device = h->device;
@@ -581,7 +691,8 @@ extern "C" int pq_program_compile(pq_handle* h, const char* tl_text, pq_program*
         st.a = ref_of(s);
         st.key = tok[3];
         st.dims = s.dims;
-        st.out = std::make_shared<Buffer>(size_t(prod(s.dims)) * es, h->stream);
+        st.save_slot = p->nsaves++;
+        p->lanes[0].outs.push_back(std::make_shared<Buffer>(size_t(prod(s.dims)) * es, h->stream));
         p->steps.push_back(std::move(st));
       } else if (cmd == "decompose") {
         throw Error(PQ_ERR_UNSUPPORTED, "decompose (SVD) is outside the contraction hot path");
@@ -590,15 +701,16 @@ extern "C" int pq_program_compile(pq_handle* h, const char* tl_text, pq_program*
     }
 
     p->arena_small_bytes = small_top;
+    LaneMem& m0 = p->lanes[0];
     for (int a = 0; a < 2; ++a) {
       p->arena_bytes2[a] = sims[a].top;
-      PQ_CUDA(cudaMalloc(&p->arena2[a], sims[a].top ? sims[a].top : ALIGN));
+      PQ_CUDA(cudaMalloc(&m0.arena2[a], sims[a].top ? sims[a].top : ALIGN));
     }
     p->arena_bytes = sims[0].top + sims[1].top;
-    PQ_CUDA(cudaMalloc(&p->arena_small, small_top ? small_top : ALIGN));
+    PQ_CUDA(cudaMalloc(&m0.arena_small, small_top ? small_top : ALIGN));
     if (p->nviews > 0) {
-      PQ_CUDA(cudaMalloc(&p->d_starts, sizeof(int32_t) * p->nviews));
-      PQ_CUDA(cudaMemcpy(p->d_starts, p->default_starts.data(), sizeof(int32_t) * p->nviews,
+      PQ_CUDA(cudaMalloc(&m0.d_starts, sizeof(int32_t) * p->nviews));
+      PQ_CUDA(cudaMemcpy(m0.d_starts, p->default_starts.data(), sizeof(int32_t) * p->nviews,
                          cudaMemcpyHostToDevice));
       PQ_CUDA(cudaMallocHost(&p->h_ring, sizeof(int32_t) * p->nviews * pq_program::RING));
       for (int i = 0; i < pq_program::RING; ++i) {
@@ -628,17 +740,13 @@ extern "C" int pq_program_compile(pq_handle* h, const char* tl_text, pq_program*
     }
   } catch (const Error& e) {
     h->last_error = e.what();
-    for (int a = 0; a < 2; ++a)
-      if (p->arena2[a]) cudaFree(p->arena2[a]);
-    if (p->arena_small) cudaFree(p->arena_small);
+    free_lanes(p);
     for (auto& l : p->leaves) l.second->pins -= 1;
     delete p;
     return e.code;
   } catch (const std::exception& e) {
     h->last_error = e.what();
-    for (int a = 0; a < 2; ++a)
-      if (p->arena2[a]) cudaFree(p->arena2[a]);
-    if (p->arena_small) cudaFree(p->arena_small);
+    free_lanes(p);
     for (auto& l : p->leaves) l.second->pins -= 1;
     delete p;
     return PQ_ERR_PARSE;
@@ -704,63 +812,157 @@ extern "C" int pq_program_prepare(pq_handle* h, pq_program* p) {
   return PQ_OK;
 }
 
+// Publishes the `save` results of one run of `lane` in the handle's store and, optionally,
+// adds them to `accumulate_into` -- on the handle's stream.
+static void publish_saves(pq_handle* h, pq_program* p, Launch& L, int lane,
+                          const char* accumulate_into) {
+  for (Step& s : p->steps) {
+    if (s.kind != ST_SAVE) continue;
+    const std::shared_ptr<Buffer>& out = p->lanes[lane].outs[s.save_slot];
+    Tensor t;
+    t.dims = s.dims;
+    t.buf = out;
+    h->tensors[s.key] = t;
+    if (!accumulate_into) continue;
+    auto it = h->tensors.find(accumulate_into);
+    int64_t n = prod(s.dims);
+    if (it == h->tensors.end()) {
+      Tensor d;
+      d.dims = s.dims;
+      d.buf = std::make_shared<Buffer>(size_t(n) * h->elem_size, h->stream);
+      L.begin(KC_COPY, 2.0 * n * h->elem_size, 0);
+      PQ_CUDA(cudaMemcpyAsync(d.buf->ptr, out->ptr, size_t(n) * h->elem_size,
+                              cudaMemcpyDeviceToDevice, h->stream));
+      L.end();
+      h->tensors[accumulate_into] = d;
+    } else {
+      PQ_REQUIRE(it->second.numel() == n, PQ_ERR_SHAPE, "accumulate: size mismatch");
+      run_accumulate(L, it->second.buf->ptr, out->ptr, n);
+    }
+  }
+}
+
+// one slice on lane 0, everything on the handle's stream
+static void run_one(pq_handle* h, pq_program* p, const int32_t* view_starts,
+                    const char* accumulate_into) {
+  if (view_starts && p->nviews > 0) {
+    int slot = p->ring_pos;
+    p->ring_pos = (p->ring_pos + 1) % pq_program::RING;
+    if (p->ring_used[slot]) PQ_CUDA(cudaEventSynchronize(p->ring_ev[slot]));
+    int32_t* src = p->h_ring + size_t(slot) * p->nviews;
+    memcpy(src, view_starts, sizeof(int32_t) * p->nviews);
+    PQ_CUDA(cudaMemcpyAsync(p->lanes[0].d_starts, src, sizeof(int32_t) * p->nviews,
+                            cudaMemcpyHostToDevice, h->stream));
+    PQ_CUDA(cudaEventRecord(p->ring_ev[slot], h->stream));
+    p->ring_used[slot] = true;
+  }
+  Launch L = h->launch_ctx();
+  // hoisting: the slice-invariant part runs once (pq_program_prepare), only the
+  // slice-dependent part is replayed per slice
+  if (!p->hoist) {
+    run_phase(h, p, L, -1);
+  } else {
+    if (!p->prepared) {
+      run_phase(h, p, L, 0);
+      p->prepared = true;
+    }
+    run_phase(h, p, L, 1);
+  }
+  h->note_tensor(p->max_elems);
+  publish_saves(h, p, L, 0, accumulate_into);
+}
+
 extern "C" int pq_program_run(pq_handle* h, pq_program* p, const int32_t* view_starts, int nviews,
                               const char* accumulate_into) {
   if (!h || !p) return PQ_ERR_INVALID;
   try {
     PQ_CUDA(cudaSetDevice(h->device));
     check_leaves(h, p);
-    if (view_starts) {
+    if (view_starts)
       PQ_REQUIRE(nviews == p->nviews, PQ_ERR_INVALID, "pq_program_run: wrong number of view starts");
-      if (p->nviews > 0) {
-        int slot = p->ring_pos;
-        p->ring_pos = (p->ring_pos + 1) % pq_program::RING;
-        if (p->ring_used[slot]) PQ_CUDA(cudaEventSynchronize(p->ring_ev[slot]));
-        int32_t* src = p->h_ring + size_t(slot) * p->nviews;
-        memcpy(src, view_starts, sizeof(int32_t) * p->nviews);
-        PQ_CUDA(cudaMemcpyAsync(p->d_starts, src, sizeof(int32_t) * p->nviews,
-                                cudaMemcpyHostToDevice, h->stream));
-        PQ_CUDA(cudaEventRecord(p->ring_ev[slot], h->stream));
-        p->ring_used[slot] = true;
+    run_one(h, p, view_starts, accumulate_into);
+  } catch (const Error& e) {
+    h->last_error = e.what();
+    return e.code;
+  } catch (const std::exception& e) {
+    h->last_error = e.what();
+    return PQ_ERR_INVALID;
+  }
+  return PQ_OK;
+}
+
+// The slice loop of a sliced contraction in one call: for s in [0, nslices) run the program
+// with view_starts[s * nviews ...] and add its saved result to `accumulate_into`, in slice
+// order (so the sum is bit-identical to nslices pq_program_run calls).  Slices are
+// independent, so up to `nlanes` of them are kept in flight: each lane has private arenas,
+// view parameters and graph instance and runs on its own stream, which hides the
+// latency-bound stretch of one slice (its ~10^3 tiny contractions) behind the GEMM steps of
+// the others.  Only the accumulations are ordered, on the handle's stream.
+extern "C" int pq_program_run_slices(pq_handle* h, pq_program* p, const int32_t* view_starts,
+                                     int nslices, int nviews, const char* accumulate_into,
+                                     int nlanes) {
+  if (!h || !p || nslices < 0) return PQ_ERR_INVALID;
+  try {
+    PQ_CUDA(cudaSetDevice(h->device));
+    check_leaves(h, p);
+    if (view_starts)
+      PQ_REQUIRE(nviews == p->nviews, PQ_ERR_INVALID,
+                 "pq_program_run_slices: wrong number of view starts");
+    if (nslices == 0) return PQ_OK;
+    const bool eager = h->profile || h->opt.graph == 1;
+    if (nlanes > pq_program::MAX_LANES) nlanes = pq_program::MAX_LANES;
+    if (nlanes > nslices) nlanes = nslices;
+    if (eager || nlanes <= 1) {
+      for (int s = 0; s < nslices; ++s)
+        run_one(h, p, view_starts ? view_starts + size_t(s) * p->nviews : nullptr, accumulate_into);
+      return PQ_OK;
+    }
+    ensure_lanes(h, p, nlanes);
+    const bool params = view_starts && p->nviews > 0;
+    if (params) {  // one upload for the whole batch
+      const size_t n = size_t(nslices) * p->nviews;
+      if (p->table_used) PQ_CUDA(cudaEventSynchronize(p->table_ev));
+      if (n > p->table_cap) {
+        if (p->h_table) PQ_CUDA(cudaFreeHost(p->h_table));
+        if (p->d_table) PQ_CUDA(cudaFree(p->d_table));
+        p->h_table = nullptr;
+        p->d_table = nullptr;
+        PQ_CUDA(cudaMallocHost(&p->h_table, sizeof(int32_t) * n));
+        PQ_CUDA(cudaMalloc(&p->d_table, sizeof(int32_t) * n));
+        p->table_cap = n;
       }
+      memcpy(p->h_table, view_starts, sizeof(int32_t) * n);
+      PQ_CUDA(cudaMemcpyAsync(p->d_table, p->h_table, sizeof(int32_t) * n, cudaMemcpyHostToDevice,
+                              h->stream));
+      PQ_CUDA(cudaEventRecord(p->table_ev, h->stream));
+      p->table_used = true;
     }
     Launch L = h->launch_ctx();
-    // hoisting: the slice-invariant part runs once (pq_program_prepare), only the
-    // slice-dependent part is replayed per slice
-    if (!p->hoist) {
-      run_phase(h, p, L, -1);
-    } else {
-      if (!p->prepared) {
-        run_phase(h, p, L, 0);
-        p->prepared = true;
-      }
-      run_phase(h, p, L, 1);
+    const bool split = p->hoist;
+    if (split && !p->prepared) {
+      run_phase(h, p, L, 0);
+      p->prepared = true;
+    }
+    // fork: the lanes start after everything queued on the handle's stream so far
+    PQ_CUDA(cudaEventRecord(p->batch_ev, h->stream));
+    for (int l = 0; l < nlanes; ++l)
+      PQ_CUDA(cudaStreamWaitEvent(p->lanes[l].stream, p->batch_ev, 0));
+    for (int s = 0; s < nslices; ++s) {
+      const int lane = s % nlanes;
+      LaneMem& m = p->lanes[lane];
+      // the lane's `save` buffer must have been consumed by the previous accumulation
+      if (s >= nlanes) PQ_CUDA(cudaStreamWaitEvent(m.stream, m.acc_ev, 0));
+      if (params)
+        PQ_CUDA(cudaMemcpyAsync(m.d_starts, p->d_table + size_t(s) * p->nviews,
+                                sizeof(int32_t) * p->nviews, cudaMemcpyDeviceToDevice, m.stream));
+      run_phase(h, p, L, split ? 1 : -1, lane, m.stream);
+      PQ_CUDA(cudaEventRecord(m.done_ev, m.stream));
+      // join: publish / accumulate in slice order on the handle's stream
+      PQ_CUDA(cudaStreamWaitEvent(h->stream, m.done_ev, 0));
+      publish_saves(h, p, L, lane, accumulate_into);
+      PQ_CUDA(cudaEventRecord(m.acc_ev, h->stream));
     }
     h->note_tensor(p->max_elems);
-    for (Step& s : p->steps) {
-      if (s.kind != ST_SAVE) continue;
-      Tensor t;
-      t.dims = s.dims;
-      t.buf = s.out;
-      h->tensors[s.key] = t;
-      if (accumulate_into) {
-        auto it = h->tensors.find(accumulate_into);
-        int64_t n = prod(s.dims);
-        if (it == h->tensors.end()) {
-          Tensor d;
-          d.dims = s.dims;
-          d.buf = std::make_shared<Buffer>(size_t(n) * h->elem_size, h->stream);
-          L.begin(KC_COPY, 2.0 * n * h->elem_size, 0);
-          PQ_CUDA(cudaMemcpyAsync(d.buf->ptr, s.out->ptr, size_t(n) * h->elem_size,
-                                  cudaMemcpyDeviceToDevice, h->stream));
-          L.end();
-          h->tensors[accumulate_into] = d;
-        } else {
-          PQ_REQUIRE(it->second.numel() == n, PQ_ERR_SHAPE, "accumulate: size mismatch");
-          run_accumulate(L, it->second.buf->ptr, s.out->ptr, n);
-        }
-      }
-    }
   } catch (const Error& e) {
     h->last_error = e.what();
     return e.code;
@@ -777,21 +979,22 @@ extern "C" int pq_program_destroy(pq_handle* h, pq_program* p) {
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
   }
-  for (int a = 0; a < 3; ++a)
-    if (p->exec2[a]) cudaGraphExecDestroy(p->exec2[a]);
+  for (LaneMem& m : p->lanes)
+    if (m.stream) cudaStreamSynchronize(m.stream);
   for (auto& e : p->step_ev) cudaEventDestroy(e);
   if (p->fork_ev) cudaEventDestroy(p->fork_ev);
   for (int i = 0; i < pq_program::NSTREAMS; ++i)
     if (p->side[i]) cudaStreamDestroy(p->side[i]);
   for (auto& l : p->leaves) l.second->pins -= 1;
-  for (int a = 0; a < 2; ++a)
-    if (p->arena2[a]) cudaFree(p->arena2[a]);
-  if (p->arena_small) cudaFree(p->arena_small);
-  if (p->d_starts) cudaFree(p->d_starts);
+  free_lanes(p);
   if (p->h_ring) {
     cudaFreeHost(p->h_ring);
     for (int i = 0; i < pq_program::RING; ++i) cudaEventDestroy(p->ring_ev[i]);
   }
+  if (p->h_table) cudaFreeHost(p->h_table);
+  if (p->d_table) cudaFree(p->d_table);
+  if (p->batch_ev) cudaEventDestroy(p->batch_ev);
+  if (p->table_ev) cudaEventDestroy(p->table_ev);
   delete p;
   return PQ_OK;
 }

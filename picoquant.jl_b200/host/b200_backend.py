@@ -42,6 +42,7 @@ ABI_SYMBOLS = [
     "pq_reset_counters", "pq_profile_enable", "pq_profile_read", "pq_kernel_class_name",
     "pq_set_option", "pq_microbench", "pq_timer_begin", "pq_timer_end",
     "pq_program_set_hoist", "pq_program_prepare", "pq_program_hoist_stats",
+    "pq_program_run_slices",
 ]
 
 _lib = None
@@ -87,6 +88,7 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
     lib.pq_program_compile.argtypes = [c_void_p, c_char_p, POINTER(c_void_p)]
     lib.pq_program_num_views.argtypes = [c_void_p]
     lib.pq_program_run.argtypes = [c_void_p, c_void_p, i32p, c_int, c_char_p]
+    lib.pq_program_run_slices.argtypes = [c_void_p, c_void_p, i32p, c_int, c_int, c_char_p, c_int]
     lib.pq_program_destroy.argtypes = [c_void_p, c_void_p]
     lib.pq_program_stats.argtypes = [c_void_p, i64p, i64p, i64p]
     lib.pq_program_set_hoist.argtypes = [c_void_p, c_int]
@@ -152,6 +154,18 @@ class Program:
             vs, n = _i32(view_starts), len(view_starts)
         acc = accumulate_into.encode() if accumulate_into else None
         b._check(b.lib.pq_program_run(b._h, self._p, vs, n, acc))
+
+    def run_slices(self, view_starts: Sequence[Sequence[int]], accumulate_into: Optional[str],
+                   lanes: int = 2) -> None:
+        """The slice loop in one call (``pq_program_run_slices``): one run per row of
+        ``view_starts``, results accumulated in row order, up to ``lanes`` slices in flight."""
+        b = self.backend
+        n = len(view_starts)
+        nv = len(view_starts[0]) if n else 0
+        flat = _i32([v for row in view_starts for v in row])
+        acc = accumulate_into.encode() if accumulate_into else None
+        b._check(b.lib.pq_program_run_slices(b._h, self._p, flat if nv else None, n, nv, acc,
+                                             int(lanes)))
 
     def close(self) -> None:
         if self._p:

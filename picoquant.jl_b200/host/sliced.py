@@ -144,16 +144,22 @@ class SlicedContraction:
         return nbytes
 
     def run(self, partitions: Sequence[int], accumulate_into: str = "partial_sum",
-            hoist: bool = False) -> None:
+            hoist: bool = False, lanes: int = 1) -> None:
         """Contracts the given partitions and accumulates their results on the device.
 
         ``hoist=False`` (default) replays the whole command stream for every partition,
         like the reference flow does.  ``hoist=True`` executes the slice-invariant part of
         the stream once per call (``pq_program_prepare``) and only the slice-dependent part
-        per partition -- same result, less work."""
+        per partition -- same result, less work.  ``lanes > 1`` keeps that many partitions
+        in flight on the device (``pq_program_run_slices``); the partial sums are still added
+        in partition order, so the result is bit-identical."""
         self.program.set_hoist(hoist)
         if hoist:
             self.program.prepare()
+        if lanes > 1 and self.rec.bond_labels and len(partitions) > 1:
+            self.program.run_slices([self.rec.view_starts(p) for p in partitions],
+                                    accumulate_into, lanes)
+            return
         for p in partitions:
             self.program.run(self.rec.view_starts(p) if self.rec.bond_labels else None,
                              accumulate_into)

@@ -178,7 +178,39 @@ def test_gemm_path_shapes(dtype, gemm):
     assert expected in prof_names, prof_names
 
 
-@pytest.mark.parametrize("cfg", [0, 1, 2])
+@pytest.mark.parametrize("cfg", [0, 3])
+def test_narrow_n_zgemm_shapes(cfg):
+    """One open bond of 8..16 on the small operand with K >= 32 (a site tensor absorbed into
+    the boundary): lowered to the fused DMMA GEMM with 128x8 tiles instead of the
+    small-operand kernel; ragged M / N / K, both gather orders."""
+    rng = np.random.default_rng(41)
+    b = B200(np.complex128, zgemm_cfg=cfg)
+    shapes = [
+        ((2,) * 19, [1, 2, 3] + [-(i + 1) for i in range(13)] + [4, 5, 6],
+         (2,) * 9, [6, 5, 4, 3, 2, 1] + [-(20 + i) for i in range(3)]),        # M=2^13 N=8 K=64
+        ((2,) * 18, [-(i + 1) for i in range(13)] + [1, 2, 3, 4, 5],
+         (2,) * 9, [-20, 5, -21, 4, 3, -22, 2, 1, -23]),                        # N=16 K=32
+        ((5000, 40), [-1, 1], (40, 12), [1, -2]),                               # ragged M, N=12
+        ((33, 4100), [1, -1], (16, 33), [-2, 1]),                               # K=33, k-first A
+        ((7, 4099, 5), [1, -1, 2], (9, 5, 7), [-2, 2, 1]),                      # N=9 K=35
+    ]
+    for ad, ai, bd, bi in shapes:
+        A = rand_tensor(rng, tuple(ad), np.complex128)
+        B = rand_tensor(rng, tuple(bd), np.complex128)
+        b.save_tensor_data("A", A)
+        b.save_tensor_data("B", B)
+        b.profile_enable(True)
+        b.contract_tensors("A", ai, "B", bi, "C")
+        prof = b.profile_read()
+        b.profile_enable(False)
+        assert set(prof) == {"gemm_tensor"}, (ad, prof)
+        got = b.load_tensor_data("C")
+        ref = layer1.contract_tensors((A, B), (ai, bi))
+        assert got.shape == ref.shape
+        assert rel_l2(got, ref) < 1e-10, (ad, ai, rel_l2(got, ref))
+
+
+@pytest.mark.parametrize("cfg", [0, 1, 2, 3])
 def test_fused_ttgt_zgemm_shapes(cfg):
     """The persistent fused-TTGT ZGEMM (operands gathered inside the GEMM, no permuted
     temporaries): ragged tiles, K tails, several tiles per CTA, low-address contracted axes."""
@@ -546,6 +578,45 @@ def test_sliced_program_replay(dtype):
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("hoist", [False, True])
+def test_slice_lanes_bit_identical(dtype, hoist):
+    """pq_program_run_slices keeps several partitions in flight on private arenas / streams;
+    the partial sums are added in partition order, so the amplitude must be BIT-identical to
+    the one-partition-at-a-time loop, for every lane count, with and without hoisting."""
+    circ = create_RQC(3, 4, 10, seed=2)
+    n = circ.n_qubits
+    P = 16
+
+    def plan_fn(tn, sliced):
+        return sweep_plan(tn, 3, 4, sliced_bonds=sliced)
+
+    rec = record_sliced_contraction(circ, P, 1, plan_fn=plan_fn, output_config="0" * n)
+    b = B200(dtype)
+    sc = SlicedContraction(b, rec)
+    sc.run(range(1, P + 1), hoist=hoist)
+    base = sc.result().copy()
+    ref = circ.simulate()[0]
+    assert abs(base - ref) / abs(ref) < 20 * TOL[np.dtype(dtype)]
+    for lanes in (2, 3, 8):
+        for rep in range(2):   # second repetition reuses the lanes' graphs and arenas
+            b.delete_tensor("partial_sum")
+            b.reset_counters()
+            sc.run(range(1, P + 1), hoist=hoist, lanes=lanes)
+            got = sc.result()
+            assert got.tobytes() == base.tobytes(), (lanes, rep, got, base)
+            if not hoist:
+                assert b.counters()["macs"] == P * sc.program.macs
+    # a partial range (one rank's share) and a following single run still work
+    b.delete_tensor("partial_sum")
+    sc.run(range(5, 12), hoist=hoist, lanes=4)
+    sc.run([12], hoist=hoist)
+    part = sc.result().copy()
+    b.delete_tensor("partial_sum")
+    sc.run(range(5, 13), hoist=hoist)
+    assert part.tobytes() == sc.result().tobytes()
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
 def test_rqc_amplitude_plans(dtype):
     """config-4 shape at test size: single amplitude of a 4x4 depth-16 RQC with the
     greedy plan (undecomposed network, GEMM-heavy) and the sweep plan (decomposed)."""
@@ -561,6 +632,51 @@ def test_rqc_amplitude_plans(dtype):
         contract_network(tn, plan)
         got = b.load_tensor_data("result")
         assert abs(got - ref) / abs(ref) < 50 * tol, (decompose, got, ref)
+
+
+def test_config4_rqc_6x6_d20_amplitude():
+    """BASELINE config 4 at full size: <0..0|C|0..0> of the 6x6 depth-20 RQC, undecomposed
+    network, noise-free greedy pair plan (489 contractions, 2^37.1 complex MACs, top step
+    M=N=2^13 K=2^11, largest intermediate 2^26 elements), as one compiled program on the GPU
+    against the NumPy/OpenBLAS oracle walking the same plan on the host cores.
+    ComplexF64: relative error <= 1e-10.  ComplexF32 (tcgen05 3xTF32): <= 1e-5 against the
+    ComplexF64 oracle, or no worse than twice the CPU's own ComplexF32 error when the
+    amplitude's cancellation puts that above 1e-5."""
+    n = 36
+    circ = create_RQC(6, 6, 20, seed=0)
+
+    def network(backend):
+        tn = convert_circuit_to_network(circ, backend, decompose=False)
+        add_input(tn, "0" * n)
+        add_output(tn, "0" * n)
+        return tn
+
+    dsl = DSLBackend()
+    tn = network(dsl)
+    plan = greedy_plan(tn)
+    contract_network(tn, plan, "")
+    refs = {}
+    for dtype in DTYPES:
+        ob = OracleBackend(dtype)
+        contract_network(network(ob), plan, "")
+        refs[np.dtype(dtype)] = complex(np.asarray(ob.load_tensor_data("result")).reshape(-1)[0])
+    ref64 = refs[np.dtype(np.complex128)]
+    for dtype in DTYPES:
+        b = B200(dtype)
+        for key, arr in dsl.store.data.items():
+            b.save_tensor_data(key, arr)
+        prog = b.compile_program(dsl.text())
+        assert prog.macs == 147285958496
+        prog.run()
+        got = complex(np.asarray(b.load_tensor_data("result")).reshape(-1)[0])
+        err = abs(got - ref64) / abs(ref64)
+        if np.dtype(dtype) == np.dtype(np.complex128):
+            assert err < 1e-10, (got, ref64, err)
+        else:
+            cpu32 = abs(refs[np.dtype(np.complex64)] - ref64) / abs(ref64)
+            assert err < max(1e-5, 2 * cpu32), (got, ref64, err, cpu32)
+        prog.close()
+        b.close()
 
 
 # ---------------------------------------------------------------------------

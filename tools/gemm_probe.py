@@ -26,6 +26,10 @@ cases = {
     "M17_K6": case(23, [3, 4, 5, 18, 20, 22]),
     "M18_K5": case(23, [3, 4, 18, 20, 22]),
     "M18_K3_N6": case(21, [18, 19, 20]),
+    "M18_N3_K6": case(24, [3, 4, 5, 18, 20, 22], nb_open=3),
+    "M18_N3_K6_low": case(24, [0, 1, 2, 19, 21, 23], nb_open=3),
+    "M18_N4_K5": case(23, [3, 4, 18, 20, 22], nb_open=4),
+    "dot_K21": ((2,) * 21, list(range(1, 22)), (2,) * 21, [((i * 5) % 21) + 1 for i in range(21)]),
 }
 out = {}
 for mode, opts in (("fused", {}), ("fused_rowfirst", {"zgemm_kfirst": 1}), ("ttgt", {"fused": 1})):
@@ -44,7 +48,8 @@ for mode, opts in (("fused", {}), ("fused_rowfirst", {"zgemm_kfirst": 1}), ("ttg
         tot_ms = sum(r["ms"] for r in prof.values()) / 3
         fl = max(r["flops"] for r in prof.values()) / 3
         g = prof.get("gemm_tensor")
-        out["%s_%s" % (name, mode)] = {"total_ms": round(tot_ms, 4), "eff_tflops": round(fl / tot_ms / 1e9, 2),
+        by = max(r["bytes"] for r in prof.values()) / 3
+        out["%s_%s" % (name, mode)] = {"total_ms": round(tot_ms, 4), "eff_tflops": round(fl / tot_ms / 1e9, 2), "eff_gbs": round(by / tot_ms / 1e6, 0),
                                        "gemm_tflops": round(g["flops"] / g["ms"] / 1e9, 2) if g else None,
                                        "kernels": {c: round(r["ms"] / 3, 4) for c, r in prof.items()}}
         print(name, mode, out["%s_%s" % (name, mode)], flush=True)

@@ -43,7 +43,9 @@ for rep in range(2):
                     agg[key][0] += r["launches"]; agg[key][1] += r["ms"]; agg[key][2] += r["bytes"]; agg[key][3] += r["flops"]
 tot = sum(v[1] for v in agg.values())
 print("total eager ms per slice: %.3f" % tot)
-for key, v in sorted(agg.items(), key=lambda kv: -kv[1][1])[:22]:
+big = [kv for kv in agg.items() if kv[1][1] / kv[1][0] > 0.012]
+print("launches with avg > 12 us: %d, %.3f ms" % (sum(v[0] for _, v in big), sum(v[1] for _, v in big)))
+for key, v in sorted(big, key=lambda kv: -kv[1][1]) + [(("--", 0, 0, 0), [1, 1e-9, 0, 0])] + sorted(agg.items(), key=lambda kv: -kv[1][1])[:12]:
     cls, m, n, k = key
     print("%-16s M=2^%-2d N=2^%-2d K=2^%-2d launches=%4d ms=%7.3f (%4.1f%%) avg_us=%7.1f GB/s=%7.0f TF=%5.1f"
           % (cls, m, n, k, v[0], v[1], 100 * v[1] / tot, 1e3 * v[1] / v[0], v[2] / v[1] / 1e6, v[3] / v[1] / 1e9))
