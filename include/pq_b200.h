@@ -96,6 +96,18 @@ int pq_reshape(pq_handle* h, const char* label, const int32_t* groups_flat,
 int pq_view(pq_handle* h, const char* view, const char* src, int axis,
             const int32_t* idx, int nidx);
 
+/* decompose_tensor!(backend, tensor, left_positions, right_positions; threshold, max_rank,
+ * left_label, right_label) -- interactive.jl:130-152 -> src/layer1.jl:146-184.
+ * Permutes `tensor` to [left | right] (1-based axis positions), views it as a matrix, takes
+ * its SVD (one-sided Jacobi on the device), keeps the chi singular values with
+ * S / norm(S) > max(threshold, sqrt(eps(real(T)))) -- at most `max_rank` when max_rank > 0 --
+ * and stores B = U * sqrt(S) under `left_label` with extents (left..., chi) and
+ * C = sqrt(S) * V^H under `right_label` with extents (chi, right...); deletes `tensor`.
+ * `*chi_out` receives chi.  Synchronous (it returns a value computed on the device). */
+int pq_decompose(pq_handle* h, const char* tensor, const int32_t* left_positions, int nleft,
+                 const int32_t* right_positions, int nright, double threshold, int max_rank,
+                 const char* left_label, const char* right_label, int* chi_out);
+
 /* delete_tensor!(backend, label) -- interactive.jl:159-161; a missing label is OK. */
 int pq_delete(pq_handle* h, const char* label);
 
@@ -167,7 +179,7 @@ int pq_reset_counters(pq_handle* h);
 /* Per-kernel-class CUDA-event timing on the handle's stream (eager mode only).
  * Classes: see pq_kernel_class_name.  Each record accumulates device time, launch
  * count, algorithmic bytes and real flops. */
-#define PQ_NUM_KERNEL_CLASSES 12
+#define PQ_NUM_KERNEL_CLASSES 13
 int pq_profile_enable(pq_handle* h, int on);
 int pq_profile_read(pq_handle* h, double* ms, int64_t* launches, double* bytes,
                     double* flops); /* arrays of PQ_NUM_KERNEL_CLASSES */

@@ -70,6 +70,17 @@ class OracleBackend(AbstractBackend):
     def permute_tensor(self, tensor, axes):
         self.tensors[tensor] = layer1.permute_tensor(self.tensors[tensor], list(axes))
 
+    def decompose_tensor(self, tensor, left_positions, right_positions, *, threshold=1e-13,
+                         max_rank=0, left_label, right_label):
+        """``src/backends/interactive.jl:130-152``."""
+        B, C, chi = layer1.decompose_tensor(self.tensors[tensor], list(left_positions),
+                                            list(right_positions), threshold, max_rank)
+        self.tensors[left_label] = B
+        self.tensors[right_label] = C
+        if tensor not in (left_label, right_label):
+            self.delete_tensor(tensor)
+        return chi
+
     def delete_tensor(self, tensor_label):
         self.tensors.pop(tensor_label, None)
 
@@ -106,6 +117,10 @@ def execute_dsl(text: str, store, dtype=np.complex64, output_store=None) -> Dict
             tensors[a["t"]] = layer1.permute_tensor(tensors[a["t"]], a["axes"])
         elif cmd == "view":
             tensors[a["v"]] = layer1.tensor_view(tensors[a["t"]], a["axis"], a["idx"])
-        elif cmd == "decompose":
-            raise NotImplementedError("decompose is outside the hot path (SURVEY §8f)")
+        elif cmd == "decompose":   # src/layer1.jl:286-300 (the source tensor is kept)
+            B, C, _ = layer1.decompose_tensor(tensors[a["t"]], a["left_idx"], a["right_idx"],
+                                              float(a["options"].get("threshold", 1e-13)),
+                                              int(a["options"].get("max_rank", 0)))
+            tensors[a["left"]] = B
+            tensors[a["right"]] = C
     return tensors

@@ -135,3 +135,32 @@ def contract_tensors(tensors_to_contract: Tuple[np.ndarray, np.ndarray],
     Ct = np.matmul(Bt, At).astype(dtype, copy=False)              # (N, M) C-contiguous
     C = Ct.T                                                       # (M, N) F-contiguous
     return np.reshape(C, out_shape, order="F")
+
+
+def decompose_tensor(tensor: np.ndarray, left_positions: Sequence[int],
+                     right_positions: Sequence[int], threshold: float = 1e-13,
+                     max_rank: int = 0):
+    """``src/layer1.jl:146-184``.  ``permutedims`` to [left | right] (1-based
+    positions), reshape to (prod left, prod right), LAPACK SVD, relative
+    threshold ``max(threshold, sqrt(eps(real(T))))`` on ``S / norm(S)``,
+    optional ``max_rank``; returns ``(U sqrt(S), sqrt(S) V^H, chi)`` reshaped to
+    (left..., chi) and (chi, right...)."""
+    dims = tensor.shape
+    left_dims = [dims[x - 1] for x in left_positions]
+    right_dims = [dims[x - 1] for x in right_positions]
+    A = permute_tensor(tensor, list(left_positions) + list(right_positions))
+    A = np.reshape(A, (_prod(left_dims), _prod(right_dims)), order="F")
+    U, S, Vh = np.linalg.svd(A, full_matrices=False)
+    real_t = np.finfo(tensor.dtype).eps
+    threshold = max(threshold, float(np.sqrt(real_t)))
+    s_norm = np.sqrt(np.sum(S.astype(np.float64) ** 2))
+    with np.errstate(invalid="ignore", divide="ignore"):
+        chi = int(np.sum(S / s_norm > threshold))
+    if max_rank > 0:
+        chi = min(max_rank, chi)
+    s_sqrt = np.sqrt(S[:chi]).astype(S.dtype)
+    B = np.reshape(np.asarray(U[:, :chi] * s_sqrt[None, :], order="F"),
+                   tuple(left_dims) + (chi,), order="F")
+    C = np.reshape(np.asarray(s_sqrt[:, None] * Vh[:chi, :], order="F"),
+                   (chi,) + tuple(right_dims), order="F")
+    return B.astype(tensor.dtype, copy=False), C.astype(tensor.dtype, copy=False), chi

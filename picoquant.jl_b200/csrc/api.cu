@@ -384,6 +384,61 @@ extern "C" int pq_view(pq_handle* h, const char* view, const char* src, int axis
   PQ_CATCH(h)
 }
 
+extern "C" int pq_decompose(pq_handle* h, const char* tensor, const int32_t* left_positions,
+                            int nleft, const int32_t* right_positions, int nright, double threshold,
+                            int max_rank, const char* left_label, const char* right_label,
+                            int* chi_out) {
+  if (!h) return PQ_ERR_INVALID;
+  PQ_TRY(h)
+  PQ_REQUIRE(tensor && left_label && right_label && nleft >= 0 && nright >= 0 &&
+                 (nleft == 0 || left_positions) && (nright == 0 || right_positions),
+             PQ_ERR_INVALID, "pq_decompose: bad arguments");
+  set_device(h);
+  Tensor& t = h->get(tensor);
+  const int rank = (int)t.dims.size();
+  PQ_REQUIRE(nleft + nright == rank, PQ_ERR_INVALID,
+             "pq_decompose: left and right positions must cover every axis exactly once");
+  std::vector<int> perm;
+  std::vector<int64_t> ldims, rdims;
+  for (int k = 0; k < nleft; ++k) {
+    PQ_REQUIRE(left_positions[k] >= 1 && left_positions[k] <= rank, PQ_ERR_INVALID,
+               "pq_decompose: position out of range");
+    perm.push_back(left_positions[k] - 1);
+    ldims.push_back(t.dims[left_positions[k] - 1]);
+  }
+  for (int k = 0; k < nright; ++k) {
+    PQ_REQUIRE(right_positions[k] >= 1 && right_positions[k] <= rank, PQ_ERR_INVALID,
+               "pq_decompose: position out of range");
+    perm.push_back(right_positions[k] - 1);
+    rdims.push_back(t.dims[right_positions[k] - 1]);
+  }
+  PermutePlan pp = lower_permute(t.dims, perm, h->elem_size, h->opt);  // validates the permutation
+  const int64_t m = prod(ldims), n = prod(rdims);
+  Launch L = h->launch_ctx();
+  // the SVD overwrites its input: always work on a private [left | right] copy
+  auto work = std::make_shared<Buffer>(size_t(m * n) * h->elem_size, h->stream);
+  if (pp.identity) {
+    L.begin(KC_COPY, 2.0 * m * n * h->elem_size, 0);
+    PQ_CUDA(cudaMemcpyAsync(work->ptr, t.buf->ptr, size_t(m * n) * h->elem_size,
+                            cudaMemcpyDeviceToDevice, h->stream));
+    L.end();
+  } else {
+    run_permute(L, pp, t.buf->ptr, work->ptr);
+  }
+  Tensor B, C;
+  const int chi = run_decompose(h, L, work->ptr, m, n, threshold, max_rank, B.buf, C.buf);
+  B.dims = ldims;
+  B.dims.push_back(chi);
+  C.dims.push_back(chi);
+  C.dims.insert(C.dims.end(), rdims.begin(), rdims.end());
+  const std::string ll = left_label, rl = right_label, src = tensor;
+  h->tensors[ll] = std::move(B);
+  h->tensors[rl] = std::move(C);
+  if (src != ll && src != rl) h->tensors.erase(src);
+  if (chi_out) *chi_out = chi;
+  PQ_CATCH(h)
+}
+
 extern "C" int pq_delete(pq_handle* h, const char* label) {
   if (!h || !label) return PQ_ERR_INVALID;
   h->tensors.erase(label);  // a missing label is not an error (interactive.jl:159-161)
@@ -491,7 +546,7 @@ extern "C" const char* pq_kernel_class_name(int cls) {
   static const char* names[PQ_NUM_KERNEL_CLASSES] = {
       "permute_tiled", "permute_generic", "contract_small", "contract_direct", "contract_dot",
       "gemm_simt",     "gemm_tensor",     "view",           "accumulate",      "copy",
-      "allreduce",     "other"};
+      "allreduce",     "svd",             "other"};
   return (cls >= 0 && cls < PQ_NUM_KERNEL_CLASSES) ? names[cls] : "?";
 }
 

@@ -101,7 +101,8 @@ enum KClass {
   KC_ACCUMULATE = 8,
   KC_COPY = 9,
   KC_ALLREDUCE = 10,
-  KC_OTHER = 11
+  KC_SVD = 11,
+  KC_OTHER = 12
 };
 static_assert(KC_OTHER + 1 == PQ_NUM_KERNEL_CLASSES, "class count");
 

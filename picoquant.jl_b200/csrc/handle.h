@@ -62,4 +62,7 @@ struct pq_handle {
 
 namespace pq {
 void comm_destroy(Comm* c);
+// kernels_svd.cu: SVD-based split of the m x n matrix in `work` (overwritten); returns chi
+int run_decompose(pq_handle* h, const Launch& L, void* work, int64_t m, int64_t n, double threshold,
+                  int max_rank, std::shared_ptr<Buffer>& Bout, std::shared_ptr<Buffer>& Cout);
 }

@@ -27,7 +27,7 @@ LIB_PATH = os.path.join(os.path.dirname(_HERE), "csrc", "libpq_b200.so")
 PQ_C64, PQ_C128 = 0, 1
 PQ_HOST_F32, PQ_HOST_F64, PQ_HOST_C64, PQ_HOST_C128 = 0, 1, 2, 3
 PQ_MAX_RANK = 64
-PQ_NUM_KERNEL_CLASSES = 12
+PQ_NUM_KERNEL_CLASSES = 13
 
 _STATUS = {-1: "PQ_ERR_INVALID", -2: "PQ_ERR_NOT_FOUND", -3: "PQ_ERR_SHAPE", -4: "PQ_ERR_CUDA",
            -5: "PQ_ERR_NCCL", -6: "PQ_ERR_PARSE", -7: "PQ_ERR_UNSUPPORTED"}
@@ -42,7 +42,7 @@ ABI_SYMBOLS = [
     "pq_reset_counters", "pq_profile_enable", "pq_profile_read", "pq_kernel_class_name",
     "pq_set_option", "pq_microbench", "pq_timer_begin", "pq_timer_end",
     "pq_program_set_hoist", "pq_program_prepare", "pq_program_hoist_stats",
-    "pq_program_run_slices",
+    "pq_program_run_slices", "pq_decompose",
 ]
 
 _lib = None
@@ -78,6 +78,8 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
     lib.pq_permute.argtypes = [c_void_p, c_char_p, i32p, c_int]
     lib.pq_reshape.argtypes = [c_void_p, c_char_p, i32p, i32p, c_int]
     lib.pq_view.argtypes = [c_void_p, c_char_p, c_char_p, c_int, i32p, c_int]
+    lib.pq_decompose.argtypes = [c_void_p, c_char_p, i32p, c_int, i32p, c_int, c_double, c_int,
+                                 c_char_p, c_char_p, POINTER(c_int)]
     lib.pq_delete.argtypes = [c_void_p, c_char_p]
     lib.pq_save_output.argtypes = [c_void_p, c_char_p, c_char_p]
     lib.pq_sync.argtypes = [c_void_p]
@@ -296,8 +298,14 @@ class B200Backend(AbstractBackend):
 
     def decompose_tensor(self, tensor, left_positions, right_positions, *, threshold=1e-13,
                          max_rank=0, left_label, right_label):
-        raise NotImplementedError("decompose_tensor! (SVD) is outside the contraction hot path "
-                                  "(SURVEY §8f)")
+        """``decompose_tensor!`` (interactive.jl:130-152): SVD split on the device
+        (``pq_decompose``, one-sided Jacobi); returns the new bond dimension chi."""
+        chi = c_int()
+        self._check(self.lib.pq_decompose(self._h, tensor.encode(), _i32(left_positions),
+                                          len(left_positions), _i32(right_positions),
+                                          len(right_positions), float(threshold), int(max_rank),
+                                          left_label.encode(), right_label.encode(), byref(chi)))
+        return chi.value
 
     def delete_tensor(self, tensor_label):
         self.lib.pq_delete(self._h, tensor_label.encode())

@@ -2,8 +2,10 @@
 calls).  Restates ``src/layer2.jl``: ``sort_indices`` (:209-216),
 ``create_ncon_indices`` (:226-240), ``contract_pair!`` (:329-405),
 ``contract_network!`` for edge plans (:250-284) and node-pair plans
-(:294-321), ``full_wavefunction_contraction!`` (:132-195) and
-``random_contraction_plan`` (:119-122).
+(:294-321), ``full_wavefunction_contraction!`` (:132-195),
+``random_contraction_plan`` (:119-122), and the SVD-based bond operations
+``decompose_tensor!`` (:487-559), ``compress_bond!`` (:450-472) and
+``compress_tensor_chain!`` (:423-440).
 
 All of this is integer / label work and must be bit-exact with the reference:
 the emitted backend call stream (labels, ncon index lists, permutation and
@@ -16,7 +18,7 @@ import random
 from typing import Dict, List, Optional, Sequence, Union
 
 from .backends import record_compute_costs
-from .layer3 import Node, TensorNetworkCircuit, new_label, _label_number
+from .layer3 import Edge, Node, TensorNetworkCircuit, new_label, _label_number
 
 
 def sort_indices(A: Node, B: Node):
@@ -200,3 +202,99 @@ def full_wavefunction_contraction(network: TensorNetworkCircuit,
 
     network.save_output(wf)
     return wf
+
+
+# ---------------------------------------------------------------------------
+# compression of a tensor network (src/layer2.jl:407-559)
+# ---------------------------------------------------------------------------
+def decompose_tensor(network: TensorNetworkCircuit, node_label: str,
+                     left_indices: Sequence[str], right_indices: Sequence[str], *,
+                     threshold: float = 1e-13, max_rank: int = 0,
+                     left_label: Optional[str] = None, right_label: Optional[str] = None):
+    """Network-level ``decompose_tensor!`` (``src/layer2.jl:487-559``): splits
+    node ``node_label`` into two nodes joined by a new virtual edge; the index
+    lists name the edges that go to either side.  The backend performs the SVD
+    and returns the bond dimension chi (0 from a DSL backend: unknown until run
+    time, in which case the upper bound min(left, right[, max_rank]) is used
+    for the graph-side dims).  Returns ``(B_label, C_label)``."""
+    node = network.nodes[node_label]
+    index_map = {v: k for k, v in enumerate(node.indices, start=1)}
+    left_positions = [index_map[x] for x in left_indices]
+    right_positions = [index_map[x] for x in right_indices]
+
+    B_label = new_label(network, "node") if left_label is None else left_label
+    C_label = new_label(network, "node") if right_label is None else right_label
+
+    chi = network.decompose_tensor(node_label, left_positions, right_positions,
+                                   threshold=threshold, max_rank=max_rank,
+                                   left_label=B_label, right_label=C_label)
+
+    B_dims = [node.dims[i - 1] for i in left_positions]
+    C_dims = [node.dims[i - 1] for i in right_positions]
+    if chi > 0:
+        virtual_dim = chi
+    else:
+        left_dim, right_dim = 1, 1
+        for d in B_dims:
+            left_dim *= d
+        for d in C_dims:
+            right_dim *= d
+        virtual_dim = min(left_dim, right_dim)
+        if max_rank > 0:
+            virtual_dim = min(virtual_dim, max_rank)
+    B_dims.append(virtual_dim)
+    C_dims.insert(0, virtual_dim)
+
+    index_label = new_label(network, "index")
+    B_node = Node(list(left_indices) + [index_label], B_dims, B_label)
+    C_node = Node([index_label] + list(right_indices), C_dims, C_label)
+    # the reference deletes the original node last (layer2.jl:555-556); when a label is
+    # re-used (compress_bond!) the new node must survive that, so drop the old entry first
+    network.nodes.pop(node_label, None)
+    network.nodes[B_label] = B_node
+    network.nodes[C_label] = C_node
+
+    for index in left_indices:
+        e = network.edges[index]
+        if e.src == node_label:
+            e.src = B_label
+        elif e.dst == node_label:
+            e.dst = B_label
+    for index in right_indices:
+        e = network.edges[index]
+        if e.src == node_label:
+            e.src = C_label
+        elif e.dst == node_label:
+            e.dst = C_label
+    network.edges[index_label] = Edge(B_label, C_label, None, True)
+
+    if node_label not in (B_label, C_label):
+        network.delete_tensor(node_label)
+    return B_label, C_label
+
+
+def compress_bond(network: TensorNetworkCircuit, node_1: str, node_2: str, *,
+                  threshold: float = 1e-13, max_rank: int = 0):
+    """``compress_bond!`` (``src/layer2.jl:450-472``): contract the two nodes,
+    then split the result again along the same bipartition, discarding singular
+    values below the threshold / beyond ``max_rank``."""
+    left_node = network.nodes[node_1]
+    right_node = network.nodes[node_2]
+    right_set, left_set = set(right_node.indices), set(left_node.indices)
+    left_indices = [x for x in left_node.indices if x not in right_set]
+    right_indices = [x for x in right_node.indices if x not in left_set]
+    combined = contract_pair(network, node_1, node_2)
+    return decompose_tensor(network, combined, left_indices, right_indices,
+                            left_label=node_1, right_label=node_2,
+                            threshold=threshold, max_rank=max_rank)
+
+
+def compress_tensor_chain(network: TensorNetworkCircuit, nodes: Sequence[str], *,
+                          threshold: float = 1e-13, max_rank: int = 0) -> None:
+    """``compress_tensor_chain!`` (``src/layer2.jl:423-440``): forward then
+    backward sweep of ``compress_bond!`` over consecutive nodes."""
+    nodes = list(nodes)
+    for i in range(len(nodes) - 1):
+        compress_bond(network, nodes[i], nodes[i + 1], threshold=threshold, max_rank=max_rank)
+    for i in range(len(nodes) - 2, -1, -1):
+        compress_bond(network, nodes[i], nodes[i + 1], threshold=threshold, max_rank=max_rank)
