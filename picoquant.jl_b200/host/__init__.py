@@ -10,7 +10,8 @@ from .layer3 import (Edge, Node, TensorNetworkCircuit, add_gate, add_input, add_
                      getnode, inedges, inneighbours, neighbours, network_from_dict,
                      network_from_json, new_label, outedges, outneighbours, to_dict,
                      to_json, virtualedges, virtualneighbours)
-from .layer2 import (compress_bond, compress_tensor_chain, contract_network, contract_pair,
+from .layer2 import (calculate_mps_amplitudes, compress_bond, compress_tensor_chain,
+                     contract_mps_tensor_network_circuit, contract_network, contract_pair,
                      create_ncon_indices, decompose_tensor, full_wavefunction_contraction,
                      random_contraction_plan, sort_indices)
 from .slicing import (multi_index_partition, partition_network_on_virtual_bonds,

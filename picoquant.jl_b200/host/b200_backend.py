@@ -341,6 +341,51 @@ class B200Backend(AbstractBackend):
     def compile_program(self, tl_text: str) -> Program:
         return Program(self, tl_text)
 
+    def execute_dsl(self, tl_text: str, store, output_store=None) -> None:
+        """``execute_dsl_file(dsl_file, tensor_data_file, output_data_file)``
+        (``src/layer1.jl:211-315``) on the device: ``tensor`` commands read from
+        ``store`` (the HDF5 stand-in), ``save`` commands write to ``output_store``
+        (default: ``store``).  A stream without ``decompose`` is compiled into one
+        program (static arena + CUDA graph).  ``decompose`` makes the shapes depend on
+        run-time singular values, so such a stream is interpreted command by command
+        through the same backend calls instead."""
+        from .backends import parse_dsl
+        ops = parse_dsl(tl_text)
+        out = output_store if output_store is not None else store
+        if not any(cmd == "decompose" for cmd, _ in ops):
+            for cmd, a in ops:
+                if cmd == "tensor":
+                    self.save_tensor_data(a["key"], store.read(a["key"]))
+            prog = self.compile_program(tl_text)
+            try:
+                prog.run()
+                for cmd, a in ops:
+                    if cmd == "save":
+                        out.write(a["key"], self.load_tensor_data(a["key"]))
+            finally:
+                prog.close()
+            return
+        for cmd, a in ops:
+            if cmd == "tensor":
+                self.save_tensor_data(a["t"], store.read(a["key"]))
+            elif cmd == "ncon":       # consumes A and B; the stream's own `del` lines are no-ops
+                self.contract_tensors(a["A"], a["a_idx"], a["B"], a["b_idx"], a["C"])
+            elif cmd == "del":
+                self.delete_tensor(a["t"])
+            elif cmd == "reshape":
+                self.reshape_tensor(a["t"], a["groups"])
+            elif cmd == "permute":
+                self.permute_tensor(a["t"], a["axes"])
+            elif cmd == "view":
+                self.view_tensor(a["v"], a["t"], a["axis"], a["idx"])
+            elif cmd == "decompose":
+                self.decompose_tensor(a["t"], a["left_idx"], a["right_idx"],
+                                      threshold=float(a["options"].get("threshold", 1e-13)),
+                                      max_rank=int(a["options"].get("max_rank", 0)),
+                                      left_label=a["left"], right_label=a["right"])
+            elif cmd == "save":
+                out.write(a["key"], self.load_tensor_data(a["t"]))
+
     def counters(self):
         a, b, c, d = c_int64(), c_int64(), c_int64(), c_int64()
         self._check(self.lib.pq_get_counters(self._h, byref(a), byref(b), byref(c), byref(d)))

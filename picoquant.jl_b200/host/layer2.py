@@ -5,7 +5,9 @@ calls).  Restates ``src/layer2.jl``: ``sort_indices`` (:209-216),
 (:294-321), ``full_wavefunction_contraction!`` (:132-195),
 ``random_contraction_plan`` (:119-122), and the SVD-based bond operations
 ``decompose_tensor!`` (:487-559), ``compress_bond!`` (:450-472) and
-``compress_tensor_chain!`` (:423-440).
+``compress_tensor_chain!`` (:423-440), and the MPS drivers
+``contract_mps_tensor_network_circuit!`` (:571-624) and
+``calculate_mps_amplitudes!`` (:633-643).
 
 All of this is integer / label work and must be bit-exact with the reference:
 the emitted backend call stream (labels, ncon index lists, permutation and
@@ -18,7 +20,7 @@ import random
 from typing import Dict, List, Optional, Sequence, Union
 
 from .backends import record_compute_costs
-from .layer3 import Edge, Node, TensorNetworkCircuit, new_label, _label_number
+from .layer3 import Edge, Node, TensorNetworkCircuit, inneighbours, new_label, _label_number
 
 
 def sort_indices(A: Node, B: Node):
@@ -298,3 +300,54 @@ def compress_tensor_chain(network: TensorNetworkCircuit, nodes: Sequence[str], *
         compress_bond(network, nodes[i], nodes[i + 1], threshold=threshold, max_rank=max_rank)
     for i in range(len(nodes) - 2, -1, -1):
         compress_bond(network, nodes[i], nodes[i + 1], threshold=threshold, max_rank=max_rank)
+
+
+# ---------------------------------------------------------------------------
+# MPS contraction of a circuit (src/layer2.jl:563-643)
+# ---------------------------------------------------------------------------
+def contract_mps_tensor_network_circuit(network: TensorNetworkCircuit, *, max_bond: int = 2,
+                                        threshold: float = 1e-13, max_rank: int = 0,
+                                        pbc: bool = False) -> List[str]:
+    """``contract_mps_tensor_network_circuit!`` (``src/layer2.jl:571-624``): the input
+    caps are the MPS sites; gate layers are absorbed in circuit order (``contract_pair!``
+    of the site with the gate half acting on it) and, after every layer, the bonds between
+    the touched neighbouring sites are compressed (``compress_bond!``: contract + SVD).
+    Gates must act on neighbouring qubits (``decompose=true`` networks).  Returns the site
+    labels, each also saved as an output under its own name."""
+    mps_nodes = [network.edges[x].src for x in network.input_qubits]
+    assert all(x is not None for x in mps_nodes), "Input qubit values must be set"
+    layer_nodes = _layer_nodes(network)
+    gate_layers = [k for k in sorted(layer_nodes) if k > 0]
+    if -1 in layer_nodes:
+        gate_layers.append(-1)
+    for gate_layer in gate_layers:
+        updated = []
+        for node in layer_nodes[gate_layer]:
+            input_node = inneighbours(network, node)[0]
+            assert input_node in mps_nodes, "%s not in mps nodes" % input_node
+            idx = mps_nodes.index(input_node)
+            mps_nodes[idx] = contract_pair(network, input_node, node)
+            updated.append(idx)
+        updated.sort()
+        for i in range(len(updated) - 1):
+            distance = updated[i + 1] - updated[i]
+            if pbc:
+                distance = min(distance, updated[i] + len(mps_nodes) - updated[i + 1])
+            assert distance == 1, "Gates between non-neighboring qubits"
+            compress_bond(network, mps_nodes[updated[i]], mps_nodes[updated[i + 1]],
+                          threshold=threshold, max_rank=max_rank)
+    for node in mps_nodes:
+        network.save_output(node, node)
+    return mps_nodes
+
+
+def calculate_mps_amplitudes(network: TensorNetworkCircuit, mps_nodes: Sequence[str],
+                             result: str = "result") -> None:
+    """``calculate_mps_amplitudes!`` (``src/layer2.jl:633-643``): contract the chain left to
+    right, permute by ``qubit_ordering``, flatten, save."""
+    output_node = mps_nodes[0]
+    for node in mps_nodes[1:]:
+        output_node = contract_pair(network, output_node, node)
+    network.permute_tensor(output_node, list(network.qubit_ordering))
+    network.reshape_tensor(output_node, [list(range(1, len(mps_nodes) + 1))])
+    network.save_output(output_node, result)

@@ -124,9 +124,23 @@ function view_tensor!(backend::B200Backend, view_node, node, bond_idx, bond_rang
                             backend.handle, String(view_node), String(node), bond_idx, idx, length(idx)))
 end
 
-# decompose_tensor! (SVD) is outside the contraction hot path and not provided yet.
-function decompose_tensor!(backend::B200Backend, args...; kwargs...)
-    error("decompose_tensor! is not implemented by the B200 backend (hot path: contraction only)")
+# src/backends/interactive.jl:130-152 -> src/layer1.jl:146-184 (SVD split on the device)
+function decompose_tensor!(backend::B200Backend,
+                           tensor::Symbol,
+                           left_positions::Array{Int, 1},
+                           right_positions::Array{Int, 1};
+                           threshold::AbstractFloat=1e-13,
+                           max_rank::Int=0,
+                           left_label::Symbol,
+                           right_label::Symbol)
+    lp = Int32.(left_positions); rp = Int32.(right_positions)
+    chi = Ref{Cint}(0)
+    pq_check(backend, ccall((:pq_decompose, libpq_b200), Cint,
+                            (Ptr{Cvoid}, Cstring, Ptr{Int32}, Cint, Ptr{Int32}, Cint, Cdouble, Cint,
+                             Cstring, Cstring, Ref{Cint}),
+                            backend.handle, String(tensor), lp, length(lp), rp, length(rp),
+                            Float64(threshold), max_rank, String(left_label), String(right_label), chi))
+    Int(chi[])
 end
 
 # ---- beyond the nine: the sliced loop of examples/dist_slicing_example.jl -----------------
@@ -165,4 +179,16 @@ function run_program(backend::B200Backend, program::Ptr{Cvoid}, view_starts::Vec
     pq_check(backend, ccall((:pq_program_run, libpq_b200), Cint,
                             (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Int32}, Cint, Cstring),
                             backend.handle, program, isempty(vs) ? C_NULL : vs, length(vs), acc))
+end
+
+"the slice loop in one call: one run per column of `view_starts` (nviews x nslices), partial
+sums added in slice order, up to `lanes` slices in flight on the device"
+function run_program_slices(backend::B200Backend, program::Ptr{Cvoid}, view_starts::Matrix{Int};
+                            accumulate_into::Union{Symbol,Nothing}=nothing, lanes::Integer=2)
+    vs = Int32.(vec(view_starts))
+    acc = accumulate_into === nothing ? C_NULL : String(accumulate_into)
+    pq_check(backend, ccall((:pq_program_run_slices, libpq_b200), Cint,
+                            (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Int32}, Cint, Cint, Cstring, Cint),
+                            backend.handle, program, vs, size(view_starts, 2), size(view_starts, 1),
+                            acc, lanes))
 end

@@ -15,8 +15,11 @@ from helpers import TOL, rel_l2
 from oracle import layer1
 from oracle.interactive import OracleBackend
 from picoquant_jl_b200.host import (DSLBackend, TensorNetworkCircuit, add_gate, add_input,
-                                    compress_tensor_chain, contract_pair,
-                                    convert_circuit_to_network, decompose_tensor,
+                                    calculate_mps_amplitudes, compress_tensor_chain,
+                                    contract_mps_tensor_network_circuit, contract_pair,
+                                    convert_circuit_to_network, create_ghz_preparation_circuit,
+                                    create_qft_circuit, create_simple_preparation_circuit,
+                                    decompose_tensor, full_wavefunction_contraction,
                                     load_qasm_as_circuit, virtualedges)
 
 DTYPES = [np.complex128, np.complex64]
@@ -174,6 +177,43 @@ def _state_of_two_nodes(tn, b):
     return np.transpose(out, order)
 
 
+def _mps_matches_full_wavefunction(backend_factory, tol):
+    """test/layer2_tests.jl:204-237 (preparation + GHZ on 3 qubits: MPS == full wave
+    function) and :307-326 (GHZ-5 through the MPS path = (|0..0> + |1..1>)/sqrt(2));
+    plus a nearest-neighbour circuit with non-trivial bond growth and a max_rank cut."""
+    circ = create_simple_preparation_circuit(3, 1).compose(create_ghz_preparation_circuit(3))
+    b = backend_factory()
+    tn = convert_circuit_to_network(circ, b, decompose=True)
+    add_input(tn, "000")
+    full_wavefunction_contraction(tn, "vector")
+    full_wf = np.array(b.load_tensor_data("result"))
+    b = backend_factory()
+    tn = convert_circuit_to_network(circ, b, decompose=True)
+    add_input(tn, "000")
+    mps_nodes = contract_mps_tensor_network_circuit(tn)
+    calculate_mps_amplitudes(tn, mps_nodes)
+    mps_wf = np.array(b.load_tensor_data("result"))
+    assert mps_wf.shape == full_wf.shape == (8,)
+    assert rel_l2(mps_wf, full_wf) < 10 * tol
+
+    n = 5
+    b = backend_factory()
+    tn = convert_circuit_to_network(create_ghz_preparation_circuit(n), b, decompose=True)
+    add_input(tn, "0" * n)
+    mps_nodes = contract_mps_tensor_network_circuit(tn)
+    for k, node in enumerate(mps_nodes):     # bond dimension 2 everywhere, saved under its label
+        shape = b.load_tensor_data(node).shape
+        assert sorted(shape) == ([2, 2] if k in (0, n - 1) else [2, 2, 2]), (node, shape)
+    calculate_mps_amplitudes(tn, mps_nodes)
+    ref = np.zeros(2 ** n, dtype=np.complex128)
+    ref[[0, -1]] = 1 / np.sqrt(2)
+    assert rel_l2(b.load_tensor_data("result"), ref) < 10 * tol
+
+
+def test_reference_mps_contraction_oracle():
+    _mps_matches_full_wavefunction(lambda: OracleBackend(np.complex128), 1e-10)
+
+
 def test_reference_threshold_and_max_rank_oracle():
     _threshold_and_max_rank(lambda: OracleBackend(np.complex128))
 
@@ -253,6 +293,60 @@ def test_gpu_decompose_rank_deficient_zero_and_errors():
 def test_gpu_reference_decompose_tests(dtype):
     _threshold_and_max_rank(lambda: _b200(dtype))
     _compress_chain(lambda: _b200(dtype))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_gpu_reference_mps_contraction(dtype):
+    _mps_matches_full_wavefunction(lambda: _b200(dtype), TOL[np.dtype(dtype)])
+
+
+def _mps_dsl_stream():
+    """The MPS contraction of prep(3,1)+GHZ-3 recorded as a .tl stream (decompose commands)."""
+    from picoquant_jl_b200.host.backends import TensorStore
+    circ = create_simple_preparation_circuit(3, 1).compose(create_ghz_preparation_circuit(3))
+    dsl = DSLBackend()
+    tn = convert_circuit_to_network(circ, dsl, decompose=True)
+    add_input(tn, "000")
+    mps_nodes = contract_mps_tensor_network_circuit(tn)
+    calculate_mps_amplitudes(tn, mps_nodes)
+    assert any(l.startswith("decompose ") for l in dsl.text().splitlines())
+    ob = OracleBackend(np.complex128)
+    tn = convert_circuit_to_network(circ, ob, decompose=True)
+    add_input(tn, "000")
+    full_wavefunction_contraction(tn, "vector")
+    return dsl, np.array(ob.load_tensor_data("result")), TensorStore
+
+
+def test_dsl_interpreter_with_decompose_oracle():
+    from oracle.interactive import execute_dsl
+    dsl, ref, TensorStore = _mps_dsl_stream()
+    out = TensorStore()
+    execute_dsl(dsl.text(), dsl.store, np.complex128, output_store=out)
+    assert rel_l2(out.read("result"), ref) < 1e-10
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_gpu_execute_dsl_with_decompose(dtype):
+    """execute_dsl_file on the device for a stream with `decompose` commands (interpreted,
+    chi is only known at run time) and for one without (compiled program)."""
+    dsl, ref, TensorStore = _mps_dsl_stream()
+    b = _b200(dtype)
+    out = TensorStore()
+    b.execute_dsl(dsl.text(), dsl.store, out)
+    assert rel_l2(out.read("result"), ref) < 10 * TOL[np.dtype(dtype)]
+    plain = DSLBackend()
+    tn = convert_circuit_to_network(create_qft_circuit(4), plain)
+    add_input(tn, "0101")
+    full_wavefunction_contraction(tn, "vector")
+    ob = OracleBackend(np.complex128)
+    tn = convert_circuit_to_network(create_qft_circuit(4), ob)
+    add_input(tn, "0101")
+    full_wavefunction_contraction(tn, "vector")
+    out = TensorStore()
+    b.execute_dsl(plain.text(), plain.store, out)
+    assert rel_l2(out.read("result"), ob.load_tensor_data("result")) < 10 * TOL[np.dtype(dtype)]
 
 
 @pytest.mark.gpu
