@@ -152,6 +152,10 @@ k_zgemm_dmma(const double2* __restrict__ A, const double2* __restrict__ B, doubl
 struct FusedParams {
   IdxMap mA, kA, nB, kB;
   long long M, N, K;
+  // De-phasing of the first wave: CTA b < first_wave starts (b / num_sms) * stagger_ns late, so
+  // the CTAs that share an SM are in different phases of their tile (fill / DMMA / store) and
+  // stay so for the whole grid, because every later CTA starts when an earlier one retires.
+  int stagger_ns, first_wave, num_sms;
 };
 
 // One output tile per CTA (a persistent variant with a cross-tile cp.async ring was
@@ -172,7 +176,13 @@ struct FusedParams {
 // the order in which consecutive threads touch consecutive addresses (k first when the
 // fastest axis of that tensor is a contracted one); otherwise every 16-byte cp.async of a
 // warp would land in a different 128-byte line.
-template <int TBM, int TBN, int WGM, int WGN, int NST, int MINB, bool AKF, bool BKF>
+// M3 ("3M", Karatsuba): a complex product from THREE real DMMAs instead of four,
+//     P1 = Ar Br,  P2 = Ai Bi,  P3 = (Ar + Ai)(Br + Bi);   Cr = P1 - P2,  Ci = P3 - P1 - P2.
+// The tensor pipe is the binding resource of the K = 32..64 sweep steps (ncu: pipe 89 % active,
+// math_pipe_throttle the dominant stall), so 25 % fewer DMMAs is worth a third accumulator set
+// and two DADDs per fragment.  Norm-wise the rounding error stays at a few eps |A||B|.
+template <int TBM, int TBN, int WGM, int WGN, int NST, int MINB, bool AKF, bool BKF, bool M3 = false,
+          bool NOMATH = false>
 __global__ void __launch_bounds__(256, MINB)
 k_zgemm_fused_t(const double2* __restrict__ A, const double2* __restrict__ B,
                 double2* __restrict__ C, const FusedParams p) {
@@ -201,6 +211,15 @@ k_zgemm_fused_t(const double2* __restrict__ A, const double2* __restrict__ B,
   const long long m0 = tm * TBM, n0 = tn * TBN;
   const int KT = (K + BK - 1) / BK;
 
+  if (p.stagger_ns > 0 && (int)blockIdx.x < p.first_wave && tid == 0) {
+    const unsigned long long wait_ns = (unsigned long long)(blockIdx.x / p.num_sms) * p.stagger_ns;
+    unsigned long long t0, t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    do {
+      __nanosleep(256);
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    } while (t1 - t0 < wait_ns);
+  }
   for (int k = tid; k < K; k += 256) {
     koffA[k] = (int)map_offset(p.kA, k);
     koffB[k] = (int)map_offset(p.kB, k);
@@ -264,13 +283,15 @@ k_zgemm_fused_t(const double2* __restrict__ A, const double2* __restrict__ B,
     }
   };
 
-  double cr[XT][YT][2], ci[XT][YT][2];
+  // M3: cr = P1, ci = P2, p3 = P3
+  double cr[XT][YT][2], ci[XT][YT][2], p3[M3 ? XT : 1][M3 ? YT : 1][2];
 #pragma unroll
   for (int x = 0; x < XT; ++x)
 #pragma unroll
     for (int y = 0; y < YT; ++y) {
       cr[x][y][0] = cr[x][y][1] = 0.0;
       ci[x][y][0] = ci[x][y][1] = 0.0;
+      if (M3) p3[x][y][0] = p3[x][y][1] = 0.0;
     }
 
 #pragma unroll
@@ -295,20 +316,38 @@ k_zgemm_fused_t(const double2* __restrict__ A, const double2* __restrict__ B,
       for (int x = 0; x < XT; ++x) a[x] = tA[(ks + fk) * PA + x * 8];
 #pragma unroll
       for (int y = 0; y < YT; ++y) b[y] = tB[(ks + fk) * PB + y * 8];
+      if (NOMATH) {   // data-movement probe: fragments are read, one DMMA per k-step
+        dmma(cr[0][0][0], cr[0][0][1], a[XT - 1].x + a[0].y, b[YT - 1].x + b[0].y);
+      } else if (M3) {
+        double as[XT], bs[YT];
 #pragma unroll
-      for (int x = 0; x < XT; ++x)
+        for (int x = 0; x < XT; ++x) as[x] = a[x].x + a[x].y;
 #pragma unroll
-        for (int y = 0; y < YT; ++y) {
-          dmma(cr[x][y][0], cr[x][y][1], a[x].x, b[y].x);
-          dmma(ci[x][y][0], ci[x][y][1], a[x].x, b[y].y);
-        }
+        for (int y = 0; y < YT; ++y) bs[y] = b[y].x + b[y].y;
 #pragma unroll
-      for (int x = 0; x < XT; ++x) {
-        const double nai = -a[x].y;
+        for (int x = 0; x < XT; ++x)
 #pragma unroll
-        for (int y = 0; y < YT; ++y) {
-          dmma(cr[x][y][0], cr[x][y][1], nai, b[y].y);
-          dmma(ci[x][y][0], ci[x][y][1], a[x].y, b[y].x);
+          for (int y = 0; y < YT; ++y) {
+            dmma(cr[x][y][0], cr[x][y][1], a[x].x, b[y].x);
+            dmma(ci[x][y][0], ci[x][y][1], a[x].y, b[y].y);
+            dmma(p3[x][y][0], p3[x][y][1], as[x], bs[y]);
+          }
+      } else {
+#pragma unroll
+        for (int x = 0; x < XT; ++x)
+#pragma unroll
+          for (int y = 0; y < YT; ++y) {
+            dmma(cr[x][y][0], cr[x][y][1], a[x].x, b[y].x);
+            dmma(ci[x][y][0], ci[x][y][1], a[x].x, b[y].y);
+          }
+#pragma unroll
+        for (int x = 0; x < XT; ++x) {
+          const double nai = -a[x].y;
+#pragma unroll
+          for (int y = 0; y < YT; ++y) {
+            dmma(cr[x][y][0], cr[x][y][1], nai, b[y].y);
+            dmma(ci[x][y][0], ci[x][y][1], a[x].y, b[y].x);
+          }
         }
       }
     }
@@ -326,9 +365,220 @@ k_zgemm_fused_t(const double2* __restrict__ A, const double2* __restrict__ B,
 #pragma unroll
       for (int x = 0; x < XT; ++x) {
         const long long m = m0 + wm * (XT * 8) + x * 8 + frow;
-        if (m < M) C[m + M * n] = make_double2(cr[x][y][c], ci[x][y][c]);
+        if (m >= M) continue;
+        if (M3)
+          C[m + M * n] = make_double2(cr[x][y][c] - ci[x][y][c],
+                                      p3[x][y][c] - cr[x][y][c] - ci[x][y][c]);
+        else
+          C[m + M * n] = make_double2(cr[x][y][c], ci[x][y][c]);
       }
     }
+}
+
+// ---------------------------------------------------------------------------
+// Persistent fused TTGT ZGEMM for the skinny sweep steps (K <= 64, 16 < N <= 64, M huge).
+//
+// Measured on the tile-per-CTA kernel above (M = 2^18, N = K = 64): with the DMMAs removed
+// the data movement alone takes 183 us of the 294 us, and a 3M variant with 25 % fewer
+// DMMAs runs in the same time -- each short-lived CTA pays a serial fill (tables, first
+// k-block, L2 latency) for 1 MFLOP of work, every A tile is fetched twice (two n-tiles) and
+// B 8192 times.  Here one CTA per SM lives for the whole GEMM:
+//   * all of B (K x N <= 64 KB) is gathered into shared memory ONCE per CTA;
+//   * a tile is 32 rows of A x ALL of K and N, so A is read exactly once and C written
+//     exactly once;
+//   * the 16 warps form TWO independent groups of 8 (2 x 4 warps, warp tile 16 x TBN/4).  Each
+//     group walks its own tiles with its own two A stages and its own named barrier: the
+//     gather of its next tile (cp.async) overlaps the DMMAs of the current one, and while one
+//     group is between tiles (stores, barrier, issuing the next gather) the other group keeps
+//     the FP64 pipe fed -- group 1 starts half a tile late so the two stay out of phase.
+// ---------------------------------------------------------------------------
+constexpr int SK_MAXK = 64, SK_THREADS = 512, SK_MAX_STAGES = 6;
+constexpr size_t SK_SMEM_BUDGET = 224 * 1024;
+
+// NG groups of 16 / NG warps; a group's tile is TBM = 64 / NG rows
+template <int TBN, int NG>
+constexpr size_t skinny_smem(int K, int stages) {
+  const int K4 = (K + 3) / 4 * 4;
+  return size_t(K4) * ((TBN + 2) + size_t(NG) * stages * (64 / NG + 2)) * sizeof(double2) +
+         size_t(K4) * 8;
+}
+template <int TBN, bool AKF, bool M3, int NG, int S>
+__global__ void __launch_bounds__(SK_THREADS, 1)
+k_zgemm_skinny(const double2* __restrict__ A, const double2* __restrict__ B,
+               double2* __restrict__ C, const FusedParams p) {
+  constexpr int GT = SK_THREADS / NG;          // threads per group
+  constexpr int WM = 4 / NG;                   // warps along m per group (x 4 along n)
+  constexpr int TBM = 16 * WM, PA = TBM + 2, PB = TBN + 2;
+  constexpr int XT = 2, YT = TBN / 4 / 8;      // warp tile 16 x (TBN / 4)
+  static_assert(NG == 2 || NG == 4, "two or four groups");
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int K = (int)p.K, K4 = (K + 3) / 4 * 4;
+  double2* sB = reinterpret_cast<double2*>(smem_raw);   // [K4][PB]
+  double2* sAall = sB + K4 * PB;                        // [group][S][K4][PA]
+  int* koffA = reinterpret_cast<int*>(sAall + NG * S * K4 * PA);
+  int* koffB = koffA + K4;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int group = warp / (16 / NG), wg = warp % (16 / NG), gtid = tid % GT;
+  const int wm = wg % WM, wn = wg / WM;
+  double2* sA = sAall + group * S * K4 * PA;
+  const long long M = p.M, N = p.N;
+  const long long tiles = (M + TBM - 1) / TBM;
+
+  for (int k = tid; k < K4; k += SK_THREADS) {
+    koffA[k] = k < K ? (int)map_offset(p.kA, k) : 0;
+    koffB[k] = k < K ? (int)map_offset(p.kB, k) : 0;
+  }
+  __syncthreads();
+
+  // B: K x TBN gathered once (columns n >= N and rows k >= K are zero-filled)
+  {
+    const int n = tid % TBN, kb0 = tid / TBN;
+    const long long rb = n < N ? map_offset(p.nB, n) : -1;
+    for (int k = kb0; k < K4; k += SK_THREADS / TBN) {
+      const bool v = (k < K) && (rb >= 0);
+      cp_async16(sB + k * PB + n, v ? (B + rb + koffB[k]) : B, v);
+    }
+  }
+  cp_async_commit();
+  cp_async_wait<0>();
+  __syncthreads();
+
+  auto issue_A = [&](int stage, long long tile) {
+    const long long m0 = tile * TBM;
+    double2* dst = sA + stage * K4 * PA;
+    if (!AKF) {   // consecutive threads walk the rows of the tile
+      const int ma = gtid % TBM, ka0 = gtid / TBM;
+      const long long ra = (m0 + ma < M) ? map_offset(p.mA, m0 + ma) : -1;
+#pragma unroll 4
+      for (int k = ka0; k < K4; k += GT / TBM) {
+        const bool v = (k < K) && (ra >= 0);
+        cp_async16(dst + k * PA + ma, v ? (A + ra + koffA[k]) : A, v);
+      }
+    } else {      // consecutive threads walk k (the fastest axis of A is a contracted one)
+      constexpr int RS = GT / 16, RQ = TBM / RS;   // rows per pass / passes
+      const int kf_k = gtid % 16, kf_r = gtid / 16;
+      long long r[RQ];
+#pragma unroll
+      for (int q = 0; q < RQ; ++q)
+        r[q] = (m0 + kf_r + q * RS < M) ? map_offset(p.mA, m0 + kf_r + q * RS) : -1;
+      for (int kb = 0; kb < K4; kb += 16) {
+        const int k = kb + kf_k;
+        if (k >= K4) break;
+        const int ko = koffA[k];
+#pragma unroll
+        for (int q = 0; q < RQ; ++q) {
+          const bool v = (k < K) && (r[q] >= 0);
+          cp_async16(dst + k * PA + kf_r + q * RS, v ? (A + r[q] + ko) : A, v);
+        }
+      }
+    }
+  };
+  auto group_barrier = [&]() {
+    asm volatile("bar.sync %0, %1;\n" ::"r"(1 + group), "r"(GT) : "memory");
+  };
+
+  const int frow = lane >> 2, fk = lane & 3;
+  const long long stride = (long long)gridDim.x * NG;
+  long long tile = (long long)blockIdx.x * NG + group;
+  // prologue: S - 1 tiles in flight (one commit group per tile, empty groups included)
+  for (int s = 0; s < S - 1; ++s) {
+    if (tile + s * stride < tiles) issue_A(s, tile + s * stride);
+    cp_async_commit();
+  }
+  if (group > 0 && tiles > 4 * stride) {
+    // the groups start 1/NG of a tile apart so that their between-tile phases do not coincide
+    // (a 64-row slab is ~8 us of FP64 pipe time at K = 64)
+    unsigned long long t0, t1;
+    const unsigned long long wait_ns = 8000ull * (unsigned)K4 / 64 * group / (NG * NG);
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    do {
+      __nanosleep(200);
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    } while (t1 - t0 < wait_ns);
+  }
+  int stage = 0, pstage = S - 1;
+  for (; tile < tiles; tile += stride) {
+    cp_async_wait<S - 2>();
+    group_barrier();   // this tile has landed; every warp of the group left the previous stage
+    const long long next = tile + (S - 1) * stride;
+    if (next < tiles) issue_A(pstage, next);
+    cp_async_commit();
+
+    // M3 (see k_zgemm_fused_t): cr = P1 = Ar Br, ci = P2 = Ai Bi, p3 = (Ar + Ai)(Br + Bi)
+    double cr[XT][YT][2], ci[XT][YT][2], p3[M3 ? XT : 1][M3 ? YT : 1][2];
+#pragma unroll
+    for (int x = 0; x < XT; ++x)
+#pragma unroll
+      for (int y = 0; y < YT; ++y) {
+        cr[x][y][0] = cr[x][y][1] = 0.0;
+        ci[x][y][0] = ci[x][y][1] = 0.0;
+        if (M3) p3[x][y][0] = p3[x][y][1] = 0.0;
+      }
+    const double2* tA = sA + stage * K4 * PA + wm * (XT * 8) + frow;
+    const double2* tB = sB + wn * (YT * 8) + frow;
+#pragma unroll 4
+    for (int ks = 0; ks < K4; ks += 4) {
+      double2 a[XT], b[YT];
+#pragma unroll
+      for (int x = 0; x < XT; ++x) a[x] = tA[(ks + fk) * PA + x * 8];
+#pragma unroll
+      for (int y = 0; y < YT; ++y) b[y] = tB[(ks + fk) * PB + y * 8];
+      if (M3) {
+        double as[XT], bs[YT];
+#pragma unroll
+        for (int x = 0; x < XT; ++x) as[x] = a[x].x + a[x].y;
+#pragma unroll
+        for (int y = 0; y < YT; ++y) bs[y] = b[y].x + b[y].y;
+#pragma unroll
+        for (int x = 0; x < XT; ++x)
+#pragma unroll
+          for (int y = 0; y < YT; ++y) {
+            dmma(cr[x][y][0], cr[x][y][1], a[x].x, b[y].x);
+            dmma(ci[x][y][0], ci[x][y][1], a[x].y, b[y].y);
+            dmma(p3[x][y][0], p3[x][y][1], as[x], bs[y]);
+          }
+      } else {
+#pragma unroll
+        for (int x = 0; x < XT; ++x)
+#pragma unroll
+          for (int y = 0; y < YT; ++y) {
+            dmma(cr[x][y][0], cr[x][y][1], a[x].x, b[y].x);
+            dmma(ci[x][y][0], ci[x][y][1], a[x].x, b[y].y);
+          }
+#pragma unroll
+        for (int x = 0; x < XT; ++x) {
+          const double nai = -a[x].y;
+#pragma unroll
+          for (int y = 0; y < YT; ++y) {
+            dmma(cr[x][y][0], cr[x][y][1], nai, b[y].y);
+            dmma(ci[x][y][0], ci[x][y][1], a[x].y, b[y].x);
+          }
+        }
+      }
+    }
+    const long long m0 = tile * TBM;
+#pragma unroll
+    for (int y = 0; y < YT; ++y)
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const long long n = wn * (YT * 8) + y * 8 + 2 * fk + c;
+        if (n >= N) continue;
+#pragma unroll
+        for (int x = 0; x < XT; ++x) {
+          const long long m = m0 + wm * (XT * 8) + x * 8 + frow;
+          if (m >= M) continue;
+          if (M3)
+            C[m + M * n] = make_double2(cr[x][y][c] - ci[x][y][c],
+                                        p3[x][y][c] - cr[x][y][c] - ci[x][y][c]);
+          else
+            C[m + M * n] = make_double2(cr[x][y][c], ci[x][y][c]);
+        }
+      }
+    stage = (stage + 1 == S) ? 0 : stage + 1;
+    pstage = (pstage + 1 == S) ? 0 : pstage + 1;
+  }
+  cp_async_wait<0>();
 }
 
 template <int TBM, int TBN, int NST>
@@ -385,12 +635,37 @@ static void init_fused() {
   PQ_CUDA(cudaFuncSetAttribute(k_zgemm_fused_t<128, 8, 8, 1, 2, 3, AKF, BKF>,
                                cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)fused_smem<128, 8, 2>(FUSED_MAX_K)));
+  PQ_CUDA(cudaFuncSetAttribute(k_zgemm_fused_t<64, 32, 4, 2, 2, 3, AKF, BKF, true>,
+                               cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)fused_smem<64, 32, 2>(FUSED_MAX_K)));
+  PQ_CUDA(cudaFuncSetAttribute(k_zgemm_fused_t<64, 32, 4, 2, 2, 4, AKF, BKF, true>,
+                               cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)fused_smem<64, 32, 2>(FUSED_MAX_K)));
+  PQ_CUDA(cudaFuncSetAttribute(k_zgemm_fused_t<64, 32, 4, 2, 2, 4, AKF, BKF, false, true>,
+                               cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)fused_smem<64, 32, 2>(FUSED_MAX_K)));
 }
 
 template <bool AKF, bool BKF>
 static void launch_fused(int cfg, const Launch& L, const FusedParams& fp, const void* A,
                          const void* B, void* C) {
-  if (cfg == 3) {
+  if (cfg == 6) {   // data-movement probe (wrong results by design)
+    long long tiles = ((fp.M + 63) / 64) * ((fp.N + 31) / 32);
+    k_zgemm_fused_t<64, 32, 4, 2, 2, 4, AKF, BKF, false, true>
+        <<<(unsigned)tiles, 256, fused_smem<64, 32, 2>((int)fp.K), L.stream>>>(
+            (const double2*)A, (const double2*)B, (double2*)C, fp);
+  } else if (cfg == 4 || cfg == 5) {
+    long long tiles = ((fp.M + 63) / 64) * ((fp.N + 31) / 32);
+    PQ_REQUIRE(tiles <= 0x7fffffffLL, PQ_ERR_UNSUPPORTED, "too many tiles");
+    if (cfg == 4)
+      k_zgemm_fused_t<64, 32, 4, 2, 2, 3, AKF, BKF, true>
+          <<<(unsigned)tiles, 256, fused_smem<64, 32, 2>((int)fp.K), L.stream>>>(
+              (const double2*)A, (const double2*)B, (double2*)C, fp);
+    else
+      k_zgemm_fused_t<64, 32, 4, 2, 2, 4, AKF, BKF, true>
+          <<<(unsigned)tiles, 256, fused_smem<64, 32, 2>((int)fp.K), L.stream>>>(
+              (const double2*)A, (const double2*)B, (double2*)C, fp);
+  } else if (cfg == 3) {
     long long tiles = ((fp.M + 127) / 128) * ((fp.N + 7) / 8);
     PQ_REQUIRE(tiles <= 0x7fffffffLL, PQ_ERR_UNSUPPORTED, "too many tiles");
     k_zgemm_fused_t<128, 8, 8, 1, 2, 3, AKF, BKF>
@@ -411,9 +686,35 @@ static void launch_fused(int cfg, const Launch& L, const FusedParams& fp, const 
   }
 }
 
+constexpr int SK_NG = 2, SK_S = 2;   // measured: four groups / deeper rings are not faster
+
+template <int TBN, bool AKF>
+static void init_skinny() {
+  PQ_CUDA(cudaFuncSetAttribute(k_zgemm_skinny<TBN, AKF, false, SK_NG, SK_S>,
+                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SK_SMEM_BUDGET));
+  PQ_CUDA(cudaFuncSetAttribute(k_zgemm_skinny<TBN, AKF, true, SK_NG, SK_S>,
+                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SK_SMEM_BUDGET));
+}
+
+template <int TBN, bool AKF>
+static void launch_skinny(bool m3, unsigned grid, const Launch& L, const FusedParams& fp,
+                          const void* A, const void* B, void* C) {
+  const size_t smem = skinny_smem<TBN, SK_NG>((int)fp.K, SK_S);
+  if (m3)
+    k_zgemm_skinny<TBN, AKF, true, SK_NG, SK_S><<<grid, SK_THREADS, smem, L.stream>>>(
+        (const double2*)A, (const double2*)B, (double2*)C, fp);
+  else
+    k_zgemm_skinny<TBN, AKF, false, SK_NG, SK_S><<<grid, SK_THREADS, smem, L.stream>>>(
+        (const double2*)A, (const double2*)B, (double2*)C, fp);
+}
+
 void init_kernels() {
   PQ_CUDA(cudaFuncSetAttribute(k_zgemm_dmma, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)SMEM_BYTES));
+  init_skinny<64, false>();
+  init_skinny<64, true>();
+  init_skinny<32, false>();
+  init_skinny<32, true>();
   init_fused<false, false>();
   init_fused<false, true>();
   init_fused<true, false>();
@@ -450,6 +751,12 @@ void run_zgemm_fused(const Launch& L, const ContractPlan& cp, const void* A, con
   // configuration with four resident CTAs per SM; option "zgemm_cfg" forces 1 (64x64) / 2 (64x32)
   int cfg = L.opt ? L.opt->zgemm_cfg : 0;
   if (cfg == 0) cfg = (cp.N <= 16) ? 3 : (cp.K <= 128) ? 2 : 1;
+  {
+    const int per_sm = (cfg == 1) ? 2 : (cfg == 3 || cfg == 4) ? 3 : 4;
+    fp.num_sms = L.num_sms;
+    fp.first_wave = L.num_sms * per_sm;
+    fp.stagger_ns = L.opt ? L.opt->zgemm_stagger : 0;
+  }
   auto min_stride = [](const IdxMap& m) {
     int64_t best = INT64_MAX;
     for (int d = 0; d < m.nd; ++d) best = m.str[d] < best ? m.str[d] : best;
@@ -458,6 +765,31 @@ void run_zgemm_fused(const Launch& L, const ContractPlan& cp, const void* A, con
   bool akf = min_stride(cp.kA) < min_stride(cp.mA), bkf = min_stride(cp.kB) < min_stride(cp.nB);
   if (L.opt && L.opt->zgemm_kfirst == 1) akf = bkf = false;  // A/B check knob
   if (cfg == 3) akf = bkf = false;  // measured: no gain for the narrow tiles (HBM-bound)
+  // persistent skinny kernel: K and N small enough for B to live in shared memory, and
+  // enough 64-row tiles to keep every SM busy for several tiles
+  const bool skinny_ok = cp.K <= SK_MAXK && cp.N <= 64 && cp.N > 16 && cp.M >= 256LL * L.num_sms;
+  const int skinny = L.opt ? L.opt->zgemm_skinny : 0;   // 0 auto, 1 off
+  if ((cfg == 7 || ((L.opt ? L.opt->zgemm_cfg : 0) == 0 && skinny == 0)) && skinny_ok) {
+    const unsigned grid = (unsigned)L.num_sms;
+    if (L.opt && L.opt->zgemm_kfirst == 1) akf = false;
+    L.begin(KC_GEMM_TENSOR, bytes, flops);
+    const bool m3 = !(L.opt && L.opt->zgemm_3m == 1);   // option zgemm_3m=1: four DMMAs per product
+    if (cp.N > 32) {
+      if (akf)
+        launch_skinny<64, true>(m3, grid, L, fp, A, B, C);
+      else
+        launch_skinny<64, false>(m3, grid, L, fp, A, B, C);
+    } else {
+      if (akf)
+        launch_skinny<32, true>(m3, grid, L, fp, A, B, C);
+      else
+        launch_skinny<32, false>(m3, grid, L, fp, A, B, C);
+    }
+    L.end();
+    PQ_CUDA(cudaGetLastError());
+    return;
+  }
+  if (cfg == 7) cfg = (cp.K <= 128) ? 2 : 1;
   L.begin(KC_GEMM_TENSOR, bytes, flops);
   if (akf && bkf)
     launch_fused<true, true>(cfg, L, fp, A, B, C);

@@ -178,6 +178,44 @@ def test_gemm_path_shapes(dtype, gemm):
     assert expected in prof_names, prof_names
 
 
+@pytest.mark.parametrize("kfirst", [0, 1])
+def test_persistent_skinny_zgemm_shapes(kfirst):
+    """K <= 64, 16 < N <= 64, M >= 4 * 148 tiles of 64 rows: the persistent fused ZGEMM with B
+    resident in shared memory (one CTA per SM walks the row tiles).  Ragged M / N / K, both
+    gather orders, several tiles per CTA, and agreement with the tile-per-CTA kernel."""
+    rng = np.random.default_rng(43)
+    shapes = [
+        ((2,) * 22, [-1, -2, -3, 1, 2, 3] + [-(i + 4) for i in range(10)] + [4, -14, 5, -15, 6, -16],
+         (2,) * 12, [6, 5, 4, 3, 2, 1] + [-(20 + i) for i in range(6)]),       # M=2^16 N=K=64
+        ((2,) * 22, [1, 2, 3] + [-(i + 1) for i in range(16)] + [4, 5, 6],
+         (2,) * 11, [6, 5, 4, 3, 2, 1] + [-(20 + i) for i in range(5)]),       # low bits contracted, N=32
+        ((40017, 35), [-1, 1], (35, 33), [1, -2]),                              # ragged everything
+        ((7, 5, 38000), [1, 2, -1], (5, 17, 7), [2, -2, 1]),                    # K=35 first, N=17
+        ((3, 50000), [1, -1], (3, 64), [1, -2]),                                # K=3
+    ]
+    for ad, ai, bd, bi in shapes:
+        A = rand_tensor(rng, tuple(ad), np.complex128)
+        B = rand_tensor(rng, tuple(bd), np.complex128)
+        ref = layer1.contract_tensors((A, B), (ai, bi))
+        outs = []
+        for opts in (dict(zgemm_kfirst=kfirst), dict(zgemm_skinny=1)):
+            b = B200(np.complex128, **opts)
+            b.save_tensor_data("A", A)
+            b.save_tensor_data("B", B)
+            b.profile_enable(True)
+            b.contract_tensors("A", ai, "B", bi, "C")
+            prof = b.profile_read()
+            b.profile_enable(False)
+            assert set(prof) == {"gemm_tensor"}, (ad, prof)
+            got = b.load_tensor_data("C")
+            assert got.shape == ref.shape
+            assert rel_l2(got, ref) < 1e-10, (ad, ai, opts, rel_l2(got, ref))
+            outs.append(got)
+            b.close()
+        # same products summed in the same k order per output element => same bits
+        assert rel_l2(outs[0], outs[1]) < 1e-14
+
+
 @pytest.mark.parametrize("cfg", [0, 3])
 def test_narrow_n_zgemm_shapes(cfg):
     """One open bond of 8..16 on the small operand with K >= 32 (a site tensor absorbed into
@@ -210,7 +248,7 @@ def test_narrow_n_zgemm_shapes(cfg):
         assert rel_l2(got, ref) < 1e-10, (ad, ai, rel_l2(got, ref))
 
 
-@pytest.mark.parametrize("cfg", [0, 1, 2, 3])
+@pytest.mark.parametrize("cfg", [0, 1, 2, 3, 4, 5])
 def test_fused_ttgt_zgemm_shapes(cfg):
     """The persistent fused-TTGT ZGEMM (operands gathered inside the GEMM, no permuted
     temporaries): ragged tiles, K tails, several tiles per CTA, low-address contracted axes."""
