@@ -450,6 +450,12 @@ def main():
             roofline = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": peak,
                         "unit": "TFLOP/s", "frac": ach / peak, "traffic": traffic,
                         "share_of_timed_slice": kernels[dom].get("share_of_timed_slice"),
+                        "note": ("achieved = algorithmic 8*M*N*K flops of the class / its "
+                                 "event-timed device time; the persistent skinny kernel forms a "
+                                 "complex product from three DMMAs (3M), i.e. issues 6*M*N*K "
+                                 "pipe flops for them" if a.dtype == "c128" else
+                                 "achieved = algorithmic 8*M*N*K flops / event-timed device time "
+                                 "(tcgen05 3xTF32: 12 TF32 MMAs per complex product)"),
                         "peak_source": "cuBLAS %s 4096^3 measured in this run "
                                        "(MEASURED_PEAKS.json has no FP64 / complex figure); the "
                                        "same library reaches %s TFLOP/s on the dominant skinny "

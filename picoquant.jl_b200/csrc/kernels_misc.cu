@@ -4,7 +4,7 @@
 
 namespace pq {
 
-double run_fp64_probe(const Launch& L, bool tensor);  // kernels_zgemm.cu
+double run_fp64_probe(const Launch& L, bool tensor, int warps_per_sm = 0);  // kernels_zgemm.cu
 
 // out[i + inner*(j + nsel*o)] = in[i + inner*((start-1+j) + ext_in*o)]
 // `start` (1-based) comes from device memory when start_dev != nullptr, so that one
@@ -75,6 +75,7 @@ __global__ void __launch_bounds__(256) k_copy16(const uint4* __restrict__ in, ui
 
 double run_microbench(const Launch& L, const std::string& what) {
   if (what == "dmma_tflops") return run_fp64_probe(L, true);
+  if (what.rfind("dmma_tflops_w", 0) == 0) return run_fp64_probe(L, true, std::stoi(what.substr(13)));
   if (what == "dfma_tflops") return run_fp64_probe(L, false);
   if (what == "copy_gbs") {
     const long long n = 1LL << 26;  // 1 GiB in + 1 GiB out, larger than L2

@@ -181,8 +181,7 @@ struct FusedParams {
 // The tensor pipe is the binding resource of the K = 32..64 sweep steps (ncu: pipe 89 % active,
 // math_pipe_throttle the dominant stall), so 25 % fewer DMMAs is worth a third accumulator set
 // and two DADDs per fragment.  Norm-wise the rounding error stays at a few eps |A||B|.
-template <int TBM, int TBN, int WGM, int WGN, int NST, int MINB, bool AKF, bool BKF, bool M3 = false,
-          bool NOMATH = false>
+template <int TBM, int TBN, int WGM, int WGN, int NST, int MINB, bool AKF, bool BKF, bool M3 = false>
 __global__ void __launch_bounds__(256, MINB)
 k_zgemm_fused_t(const double2* __restrict__ A, const double2* __restrict__ B,
                 double2* __restrict__ C, const FusedParams p) {
@@ -316,9 +315,7 @@ k_zgemm_fused_t(const double2* __restrict__ A, const double2* __restrict__ B,
       for (int x = 0; x < XT; ++x) a[x] = tA[(ks + fk) * PA + x * 8];
 #pragma unroll
       for (int y = 0; y < YT; ++y) b[y] = tB[(ks + fk) * PB + y * 8];
-      if (NOMATH) {   // data-movement probe: fragments are read, one DMMA per k-step
-        dmma(cr[0][0][0], cr[0][0][1], a[XT - 1].x + a[0].y, b[YT - 1].x + b[0].y);
-      } else if (M3) {
+      if (M3) {
         double as[XT], bs[YT];
 #pragma unroll
         for (int x = 0; x < XT; ++x) as[x] = a[x].x + a[x].y;
@@ -391,6 +388,10 @@ k_zgemm_fused_t(const double2* __restrict__ A, const double2* __restrict__ B,
 //     gather of its next tile (cp.async) overlaps the DMMAs of the current one, and while one
 //     group is between tiles (stores, barrier, issuing the next gather) the other group keeps
 //     the FP64 pipe fed -- group 1 starts half a tile late so the two stay out of phase.
+// Probes on M = 2^18, N = K = 64 (B200, throw-away builds): data movement alone (one DMMA per
+// k-step) 132 us = 4.1 TB/s; without the C stores -5 %; without the 3M DADDs -1 %; four groups
+// of four warps or a deeper A ring: no gain.  What remains between the 173 us of pure 3M DMMA
+// issue time and the measured ~255 us is operand delivery to the FP64 pipe (LDS -> DMMA).
 // ---------------------------------------------------------------------------
 constexpr int SK_MAXK = 64, SK_THREADS = 512, SK_MAX_STAGES = 6;
 constexpr size_t SK_SMEM_BUDGET = 224 * 1024;
@@ -589,7 +590,7 @@ constexpr size_t fused_smem(int K) {
 
 // FP64 issue-rate probes for the roofline denominators (dependent chains per warp are
 // kept short enough to saturate the pipe with 8 warps x 4 independent accumulators).
-__global__ void __launch_bounds__(256) k_probe_dmma(double* out, int iters) {
+__global__ void __launch_bounds__(1024) k_probe_dmma(double* out, int iters) {
   double c[8][2];
 #pragma unroll
   for (int i = 0; i < 8; ++i) c[i][0] = c[i][1] = 0.0;
@@ -638,33 +639,17 @@ static void init_fused() {
   PQ_CUDA(cudaFuncSetAttribute(k_zgemm_fused_t<64, 32, 4, 2, 2, 3, AKF, BKF, true>,
                                cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)fused_smem<64, 32, 2>(FUSED_MAX_K)));
-  PQ_CUDA(cudaFuncSetAttribute(k_zgemm_fused_t<64, 32, 4, 2, 2, 4, AKF, BKF, true>,
-                               cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               (int)fused_smem<64, 32, 2>(FUSED_MAX_K)));
-  PQ_CUDA(cudaFuncSetAttribute(k_zgemm_fused_t<64, 32, 4, 2, 2, 4, AKF, BKF, false, true>,
-                               cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               (int)fused_smem<64, 32, 2>(FUSED_MAX_K)));
 }
 
 template <bool AKF, bool BKF>
 static void launch_fused(int cfg, const Launch& L, const FusedParams& fp, const void* A,
                          const void* B, void* C) {
-  if (cfg == 6) {   // data-movement probe (wrong results by design)
-    long long tiles = ((fp.M + 63) / 64) * ((fp.N + 31) / 32);
-    k_zgemm_fused_t<64, 32, 4, 2, 2, 4, AKF, BKF, false, true>
-        <<<(unsigned)tiles, 256, fused_smem<64, 32, 2>((int)fp.K), L.stream>>>(
-            (const double2*)A, (const double2*)B, (double2*)C, fp);
-  } else if (cfg == 4 || cfg == 5) {
+  if (cfg == 4) {   // 64x32 tiles with 3M products, 3 CTAs/SM (A/B: same time as cfg 2)
     long long tiles = ((fp.M + 63) / 64) * ((fp.N + 31) / 32);
     PQ_REQUIRE(tiles <= 0x7fffffffLL, PQ_ERR_UNSUPPORTED, "too many tiles");
-    if (cfg == 4)
-      k_zgemm_fused_t<64, 32, 4, 2, 2, 3, AKF, BKF, true>
-          <<<(unsigned)tiles, 256, fused_smem<64, 32, 2>((int)fp.K), L.stream>>>(
-              (const double2*)A, (const double2*)B, (double2*)C, fp);
-    else
-      k_zgemm_fused_t<64, 32, 4, 2, 2, 4, AKF, BKF, true>
-          <<<(unsigned)tiles, 256, fused_smem<64, 32, 2>((int)fp.K), L.stream>>>(
-              (const double2*)A, (const double2*)B, (double2*)C, fp);
+    k_zgemm_fused_t<64, 32, 4, 2, 2, 3, AKF, BKF, true>
+        <<<(unsigned)tiles, 256, fused_smem<64, 32, 2>((int)fp.K), L.stream>>>(
+            (const double2*)A, (const double2*)B, (double2*)C, fp);
   } else if (cfg == 3) {
     long long tiles = ((fp.M + 127) / 128) * ((fp.N + 7) / 8);
     PQ_REQUIRE(tiles <= 0x7fffffffLL, PQ_ERR_UNSUPPORTED, "too many tiles");
@@ -753,6 +738,7 @@ void run_zgemm_fused(const Launch& L, const ContractPlan& cp, const void* A, con
   if (cfg == 0) cfg = (cp.N <= 16) ? 3 : (cp.K <= 128) ? 2 : 1;
   {
     const int per_sm = (cfg == 1) ? 2 : (cfg == 3 || cfg == 4) ? 3 : 4;
+    PQ_REQUIRE(cfg >= 1 && cfg <= 4 || cfg == 7, PQ_ERR_INVALID, "zgemm_cfg must be 0..4 or 7");
     fp.num_sms = L.num_sms;
     fp.first_wave = L.num_sms * per_sm;
     fp.stagger_ns = L.opt ? L.opt->zgemm_stagger : 0;
@@ -804,7 +790,32 @@ void run_zgemm_fused(const Launch& L, const ContractPlan& cp, const void* A, con
 }
 
 // returns achieved TFLOP/s of the probe ("dmma" or "dfma")
-double run_fp64_probe(const Launch& L, bool tensor) {
+// warps_per_sm = 0: the default saturating shape (8 CTAs of 8 warps per SM); otherwise ONE
+// CTA of that many warps per SM -- how many resident warps the FP64 pipe needs
+double run_fp64_probe(const Launch& L, bool tensor, int warps_per_sm) {
+  if (warps_per_sm > 0) {
+    const int blocks = L.num_sms, threads = 32 * warps_per_sm, iters = 8192;
+    double* out = nullptr;
+    PQ_CUDA(cudaMalloc(&out, size_t(blocks) * threads * sizeof(double)));
+    cudaEvent_t e0, e1;
+    PQ_CUDA(cudaEventCreate(&e0));
+    PQ_CUDA(cudaEventCreate(&e1));
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; ++rep) {
+      PQ_CUDA(cudaEventRecord(e0, L.stream));
+      k_probe_dmma<<<blocks, threads, 0, L.stream>>>(out, iters);
+      PQ_CUDA(cudaEventRecord(e1, L.stream));
+      PQ_CUDA(cudaEventSynchronize(e1));
+      float ms = 0;
+      PQ_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+      if (rep > 0 && ms < best) best = ms;
+    }
+    PQ_CUDA(cudaGetLastError());
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(out);
+    return double(blocks) * warps_per_sm * iters * 8.0 * (8 * 8 * 4 * 2) / (best * 1e-3) / 1e12;
+  }
   const int blocks = L.num_sms * 8, iters = 4096;
   double* out = nullptr;
   PQ_CUDA(cudaMalloc(&out, size_t(blocks) * 256 * sizeof(double)));

@@ -248,7 +248,7 @@ def test_narrow_n_zgemm_shapes(cfg):
         assert rel_l2(got, ref) < 1e-10, (ad, ai, rel_l2(got, ref))
 
 
-@pytest.mark.parametrize("cfg", [0, 1, 2, 3, 4, 5])
+@pytest.mark.parametrize("cfg", [0, 1, 2, 3, 4, 7])
 def test_fused_ttgt_zgemm_shapes(cfg):
     """The persistent fused-TTGT ZGEMM (operands gathered inside the GEMM, no permuted
     temporaries): ragged tiles, K tails, several tiles per CTA, low-address contracted axes."""
