@@ -54,7 +54,15 @@ if rep:
             "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "lts__t_bytes.sum"]
     md += ["# ncu --set full, selected counters per captured launch", "",
            "Source: `%s`." % os.path.basename(rep), ""]
+    min_us = float(os.environ.get("NCU_MIN_US", "0"))   # skip short launches in the detail part
     for r in rows[2:]:
+        try:
+            dur = float(r[idx["gpu__time_duration.sum"]].replace(",", ""))
+            dur = {"ns": dur / 1e3, "us": dur, "ms": dur * 1e3}.get(units[idx["gpu__time_duration.sum"]], dur)
+        except Exception:  # noqa: BLE001
+            dur = 1e9
+        if dur < min_us:
+            continue
         name = re.sub(r"\(.*", "", r[idx["Kernel Name"]]).replace("void ", "")
         md.append("## `%s`" % name)
         md.append("")
