@@ -141,6 +141,122 @@ k_zgemm_dmma(const double2* __restrict__ A, const double2* __restrict__ B, doubl
 }
 
 // ---------------------------------------------------------------------------
+// The same GEMM with 3M complex products (see k_zgemm_fused_t / k_zgemm_skinny): long
+// contractions on canonical layouts are bound by the FP64 pipe, so issuing three DMMAs per
+// complex product instead of four is worth ~25 %.  The third accumulator set does not fit the
+// 128-register budget of two 256-thread CTAs per SM with 32x16 warp tiles, hence ONE CTA of
+// 16 warps (4 x 4, warp tile 16x16) per SM, 64x64x32 tiles, 3 stages (203 KB).
+// ---------------------------------------------------------------------------
+constexpr int M3_BK = 32, M3_STAGES = 3, M3_THREADS = 512;
+constexpr int M3_STAGE_ELEMS = M3_BK * PITCH;
+constexpr size_t M3_SMEM_BYTES = size_t(M3_STAGES) * 2 * M3_STAGE_ELEMS * sizeof(double2);
+
+__global__ void __launch_bounds__(M3_THREADS, 1)
+k_zgemm_dmma3m(const double2* __restrict__ A, const double2* __restrict__ B, double2* __restrict__ C,
+               long long M, long long N, long long K) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double2* sA = reinterpret_cast<double2*>(smem_raw);
+  double2* sB = sA + M3_STAGES * M3_STAGE_ELEMS;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm = warp & 3, wn = warp >> 2;  // 4 x 4 warps
+  // n-tiles in groups of 8 per sweep over m: a wave of CTAs re-uses 8 column tiles of B and a
+  // band of A out of L2 instead of streaming all of A once per column tile
+  const long long tiles_m = (M + BM - 1) / BM, tiles_n = (N + BN - 1) / BN;
+  constexpr long long GROUP_N = 8;
+  const long long bid = blockIdx.x;
+  const long long group = bid / (GROUP_N * tiles_m);
+  const long long gn = (tiles_n - group * GROUP_N) < GROUP_N ? (tiles_n - group * GROUP_N) : GROUP_N;
+  const long long rem = bid - group * GROUP_N * tiles_m;
+  const long long m0 = (rem / gn) * BM, n0 = (group * GROUP_N + rem % gn) * BN;
+  const long long KT = (K + M3_BK - 1) / M3_BK;
+
+  auto load_stage = [&](int stage, long long kt) {
+    double2* dA = sA + stage * M3_STAGE_ELEMS;
+    double2* dB = sB + stage * M3_STAGE_ELEMS;
+    const long long k0 = kt * M3_BK;
+#pragma unroll
+    for (int q = 0; q < BM * M3_BK / M3_THREADS; ++q) {
+      int idx = tid + q * M3_THREADS;
+      int kk = idx >> 6, mm = idx & 63;
+      long long k = k0 + kk;
+      bool va = (k < K) && (m0 + mm < M);
+      bool vb = (k < K) && (n0 + mm < N);
+      const double2* ga = va ? (A + (m0 + mm) + M * k) : A;
+      const double2* gb = vb ? (B + (n0 + mm) + N * k) : B;
+      cp_async16(dA + kk * PITCH + mm, ga, va);
+      cp_async16(dB + kk * PITCH + mm, gb, vb);
+    }
+  };
+
+  double p1[2][2][2], p2[2][2][2], p3[2][2][2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      p1[i][j][0] = p1[i][j][1] = 0.0;
+      p2[i][j][0] = p2[i][j][1] = 0.0;
+      p3[i][j][0] = p3[i][j][1] = 0.0;
+    }
+
+#pragma unroll
+  for (int s = 0; s < M3_STAGES - 1; ++s) {
+    if (s < KT) load_stage(s, s);
+    cp_async_commit();
+  }
+
+  const int frow = lane >> 2, fk = lane & 3;
+  int ring = 0, pring = M3_STAGES - 1;
+  for (long long kt = 0; kt < KT; ++kt) {
+    cp_async_wait<M3_STAGES - 2>();
+    __syncthreads();
+    if (kt + M3_STAGES - 1 < KT) load_stage(pring, kt + M3_STAGES - 1);
+    cp_async_commit();
+    const double2* tA = sA + ring * M3_STAGE_ELEMS + wm * 16 + frow;
+    const double2* tB = sB + ring * M3_STAGE_ELEMS + wn * 16 + frow;
+#pragma unroll
+    for (int ks = 0; ks < M3_BK; ks += 4) {
+      double2 a[2], b[2];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) a[i] = tA[(ks + fk) * PITCH + i * 8];
+#pragma unroll
+      for (int j = 0; j < 2; ++j) b[j] = tB[(ks + fk) * PITCH + j * 8];
+      double as[2], bs[2];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) as[i] = a[i].x + a[i].y;
+#pragma unroll
+      for (int j = 0; j < 2; ++j) bs[j] = b[j].x + b[j].y;
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          dmma(p1[i][j][0], p1[i][j][1], a[i].x, b[j].x);
+          dmma(p2[i][j][0], p2[i][j][1], a[i].y, b[j].y);
+          dmma(p3[i][j][0], p3[i][j][1], as[i], bs[j]);
+        }
+    }
+    ring = (ring + 1 == M3_STAGES) ? 0 : ring + 1;
+    pring = (pring + 1 == M3_STAGES) ? 0 : pring + 1;
+  }
+  cp_async_wait<0>();
+
+#pragma unroll
+  for (int j = 0; j < 2; ++j)
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      long long n = n0 + wn * 16 + j * 8 + 2 * fk + c;
+      if (n >= N) continue;
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        long long m = m0 + wm * 16 + i * 8 + frow;
+        if (m < M)
+          C[m + M * n] = make_double2(p1[i][j][c] - p2[i][j][c],
+                                      p3[i][j][c] - p1[i][j][c] - p2[i][j][c]);
+      }
+    }
+}
+
+// ---------------------------------------------------------------------------
 // Fused TTGT: the same tile pipeline, but the operand tiles are gathered straight from
 // the un-permuted tensors -- the "transpose" of TTGT happens in the cp.async that fills
 // shared memory, so no permuted copy of A or B is ever written to HBM.  An element of
@@ -696,6 +812,8 @@ static void launch_skinny(bool m3, unsigned grid, const Launch& L, const FusedPa
 void init_kernels() {
   PQ_CUDA(cudaFuncSetAttribute(k_zgemm_dmma, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)SMEM_BYTES));
+  PQ_CUDA(cudaFuncSetAttribute(k_zgemm_dmma3m, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)M3_SMEM_BYTES));
   init_skinny<64, false>();
   init_skinny<64, true>();
   init_skinny<32, false>();
@@ -711,9 +829,16 @@ void run_zgemm_dmma(const Launch& L, const void* A, const void* B, void* C, int6
   dim3 grid((unsigned)((M + BM - 1) / BM), (unsigned)((N + BN - 1) / BN));
   PQ_REQUIRE(grid.y <= 65535, PQ_ERR_UNSUPPORTED, "N too large for the ZGEMM grid");
   double bytes = double(M * K + N * K + M * N) * 16.0, flops = 8.0 * M * N * K;
+  // long contractions are bound by the FP64 pipe: 3M products (option zgemm_3m=1: four DMMAs)
+  const long long tiles = (long long)grid.x * grid.y;
+  const bool m3 = !(L.opt && L.opt->zgemm_3m == 1) && K >= 256 && tiles <= 0x7fffffffLL;
   L.begin(KC_GEMM_TENSOR, bytes, flops);
-  k_zgemm_dmma<<<grid, 256, SMEM_BYTES, L.stream>>>((const double2*)A, (const double2*)B,
-                                                    (double2*)C, M, N, K);
+  if (m3)
+    k_zgemm_dmma3m<<<(unsigned)tiles, M3_THREADS, M3_SMEM_BYTES, L.stream>>>(
+        (const double2*)A, (const double2*)B, (double2*)C, M, N, K);
+  else
+    k_zgemm_dmma<<<grid, 256, SMEM_BYTES, L.stream>>>((const double2*)A, (const double2*)B,
+                                                      (double2*)C, M, N, K);
   L.end();
   PQ_CUDA(cudaGetLastError());
 }

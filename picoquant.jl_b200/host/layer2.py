@@ -7,7 +7,8 @@ calls).  Restates ``src/layer2.jl``: ``sort_indices`` (:209-216),
 ``decompose_tensor!`` (:487-559), ``compress_bond!`` (:450-472) and
 ``compress_tensor_chain!`` (:423-440), and the MPS drivers
 ``contract_mps_tensor_network_circuit!`` (:571-624) and
-``calculate_mps_amplitudes!`` (:633-643).
+``calculate_mps_amplitudes!`` (:633-643), and the bond-merging in-order driver
+``merge_common_bonds!`` (:25-69) / ``inorder_contraction!`` (:76-112).
 
 All of this is integer / label work and must be bit-exact with the reference:
 the emitted backend call stream (labels, ncon index lists, permutation and
@@ -351,3 +352,72 @@ def calculate_mps_amplitudes(network: TensorNetworkCircuit, mps_nodes: Sequence[
     network.permute_tensor(output_node, list(network.qubit_ordering))
     network.reshape_tensor(output_node, [list(range(1, len(mps_nodes) + 1))])
     network.save_output(output_node, result)
+
+
+# ---------------------------------------------------------------------------
+# in-order contraction with bond merging (src/layer2.jl:25-112)
+# ---------------------------------------------------------------------------
+def merge_common_bonds(network: TensorNetworkCircuit, a_label: str, b_label: str) -> None:
+    """``merge_common_bonds!`` (``src/layer2.jl:25-69``): when two nodes share more than one
+    index, both tensors are permuted to [remaining..., common...] and the common axes are
+    fused into one (``permute_tensor`` + ``reshape_tensor`` on the backend); the shared edges
+    are replaced by a single new virtual edge."""
+    a = network.nodes[a_label]
+    b = network.nodes[b_label]
+    b_set, a_set = set(b.indices), set(a.indices)
+    common_edges = [x for x in a.indices if x in b_set]
+    if len(common_edges) <= 1:
+        return
+    a_common = [k for k, x in enumerate(a.indices, start=1) if x in b_set]
+    a_remaining = [k for k, x in enumerate(a.indices, start=1) if x not in b_set]
+    network.permute_tensor(a_label, a_remaining + a_common)
+    b_common = [k for k, x in enumerate(b.indices, start=1) if x in a_set]
+    b_remaining = [k for k, x in enumerate(b.indices, start=1) if x not in a_set]
+    network.permute_tensor(b_label, b_remaining + b_common)
+
+    new_edge = new_label(network, "index")
+    indices_a = [a.indices[k - 1] for k in a_remaining] + [new_edge]
+    indices_b = [b.indices[k - 1] for k in b_remaining] + [new_edge]
+    dims_map_a = dict(zip(a.indices, a.dims))
+    dims_map_b = dict(zip(b.indices, b.dims))
+    merged = 1
+    for k in a_common:
+        merged *= dims_map_a[a.indices[k - 1]]
+    dims_map_a[new_edge] = dims_map_b[new_edge] = merged
+    network.nodes[a_label] = Node(indices_a, [dims_map_a[i] for i in indices_a], a_label)
+    network.nodes[b_label] = Node(indices_b, [dims_map_b[i] for i in indices_b], b_label)
+
+    l, m = len(a_remaining), len(a_common)
+    network.reshape_tensor(a_label, [[x] for x in range(1, l + 1)] + [list(range(l + 1, l + m + 1))])
+    l, m = len(b_remaining), len(b_common)
+    network.reshape_tensor(b_label, [[x] for x in range(1, l + 1)] + [list(range(l + 1, l + m + 1))])
+
+    network.edges[new_edge] = Edge(a_label, b_label, None, True)
+    for e in common_edges:
+        del network.edges[e]
+
+
+def inorder_contraction(network: TensorNetworkCircuit) -> None:
+    """``inorder_contraction!`` (``src/layer2.jl:76-112``): layer by layer, every gate node
+    absorbs its (unique) in-neighbours; afterwards multiple bonds between the new nodes of
+    a layer are merged.  ``y > x`` compares the labels as strings, like Julia Symbols."""
+    layer_nodes = _layer_nodes(network)
+    gate_layers = [k for k in sorted(layer_nodes) if k > 0]
+    if -1 in layer_nodes:
+        gate_layers.append(-1)
+    for layer in gate_layers:
+        new_nodes = []
+        for node in layer_nodes[layer]:
+            in_nodes, seen = [], set()
+            for n in inneighbours(network, node):
+                if n not in seen:
+                    seen.add(n)
+                    in_nodes.append(n)
+            for in_node in in_nodes:
+                node = contract_pair(network, in_node, node)
+            new_nodes.append(node)
+        # Iterators.product(new_nodes, new_nodes): the first factor varies fastest
+        for y in new_nodes:
+            for x in new_nodes:
+                if y > x:
+                    merge_common_bonds(network, x, y)

@@ -20,7 +20,7 @@ from picoquant_jl_b200.host import (DSLBackend, TensorNetworkCircuit, add_gate, 
                                     convert_circuit_to_network, create_ghz_preparation_circuit,
                                     create_qft_circuit, create_simple_preparation_circuit,
                                     decompose_tensor, full_wavefunction_contraction,
-                                    load_qasm_as_circuit, virtualedges)
+                                    inorder_contraction, load_qasm_as_circuit, virtualedges)
 
 DTYPES = [np.complex128, np.complex64]
 
@@ -210,6 +210,41 @@ def _mps_matches_full_wavefunction(backend_factory, tol):
     assert rel_l2(b.load_tensor_data("result"), ref) < 10 * tol
 
 
+def _inorder_with_bond_merging(backend_factory, tol):
+    """``inorder_contraction!`` + ``merge_common_bonds!`` (src/layer2.jl:25-112; the reference
+    has no test for them): on a decomposed 4-qubit preparation + QFT network every qubit's
+    world-line collapses into one node, multiple virtual bonds between two nodes are fused by
+    permute + reshape on the backend, and contracting what is left reproduces the state."""
+    circ = create_simple_preparation_circuit(4, 2, 3).compose(create_qft_circuit(4))
+    ob = OracleBackend(np.complex128)
+    tn = convert_circuit_to_network(circ, ob, decompose=True)
+    add_input(tn, "0000")
+    full_wavefunction_contraction(tn, "vector")
+    ref = np.array(ob.load_tensor_data("result"))
+
+    b = backend_factory()
+    tn = convert_circuit_to_network(circ, b, decompose=True)
+    add_input(tn, "0000")
+    inorder_contraction(tn)
+    labels = list(tn.nodes)
+    assert len(labels) == 4
+    for i, x in enumerate(labels):
+        assert list(b.load_tensor_data(x).shape) == tn.nodes[x].dims      # graph dims == data dims
+        for y in labels[i + 1:]:
+            assert len(set(tn.nodes[x].indices) & set(tn.nodes[y].indices)) <= 1
+    assert sorted(max(v.dims) for v in tn.nodes.values()) == [8, 8, 16, 16]   # fused bonds
+    for e in tn.edges.values():
+        if e.src is not None and e.dst is not None:
+            assert e.virtual
+    sites = [tn.edges[x].src for x in tn.output_qubits]
+    calculate_mps_amplitudes(tn, sites)
+    assert rel_l2(b.load_tensor_data("result"), ref) < 10 * tol
+
+
+def test_inorder_contraction_with_bond_merging_oracle():
+    _inorder_with_bond_merging(lambda: OracleBackend(np.complex128), 1e-10)
+
+
 def test_reference_mps_contraction_oracle():
     _mps_matches_full_wavefunction(lambda: OracleBackend(np.complex128), 1e-10)
 
@@ -299,6 +334,7 @@ def test_gpu_reference_decompose_tests(dtype):
 @pytest.mark.parametrize("dtype", DTYPES)
 def test_gpu_reference_mps_contraction(dtype):
     _mps_matches_full_wavefunction(lambda: _b200(dtype), TOL[np.dtype(dtype)])
+    _inorder_with_bond_merging(lambda: _b200(dtype), TOL[np.dtype(dtype)])
 
 
 def _mps_dsl_stream():

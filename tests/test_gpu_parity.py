@@ -178,6 +178,40 @@ def test_gemm_path_shapes(dtype, gemm):
     assert expected in prof_names, prof_names
 
 
+def test_long_k_zgemm_3m():
+    """Long contractions (canonical TTGT layouts behind K1): the 3M DMMA kernel (three real
+    products per complex product, 16 warps, grouped rasterisation) against the oracle and
+    against the four-product kernel, ragged M / N / K and several n-tile groups."""
+    rng = np.random.default_rng(47)
+    shapes = [
+        ((200, 300), [-1, 1], (300, 130), [1, -2], dict(fused=1)),               # K=300, fused off
+        ((1030, 70), [1, -1], (45, 1030), [-2, 1], dict()),                      # K > 1024: default path
+        ((4, 100, 260), [1, -1, 2], (260, 4, 9, 77), [2, 1, -2, -3], dict()),    # K=1040, N=693 (11 n-tiles)
+        ((2,) * 17, [1, -1, 2, -2, 3, -3, 4, -4, 5, 6, 7, 8, 9, 10, 11, -5, -6],
+         (2,) * 15, [11, 10, 9, 8, 7, 6, 5, 4, 3, 2, 1, -7, -8, -9, -10], dict()),  # K=2048, bit-permuted
+    ]
+    for ad, ai, bd, bi, opts in shapes:
+        A = rand_tensor(rng, tuple(ad), np.complex128)
+        B = rand_tensor(rng, tuple(bd), np.complex128)
+        ref = layer1.contract_tensors((A, B), (ai, bi))
+        outs = []
+        for extra in (dict(), dict(zgemm_3m=1)):
+            b = B200(np.complex128, **opts, **extra)
+            b.save_tensor_data("A", A)
+            b.save_tensor_data("B", B)
+            b.profile_enable(True)
+            b.contract_tensors("A", ai, "B", bi, "C")
+            prof = b.profile_read()
+            b.profile_enable(False)
+            assert "gemm_tensor" in prof and "gemm_simt" not in prof, prof
+            got = b.load_tensor_data("C")
+            assert got.shape == ref.shape
+            assert rel_l2(got, ref) < 1e-10, (ad, extra, rel_l2(got, ref))
+            outs.append(got)
+            b.close()
+        assert rel_l2(outs[0], outs[1]) < 1e-13
+
+
 @pytest.mark.parametrize("kfirst", [0, 1])
 def test_persistent_skinny_zgemm_shapes(kfirst):
     """K <= 64, 16 < N <= 64, M >= 4 * 148 tiles of 64 rows: the persistent fused ZGEMM with B
