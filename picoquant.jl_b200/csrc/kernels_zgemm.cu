@@ -506,8 +506,12 @@ k_zgemm_fused_t(const double2* __restrict__ A, const double2* __restrict__ B,
 //     the FP64 pipe fed -- group 1 starts half a tile late so the two stay out of phase.
 // Probes on M = 2^18, N = K = 64 (B200, throw-away builds): data movement alone (one DMMA per
 // k-step) 132 us = 4.1 TB/s; without the C stores -5 %; without the 3M DADDs -1 %; four groups
-// of four warps or a deeper A ring: no gain.  What remains between the 173 us of pure 3M DMMA
-// issue time and the measured ~255 us is operand delivery to the FP64 pipe (LDS -> DMMA).
+// of four warps or a deeper A ring: no gain; fragments kept in registers across the k loop (no
+// LDS) -7.5 %; leaving 4-8 SMs free for the tiny kernels of other graph branches: +-0.
+// The two groups keep one 32 KB tile each in flight per SM (all the shared memory left beside
+// B at K = N = 64), which at the ~4 TB/s this gather + store pattern sustains arrives in
+// ~2.4 us -- about the DMMA time of a tile -- so the remaining gap between the 173 us of
+// pure 3M DMMA issue time and the measured ~255 us is load latency not fully hidden.
 // ---------------------------------------------------------------------------
 constexpr int SK_MAXK = 64, SK_THREADS = 512, SK_MAX_STAGES = 6;
 constexpr size_t SK_SMEM_BUDGET = 224 * 1024;
