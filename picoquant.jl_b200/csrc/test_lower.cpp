@@ -157,17 +157,31 @@ static void test_permutations(std::mt19937& rng) {
   CHECK(tiled_cases > 20, "too few tiled cases exercised");
 }
 
-static void test_contractions(std::mt19937& rng) {
+// shaped = 0: random small label sets (small / direct kernels).  shaped = 1..3: label sets that
+// reach the other lowerings -- 1: long contraction with a tiny output (CK_DOT, with its
+// re-ordered k enumeration), 2: GEMM-shaped (fused and materialised TTGT), 3: narrow-N GEMM.
+static void test_contractions(std::mt19937& rng, int shaped, int iters) {
   int kinds[5] = {0, 0, 0, 0, 0};
-  for (int iter = 0; iter < 600; ++iter) {
+  for (int iter = 0; iter < iters; ++iter) {
     Options opt;
     if (iter % 5 == 1) opt.fused = 1;
-    if (iter % 5 == 2) opt.gemm = 3;
+    if (iter % 5 == 2 && shaped == 0) opt.gemm = 3;
     // random label assignment: each label goes to A only, B only, or both
     int nlab = 1 + (int)(rng() % (iter % 3 == 0 ? 12 : 7));
     std::vector<int64_t> ad, bd;
     std::vector<int32_t> ai, bi;
     int nopen = 0, ncon = 0;
+    if (shaped != 0) {
+      // numbers of extent-2 labels that are A-open, B-open and contracted
+      int na2, nb2, nc2;
+      if (shaped == 1) { na2 = (int)(rng() % 3); nb2 = (int)(rng() % (3 - na2)); nc2 = 9 + (int)(rng() % 4); }
+      else if (shaped == 2) { na2 = 6 + (int)(rng() % 2); nb2 = 6; nc2 = 5 + (int)(rng() % 2); }
+      else { na2 = 12; nb2 = 3 + (int)(rng() % 2); nc2 = 5 + (int)(rng() % 2); }
+      for (int l = 0; l < na2; ++l) { ad.push_back(2); ai.push_back(-(++nopen)); }
+      for (int l = 0; l < nb2; ++l) { bd.push_back(2); bi.push_back(-(++nopen)); }
+      for (int l = 0; l < nc2; ++l) { ++ncon; ad.push_back(2); ai.push_back(ncon); bd.push_back(2); bi.push_back(ncon); }
+      nlab = 0;
+    }
     for (int l = 0; l < nlab; ++l) {
       int64_t e = (iter % 4 == 0) ? (int64_t)(1 + rng() % 4) : (int64_t(1) << (rng() % 3));
       int where = (int)(rng() % 3);
@@ -247,7 +261,7 @@ static void test_contractions(std::mt19937& rng) {
         break;
       }
     // canonical TTGT layouts: A' = [M|K], B' = [N|K]
-    if (P.kind == CK_GEMM) {
+    if (P.kind == CK_GEMM && !P.fused_gemm) {
       std::vector<cd> Ap(M * K), Bp(N * K);
       if (P.permA.identity) Ap = A;
       else for (int64_t i = 0; i < M * K; ++i) Ap[i] = A[map_offset(P.permA.gmap, i)];
@@ -264,8 +278,10 @@ static void test_contractions(std::mt19937& rng) {
         }
     }
   }
-  std::printf("contractions: small_right %d small_left %d direct %d dot %d gemm %d\n", kinds[0],
-              kinds[1], kinds[2], kinds[3], kinds[4]);
+  std::printf("contractions (shape class %d): small_right %d small_left %d direct %d dot %d gemm %d\n",
+              shaped, kinds[0], kinds[1], kinds[2], kinds[3], kinds[4]);
+  if (shaped == 1) CHECK(kinds[3] > iters / 2, "dot lowering not exercised");
+  if (shaped == 2 || shaped == 3) CHECK(kinds[4] > iters / 2, "GEMM lowering not exercised");
 }
 
 static void test_big_shapes() {
@@ -298,7 +314,10 @@ int main() {
   std::mt19937 rng(12345);
   try {
     test_permutations(rng);
-    test_contractions(rng);
+    test_contractions(rng, 0, 600);
+    test_contractions(rng, 1, 40);
+    test_contractions(rng, 2, 30);
+    test_contractions(rng, 3, 6);
     test_big_shapes();
   } catch (const Error& e) {
     std::printf("FAIL: exception %d %s\n", e.code, e.what());
