@@ -583,6 +583,7 @@ extern "C" int pq_set_option(pq_handle* h, const char* key, int value) {
   else if (k == "fused") h->opt.fused = value;
   else if (k == "graph") h->opt.graph = value;
   else if (k == "prio") h->opt.prio = value;
+  else if (k == "chain") h->opt.chain = value;
   else if (k == "zgemm_stagger") h->opt.zgemm_stagger = value;
   else if (k == "zgemm_skinny") h->opt.zgemm_skinny = value;
   else if (k == "zgemm_3m") h->opt.zgemm_3m = value;

@@ -121,6 +121,7 @@ struct Options {
   int zgemm_3m = 0;       // persistent skinny ZGEMM: 0 = 3M (three DMMAs per complex product), 1 = 4M
   int zgemm_skinny = 0;   // persistent skinny fused ZGEMM: 0 auto, 1 off
   int zgemm_stagger = 0;  // ns of start delay per resident-CTA slot in the first wave (0 = off)
+  int chain = 0;    // compiled programs: 0 = batch chains of tiny contractions into one launch, 1 = off
   int prio = 0;     // 0: small-grid graph nodes get the highest launch priority, 1: off
   int graph = 0;    // 0 CUDA graph with parallel branches, 1 eager replay, 2 single-chain graph
 };
@@ -176,6 +177,28 @@ ContractPlan lower_contract(const std::vector<int64_t>& a_dims, const std::vecto
 // tempA/tempB/ws must hold the sizes the plan asks for (may be null when 0)
 void run_contract(const Launch& L, const ContractPlan& p, const void* A, const void* B, void* C,
                   void* tempA, void* tempB, void* ws);
+
+// ---------------------------------------------------------------------------
+// chains of tiny contractions (kernels_contract.cu, used by compiled programs)
+// ---------------------------------------------------------------------------
+constexpr int MINI_ND = 12;
+struct MiniMap {   // IdxMap for tensors of < 2^31 elements and <= MINI_ND fused dims
+  int nd, pow2;
+  int sh[MINI_ND], ext[MINI_ND], str[MINI_ND];
+};
+struct ChainItem {   // C[m + M n] = sum_k A[mA(m) + kA(k)] * B[nB(n) + kB(k)]
+  MiniMap mA, kA, nB, kB;
+  int M, N, K, pad;
+  const void* A;
+  const void* B;
+  void* C;
+};
+struct ChainRange {  // items [begin, begin + count) are executed in order by one CTA
+  int begin, count;
+};
+// false when the plan does not fit a ChainItem (too many fused dims, sizes beyond int)
+bool chain_item_from_plan(const ContractPlan& p, ChainItem& it);
+void run_chains(const Launch& L, const ChainItem* d_items, const ChainRange* d_ranges, int nchains);
 
 void init_kernels();
 void init_kernels_cgemm();

@@ -232,6 +232,108 @@ k_contract_direct(const typename C2<R>::type* __restrict__ A,
 }
 
 // ---------------------------------------------------------------------------
+// chains of tiny contractions: one CTA executes a list of contractions one after another.
+// A slice of an RQC amplitude starts with ~10^3 contractions of a few dozen elements (every
+// qubit's world-line collapses gate by gate); each is one dependent step of a chain, so as
+// separate launches they cost a kernel dispatch apiece.  Here a chain is a single CTA walking
+// its descriptors (copied to shared memory one at a time), chains that become ready together
+// share one launch, and the intermediate tensors stay in L2.  Operands are read with ld.cg:
+// they were written by other threads of the same CTA a barrier earlier.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ int mini_offset(const MiniMap& m, int i) {
+  int off = 0;
+  if (m.pow2) {
+    for (int d = 0; d < m.nd; ++d) {
+      off += (i & (m.ext[d] - 1)) * m.str[d];
+      i >>= m.sh[d];
+    }
+  } else {
+    for (int d = 0; d < m.nd; ++d) {
+      const int q = i / m.ext[d];
+      off += (i - q * m.ext[d]) * m.str[d];
+      i = q;
+    }
+  }
+  return off;
+}
+
+template <typename R>
+__global__ void __launch_bounds__(128)
+k_contract_chain(const ChainItem* __restrict__ items, const ChainRange* __restrict__ ranges) {
+  using V = typename C2<R>::type;
+  __shared__ ChainItem it;
+  const ChainRange rg = ranges[blockIdx.x];
+  for (int s = 0; s < rg.count; ++s) {
+    __syncthreads();   // results of the previous item are visible; `it` may be overwritten
+    {
+      const int* src = reinterpret_cast<const int*>(items + rg.begin + s);
+      int* dst = reinterpret_cast<int*>(&it);
+      for (int i = threadIdx.x; i < (int)(sizeof(ChainItem) / sizeof(int)); i += blockDim.x)
+        dst[i] = src[i];
+    }
+    __syncthreads();
+    const V* A = static_cast<const V*>(it.A);
+    const V* B = static_cast<const V*>(it.B);
+    V* C = static_cast<V*>(it.C);
+    const int total = it.M * it.N;
+    for (int c = threadIdx.x; c < total; c += blockDim.x) {
+      const int n = c / it.M, m = c - n * it.M;
+      const V* a = A + mini_offset(it.mA, m);
+      const V* b = B + mini_offset(it.nB, n);
+      V acc;
+      acc.x = 0;
+      acc.y = 0;
+      for (int k = 0; k < it.K; ++k)
+        cfma<V, R>(acc, __ldcg(a + mini_offset(it.kA, k)), __ldcg(b + mini_offset(it.kB, k)));
+      C[c] = acc;
+    }
+  }
+}
+
+static bool to_mini(const IdxMap& m, MiniMap& o) {
+  if (m.nd > MINI_ND) return false;
+  o.nd = m.nd;
+  o.pow2 = m.pow2;
+  for (int d = 0; d < MINI_ND; ++d) {
+    o.sh[d] = 0;
+    o.ext[d] = 1;
+    o.str[d] = 0;
+  }
+  for (int d = 0; d < m.nd; ++d) {
+    if (m.ext[d] >= (int64_t(1) << 30) || m.str[d] >= (int64_t(1) << 30) || m.str[d] < 0) return false;
+    o.sh[d] = m.sh[d];
+    o.ext[d] = (int)m.ext[d];
+    o.str[d] = (int)m.str[d];
+  }
+  return true;
+}
+
+bool chain_item_from_plan(const ContractPlan& p, ChainItem& it) {
+  if (p.M * p.N >= (int64_t(1) << 24) || p.K >= (int64_t(1) << 24)) return false;
+  if (!to_mini(p.mA, it.mA) || !to_mini(p.kA, it.kA) || !to_mini(p.nB, it.nB) ||
+      !to_mini(p.kB, it.kB))
+    return false;
+  it.M = (int)p.M;
+  it.N = (int)p.N;
+  it.K = (int)p.K;
+  it.pad = 0;
+  it.A = it.B = nullptr;
+  it.C = nullptr;
+  return true;
+}
+
+void run_chains(const Launch& L, const ChainItem* d_items, const ChainRange* d_ranges, int nchains) {
+  if (nchains <= 0) return;
+  L.begin(KC_CONTRACT_SMALL, 0, 0);
+  if (L.elem_size == 16)
+    k_contract_chain<double><<<nchains, 128, 0, L.stream>>>(d_items, d_ranges);
+  else
+    k_contract_chain<float><<<nchains, 128, 0, L.stream>>>(d_items, d_ranges);
+  L.end();
+  PQ_CUDA(cudaGetLastError());
+}
+
+// ---------------------------------------------------------------------------
 // dot kernel (M*N <= 16, long K)
 // ---------------------------------------------------------------------------
 struct DotParams {

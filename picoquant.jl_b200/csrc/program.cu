@@ -11,6 +11,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <set>
 #include <sstream>
 
 #include "handle.h"
@@ -132,6 +133,8 @@ struct LaneMem {
   int32_t* d_starts = nullptr;
   // graph instances: invariant part (lane 0 only), dependent part, whole stream
   cudaGraphExec_t exec2[3] = {nullptr, nullptr, nullptr};
+  void* chain_items[3] = {nullptr, nullptr, nullptr};   // resolved ChainItem arrays, per graph
+  int64_t graph_launches[3] = {0, 0, 0};                // kernel launches inside each graph
   std::vector<std::shared_ptr<Buffer>> outs;  // one per `save` step
   cudaStream_t stream = nullptr;              // run_slices: the lane's own stream
   cudaEvent_t done_ev = nullptr, acc_ev = nullptr;
@@ -164,11 +167,25 @@ struct pq_program {
   cudaEvent_t table_ev = nullptr, batch_ev = nullptr;
   bool table_used = false;
   int64_t launches = 0, macs = 0, ncontract = 0, max_elems = 0;
+  int64_t launches_batched = 0;   // launches per run when chains are batched (graph mode)
   int device = 0;
   // leaf tensors the program is bound to: (store key, pinned buffer)
   std::vector<std::pair<std::string, std::shared_ptr<Buffer>>> leaves;
   // dependency DAG for multi-stream capture: deps[j] = earlier steps j must wait for
   std::vector<std::vector<int>> deps;
+  // chains of tiny contractions that one CTA executes back to back; chains with the same
+  // external dependencies form a group = one launch (see k_contract_chain)
+  struct ChainGroup {
+    std::vector<int> steps;          // member steps, chain by chain
+    std::vector<ChainRange> ranges;  // one per chain, `begin` relative to the group's items
+    std::vector<int> deps;           // steps outside the group that it waits for
+    int first = 0;                   // issue position: the smallest member index
+    int item_base = 0, range_base = 0;
+    bool dep = false;
+  };
+  std::vector<ChainGroup> groups;
+  std::vector<int> group_of;         // per step: its group or -1
+  ChainRange* d_ranges = nullptr;
   static constexpr int NSTREAMS = 8;
   cudaStream_t side[NSTREAMS] = {nullptr};
   std::vector<cudaEvent_t> step_ev;
@@ -272,10 +289,141 @@ static void build_dag(pq_handle* h, pq_program* p) {
   }
 }
 
+// Finds the chains of tiny contractions (each member depends on the previous member and on
+// steps that precede the whole chain) and groups chains with identical outside dependencies.
+// Members write to the never-recycled small arena, so running a chain earlier than its
+// position in the stream cannot create a hazard.
+static void build_chains(pq_handle* h, pq_program* p) {
+  const int n = (int)p->steps.size();
+  p->group_of.assign(n, -1);
+  p->groups.clear();
+  if (h->opt.chain != 0) return;
+  auto tiny = [&](int j) {
+    const Step& s = p->steps[j];
+    if (s.kind != ST_CONTRACT) return false;
+    const ContractPlan& c = s.cp;
+    if (c.kind != CK_SMALL_RIGHT && c.kind != CK_SMALL_LEFT && c.kind != CK_DIRECT) return false;
+    if (c.M * c.N > 2048 || c.K > 64 || c.M * c.K > 4096 || c.N * c.K > 4096) return false;
+    if (!s.c.small) return false;
+    ChainItem it;
+    return chain_item_from_plan(c, it);
+  };
+  struct Chain {
+    std::vector<int> m;
+    bool dep;
+  };
+  std::vector<Chain> chains;
+  std::vector<int> chain_of(n, -1);
+  for (int j = 0; j < n; ++j) {
+    if (!tiny(j)) continue;
+    int best = -1;
+    for (int d : p->deps[j]) {
+      const int c = chain_of[d];
+      if (c < 0 || chains[c].m.back() != d || chains[c].dep != p->steps[j].dep) continue;
+      bool ok = true;
+      for (int e : p->deps[j])
+        if (e != d && chain_of[e] != c && e >= chains[c].m.front()) ok = false;
+      if (ok) {
+        best = c;
+        break;
+      }
+    }
+    if (best < 0) {
+      chains.push_back(Chain{{j}, p->steps[j].dep});
+      best = (int)chains.size() - 1;
+    } else {
+      chains[best].m.push_back(j);
+    }
+    chain_of[j] = best;
+  }
+  // group by (phase, outside dependencies)
+  std::map<std::pair<bool, std::vector<int>>, int> index;
+  for (size_t c = 0; c < chains.size(); ++c) {
+    std::set<int> ext;
+    for (int m : chains[c].m)
+      for (int d : p->deps[m])
+        if (chain_of[d] != (int)c) ext.insert(d);
+    std::vector<int> key(ext.begin(), ext.end());
+    auto it = index.find({chains[c].dep, key});
+    int g;
+    if (it == index.end()) {
+      g = (int)p->groups.size();
+      index[{chains[c].dep, key}] = g;
+      pq_program::ChainGroup G;
+      G.deps = key;
+      G.dep = chains[c].dep;
+      G.first = chains[c].m.front();
+      p->groups.push_back(G);
+    } else {
+      g = it->second;
+    }
+    pq_program::ChainGroup& G = p->groups[g];
+    G.ranges.push_back(ChainRange{(int)G.steps.size(), (int)chains[c].m.size()});
+    for (int m : chains[c].m) {
+      G.steps.push_back(m);
+      p->group_of[m] = g;
+    }
+    if (chains[c].m.front() < G.first) G.first = chains[c].m.front();
+  }
+  // a group of one single-step chain is just that step
+  for (size_t g = 0; g < p->groups.size(); ++g)
+    if (p->groups[g].steps.size() == 1) {
+      p->group_of[p->groups[g].steps[0]] = -1;
+      p->groups[g].steps.clear();
+      p->groups[g].ranges.clear();
+    }
+  int ib = 0, rb = 0;
+  std::vector<ChainRange> all;
+  for (auto& G : p->groups) {
+    G.item_base = ib;
+    G.range_base = rb;
+    ib += (int)G.steps.size();
+    rb += (int)G.ranges.size();
+    all.insert(all.end(), G.ranges.begin(), G.ranges.end());
+  }
+  if (!all.empty()) {
+    PQ_CUDA(cudaMalloc(&p->d_ranges, sizeof(ChainRange) * all.size()));
+    PQ_CUDA(cudaMemcpy(p->d_ranges, all.data(), sizeof(ChainRange) * all.size(),
+                       cudaMemcpyHostToDevice));
+  }
+  if (getenv("PQ_B200_DEBUG")) {
+    size_t members = 0, nch = 0, ng = 0;
+    for (auto& G : p->groups)
+      if (!G.steps.empty()) {
+        members += G.steps.size();
+        nch += G.ranges.size();
+        ++ng;
+      }
+    fprintf(stderr, "[pq_b200] chains: %zu tiny steps in %zu chains, %zu group launches\n", members,
+            nch, ng);
+  }
+}
+
+// device descriptors of every group for one (lane, graph): operand addresses resolved
+static void upload_chain_items(pq_handle* h, pq_program* p, int slot, Where w) {
+  LaneMem& m = p->lanes[w.lane];
+  if (m.chain_items[slot]) return;
+  std::vector<ChainItem> items;
+  for (auto& G : p->groups)
+    for (int j : G.steps) {
+      ChainItem it;
+      const Step& s = p->steps[j];
+      chain_item_from_plan(s.cp, it);
+      it.A = resolve(p, s.a, w);
+      it.B = resolve(p, s.b, w);
+      it.C = resolve(p, s.c, w);
+      items.push_back(it);
+    }
+  if (items.empty()) return;
+  PQ_CUDA(cudaMalloc(&m.chain_items[slot], sizeof(ChainItem) * items.size()));
+  PQ_CUDA(cudaMemcpy(m.chain_items[slot], items.data(), sizeof(ChainItem) * items.size(),
+                     cudaMemcpyHostToDevice));
+}
+
 // Issues every step during stream capture, spreading independent steps over several
 // capture streams joined by events, so the instantiated graph is a DAG rather than a
 // chain: the ~10^3 tiny world-line contractions of a slice run concurrently.
-static void issue_steps_dag(pq_handle* h, pq_program* p, Launch& L0, int phase, Where w) {
+static void issue_steps_dag(pq_handle* h, pq_program* p, Launch& L0, int phase, Where w, int slot) {
   const int n = (int)p->steps.size();
   const int S = pq_program::NSTREAMS;
   cudaStream_t streams[pq_program::NSTREAMS + 1];
@@ -284,36 +432,58 @@ static void issue_steps_dag(pq_handle* h, pq_program* p, Launch& L0, int phase, 
   const int NS = S + 1;
   PQ_CUDA(cudaEventRecord(p->fork_ev, streams[0]));
   for (int s = 1; s < NS; ++s) PQ_CUDA(cudaStreamWaitEvent(streams[s], p->fork_ev, 0));
-  std::vector<int> tail(NS, -1);            // last step issued on each stream
-  std::vector<int> where(n, 0);             // stream of each step
-  std::vector<std::vector<int>> synced(NS, std::vector<int>(NS, -1));
+  // issue order: nodes (a step, or a whole group of chains) get increasing sequence numbers;
+  // events recorded on a stream cover everything issued on it up to that sequence number
+  std::vector<long long> seq(n, -1);
+  std::vector<int> where(n, 0);
+  std::vector<long long> tail(NS, -1);   // sequence number of the last node on each stream
+  std::vector<std::vector<long long>> synced(NS, std::vector<long long>(NS, -1));
+  long long counter = 0;
+  const ChainItem* items = static_cast<const ChainItem*>(p->lanes[w.lane].chain_items[slot]);
   for (int j = 0; j < n; ++j) {
     if (phase >= 0 && (p->steps[j].dep ? 1 : 0) != phase) continue;
+    const int g = p->group_of[j];
+    if (g >= 0 && j != p->groups[g].first) continue;   // issued with its group
     // hazards towards the other phase are ordered by the graph launches themselves
     std::vector<int> deps;
-    for (int d : p->deps[j])  // descending order
+    for (int d : (g >= 0 ? p->groups[g].deps : p->deps[j]))
       if (phase < 0 || (p->steps[d].dep ? 1 : 0) == phase) deps.push_back(d);
     int best = -1;
-    for (int d : deps)
-      for (int s = 0; s < NS; ++s)
-        if (tail[s] == d && (best < 0 || tail[s] > tail[best])) best = s;
+    for (int d : deps) {
+      const int sd = where[d];
+      if (seq[d] == tail[sd] && (best < 0 || tail[sd] > tail[best])) best = sd;
+    }
     if (best < 0) {
       best = 0;
       for (int s = 1; s < NS; ++s)
         if (tail[s] < tail[best]) best = s;
     }
     for (int d : deps) {
-      int sd = where[d];
-      if (sd == best || synced[best][sd] >= d) continue;
-      PQ_CUDA(cudaStreamWaitEvent(streams[best], p->step_ev[d], 0));
-      synced[best][sd] = d;
+      const int sd = where[d];
+      if (sd == best || synced[best][sd] >= seq[d]) continue;
+      const int gd = p->group_of[d];   // a group records one event, on its first member
+      PQ_CUDA(cudaStreamWaitEvent(streams[best], p->step_ev[gd >= 0 ? p->groups[gd].first : d], 0));
+      synced[best][sd] = seq[d];
     }
     Launch L = L0;
     L.stream = streams[best];
-    issue_step(h, p, p->steps[j], L, w);
-    PQ_CUDA(cudaEventRecord(p->step_ev[j], streams[best]));
-    tail[best] = j;
-    where[j] = best;
+    const long long me = counter++;
+    if (g >= 0) {
+      const pq_program::ChainGroup& G = p->groups[g];
+      run_chains(L, items + G.item_base, p->d_ranges + G.range_base, (int)G.ranges.size());
+      // one event for the group: every member maps to it
+      PQ_CUDA(cudaEventRecord(p->step_ev[G.first], streams[best]));
+      for (int m : G.steps) {
+        seq[m] = me;
+        where[m] = best;
+      }
+    } else {
+      issue_step(h, p, p->steps[j], L, w);
+      PQ_CUDA(cudaEventRecord(p->step_ev[j], streams[best]));
+      seq[j] = me;
+      where[j] = best;
+    }
+    tail[best] = me;
   }
   for (int s = 1; s < NS; ++s) {  // join every side stream back into the origin
     PQ_CUDA(cudaEventRecord(p->fork_ev, streams[s]));
@@ -396,15 +566,17 @@ static void run_phase(pq_handle* h, pq_program* p, Launch& L, int phase, int lan
       // on any stream
       Launch LC = L;
       LC.stream = h->stream;
-      LC.launch_counter = nullptr;
+      int64_t captured = 0;
+      LC.launch_counter = &captured;
       LC.profile = false;
+      if (h->opt.graph != 2) upload_chain_items(h, p, slot, w);
       cudaGraph_t graph = nullptr;
       PQ_CUDA(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
       try {
         if (h->opt.graph == 2)
           issue_steps(h, p, LC, phase, w);       // single-stream chain (A/B against the DAG)
         else
-          issue_steps_dag(h, p, LC, phase, w);   // independent steps on parallel branches
+          issue_steps_dag(h, p, LC, phase, w, slot);   // independent steps on parallel branches
       } catch (...) {
         cudaStreamEndCapture(h->stream, &graph);
         if (graph) cudaGraphDestroy(graph);
@@ -415,9 +587,10 @@ static void run_phase(pq_handle* h, pq_program* p, Launch& L, int phase, int lan
       cudaError_t e = cudaGraphInstantiate(&m.exec2[slot], graph, 0);
       cudaGraphDestroy(graph);
       PQ_CUDA(e);
+      m.graph_launches[slot] = captured;
     }
     PQ_CUDA(cudaGraphLaunch(m.exec2[slot], on ? on : h->stream));
-    h->launches += nl;
+    h->launches += m.graph_launches[slot];
   }
   h->n_contract += phase < 0 ? p->ncontract : p->ncontract2[phase];
   h->macs += phase < 0 ? p->macs : p->macs2[phase];
@@ -455,8 +628,10 @@ static void ensure_lanes(pq_handle* h, pq_program* p, int n) {
 
 static void free_lanes(pq_program* p) {
   for (LaneMem& m : p->lanes) {
-    for (int a = 0; a < 3; ++a)
+    for (int a = 0; a < 3; ++a) {
       if (m.exec2[a]) cudaGraphExecDestroy(m.exec2[a]);
+      if (m.chain_items[a]) cudaFree(m.chain_items[a]);
+    }
     for (int a = 0; a < 2; ++a)
       if (m.arena2[a]) cudaFree(m.arena2[a]);
     if (m.arena_small) cudaFree(m.arena_small);
@@ -719,6 +894,7 @@ extern "C" int pq_program_compile(pq_handle* h, const char* tl_text, pq_program*
       }
     }
     build_dag(h, p);
+    build_chains(h, p);
     for (int i = 0; i < pq_program::NSTREAMS; ++i)
       PQ_CUDA(cudaStreamCreateWithFlags(&p->side[i], cudaStreamNonBlocking));
     PQ_CUDA(cudaEventCreateWithFlags(&p->fork_ev, cudaEventDisableTiming));
@@ -737,6 +913,11 @@ extern "C" int pq_program_compile(pq_handle* h, const char* tl_text, pq_program*
         p->launches2[s.dep ? 1 : 0] += n;
       }
       p->launches = p->launches2[0] + p->launches2[1];
+      // what one replay launches in graph mode: a group of chains is a single launch
+      p->launches_batched = p->launches;
+      if (h->opt.graph == 0 || h->opt.graph > 2)
+        for (const auto& G : p->groups)
+          if (!G.steps.empty()) p->launches_batched -= (int64_t)G.steps.size() - 1;
     }
   } catch (const Error& e) {
     h->last_error = e.what();
@@ -761,7 +942,7 @@ extern "C" int pq_program_stats(const pq_program* p, int64_t* arena_bytes, int64
                                 int64_t* macs) {
   if (!p) return PQ_ERR_INVALID;
   if (arena_bytes) *arena_bytes = (int64_t)(p->arena_bytes + p->arena_small_bytes);
-  if (launches) *launches = p->launches;
+  if (launches) *launches = p->launches_batched;
   if (macs) *macs = p->macs;
   return PQ_OK;
 }
@@ -993,6 +1174,7 @@ extern "C" int pq_program_destroy(pq_handle* h, pq_program* p) {
   }
   if (p->h_table) cudaFreeHost(p->h_table);
   if (p->d_table) cudaFree(p->d_table);
+  if (p->d_ranges) cudaFree(p->d_ranges);
   if (p->batch_ev) cudaEventDestroy(p->batch_ev);
   if (p->table_ev) cudaEventDestroy(p->table_ev);
   delete p;

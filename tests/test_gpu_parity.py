@@ -615,6 +615,46 @@ def test_large_program_dag_vs_chain(graph):
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
+def test_chains_of_tiny_contractions(dtype):
+    """Compiled programs batch chains of tiny contractions (the world-lines of a slice) into a
+    few launches, one CTA per chain.  Same amplitude as with one launch per contraction and as
+    the oracle, far fewer launches per replay, with and without hoisting and with lanes."""
+    tol = TOL[np.dtype(dtype)]
+    circ = create_RQC(4, 5, 14, seed=5)
+    n = circ.n_qubits
+    P = 8
+
+    def plan_fn(tn, sliced):
+        return sweep_plan(tn, 4, 5, sliced_bonds=sliced)
+
+    rec = record_sliced_contraction(circ, P, 1, plan_fn=plan_fn, output_config="0" * n)
+    ref = circ.simulate()[0]
+    results, launches = {}, {}
+    for chain in (0, 1):
+        b = B200(dtype, chain=chain)
+        sc = SlicedContraction(b, rec)
+        for hoist, lanes in ((False, 1), (True, 1), (False, 3), (True, 2)):
+            b.delete_tensor("partial_sum")
+            b.reset_counters()
+            sc.run(range(1, P + 1), hoist=hoist, lanes=lanes)
+            got = sc.result()
+            assert abs(got - ref) / abs(ref) < 20 * tol, (chain, hoist, lanes, got, ref)
+            results[(chain, hoist, lanes)] = got.copy()
+            if not hoist and lanes == 1:
+                launches[chain] = b.counters()["kernel_launches"] // P
+            assert b.counters()["macs"] == ((sc.program.macs_invariant + P * sc.program.macs_dependent)
+                                            if hoist else P * sc.program.macs)
+        # every way of running the same program gives the same bits
+        base = results[(chain, False, 1)]
+        for key, v in results.items():
+            if key[0] == chain:
+                assert v.tobytes() == base.tobytes(), key
+        b.close()
+    assert launches[0] < launches[1] / 3, launches
+    assert abs(results[(0, False, 1)] - results[(1, False, 1)]) / abs(ref) < tol
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
 def test_sliced_program_replay(dtype):
     """One compiled plan replayed for every partition; the stream for partition p
     equals the one the host mirror emits for p (only view indices differ)."""
