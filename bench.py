@@ -53,7 +53,7 @@ def parse_args():
     ap.add_argument("--depth", type=int, default=24)
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--slices", type=int, default=64)
-    ap.add_argument("--lanes", type=int, default=2,
+    ap.add_argument("--lanes", type=int, default=4,
                     help="slices kept in flight per GPU (pq_program_run_slices)")
     ap.add_argument("--cpu-sample-slices", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
