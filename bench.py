@@ -428,6 +428,9 @@ def main():
         slice_ms = ms_per_step / max(1, len(mine))
         long_cls = [c for c, v in prof.items() if v["ms"] / v["launches"] >= 0.02]
         long_ms = sum(prof[c]["ms"] / reps for c in long_cls)
+        # several slices are in flight (lanes), so a slice's share of the wall time can be
+        # smaller than the device time of its long kernels measured one by one
+        slice_ms = max(slice_ms, long_ms)
         for cls in kernels:
             if cls in long_cls:
                 kernels[cls]["share_of_timed_slice"] = (prof[cls]["ms"] / reps) / slice_ms

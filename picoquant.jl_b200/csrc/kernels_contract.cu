@@ -261,17 +261,40 @@ template <typename R>
 __global__ void __launch_bounds__(128)
 k_contract_chain(const ChainItem* __restrict__ items, const ChainRange* __restrict__ ranges) {
   using V = typename C2<R>::type;
+  constexpr int WORDS = (int)(sizeof(ChainItem) / sizeof(int));
+  constexpr int PER = (WORDS + 127) / 128;   // descriptor words per thread
   __shared__ ChainItem it;
   const ChainRange rg = ranges[blockIdx.x];
+  // the descriptor of item s + 1 is fetched into registers while item s is computed, so
+  // only the operand round trips through L2 remain on the chain's critical path
+  int pre[PER];
+  {
+    const int* src = reinterpret_cast<const int*>(items + rg.begin);
+#pragma unroll
+    for (int q = 0; q < PER; ++q) {
+      const int i = threadIdx.x + q * 128;
+      pre[q] = (i < WORDS && rg.count > 0) ? src[i] : 0;
+    }
+  }
   for (int s = 0; s < rg.count; ++s) {
     __syncthreads();   // results of the previous item are visible; `it` may be overwritten
     {
-      const int* src = reinterpret_cast<const int*>(items + rg.begin + s);
       int* dst = reinterpret_cast<int*>(&it);
-      for (int i = threadIdx.x; i < (int)(sizeof(ChainItem) / sizeof(int)); i += blockDim.x)
-        dst[i] = src[i];
+#pragma unroll
+      for (int q = 0; q < PER; ++q) {
+        const int i = threadIdx.x + q * 128;
+        if (i < WORDS) dst[i] = pre[q];
+      }
     }
     __syncthreads();
+    if (s + 1 < rg.count) {
+      const int* src = reinterpret_cast<const int*>(items + rg.begin + s + 1);
+#pragma unroll
+      for (int q = 0; q < PER; ++q) {
+        const int i = threadIdx.x + q * 128;
+        if (i < WORDS) pre[q] = src[i];
+      }
+    }
     const V* A = static_cast<const V*>(it.A);
     const V* B = static_cast<const V*>(it.B);
     V* C = static_cast<V*>(it.C);
