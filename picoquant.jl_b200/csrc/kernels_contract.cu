@@ -257,12 +257,14 @@ __device__ __forceinline__ int mini_offset(const MiniMap& m, int i) {
   return off;
 }
 
+constexpr int CHAIN_THREADS = 256;
+
 template <typename R>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(CHAIN_THREADS)
 k_contract_chain(const ChainItem* __restrict__ items, const ChainRange* __restrict__ ranges) {
   using V = typename C2<R>::type;
   constexpr int WORDS = (int)(sizeof(ChainItem) / sizeof(int));
-  constexpr int PER = (WORDS + 127) / 128;   // descriptor words per thread
+  constexpr int PER = (WORDS + CHAIN_THREADS - 1) / CHAIN_THREADS;   // descriptor words per thread
   __shared__ ChainItem it;
   const ChainRange rg = ranges[blockIdx.x];
   // the descriptor of item s + 1 is fetched into registers while item s is computed, so
@@ -272,7 +274,7 @@ k_contract_chain(const ChainItem* __restrict__ items, const ChainRange* __restri
     const int* src = reinterpret_cast<const int*>(items + rg.begin);
 #pragma unroll
     for (int q = 0; q < PER; ++q) {
-      const int i = threadIdx.x + q * 128;
+      const int i = threadIdx.x + q * CHAIN_THREADS;
       pre[q] = (i < WORDS && rg.count > 0) ? src[i] : 0;
     }
   }
@@ -282,7 +284,7 @@ k_contract_chain(const ChainItem* __restrict__ items, const ChainRange* __restri
       int* dst = reinterpret_cast<int*>(&it);
 #pragma unroll
       for (int q = 0; q < PER; ++q) {
-        const int i = threadIdx.x + q * 128;
+        const int i = threadIdx.x + q * CHAIN_THREADS;
         if (i < WORDS) dst[i] = pre[q];
       }
     }
@@ -291,7 +293,7 @@ k_contract_chain(const ChainItem* __restrict__ items, const ChainRange* __restri
       const int* src = reinterpret_cast<const int*>(items + rg.begin + s + 1);
 #pragma unroll
       for (int q = 0; q < PER; ++q) {
-        const int i = threadIdx.x + q * 128;
+        const int i = threadIdx.x + q * CHAIN_THREADS;
         if (i < WORDS) pre[q] = src[i];
       }
     }
@@ -349,9 +351,9 @@ void run_chains(const Launch& L, const ChainItem* d_items, const ChainRange* d_r
   if (nchains <= 0) return;
   L.begin(KC_CONTRACT_SMALL, 0, 0);
   if (L.elem_size == 16)
-    k_contract_chain<double><<<nchains, 128, 0, L.stream>>>(d_items, d_ranges);
+    k_contract_chain<double><<<nchains, CHAIN_THREADS, 0, L.stream>>>(d_items, d_ranges);
   else
-    k_contract_chain<float><<<nchains, 128, 0, L.stream>>>(d_items, d_ranges);
+    k_contract_chain<float><<<nchains, CHAIN_THREADS, 0, L.stream>>>(d_items, d_ranges);
   L.end();
   PQ_CUDA(cudaGetLastError());
 }

@@ -23,6 +23,19 @@ namespace {
 constexpr size_t ALIGN = 256;
 inline size_t round_up(size_t x) { return (x + ALIGN - 1) / ALIGN * ALIGN; }
 
+// Host -> device upload that has LANDED when the call returns.  cudaMemcpy from pageable
+// memory may return once the data sits in the driver's staging buffer, and the handle's /
+// lanes' streams are non-blocking, i.e. not ordered after the legacy default stream: a graph
+// launched right afterwards could read the destination before the DMA has finished.
+void upload_now(void* dst, const void* src, size_t bytes) {
+  cudaStream_t up = nullptr;   // per call: these uploads happen a few times per program
+  PQ_CUDA(cudaStreamCreateWithFlags(&up, cudaStreamNonBlocking));
+  cudaError_t e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, up);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(up);
+  cudaStreamDestroy(up);
+  PQ_CUDA(e);
+}
+
 // offset allocator used at compile time only
 struct ArenaSim {
   std::map<size_t, size_t> free_blocks;  // offset -> size
@@ -94,7 +107,7 @@ struct Ref {  // pointer = leaf ? leafptr : (small ? arena_small : arena) + offs
 // Tensors up to this size are bump-allocated and never recycled within a program, so
 // that the only hazards between the ~10^3 tiny contractions of a slice are true data
 // dependencies and independent world-lines can run on parallel graph branches.
-constexpr size_t SMALL_TENSOR_BYTES = 64 * 1024;
+constexpr size_t SMALL_TENSOR_BYTES = 256 * 1024;
 
 struct Step {
   StepKind kind;
@@ -303,7 +316,7 @@ static void build_chains(pq_handle* h, pq_program* p) {
     if (s.kind != ST_CONTRACT) return false;
     const ContractPlan& c = s.cp;
     if (c.kind != CK_SMALL_RIGHT && c.kind != CK_SMALL_LEFT && c.kind != CK_DIRECT) return false;
-    if (c.M * c.N > 2048 || c.K > 64 || c.M * c.K > 4096 || c.N * c.K > 4096) return false;
+    if (c.M * c.N > 8192 || c.K > 64 || c.M * c.K > 8192 || c.N * c.K > 8192) return false;
     if (!s.c.small) return false;
     ChainItem it;
     return chain_item_from_plan(c, it);
@@ -383,8 +396,7 @@ static void build_chains(pq_handle* h, pq_program* p) {
   }
   if (!all.empty()) {
     PQ_CUDA(cudaMalloc(&p->d_ranges, sizeof(ChainRange) * all.size()));
-    PQ_CUDA(cudaMemcpy(p->d_ranges, all.data(), sizeof(ChainRange) * all.size(),
-                       cudaMemcpyHostToDevice));
+    upload_now(p->d_ranges, all.data(), sizeof(ChainRange) * all.size());
   }
   if (getenv("PQ_B200_DEBUG")) {
     size_t members = 0, nch = 0, ng = 0;
@@ -416,8 +428,7 @@ static void upload_chain_items(pq_handle* h, pq_program* p, int slot, Where w) {
     }
   if (items.empty()) return;
   PQ_CUDA(cudaMalloc(&m.chain_items[slot], sizeof(ChainItem) * items.size()));
-  PQ_CUDA(cudaMemcpy(m.chain_items[slot], items.data(), sizeof(ChainItem) * items.size(),
-                     cudaMemcpyHostToDevice));
+  upload_now(m.chain_items[slot], items.data(), sizeof(ChainItem) * items.size());
 }
 
 // Issues every step during stream capture, spreading independent steps over several
@@ -605,8 +616,7 @@ static void ensure_lanes(pq_handle* h, pq_program* p, int n) {
     PQ_CUDA(cudaMalloc(&m.arena_small, p->arena_small_bytes ? p->arena_small_bytes : ALIGN));
     if (p->nviews > 0) {
       PQ_CUDA(cudaMalloc(&m.d_starts, sizeof(int32_t) * p->nviews));
-      PQ_CUDA(cudaMemcpy(m.d_starts, p->default_starts.data(), sizeof(int32_t) * p->nviews,
-                         cudaMemcpyHostToDevice));
+      upload_now(m.d_starts, p->default_starts.data(), sizeof(int32_t) * p->nviews);
     }
     for (const Step& s : p->steps)
       if (s.kind == ST_SAVE)
@@ -885,8 +895,7 @@ extern "C" int pq_program_compile(pq_handle* h, const char* tl_text, pq_program*
     PQ_CUDA(cudaMalloc(&m0.arena_small, small_top ? small_top : ALIGN));
     if (p->nviews > 0) {
       PQ_CUDA(cudaMalloc(&m0.d_starts, sizeof(int32_t) * p->nviews));
-      PQ_CUDA(cudaMemcpy(m0.d_starts, p->default_starts.data(), sizeof(int32_t) * p->nviews,
-                         cudaMemcpyHostToDevice));
+      upload_now(m0.d_starts, p->default_starts.data(), sizeof(int32_t) * p->nviews);
       PQ_CUDA(cudaMallocHost(&p->h_ring, sizeof(int32_t) * p->nviews * pq_program::RING));
       for (int i = 0; i < pq_program::RING; ++i) {
         PQ_CUDA(cudaEventCreateWithFlags(&p->ring_ev[i], cudaEventDisableTiming));
