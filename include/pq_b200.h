@@ -191,8 +191,20 @@ const char* pq_kernel_class_name(int cls);
 int pq_timer_begin(pq_handle* h);
 int pq_timer_end(pq_handle* h, double* ms);
 
-/* Behaviour knobs for A/B checks ("gemm": 0 auto, 1 SIMT, 2 DMMA/tensor;
- * "permute": 0 auto, 1 generic, 2 tiled; "fused": 0 auto, 1 off; "graph": 0 auto, 1 off). */
+/* Behaviour knobs for A/B checks (0 is always the default / automatic choice):
+ *   "gemm"          1 SIMT GEMM, 2 tensor-core GEMM, 3 direct kernel everywhere
+ *   "permute"       1 generic permute kernel, 2 tiled bit-permutation
+ *   "fused"         1 disables the fused small-operand / dot kernels and the fused-TTGT GEMMs
+ *   "graph"         1 eager replay of programs, 2 single-chain CUDA graph (default: DAG graph)
+ *   "chain"         1 one launch per tiny contraction in programs (default: batched chains)
+ *   "prio"          1 no launch priorities on graph nodes
+ *   "zgemm_cfg"     fused ZGEMM tile configuration: 1 64x64, 2 64x32, 3 128x8, 4 64x32 with 3M
+ *                   products, 7 persistent skinny kernel where eligible
+ *   "zgemm_skinny"  1 disables the persistent skinny ZGEMM
+ *   "zgemm_3m"      1 four DMMAs per complex product instead of three (3M)
+ *   "zgemm_kfirst"  1 row-first gather order only
+ *   "zgemm_stagger" ns of start delay per resident-CTA slot in the first wave (tile-per-CTA ZGEMM)
+ * Every alternative computes the same contraction; the tests run them against each other. */
 int pq_set_option(pq_handle* h, const char* key, int value);
 
 /* Stand-alone micro-benchmarks used by bench.py for roofline denominators measured on

@@ -931,12 +931,14 @@ extern "C" int pq_program_compile(pq_handle* h, const char* tl_text, pq_program*
   } catch (const Error& e) {
     h->last_error = e.what();
     free_lanes(p);
+    if (p->d_ranges) cudaFree(p->d_ranges);
     for (auto& l : p->leaves) l.second->pins -= 1;
     delete p;
     return e.code;
   } catch (const std::exception& e) {
     h->last_error = e.what();
     free_lanes(p);
+    if (p->d_ranges) cudaFree(p->d_ranges);
     for (auto& l : p->leaves) l.second->pins -= 1;
     delete p;
     return PQ_ERR_PARSE;
