@@ -15,6 +15,7 @@ from .layer2 import (calculate_mps_amplitudes, compress_bond, compress_tensor_ch
                      create_ncon_indices, decompose_tensor, full_wavefunction_contraction,
                      inorder_contraction, merge_common_bonds, random_contraction_plan,
                      sort_indices)
+from .mps import MPSState
 from .slicing import (multi_index_partition, partition_network_on_virtual_bonds,
                       replace_with_view, slice_tensor_network)
 from .algorithms import (create_ghz_preparation_circuit, create_qft_circuit, create_RQC,

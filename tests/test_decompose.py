@@ -245,6 +245,35 @@ def test_inorder_contraction_with_bond_merging_oracle():
     _inorder_with_bond_merging(lambda: OracleBackend(np.complex128), 1e-10)
 
 
+def test_mps_state_amplitudes_oracle():
+    """src/mps.jl + test/layer2_tests.jl:330-351: GHZ-5 amplitudes through the array
+    interface of MPSState; and, for a state without the GHZ symmetry, every amplitude equals
+    the corresponding entry of calculate_mps_amplitudes!."""
+    import itertools
+    from picoquant_jl_b200.host import MPSState
+    n = 5
+    b = OracleBackend(np.complex128)
+    tn = convert_circuit_to_network(create_ghz_preparation_circuit(n), b, decompose=True)
+    add_input(tn, "0" * n)
+    mps_nodes = contract_mps_tensor_network_circuit(tn)
+    state = MPSState(tn, mps_nodes)
+    assert state.shape == (2,) * n and len(state) == 2 ** n
+    assert abs(state["11111"] - 1 / np.sqrt(2)) < 1e-6 and abs(state["00000"] - 1 / np.sqrt(2)) < 1e-6
+    assert abs(state["10101"]) < 1e-6
+    assert abs(state[2, 2, 2, 2, 2] - state["11111"]) == 0
+
+    circ = create_simple_preparation_circuit(3, 1).compose(create_ghz_preparation_circuit(3))
+    b = OracleBackend(np.complex128)
+    tn = convert_circuit_to_network(circ, b, decompose=True)
+    add_input(tn, "000")
+    mps_nodes = contract_mps_tensor_network_circuit(tn)
+    state = MPSState(tn, mps_nodes, dtype=np.complex128)
+    calculate_mps_amplitudes(tn, mps_nodes)
+    full = np.reshape(np.array(b.load_tensor_data("result")), (2, 2, 2), order="F")
+    for bits in itertools.product([0, 1], repeat=3):
+        assert abs(state["".join(str(x) for x in bits)] - full[bits]) < 1e-12, bits
+
+
 def test_reference_mps_contraction_oracle():
     _mps_matches_full_wavefunction(lambda: OracleBackend(np.complex128), 1e-10)
 
