@@ -224,3 +224,29 @@ def test_oracle_contract_matches_einsum():
     # view keeps the axis, 1-based
     V = layer1.tensor_view(A, 3, range(2, 3))
     assert V.shape == (2, 3, 1, 2) and np.array_equal(V[:, :, 0, :], A[:, :, 1, :])
+
+
+def test_qasm_load_and_json_round_trip():
+    """test/layer3_tests.jl:10-36: qasm -> circuit -> network; to_json(network_from_json(j)) == j."""
+    from picoquant_jl_b200.host import network_from_json, to_json
+    qasm = """OPENQASM 2.0;
+              include "qelib1.inc";
+              qreg q[3];
+              h q[0];
+              cx q[0],q[1];
+              cx q[1],q[2];"""
+    circ = load_qasm_as_circuit(qasm)
+    assert circ.n_qubits == 3 and len(circ.data) == 3
+    tng = convert_circuit_to_network(circ, OracleBackend(C128))
+    j = to_json(tng)
+    assert to_json(network_from_json(j, OracleBackend(C128))) == j
+
+
+def test_network_data_structure_counts():
+    """test/layer3_tests.jl:38-55: empty network, one node and four edges after one
+    single-qubit gate on a 3-qubit register."""
+    tn = TensorNetworkCircuit(3, OracleBackend(C128))
+    assert len(tn.nodes) == 0
+    add_gate(tn, np.array([[1, 1], [1, -1]]) / np.sqrt(2), [1])
+    assert len(tn.nodes) == 1
+    assert len(tn.edges) == 4
