@@ -342,6 +342,34 @@ def contract_mps_tensor_network_circuit(network: TensorNetworkCircuit, *, max_bo
     return mps_nodes
 
 
+def contract_tensor_network_circuit_with_compression(network: TensorNetworkCircuit, *,
+                                                     max_bond: int = 2, threshold: float = 1e-13,
+                                                     max_rank: int = 0) -> List[str]:
+    """``contract_tensor_network_circuit_with_compression!`` (``src/layer2.jl:657-702``): like
+    the MPS driver but without the neighbour requirement -- after every layer the bonds
+    between consecutively touched sites are compressed in the order the gates were met."""
+    network_nodes = [network.edges[x].src for x in network.input_qubits]
+    assert all(x is not None for x in network_nodes), "Input qubit values must be set"
+    layer_nodes = _layer_nodes(network)
+    gate_layers = [k for k in sorted(layer_nodes) if k > 0]
+    if -1 in layer_nodes:
+        gate_layers.append(-1)
+    for gate_layer in gate_layers:
+        updated = []
+        for node in layer_nodes[gate_layer]:
+            input_node = inneighbours(network, node)[0]
+            assert input_node in network_nodes, "%s not in network nodes" % input_node
+            idx = network_nodes.index(input_node)
+            network_nodes[idx] = contract_pair(network, input_node, node)
+            updated.append(idx)
+        for i in range(len(updated) - 1):
+            compress_bond(network, network_nodes[updated[i]], network_nodes[updated[i + 1]],
+                          threshold=threshold, max_rank=max_rank)
+    for node in network_nodes:
+        network.save_output(node, node)
+    return network_nodes
+
+
 def calculate_mps_amplitudes(network: TensorNetworkCircuit, mps_nodes: Sequence[str],
                              result: str = "result") -> None:
     """``calculate_mps_amplitudes!`` (``src/layer2.jl:633-643``): contract the chain left to

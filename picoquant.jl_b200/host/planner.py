@@ -259,3 +259,165 @@ def sweep_plan(network: TensorNetworkCircuit, rows: int, cols: int, *,
     if l is not None and r is not None:
         contract(l, r)
     return plan
+
+
+# ---------------------------------------------------------------------------
+# the reference's own planners, restated (src/layer2/bgreedy_contraction.jl,
+# src/layer2/netcon_contraction.jl).  Plans are inputs to the hot path; these exist so
+# that scripts written against PicoQuant's planner API keep working.
+# ---------------------------------------------------------------------------
+def contraction_cost(A, B, alpha: float):
+    """``contraction_cost`` (``bgreedy_contraction.jl:73-91``): Gray-Kourtis heuristic
+    ``|C| - alpha (|A| + |B|)``, the result's indices / dims, and [time, space] costs."""
+    from .layer2 import sort_indices
+    _, c_indices = sort_indices(A, B)
+    cset = set(c_indices)
+    a_open = [d for i, d in zip(A.indices, A.dims) if i in cset]
+    b_open = [d for i, d in zip(B.indices, B.dims) if i in cset]
+    c_dims = a_open + b_open
+    size_c = math.prod(c_dims)
+    size_a = math.prod(A.dims)
+    size_b = math.prod(B.dims)
+    costs = [math.sqrt(size_a * size_b * size_c), size_c]
+    return size_c - alpha * (size_a + size_b), c_indices, c_dims, costs
+
+
+def bgreedy(network: TensorNetworkCircuit, alpha: float = 1.0, tau: float = 1.0,
+            N: Optional[int] = None, rng: Optional[random.Random] = None):
+    """``bgreedy`` (``bgreedy_contraction.jl:17-65``): contract a random pair drawn from
+    the Boltzmann distribution ``exp(-cost / tau)`` over ALL pairs until one tensor is left.
+    With ``N`` the best of N samples by time cost is returned as ``(plan, time_cost)``;
+    without it one sample as ``(plan, time_cost, space_cost)``.  (StatsBase's sampler and
+    Julia's RNG stream cannot be matched; pass ``rng`` for reproducibility.)"""
+    from .layer3 import Node
+    rng = rng or random.Random()
+
+    def once():
+        tensors = dict(network.nodes)
+        plan: List[List[str]] = []
+        count = network.counters["node"]
+        time_cost, space_cost = 0.0, 0.0
+        while len(tensors) > 1:
+            items = list(tensors.items())
+            pairs, energy, cinds, cdims, costs = [], [], [], [], []
+            for i in range(len(items)):
+                for j in range(i + 1, len(items)):
+                    e, ci, cd, co = contraction_cost(items[i][1], items[j][1], alpha)
+                    pairs.append((items[i][0], items[j][0]))
+                    energy.append(e)
+                    cinds.append(ci)
+                    cdims.append(cd)
+                    costs.append(co)
+            emin = min(energy)     # shift: same distribution, no overflow in exp
+            weights = [math.exp(-(e - emin) / tau) for e in energy]
+            k = rng.choices(range(len(pairs)), weights=weights)[0]
+            a, b = pairs[k]
+            count += 1
+            c = "node_%d" % count
+            del tensors[a]
+            del tensors[b]
+            tensors[c] = Node(cinds[k], cdims[k], "intermediate_tensor")
+            plan.append([a, b])
+            time_cost += costs[k][0]
+            space_cost = max(space_cost, costs[k][1])
+        return plan, time_cost, space_cost
+
+    if N is None:
+        return once()
+    best_plan, best_cost = [], math.inf
+    for _ in range(N):
+        plan, t, _ = once()
+        if t < best_cost:
+            best_plan, best_cost = plan, t
+    return best_plan, best_cost
+
+
+def bgreedy_contraction(network: TensorNetworkCircuit, alpha: float = 1.0, tau: float = 1.0,
+                        N: int = 10, output_shape="", rng: Optional[random.Random] = None):
+    """``bgreedy_contraction!`` (``bgreedy_contraction.jl:140-145``)."""
+    from .layer2 import contract_network
+    plan, _ = bgreedy(network, alpha, tau, N, rng)
+    return contract_network(network, plan, output_shape)
+
+
+def netcon(network: TensorNetworkCircuit) -> List[List[str]]:
+    """``netcon`` (``netcon_contraction.jl:15-41``) returns the pair plan of a
+    minimum-flop contraction tree.  The reference delegates the search to
+    TensorOperations.jl's ``optimaltree`` (un-vendored); here the optimum over all binary
+    trees is found by dynamic programming over subsets of tensors (cost of joining two
+    groups = product of the dims of every index either group still exposes), which the
+    reference's 36-node limit does not need but its tests (3-qubit circuits) fit easily:
+    at most 16 tensors are accepted.  The tree is converted to a plan exactly like
+    ``convert_tree_to_plan`` (``:97-123``): left subtree, right subtree, then the pair."""
+    labels = list(network.nodes)
+    n = len(labels)
+    if n > 16:
+        raise ValueError("netcon (subset DP) handles at most 16 tensors, got %d" % n)
+    if n == 0:
+        return []
+    dims: Dict[str, int] = {}
+    owners: Dict[str, int] = {}
+    for t, lab in enumerate(labels):
+        node = network.nodes[lab]
+        for ind, d in zip(node.indices, node.dims):
+            dims[ind] = int(d)
+            owners[ind] = owners.get(ind, 0) | (1 << t)
+    full = (1 << n) - 1
+
+    def exposed(mask: int) -> int:
+        # product of dims of indices with an owner inside and (an owner outside or open)
+        p = 1
+        for ind, own in owners.items():
+            if own & mask and (own & ~mask & full or bin(own).count("1") == 1):
+                p *= dims[ind]
+        return p
+
+    def join_cost(a: int, b: int) -> int:
+        p = 1
+        for ind, own in owners.items():
+            if own & (a | b):
+                inside_only = (own & ~(a | b) & full) == 0 and bin(own).count("1") > 1
+                shared = bool(own & a) and bool(own & b)
+                if shared or not inside_only:
+                    p *= dims[ind]
+        return p
+
+    best: Dict[int, Tuple[int, object]] = {1 << t: (0, t) for t in range(n)}
+    for size in range(2, n + 1):
+        for mask in range(1, full + 1):
+            if bin(mask).count("1") != size:
+                continue
+            low = mask & -mask
+            sub = (mask - 1) & mask
+            cand = None
+            while sub:
+                if sub & low and sub != mask:       # each split once
+                    other = mask ^ sub
+                    if sub in best and other in best:
+                        c = best[sub][0] + best[other][0] + join_cost(sub, other)
+                        if cand is None or c < cand[0]:
+                            cand = (c, (best[sub][1], best[other][1]))
+                sub = (sub - 1) & mask
+            if cand is not None:
+                best[mask] = cand
+    tree = best[full][1]
+    plan: List[List[str]] = []
+    counter = [network.counters["node"]]
+
+    def convert(t):
+        if isinstance(t, int):
+            return labels[t]
+        a = convert(t[0])
+        b = convert(t[1])
+        plan.append([a, b])
+        counter[0] += 1
+        return "node_%d" % counter[0]
+
+    convert(tree)
+    return plan
+
+
+def netcon_contraction(network: TensorNetworkCircuit, output_shape=""):
+    """``netcon_contraction!`` (``netcon_contraction.jl:152-160``)."""
+    from .layer2 import contract_network
+    return contract_network(network, netcon(network), output_shape)
