@@ -3,7 +3,7 @@ minus the Julia ``!``)."""
 from .backends import (AbstractBackend, DSLBackend, Metrics, TensorStore, parse_dsl,
                        record_compute_costs, record_memory_costs)
 from .circuit import (Circuit, gate_matrix, load_qasm_as_circuit,
-                      load_qasm_as_circuit_from_file)
+                      load_qasm_as_circuit_from_file, transpile_circuit)
 from .layer3 import (Edge, Node, TensorNetworkCircuit, add_gate, add_input, add_output,
                      convert_circuit_to_network, convert_qiskit_circ_to_network,
                      decompose_gate, edges, gate_data_from_matrix, gate_tensor, getedge,

@@ -342,3 +342,62 @@ def load_qasm_as_circuit_from_file(qasm_path: str):
         with open(qasm_path) as f:
             return load_qasm_as_circuit(f.read())
     return False
+
+
+def transpile_circuit(circ: Circuit, couplings=None):
+    """``transpile_circuit`` (``src/layer3.jl:493-527``): make every two-qubit gate act on
+    coupled qubits.  The reference runs qiskit's ``BasicSwap`` pass; its published algorithm
+    is restated here: walk the gates in order under a logical -> physical layout; when a
+    two-qubit gate's qubits are further apart than one coupling, take the shortest
+    (undirected) path between them and swap the FIRST qubit along it until the two are
+    neighbours -- ``for k in range(len(path) - 2): swap(path[k], path[k+1])`` -- updating the
+    layout (nothing is swapped back).  ``couplings`` defaults to the line
+    ``[[i-1, i] for i = 1:n]`` like the reference (pairs naming a qubit >= n are ignored).
+    Returns ``(circuit on physical qubits, qubit_ordering)`` with
+    ``qubit_ordering[c] = 1 + physical qubit holding logical qubit c`` -- what the reference
+    reads back from the measurements it appended (``layer3.jl:516-524``); its own test pins
+    ``[2, 1, 3]`` for ``h q0; cx q0,q2`` (``test/layer3_tests.jl:89-102``)."""
+    n = circ.n_qubits
+    if couplings is None:
+        couplings = [[i - 1, i] for i in range(1, n + 1)]
+    adj = {q: set() for q in range(n)}
+    for a, b in couplings:
+        if 0 <= a < n and 0 <= b < n and a != b:
+            adj[a].add(b)
+            adj[b].add(a)
+
+    def shortest_path(src: int, dst: int):
+        prev = {src: None}
+        frontier = [src]
+        while frontier and dst not in prev:
+            nxt = []
+            for u in frontier:
+                for v in sorted(adj[u]):
+                    if v not in prev:
+                        prev[v] = u
+                        nxt.append(v)
+            frontier = nxt
+        if dst not in prev:
+            raise ValueError("qubits %d and %d are not connected by the coupling map" % (src, dst))
+        path = [dst]
+        while prev[path[-1]] is not None:
+            path.append(prev[path[-1]])
+        return path[::-1]
+
+    layout = list(range(n))          # logical -> physical
+    out = Circuit(n)
+    for name, params, qubits in circ.data:
+        if name == "barrier":
+            out.data.append((name, params, tuple(layout[q] for q in qubits)))
+            continue
+        if len(qubits) > 2:
+            raise ValueError("transpile_circuit handles one- and two-qubit gates only")
+        if len(qubits) == 2:
+            path = shortest_path(layout[qubits[0]], layout[qubits[1]])
+            for k in range(len(path) - 2):
+                a, b = path[k], path[k + 1]
+                out.swap(a, b)
+                la, lb = layout.index(a), layout.index(b)
+                layout[la], layout[lb] = b, a
+        out.append(name, params, [layout[q] for q in qubits])
+    return out, [layout[c] + 1 for c in range(n)]

@@ -295,11 +295,16 @@ def convert_circuit_to_network(circ: Circuit, backend: AbstractBackend, *,
                                decompose: bool = False, transpile: bool = False,
                                couplings=None) -> TensorNetworkCircuit:
     """``convert_qiskit_circ_to_network`` (``src/layer3.jl:543-573``) for the
-    qiskit-free ``Circuit``.  ``transpile=True`` is qiskit's BasicSwap pass in
-    the reference and is out of scope here (SURVEY §2 #7)."""
+    qiskit-free ``Circuit``.  ``transpile=True`` routes the circuit onto the coupling map
+    with the restated BasicSwap pass (``circuit.transpile_circuit``) and records where each
+    logical qubit ended up in ``qubit_ordering`` (``layer3.jl:553-560``)."""
+    qubit_ordering = None
     if transpile:
-        raise NotImplementedError("transpile=True needs qiskit's BasicSwap pass (out of scope)")
+        from .circuit import transpile_circuit
+        circ, qubit_ordering = transpile_circuit(circ, couplings)
     tng = TensorNetworkCircuit(circ.n_qubits, backend)
+    if qubit_ordering is not None:
+        tng.qubit_ordering[:] = qubit_ordering
     for name, params, qubits in circ.data:
         if name == "barrier":
             continue

@@ -250,3 +250,33 @@ def test_network_data_structure_counts():
     add_gate(tn, np.array([[1, 1], [1, -1]]) / np.sqrt(2), [1])
     assert len(tn.nodes) == 1
     assert len(tn.edges) == 4
+
+
+def test_transpile_qubit_ordering_golden_and_state():
+    """test/layer3_tests.jl:89-102: ``h q0; cx q0,q2`` transpiled onto a line gives
+    qubit_ordering == [2, 1, 3].  And routing must not change the state: QFT-4/5 after a
+    preparation layer, plain and through the MPS driver (which needs neighbouring gates)."""
+    from picoquant_jl_b200.host import (calculate_mps_amplitudes, contract_mps_tensor_network_circuit,
+                                        transpile_circuit)
+    qasm = """OPENQASM 2.0;
+              include "qelib1.inc";
+              qreg q[3];
+              h q[0];
+              cx q[0],q[2];"""
+    tng = convert_circuit_to_network(load_qasm_as_circuit(qasm), OracleBackend(C128), transpile=True)
+    assert tng.qubit_ordering == [2, 1, 3]
+    routed, order = transpile_circuit(load_qasm_as_circuit(qasm))
+    assert [g[0] for g in routed.gates()] == ["h", "swap", "cx"] and order == [2, 1, 3]
+    assert routed.gates()[1][2] == (0, 1) and routed.gates()[2][2] == (1, 2)
+    for n in (4, 5):
+        circ = create_simple_preparation_circuit(n, 2, 3).compose(create_qft_circuit(n))
+        ref = statevector(circ, OracleBackend(C128))
+        assert rel_l2(statevector(circ, OracleBackend(C128), transpile=True), ref) < 1e-12
+        routed, _ = transpile_circuit(circ)
+        assert all(abs(q[0] - q[1]) == 1 for _, _, q in routed.gates() if len(q) == 2)
+        b = OracleBackend(C128)
+        tn = convert_circuit_to_network(circ, b, decompose=True, transpile=True)
+        add_input(tn, "0" * n)
+        mps_nodes = contract_mps_tensor_network_circuit(tn)
+        calculate_mps_amplitudes(tn, mps_nodes)
+        assert rel_l2(b.load_tensor_data("result"), ref) < 1e-10
