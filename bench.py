@@ -40,6 +40,15 @@ from picoquant_jl_b200.host.sliced import (SlicedContraction, partitions_of_rank
 METRIC = "rqc_amplitude_contraction_tflops"
 UNIT = "TFLOP/s"
 
+# BASELINE.json configs: name -> (config number, description)
+WORKLOADS = {
+    "ghz3": (1, "GHZ-3 full wave function from ghz_3.qasm (bin/contract_qasm.jl flow)"),
+    "qft10": (2, "QFT-10 full wave function from qft_10.qasm"),
+    "qft26": (3, "QFT-26 full wave function, create_qft_circuit(26), 2^26 amplitudes"),
+    "rqc6x6": (4, "RQC 6x6 depth 20 single amplitude, un-decomposed network, greedy plan"),
+    "rqc7x7_sliced": (5, "sliced RQC 7x7 depth 24 single amplitude (dist_slicing_example.jl path)"),
+}
+
 
 def parse_args():
     ap = argparse.ArgumentParser()
@@ -47,7 +56,12 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--dtype", default="c128", choices=["c128", "c64"])
+    ap.add_argument("--dtype", default=None, choices=["c128", "c64"],
+                    help="backend element type (default: c64 for ghz3 like bin/contract_qasm.jl, "
+                         "c128 otherwise)")
+    ap.add_argument("--workload", default="rqc7x7_sliced", choices=sorted(WORKLOADS),
+                    help="rqc7x7_sliced = BASELINE config 5 (the headline, default); the others "
+                         "are BASELINE configs 1-4, single GPU, same JSON contract")
     ap.add_argument("--rows", type=int, default=7)
     ap.add_argument("--cols", type=int, default=7)
     ap.add_argument("--depth", type=int, default=24)
@@ -58,7 +72,10 @@ def parse_args():
     ap.add_argument("--cpu-sample-slices", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
-    return ap.parse_args()
+    a = ap.parse_args()
+    if a.dtype is None:
+        a.dtype = "c64" if a.workload == "ghz3" else "c128"
+    return a
 
 
 def build_workload(a):
@@ -167,6 +184,295 @@ def reference_arm(a):
 
 
 # ---------------------------------------------------------------------------
+# BASELINE configs 1-4 (single GPU): --workload ghz3 | qft10 | qft26 | rqc6x6
+# ---------------------------------------------------------------------------
+def stream_costs(text, store, itemsize):
+    """Algorithmic units of a command stream on data extents: complex MACs,
+    bytes = (MK + KN + MN) * sizeof per ``ncon`` + 2 * numel * sizeof per non-identity
+    ``permute`` and per ``view``, the number of contractions and the largest tensor."""
+    shapes, macs, nbytes, ncon, biggest = {}, 0, 0, 0, 0
+    for cmd, x in parse_dsl(text):
+        if cmd == "tensor":
+            shapes[x["t"]] = list(store.read(x["key"]).shape)
+        elif cmd == "view":
+            sh = list(shapes[x["t"]])
+            sh[x["axis"] - 1] = len(x["idx"])
+            shapes[x["v"]] = sh
+            nbytes += 2 * int(np.prod(sh)) * itemsize
+        elif cmd == "permute":
+            sh = shapes[x["t"]]
+            if list(x["axes"]) != list(range(1, len(sh) + 1)):
+                nbytes += 2 * int(np.prod(sh)) * itemsize
+            shapes[x["t"]] = [sh[i - 1] for i in x["axes"]]
+        elif cmd == "reshape":
+            sh = shapes[x["t"]]
+            shapes[x["t"]] = [int(np.prod([sh[i - 1] for i in g])) for g in x["groups"]]
+        elif cmd == "ncon":
+            sa, sb = shapes[x["A"]], shapes[x["B"]]
+            aset, bset = set(x["a_idx"]), set(x["b_idx"])
+            k = 1
+            for d, lab in zip(sa, x["a_idx"]):
+                if lab in bset:
+                    k *= d
+            m = int(np.prod(sa)) // k
+            nn = int(np.prod(sb)) // k
+            macs += m * nn * k
+            nbytes += (m * k + k * nn + m * nn) * itemsize
+            ncon += 1
+            biggest = max(biggest, m * nn, m * k, nn * k)
+            shapes[x["C"]] = [d for d, lab in zip(sa, x["a_idx"]) if lab not in bset] + \
+                             [d for d, lab in zip(sb, x["b_idx"]) if lab not in aset]
+        elif cmd == "del":
+            shapes.pop(x["t"], None)
+    return {"macs": macs, "bytes": nbytes, "contractions": ncon, "largest_elems": biggest}
+
+
+class ConfigWorkload:
+    """One of BASELINE configs 1-4: the circuit, the reference-facing call sequence a user
+    makes (``flow``) and that sequence recorded as a ``.tl`` command stream."""
+
+    def __init__(self, workload, seed=0, qft_n=26):
+        from picoquant_jl_b200.host import (DSLBackend, add_input, add_output, contract_network,
+                                            convert_circuit_to_network, create_qft_circuit,
+                                            full_wavefunction_contraction, load_qasm_as_circuit)
+        from picoquant_jl_b200.host.planner import greedy_plan
+        golden = os.path.join(ROOT, "tests", "golden")
+        self.amplitude = workload == "rqc6x6"
+        if workload == "ghz3":
+            with open(os.path.join(golden, "ghz_3.qasm")) as f:
+                self.circ = load_qasm_as_circuit(f.read())
+            self.name = "ghz_3.qasm_full_wavefunction"
+        elif workload == "qft10":
+            with open(os.path.join(golden, "qft_10.qasm")) as f:
+                self.circ = load_qasm_as_circuit(f.read())
+            self.name = "qft_10.qasm_full_wavefunction"
+        elif workload == "qft26":
+            self.circ = create_qft_circuit(qft_n)
+            self.name = "qft_%d_full_wavefunction" % qft_n
+        elif workload == "rqc6x6":
+            self.circ = create_RQC(6, 6, 20, seed=seed)
+            self.name = "rqc_6x6_d20_seed%d_amplitude" % seed
+        else:
+            raise ValueError(workload)
+        n = self.n = self.circ.n_qubits
+        self.plan = None
+
+        def flow(backend):
+            tn = convert_circuit_to_network(self.circ, backend)
+            add_input(tn, "0" * n)
+            if self.amplitude:
+                add_output(tn, "0" * n)
+                if self.plan is None:
+                    self.plan = greedy_plan(tn)
+                contract_network(tn, self.plan, "")
+            else:
+                full_wavefunction_contraction(tn, "vector")
+            return tn
+
+        self.flow = flow
+        dsl = DSLBackend()
+        flow(dsl)
+        self.text, self.store = dsl.text(), dsl.store
+
+    def h2d_bytes(self, itemsize):
+        return sum(int(self.store.read(a["key"]).size) * itemsize
+                   for cmd, a in parse_dsl(self.text) if cmd == "tensor")
+
+
+def cpu_flow_seconds(w, dtype, min_seconds=1.0, max_reps=200):
+    """The reference-facing flow through the oracle backend, repeated until ``min_seconds``
+    of CPU time have been spent; returns (seconds per flow, repetitions, result)."""
+    from oracle.interactive import OracleBackend
+    use_all_host_threads()
+    w.flow(OracleBackend(dtype))   # warm-up
+    reps, t0 = 0, time.perf_counter()
+    while True:
+        ob = OracleBackend(dtype)
+        w.flow(ob)
+        reps += 1
+        dt = time.perf_counter() - t0
+        if dt >= min_seconds or reps >= max_reps:
+            break
+    return dt / reps, reps, np.asarray(ob.load_tensor_data("result"))
+
+
+def cpu_config_sample(a, w, dtype):
+    """CPU figure for a config: the whole flow for configs 1, 2 and 4; for QFT-26 (minutes
+    of NumPy transposes of a 1 GiB state per pass) QFT-22 timed and scaled by the ratio of
+    algorithmic bytes -- every step of either circuit is a bandwidth-bound gate application."""
+    itemsize = np.dtype(dtype).itemsize
+    if a.workload == "qft26":
+        small = ConfigWorkload("qft26", qft_n=22)
+        sec, reps, _ = cpu_flow_seconds(small, dtype, min_seconds=0.0, max_reps=1)
+        scale = stream_costs(w.text, w.store, itemsize)["bytes"] / \
+            stream_costs(small.text, small.store, itemsize)["bytes"]
+        return sec * scale, "QFT-22 flow (%.1f s) x %.1f (ratio of algorithmic bytes)" % (sec, scale), None
+    sec, reps, res = cpu_flow_seconds(w, dtype)
+    return sec, "whole flow, mean of %d repetitions" % reps, res
+
+
+def config_line(a, w, costs, ms, impl=None):
+    """Metric fields of a config line: wall time for the full-wave-function configs, the
+    headline TFLOP/s metric for the single-amplitude RQC."""
+    if w.amplitude:
+        return {"metric": METRIC, "value": 8.0 * costs["macs"] / (ms * 1e-3) / 1e12, "unit": UNIT,
+                "higher_is_better": True}
+    return {"metric": "full_wavefunction_contraction_wall_ms", "value": ms, "unit": "ms",
+            "higher_is_better": False}
+
+
+def config_arm(a):
+    """BASELINE configs 1-4 with the same JSON contract as the headline workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return   # single-GPU configurations ("replicas only", DESIGN 3.4)
+    dtype = np.complex128 if a.dtype == "c128" else np.complex64
+    itemsize = np.dtype(dtype).itemsize
+    w = ConfigWorkload(a.workload, seed=a.seed)
+    costs = stream_costs(w.text, w.store, itemsize)
+    cfg = {"workload": w.name, "baseline_config": WORKLOADS[a.workload][0],
+           "contract_calls": costs["contractions"], "complex_macs": costs["macs"],
+           "algorithmic_bytes": costs["bytes"], "largest_tensor_elems": costs["largest_elems"]}
+    base = {"n_gpus": 1, "steps": a.steps, "warmup": a.warmup, "scaling": "strong",
+            "vs_baseline": None, "dtype": a.dtype, "data": "synthetic"}
+
+    if a.impl == "reference":
+        for _ in range(a.warmup if a.workload != "qft26" else 0):
+            cpu_config_sample(a, w, dtype)
+        secs = []
+        for _ in range(a.steps if a.workload != "qft26" else 1):
+            sec, sample, _ = cpu_config_sample(a, w, dtype)
+            secs.append(sec)
+        ms = 1e3 * float(np.mean(secs))
+        line = dict(base)
+        line.update(config_line(a, w, costs, ms))
+        line.update({"impl": "reference", "ms_per_step": ms, "config": cfg,
+                     "cpu_baseline": {"value": line["value"], "unit": line["unit"],
+                                      "cores": cpu_threads(), "kind": "port", "sample": sample},
+                     "e2e": {"value": line["value"], "unit": line["unit"],
+                             "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+        emit(line)
+        return
+
+    import torch
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    from picoquant_jl_b200.host.b200_backend import B200Backend
+    b = B200Backend(dtype, device=0)
+    for cmd, x in parse_dsl(w.text):
+        if cmd == "tensor":
+            b.save_tensor_data(x["key"], w.store.read(x["key"]))
+    prog = b.compile_program(w.text)
+    assert prog.macs == costs["macs"], (prog.macs, costs["macs"])
+    for _ in range(max(3, a.warmup)):
+        prog.run()
+    b.sync()
+    sampler = ClockSampler(0)
+    sampler.start()
+    b.reset_counters()
+    b.timer_begin()
+    for _ in range(a.steps):
+        prog.run()
+    ms = b.timer_end() / a.steps
+    launches = b.counters()["kernel_launches"]
+    clocks = sampler.stop()
+    result = np.asarray(b.load_tensor_data("result")).reshape(-1)
+
+    # end to end: the reference-facing calls from host arrays on a fresh backend (upload of
+    # every gate tensor, one backend call per contraction, D2H of the result)
+    e2e_times, d2h = [], 0
+    for it in range(3):
+        be = B200Backend(dtype, device=0)
+        be.sync()
+        t0 = time.perf_counter()
+        w.flow(be)
+        res_e2e = np.asarray(be.load_tensor_data("result")).reshape(-1)
+        e2e_times.append(time.perf_counter() - t0)
+        d2h = int(res_e2e.size) * itemsize
+        be.close()
+    e2e_ms = 1e3 * float(np.mean(e2e_times[1:]))
+
+    # per-kernel split of one eager, event-timed pass
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            hbm, hbm_src = float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json (driver-written)"
+    except Exception:  # noqa: BLE001
+        hbm, hbm_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+    b.profile_enable(True)
+    prog.run()
+    prof = b.profile_read()
+    b.profile_enable(False)
+    kernels = {c: {"launches": v["launches"], "ms": v["ms"],
+                   "avg_launch_us": 1e3 * v["ms"] / v["launches"],
+                   "achieved_gbs": v["bytes"] / (v["ms"] * 1e-3) / 1e9 if v["bytes"] else None,
+                   "achieved_tflops": v["flops"] / (v["ms"] * 1e-3) / 1e12 if v["flops"] else None}
+               for c, v in prof.items()}
+    dom = max(prof, key=lambda c: prof[c]["ms"])
+    if w.amplitude and dom in ("gemm_tensor", "gemm_simt"):
+        tdt = torch.complex128 if a.dtype == "c128" else torch.complex64
+        x = torch.randn(4096, 4096, dtype=tdt, device="cuda")
+        torch.matmul(x, x)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        best = 1e30
+        for _ in range(3):
+            e0.record()
+            torch.matmul(x, x)
+            e1.record()
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        peak = 8.0 * 4096 ** 3 / (best * 1e-3) / 1e12
+        ach = kernels[dom]["achieved_tflops"]
+        roofline = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": peak,
+                    "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+                    "peak_source": "cuBLAS %s 4096^3 measured in this run"
+                                   % ("ZGEMM" if a.dtype == "c128" else "CGEMM")}
+    else:
+        # whole-stream figure: algorithmic bytes of every step / device time of the replay
+        ach = costs["bytes"] / (ms * 1e-3) / 1e9
+        roofline = {"kernel": "whole stream (dominant class: %s)" % dom, "bound": "hbm",
+                    "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
+                    "traffic": None, "peak_source": hbm_src}
+
+    cpu = None
+    if not a.no_cpu_baseline:
+        sec, sample, ref = cpu_config_sample(a, w, dtype)
+        cl = config_line(a, w, costs, 1e3 * sec)
+        cpu = {"value": cl["value"], "unit": cl["unit"], "cores": cpu_threads(), "kind": "port",
+               "sample": sample + ", NumPy/OpenBLAS oracle"}
+        if ref is not None:
+            ref = ref.reshape(-1)
+            err = float(np.linalg.norm(result - ref) / np.linalg.norm(ref))
+        else:   # QFT|0..0> = uniform superposition (closed form)
+            err = float(np.linalg.norm(result - 2.0 ** (-w.n / 2)) / 1.0)
+        cpu["parity_rel_l2_device_vs_oracle"] = err
+        tol = 1e-10 if a.dtype == "c128" else 1e-5
+        if not err < tol:
+            raise SystemExit("parity failure on %s: rel-L2 %g" % (w.name, err))
+
+    working_set = costs["largest_elems"] * itemsize
+    cfg.update({"kernel_launches_per_step": prog.launches, "arena_bytes": prog.arena_bytes,
+                "us_per_contract_call": 1e3 * ms / max(1, costs["contractions"]),
+                "l2": ("tensors larger than L2 (largest %d MiB)" % (working_set >> 20))
+                if working_set > (126 << 20) else
+                "working set (largest tensor %d KiB) fits L2: this configuration is launch / "
+                "latency bound by construction; no flush between steps" % (working_set >> 10)})
+    line = dict(base)
+    line.update(config_line(a, w, costs, ms))
+    e2e_line = config_line(a, w, costs, e2e_ms)
+    line.update({"ms_per_step": ms, "config": cfg,
+                 "e2e": {"value": e2e_line["value"], "unit": e2e_line["unit"],
+                         "h2d_bytes_per_step": w.h2d_bytes(itemsize), "d2h_bytes_per_step": d2h,
+                         "ms_per_step": e2e_ms,
+                         "note": "eager backend calls from host arrays on a fresh handle, "
+                                 "Python host mirror included"},
+                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
+                 "kernels": kernels, "cpu_baseline": cpu})
+    emit(line)
+    prog.close()
+    b.close()
+
+
+# ---------------------------------------------------------------------------
 # clocks sampler (nvidia-smi, during the timed region)
 # ---------------------------------------------------------------------------
 class ClockSampler:
@@ -245,6 +551,9 @@ def main():
     sys.stdout.flush()
     _REAL_STDOUT = os.dup(1)
     os.dup2(2, 1)
+    if a.workload != "rqc7x7_sliced":
+        config_arm(a)
+        return
     if a.impl == "reference":
         reference_arm(a)
         return
