@@ -119,6 +119,7 @@ extern "C" int pq_create(int device, int dtype, pq_handle** out) {
     PQ_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold));
     init_kernels();
     init_kernels_cgemm();
+    init_kernels_ozaki();
   } catch (const std::exception&) {
     delete h;
     return PQ_ERR_CUDA;
@@ -587,6 +588,13 @@ extern "C" int pq_set_option(pq_handle* h, const char* key, int value) {
   else if (k == "zgemm_stagger") h->opt.zgemm_stagger = value;
   else if (k == "zgemm_skinny") h->opt.zgemm_skinny = value;
   else if (k == "zgemm_3m") h->opt.zgemm_3m = value;
+  else if (k == "zgemm_ozaki") {
+    if (value != 0 && value != 7 && value != 8) {
+      h->last_error = "zgemm_ozaki must be 0, 7 or 8";
+      return PQ_ERR_INVALID;
+    }
+    h->opt.zgemm_ozaki = value;
+  }
   else if (k == "zgemm_cfg") h->opt.zgemm_cfg = value;
   else if (k == "zgemm_kfirst") h->opt.zgemm_kfirst = value;
   else {

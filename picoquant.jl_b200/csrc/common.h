@@ -120,6 +120,7 @@ struct Options {
   int zgemm_cfg = 0;  // fused ZGEMM: 0 auto, 1 = 64x64 (2 CTAs/SM), 2 = 64x32 (4 CTAs/SM), 3 = 128x8, 4 = 64x32 3M, 7 = persistent skinny where eligible
   int zgemm_3m = 0;       // persistent skinny ZGEMM: 0 = 3M (three DMMAs per complex product), 1 = 4M
   int zgemm_skinny = 0;   // persistent skinny fused ZGEMM: 0 auto, 1 off
+  int zgemm_ozaki = 0;    // EXPERIMENTAL int8 tensor-core ZGEMM (kernels_zgemm_ozaki.cu): 0 off, 7 / 8 = accumulator groups
   int zgemm_stagger = 0;  // ns of start delay per resident-CTA slot in the first wave (0 = off)
   int chain = 0;    // compiled programs: 0 = batch chains of tiny contractions into one launch, 1 = off
   int prio = 0;     // 0: small-grid graph nodes get the highest launch priority, 1: off
@@ -199,6 +200,22 @@ struct ChainRange {  // items [begin, begin + count) are executed in order by on
 // false when the plan does not fit a ChainItem (too many fused dims, sizes beyond int)
 bool chain_item_from_plan(const ContractPlan& p, ChainItem& it);
 void run_chains(const Launch& L, const ChainItem* d_items, const ChainRange* d_ranges, int nchains);
+
+// operands of the gather-fused ZGEMM kernels (kernels_zgemm.cu, kernels_zgemm_ozaki.cu):
+// C[m + M n] = sum_k A[mA(m) + kA(k)] * B[nB(n) + kB(k)]
+struct FusedParams {
+  IdxMap mA, kA, nB, kB;
+  long long M, N, K;
+  // De-phasing of the first wave: CTA b < first_wave starts (b / num_sms) * stagger_ns late, so
+  // the CTAs that share an SM are in different phases of their tile (fill / DMMA / store) and
+  // stay so for the whole grid, because every later CTA starts when an earlier one retires.
+  int stagger_ns, first_wave, num_sms;
+};
+
+void init_kernels_ozaki();
+bool zgemm_ozaki_eligible(const ContractPlan& cp);
+void run_zgemm_ozaki(const Launch& L, const FusedParams& fp, int groups, const void* A,
+                     const void* B, void* C);
 
 void init_kernels();
 void init_kernels_cgemm();

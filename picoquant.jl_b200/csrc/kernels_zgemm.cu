@@ -265,14 +265,7 @@ k_zgemm_dmma3m(const double2* __restrict__ A, const double2* __restrict__ B, dou
 // lowest open bits of A are its 6 lowest-address open bits, a k-row of the tile is made
 // of long contiguous runs and the gather stays sector-efficient.
 // ---------------------------------------------------------------------------
-struct FusedParams {
-  IdxMap mA, kA, nB, kB;
-  long long M, N, K;
-  // De-phasing of the first wave: CTA b < first_wave starts (b / num_sms) * stagger_ns late, so
-  // the CTAs that share an SM are in different phases of their tile (fill / DMMA / store) and
-  // stay so for the whole grid, because every later CTA starts when an earlier one retires.
-  int stagger_ns, first_wave, num_sms;
-};
+// (struct FusedParams: common.h)
 
 // One output tile per CTA (a persistent variant with a cross-tile cp.async ring was
 // measured ~7 % slower on B200: the hardware CTA scheduler de-phases resident CTAs better).
@@ -880,6 +873,17 @@ void run_zgemm_fused(const Launch& L, const ContractPlan& cp, const void* A, con
   bool akf = min_stride(cp.kA) < min_stride(cp.mA), bkf = min_stride(cp.kB) < min_stride(cp.nB);
   if (L.opt && L.opt->zgemm_kfirst == 1) akf = bkf = false;  // A/B check knob
   if (cfg == 3) akf = bkf = false;  // measured: no gain for the narrow tiles (HBM-bound)
+  // EXPERIMENTAL (off unless option "zgemm_ozaki" = 7 / 8): INT8 tensor-core Ozaki product
+  {
+    const int oz = L.opt ? L.opt->zgemm_ozaki : 0;
+    if (oz != 0 && zgemm_ozaki_eligible(cp)) {
+      L.begin(KC_GEMM_TENSOR, bytes, flops);
+      run_zgemm_ozaki(L, fp, oz, A, B, C);
+      L.end();
+      PQ_CUDA(cudaGetLastError());
+      return;
+    }
+  }
   // persistent skinny kernel: K and N small enough for B to live in shared memory, and
   // enough 64-row tiles to keep every SM busy for several tiles
   const bool skinny_ok = cp.K <= SK_MAXK && cp.N <= 64 && cp.N > 16 && cp.M >= 256LL * L.num_sms;

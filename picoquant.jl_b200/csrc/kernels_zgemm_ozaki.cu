@@ -1,0 +1,402 @@
+// K2o (EXPERIMENTAL, opt-in: option "zgemm_ozaki" = 7 or 8; NOT yet run on hardware, see
+// DESIGN.md section 2.1): ComplexF64 GEMM for the skinny sweep steps on the INT8 tensor cores
+// of sm_100a (tcgen05.mma kind::i8, int32 accumulators in TMEM) -- an Ozaki-scheme
+// ("error-free slicing") product.
+//
+// Why.  tcgen05 has no f64 kind; the FP64 tensor pipe (DMMA) tops out at ~37 TFLOP/s, and the
+// dominant sweep step of the bench workload (M = 2^18, N = K = 64) is bound by it: 246 us,
+// although its operands and result stream through HBM in ~85 us.  The INT8 pipe is two orders
+// of magnitude wider, and the backend's ComplexF64 contract is a 1e-10 relative L2 tolerance,
+// not 53 mantissa bits per product.
+//
+// The arithmetic (ozaki_math.h; executed on the host by test_lower.cpp: test_ozaki, with the
+// tensor core replaced by an integer GEMM reading through the same LBO / SBO addressing).
+// Every row of A (all k, re and im together) gets one power-of-two scale 2^EA with
+// |x| < 2^EA; likewise every column n of B.  A real x of that row becomes the integer
+//     q = rint(x * 2^(47 - EA)),   |q| <= 2^47,
+// written in balanced base 128:  q = sum_{i<7} d_i 128^i,  d_i in [-64, 63]  (int8).
+// The digits come out of q + BIAS (BIAS = sum 64*128^i) as plain 7-bit fields, so there is no
+// carry chain.  With s counting digits from the most significant one, the product of digit
+// planes s of A and t of B has weight 128^(12 - s - t); all pairs with the same g = s + t are
+// summed EXACTLY by the tensor core in one int32 accumulator (|acc| < 2^23 for K <= 64), and
+// pairs with g >= G are dropped (G = 7: 28 pairs, rel-L2 ~1e-13 on well-scaled rows; G = 8:
+// 34 pairs, ~1e-14).  The complex product uses four real ones; the minus sign of
+// Cr = Ar Br - Ai Bi is carried by a third, negated set of B planes (B is tiny and resident).
+// Epilogue:  C = 2^(EA + EB - 10) * sum_g acc_g 2^(-7 g), evaluated as two int64 Horner sums
+// (g < 4 and g >= 4), two int64 -> f64 conversions and one FMA per real number.
+//
+// The kernel (same envelope as k_zgemm_skinny: K <= 64, N <= 64, gather straight from the
+// un-permuted operands).  One persistent CTA per SM, 16 worker warps + 1 MMA-issue warp:
+//   * B (K x N) is gathered, scaled and sliced into 3 x 7 resident int8 planes once per CTA;
+//   * a tile is 128 rows of A x all of K: worker thread (row, 16-k chunk) loads its 16 complex
+//     numbers, the row exponent is an atomicMax over the four chunk threads, and each thread
+//     writes one 16-byte core-matrix row per plane (7 re + 7 im planes, no-swizzle K-major
+//     UMMA layout, conflict-free STS.128);
+//   * the MMA warp issues, per 32-column half of N, G x (pairs) x 4 x (K/32) MMAs of shape
+//     128 x 32 x 32 into 2 G accumulators of 32 TMEM columns (G = 8 fills all 512 columns);
+//   * the worker warps drain TMEM (tcgen05.ld), combine, scale and store C[m + M n]
+//     (lane = row: 512-byte coalesced stores); the next tile of A is L2-prefetched meanwhile.
+// Phases of a tile are serialised (one set of A planes is all that fits beside B in 227 KB);
+// the expected bound is TMEM read bandwidth + slicing ALU work, ~2x under the DMMA time.
+#include "common.h"
+#include "ozaki_math.h"
+
+namespace pq {
+
+namespace {
+
+constexpr int OZ_TM = 128;                 // rows per tile = UMMA M
+constexpr int OZ_S = oz::S;                // int8 digits per real number (ozaki_math.h)
+constexpr int OZ_WORKERS = 512;            // 16 worker warps: (row, 16-k chunk)
+constexpr int OZ_THREADS = OZ_WORKERS + 32;
+constexpr int OZ_KMAX = 64, OZ_NMAX = 64;
+constexpr int OZ_A_PLANE = OZ_TM * OZ_KMAX;     // bytes (int8)
+constexpr int OZ_B_PLANE = OZ_NMAX * OZ_KMAX;
+constexpr int OZ_A_BYTES = 2 * OZ_S * OZ_A_PLANE;   // re planes, then im planes
+constexpr int OZ_B_BYTES = 3 * OZ_S * OZ_B_PLANE;   // re, im, -im
+
+struct OzSmem {
+  static constexpr int kA = 0;
+  static constexpr int kB = kA + OZ_A_BYTES;
+  static constexpr int kKoffA = kB + OZ_B_BYTES;            // int[64]
+  static constexpr int kKoffB = kKoffA + OZ_KMAX * 4;       // int[64]
+  static constexpr int kRowE = kKoffB + OZ_KMAX * 4;        // int[2][128]
+  static constexpr int kColE = kRowE + 2 * OZ_TM * 4;       // int[64]
+  static constexpr int kBars = kColE + OZ_NMAX * 4;         // 2 mbarriers + tmem slot
+  static constexpr int kTotal = kBars + 32;
+};
+static_assert(OzSmem::kTotal <= 227 * 1024, "shared memory budget");
+
+__device__ __forceinline__ uint32_t oz_smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void oz_mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(oz_smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void oz_mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(oz_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void oz_mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(oz_smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
+// no-swizzle K-major shared-memory matrix descriptor: core matrix = 8 rows x 16 bytes
+// (16 int8 k-elements); LBO = bytes between core matrices adjacent in K, SBO = between
+// 8-row groups (cute/arch/mma_sm100_desc.hpp: SmemDescriptor, version 1, SWIZZLE_NONE)
+__device__ __forceinline__ uint64_t oz_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  return d;
+}
+// instruction descriptor for kind::i8 (cute InstrDescriptor): c_format S32 = 2 at bit 4,
+// a_format / b_format INT8 (signed) = 1 at bits 7 / 10, both K-major, N >> 3 at bit 17,
+// M >> 4 at bit 24, no saturation
+__host__ __device__ constexpr uint32_t oz_idesc(int M, int N) {
+  return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) |
+         ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void oz_umma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
+                                           uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void oz_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(
+                   oz_smem_u32(bar))
+               : "memory");
+}
+
+#define OZ_TMEM_LD8(r, addr)                                                                  \
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n"    \
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]),     \
+                 "=r"(r[6]), "=r"(r[7])                                                       \
+               : "r"(addr))
+
+__device__ __forceinline__ void oz_store(unsigned char* dst, const oz::Word4& v) {
+  *reinterpret_cast<uint4*>(dst) = make_uint4(v.w[0], v.w[1], v.w[2], v.w[3]);
+}
+
+// G = number of accumulator groups kept (pairs of digit planes with s + t < G)
+template <int G>
+__global__ void __launch_bounds__(OZ_THREADS, 1)
+k_zgemm_ozaki(const double2* __restrict__ A, const double2* __restrict__ B,
+              double2* __restrict__ C, const FusedParams p) {
+  static_assert(G >= 5 && G <= 8, "2 * G * 32 accumulator columns must fit 512");
+  extern __shared__ __align__(1024) unsigned char smem[];
+  unsigned char* sA = smem + OzSmem::kA;
+  unsigned char* sB = smem + OzSmem::kB;
+  int* koffA = reinterpret_cast<int*>(smem + OzSmem::kKoffA);
+  int* koffB = reinterpret_cast<int*>(smem + OzSmem::kKoffB);
+  int* rowE = reinterpret_cast<int*>(smem + OzSmem::kRowE);     // [2][128] biased exponent fields
+  int* colE = reinterpret_cast<int*>(smem + OzSmem::kColE);
+  uint64_t* ready = reinterpret_cast<uint64_t*>(smem + OzSmem::kBars);   // workers -> MMA
+  uint64_t* done = ready + 1;                                            // MMA -> workers
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int K = (int)p.K, N = (int)p.N;
+  const long long M = p.M;
+  const int KS = (K + 31) / 32;              // UMMA k-steps (32 int8 each)
+  const int NH = N > 32 ? 2 : 1;             // 32-column halves of N
+  const long long tiles = (M + OZ_TM - 1) / OZ_TM;
+
+  if (tid < OZ_KMAX) {
+    koffA[tid] = tid < K ? (int)map_offset(p.kA, tid) : 0;
+    koffB[tid] = tid < K ? (int)map_offset(p.kB, tid) : 0;
+    colE[tid] = 0;
+  }
+  if (tid < 2 * OZ_TM) rowE[tid] = 0;
+  if (tid == 0) {
+    oz_mbar_init(ready, OZ_WORKERS / 32);
+    oz_mbar_init(done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(
+                     oz_smem_u32(tmem_slot)),
+                 "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  constexpr uint32_t A_LBO = OZ_TM * 16, B_LBO = OZ_NMAX * 16, SBO = 128;
+
+  if (warp == OZ_WORKERS / 32) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t IDESC = oz_idesc(OZ_TM, 32);
+      const uint64_t a_base = oz_desc(oz_smem_u32(sA), A_LBO, SBO);
+      const uint64_t b_base = oz_desc(oz_smem_u32(sB), B_LBO, SBO);
+      uint32_t it = 0;
+      for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        for (int h = 0; h < NH; ++h, ++it) {
+          oz_mbar_wait(ready, it & 1u);
+          asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+          // descriptor address fields are in 16-byte units; one K-step = two core matrices
+          oz::for_each_mma<G>(KS, [&](int accum, int a_plane, int b_plane, int ks, uint32_t acc) {
+            const uint64_t ad = a_base + (uint64_t)((a_plane * OZ_A_PLANE + ks * 2 * A_LBO) >> 4);
+            const uint64_t bd =
+                b_base + (uint64_t)((b_plane * OZ_B_PLANE + ks * 2 * B_LBO + h * 4 * SBO) >> 4);
+            oz_umma_i8(tmem_base + (uint32_t)(accum * 32), ad, bd, IDESC, acc);
+          });
+          oz_commit(done);
+        }
+      }
+    }
+  } else {
+    // ===================== workers: gather + slice, then drain TMEM =====================
+    const int row = tid & (OZ_TM - 1), chunk = tid >> 7;       // chunk = 16 consecutive k
+    const bool chunk_on = chunk * 16 < KS * 32;                // inside the padded K
+    auto workers_barrier = [&]() {
+      asm volatile("bar.sync 1, %0;\n" ::"r"(OZ_WORKERS) : "memory");
+    };
+
+    // ---- B: gathered, scaled per column n, sliced into re / im / -im planes, once ----
+    {
+      const int n = tid & (OZ_NMAX - 1), bchunk = (tid >> 6) & 3;
+      const bool mine = tid < 4 * OZ_NMAX && n < NH * 32 && bchunk * 16 < KS * 32;
+      double xr[16], xi[16];
+      int ef = 0;
+      if (mine) {
+        const long long rb = n < N ? map_offset(p.nB, n) : -1;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int k = bchunk * 16 + j;
+          double2 v = make_double2(0.0, 0.0);
+          if (rb >= 0 && k < K) v = B[rb + koffB[k]];
+          xr[j] = v.x;
+          xi[j] = v.y;
+          ef = max(ef, max(oz::abs_hi(v.x), oz::abs_hi(v.y)));
+        }
+        atomicMax(&colE[n], ef >> 20);
+      }
+      workers_barrier();
+      if (mine) {
+        const int e = colE[n];
+        const double scale = oz::slice_scale(e);
+        oz::Word4 pl[OZ_S];
+        unsigned char* dst = sB + oz::plane_off(OZ_NMAX, n, bchunk);
+        oz::slice16(xr, scale, false, pl);
+#pragma unroll
+        for (int s = 0; s < OZ_S; ++s) oz_store(dst + s * OZ_B_PLANE, pl[s]);
+        oz::slice16(xi, scale, false, pl);
+#pragma unroll
+        for (int s = 0; s < OZ_S; ++s)
+          oz_store(dst + (OZ_S + s) * OZ_B_PLANE, pl[s]);
+        oz::slice16(xi, scale, true, pl);
+#pragma unroll
+        for (int s = 0; s < OZ_S; ++s)
+          oz_store(dst + (2 * OZ_S + s) * OZ_B_PLANE, pl[s]);
+      }
+      // (made visible to the tensor core by the proxy fence before the first `ready` arrival)
+    }
+
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;   // this warp's TMEM lanes
+    const int cpart = warp >> 2;                                    // 8 of the 32 columns
+    uint32_t it = 0;
+    int buf = 0;
+    for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, buf ^= 1) {
+      const long long m = tile * OZ_TM + row;
+      const long long ra = m < M ? map_offset(p.mA, m) : -1;
+      // ---- gather this thread's 16 complex numbers, row exponent ----
+      double xr[16], xi[16];
+      int ef = 0;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int k = chunk * 16 + j;
+        double2 v = make_double2(0.0, 0.0);
+        if (chunk_on && ra >= 0 && k < K) v = A[ra + koffA[k]];
+        xr[j] = v.x;
+        xi[j] = v.y;
+        ef = max(ef, max(oz::abs_hi(v.x), oz::abs_hi(v.y)));
+      }
+      if (chunk_on) atomicMax(&rowE[buf * OZ_TM + row], ef >> 20);
+      workers_barrier();
+      const int ea = rowE[buf * OZ_TM + row];
+      if (tid < OZ_TM) rowE[(buf ^ 1) * OZ_TM + tid] = 0;    // for the next tile (see header)
+      // ---- slice into the 7 + 7 planes of this tile ----
+      if (chunk_on) {
+        const double scale = oz::slice_scale(ea);
+        oz::Word4 pl[OZ_S];
+        unsigned char* dst = sA + oz::plane_off(OZ_TM, row, chunk);
+        oz::slice16(xr, scale, false, pl);
+#pragma unroll
+        for (int s = 0; s < OZ_S; ++s) oz_store(dst + s * OZ_A_PLANE, pl[s]);
+        oz::slice16(xi, scale, false, pl);
+#pragma unroll
+        for (int s = 0; s < OZ_S; ++s)
+          oz_store(dst + (OZ_S + s) * OZ_A_PLANE, pl[s]);
+      }
+      // L2 prefetch of the next tile's rows (registers are needed by the epilogue)
+      {
+        const long long mn = m + (long long)gridDim.x * OZ_TM;
+        if (chunk_on && mn < M) {
+          const long long rn = map_offset(p.mA, mn);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int k = chunk * 16 + j;
+            if (k < K) asm volatile("prefetch.global.L2 [%0];\n" ::"l"(A + rn + koffA[k]));
+          }
+        }
+      }
+      // output scale of this row: 2^(EA - 5) with |x| < 2^EA, EA = ea - 1022
+      const double sa = oz::out_scale(ea);
+
+      for (int h = 0; h < NH; ++h, ++it) {
+        // h = 0: the planes are written; h = 1: this warp has drained the accumulators
+        asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+        __syncwarp();
+        if (lane == 0) oz_mbar_arrive(ready);
+        oz_mbar_wait(done, it & 1u);
+        asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+
+        const int n0 = h * 32 + cpart * 8;
+        long long hr[8], hq[8];   // Horner sums over the groups, re / im
+        double vr[8], vq[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) hr[j] = hq[j] = 0;
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+          if (g == 4) {   // groups 0..3 done: weight 2^-21 relative to group 0
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              vr[j] = (double)hr[j] * (1.0 / 2097152.0);
+              vq[j] = (double)hq[j] * (1.0 / 2097152.0);
+              hr[j] = hq[j] = 0;
+            }
+          }
+          uint32_t r[8], q[8];
+          const uint32_t col = tmem_base + lane_base + (uint32_t)((2 * g) * 32 + cpart * 8);
+          OZ_TMEM_LD8(r, col);
+          OZ_TMEM_LD8(q, col + 32);
+          asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            hr[j] = hr[j] * 128 + (long long)(int)r[j];
+            hq[j] = hq[j] * 128 + (long long)(int)q[j];
+          }
+        }
+        constexpr double LOW = 1.0 / (double)(1ull << (7 * (G - 1)));   // weight of the last group
+        if (m < M) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int n = n0 + j;
+            if (n < N) {
+              const double sc = sa * oz::out_scale(colE[n]);
+              const double re = fma((double)hr[j], LOW, vr[j]);
+              const double im = fma((double)hq[j], LOW, vq[j]);
+              C[m + M * n] = make_double2(re * sc, im * sc);
+            }
+          }
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base),
+                 "r"(512u)
+                 : "memory");
+  }
+}
+
+}  // namespace
+
+// The default path never depends on this experimental kernel: if its attributes cannot be set
+// the error is swallowed here and the option is refused later (run_zgemm_ozaki).
+static bool g_ozaki_ready = false;
+
+void init_kernels_ozaki() {
+  cudaError_t e7 = cudaFuncSetAttribute(k_zgemm_ozaki<7>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        OzSmem::kTotal);
+  cudaError_t e8 = cudaFuncSetAttribute(k_zgemm_ozaki<8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        OzSmem::kTotal);
+  if (e7 != cudaSuccess || e8 != cudaSuccess) (void)cudaGetLastError();
+  g_ozaki_ready = (e7 == cudaSuccess && e8 == cudaSuccess);
+}
+
+bool zgemm_ozaki_eligible(const ContractPlan& cp) {
+  return cp.K >= 1 && cp.K <= OZ_KMAX && cp.N >= 1 && cp.N <= OZ_NMAX && cp.M >= 1;
+}
+
+// groups = 7 or 8 (option "zgemm_ozaki")
+void run_zgemm_ozaki(const Launch& L, const FusedParams& fp, int groups, const void* A,
+                     const void* B, void* C) {
+  PQ_REQUIRE(groups == 7 || groups == 8, PQ_ERR_INVALID, "zgemm_ozaki must be 0, 7 or 8");
+  PQ_REQUIRE(g_ozaki_ready, PQ_ERR_UNSUPPORTED, "zgemm_ozaki: kernel attributes could not be set");
+  const long long tiles = (fp.M + OZ_TM - 1) / OZ_TM;
+  const unsigned grid = (unsigned)(tiles < L.num_sms ? tiles : L.num_sms);
+  if (groups == 7)
+    k_zgemm_ozaki<7><<<grid, OZ_THREADS, OzSmem::kTotal, L.stream>>>(
+        (const double2*)A, (const double2*)B, (double2*)C, fp);
+  else
+    k_zgemm_ozaki<8><<<grid, OZ_THREADS, OzSmem::kTotal, L.stream>>>(
+        (const double2*)A, (const double2*)B, (double2*)C, fp);
+}
+
+}  // namespace pq

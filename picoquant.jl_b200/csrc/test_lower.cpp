@@ -10,6 +10,7 @@
 #include <random>
 
 #include "common.h"
+#include "ozaki_math.h"
 #include "tile_math.h"
 
 using namespace pq;
@@ -310,6 +311,169 @@ static void test_big_shapes() {
               P.permA.tp.b);
 }
 
+
+// ---------------------------------------------------------------------------
+// INT8 Ozaki-scheme ZGEMM (kernels_zgemm_ozaki.cu): the kernel's own slicing, plane layout,
+// MMA schedule, recombination and scaling (ozaki_math.h) executed on the host, with the
+// tensor core replaced by an integer GEMM that reads its operands through the UMMA
+// no-swizzle K-major addressing (LBO / SBO), against a long double reference.
+// ---------------------------------------------------------------------------
+static int8_t plane_elem(const std::vector<int8_t>& buf, size_t plane_base, int lbo, int sbo, int row,
+                         int k) {
+  return buf[plane_base + (size_t)(k / 16) * lbo + (size_t)(row / 8) * sbo + (row % 8) * 16 + k % 16];
+}
+
+template <int G>
+static double ozaki_tile_error(std::mt19937& rng, int Mrows, int N, int K, double spread_sigma,
+                               double sparsity) {
+  const int TM = 128, NMAX = 64, KMAX = 64;
+  const int KS = (K + 31) / 32, NH = N > 32 ? 2 : 1;
+  const int A_PLANE = TM * KMAX, B_PLANE = NMAX * KMAX, A_LBO = TM * 16, B_LBO = NMAX * 16, SBO = 128;
+  std::normal_distribution<double> g(0.0, 1.0);
+  std::uniform_real_distribution<double> u(0.0, 1.0);
+  auto draw = [&]() {
+    if (u(rng) < sparsity) return 0.0;
+    return g(rng) * std::exp(spread_sigma * g(rng));
+  };
+  std::vector<cd> A((size_t)Mrows * K), B((size_t)N * K);   // A[m + Mrows k], B[n + N k]
+  for (auto& x : A) x = cd(draw(), draw());
+  for (auto& x : B) x = cd(draw(), draw());
+  if (Mrows > 3)
+    for (int k = 0; k < K; ++k) A[3 + (size_t)Mrows * k] = 0.0;   // an all-zero row
+  if (Mrows > 5)
+    for (int k = 0; k < K; ++k) A[5 + (size_t)Mrows * k] *= 1e-300;   // a tiny row (still normal)
+
+  std::vector<int8_t> sA((size_t)2 * oz::S * A_PLANE, 0), sB((size_t)3 * oz::S * B_PLANE, 0);
+  std::vector<int> rowE(TM, 0), colE(NMAX, 0);
+  auto fill = [&](std::vector<int8_t>& planes, int plane_bytes, int rows_layout, int nplanesets,
+                  std::vector<int>& E, int row, const cd* src, size_t ld, bool valid) {
+    // exponent over the whole row, then the (row, chunk) work items of the kernel
+    int ef = 0;
+    for (int k = 0; k < K; ++k) {
+      const cd v = valid ? src[(size_t)k * ld] : cd(0, 0);
+      ef = std::max(ef, std::max(oz::abs_hi(v.real()), oz::abs_hi(v.imag())));
+    }
+    E[row] = ef >> 20;
+    const double scale = oz::slice_scale(E[row]);
+    for (int chunk = 0; chunk * 16 < KS * 32; ++chunk) {
+      double xr[16], xi[16];
+      for (int j = 0; j < 16; ++j) {
+        const int k = chunk * 16 + j;
+        const cd v = (valid && k < K) ? src[(size_t)k * ld] : cd(0, 0);
+        xr[j] = v.real();
+        xi[j] = v.imag();
+      }
+      const uint32_t off = oz::plane_off(rows_layout, row, chunk);
+      oz::Word4 pl[oz::S];
+      for (int set = 0; set < nplanesets; ++set) {
+        oz::slice16(set == 0 ? xr : xi, scale, set == 2, pl);
+        for (int s = 0; s < oz::S; ++s)
+          std::memcpy(&planes[(size_t)(set * oz::S + s) * plane_bytes + off], pl[s].w, 16);
+      }
+    }
+  };
+  for (int n = 0; n < NH * 32; ++n) fill(sB, B_PLANE, NMAX, 3, colE, n, &B[n < N ? n : 0], N, n < N);
+  for (int r = 0; r < TM; ++r) fill(sA, A_PLANE, TM, 2, rowE, r, &A[r < Mrows ? r : 0], Mrows, r < Mrows);
+
+  // digits reconstruct q exactly and stay inside int8's balanced range
+  for (int r = 0; r < std::min(Mrows, 8); ++r)
+    for (int k = 0; k < K; ++k) {
+      long long q = 0;
+      for (int s = 0; s < oz::S; ++s) {
+        const int d = plane_elem(sA, (size_t)s * A_PLANE, A_LBO, SBO, r, k);
+        CHECK(d >= -64 && d <= 64, "digit range %d", d);
+        q = q * 128 + d;
+      }
+      const long long want = std::llrint(A[r + (size_t)Mrows * k].real() * oz::slice_scale(rowE[r]));
+      CHECK(q == want, "digits of A[%d,%d]: %lld vs %lld", r, k, q, want);
+    }
+
+  std::vector<cd> C((size_t)Mrows * N);
+  for (int h = 0; h < NH; ++h) {
+    std::vector<int32_t> acc((size_t)2 * G * TM * 32, 0);   // [accumulator][row][column]
+    long long worst = 0;
+    oz::for_each_mma<G>(KS, [&](int accum, int a_plane, int b_plane, int ks, unsigned accumulate) {
+      const size_t ab = (size_t)a_plane * A_PLANE + (size_t)ks * 2 * A_LBO;
+      const size_t bb = (size_t)b_plane * B_PLANE + (size_t)ks * 2 * B_LBO + (size_t)h * 4 * SBO;
+      for (int r = 0; r < TM; ++r)
+        for (int c = 0; c < 32; ++c) {
+          long long sum = 0;
+          for (int k = 0; k < 32; ++k)
+            sum += (int)plane_elem(sA, ab, A_LBO, SBO, r, k) * (int)plane_elem(sB, bb, B_LBO, SBO, c, k);
+          int32_t& a = acc[((size_t)accum * TM + r) * 32 + c];
+          const long long v = (accumulate ? (long long)a : 0) + sum;
+          worst = std::max(worst, std::llabs(v));
+          a = (int32_t)v;
+        }
+    });
+    CHECK(worst < (1ll << 31), "int32 accumulator overflow: %lld", worst);
+    for (int r = 0; r < Mrows; ++r)
+      for (int c = 0; c < 32; ++c) {
+        const int n = h * 32 + c;
+        if (n >= N) continue;
+        long long hr = 0, hq = 0, lr = 0, lq = 0;
+        for (int gi = 0; gi < G; ++gi) {
+          const long long ar = acc[((size_t)(2 * gi) * TM + r) * 32 + c];
+          const long long aq = acc[((size_t)(2 * gi + 1) * TM + r) * 32 + c];
+          if (gi < 4) {
+            hr = hr * 128 + ar;
+            hq = hq * 128 + aq;
+          } else {
+            lr = lr * 128 + ar;
+            lq = lq * 128 + aq;
+          }
+        }
+        const double sc = oz::out_scale(rowE[r]) * oz::out_scale(colE[n]);
+        C[r + (size_t)Mrows * n] = cd(oz::combine(hr, lr, G) * sc, oz::combine(hq, lq, G) * sc);
+      }
+  }
+  long double num = 0, den = 0;
+  for (int r = 0; r < Mrows; ++r)
+    for (int n = 0; n < N; ++n) {
+      long double rr = 0, ri = 0;
+      for (int k = 0; k < K; ++k) {
+        const cd a = A[r + (size_t)Mrows * k], b = B[n + (size_t)N * k];
+        rr += (long double)a.real() * b.real() - (long double)a.imag() * b.imag();
+        ri += (long double)a.real() * b.imag() + (long double)a.imag() * b.real();
+      }
+      const cd got = C[r + (size_t)Mrows * n];
+      if (r == 5) continue;   // the 1e-300 row: its products underflow, checked separately below
+      num += (got.real() - rr) * (got.real() - rr) + (got.imag() - ri) * (got.imag() - ri);
+      den += rr * rr + ri * ri;
+      if (r == 3) CHECK(got == cd(0, 0), "zero row must give exact zeros");
+    }
+  return (double)std::sqrt(num / den);
+}
+
+static void test_ozaki(std::mt19937& rng) {
+  // bit tricks against plain arithmetic
+  for (int e = 0; e < 128; ++e) {
+    const uint32_t p = oz::unbias((uint32_t)e * 0x01010101u);
+    CHECK((int8_t)(p & 0xff) == e - 64 && (int8_t)(p >> 24) == e - 64, "unbias(%d)", e);
+  }
+  CHECK(oz::spread(0x0FFFFFFFu) == 0x7F7F7F7Fu && oz::spread(1u << 7) == 0x100u &&
+            oz::spread(1u << 27) == 0x40000000u, "spread");
+  CHECK(oz::pow2_field(1023) == 1.0 && oz::pow2_field(1033) == 1024.0, "pow2_field");
+  CHECK(oz::BIAS == 283691315109952ull, "bias constant");
+  struct Case { int M, N, K; double sigma, sparsity, tol7, tol8; };
+  const Case cases[] = {
+      {128, 64, 64, 0.0, 0.0, 1e-12, 2e-13},   // the dominant sweep step's tile
+      {128, 64, 32, 0.0, 0.0, 1e-12, 2e-13},
+      {100, 33, 40, 0.0, 0.5, 1e-12, 2e-13},   // ragged M, N, K; zeros
+      {128, 32, 8, 0.0, 0.0, 1e-12, 2e-13},
+      {77, 17, 64, 3.0, 0.0, 2e-10, 1e-11},    // log-normal magnitudes inside a row (sigma 3)
+      {1, 1, 1, 0.0, 0.0, 1e-12, 2e-13},
+  };
+  for (const Case& c : cases) {
+    const double e7 = ozaki_tile_error<7>(rng, c.M, c.N, c.K, c.sigma, c.sparsity);
+    const double e8 = ozaki_tile_error<8>(rng, c.M, c.N, c.K, c.sigma, c.sparsity);
+    CHECK(e7 < c.tol7, "ozaki G=7 M=%d N=%d K=%d: rel-L2 %.3e", c.M, c.N, c.K, e7);
+    CHECK(e8 < c.tol8, "ozaki G=8 M=%d N=%d K=%d: rel-L2 %.3e", c.M, c.N, c.K, e8);
+    std::printf("ozaki M=%d N=%d K=%d sigma=%.0f: rel-L2 G=7 %.2e, G=8 %.2e\n", c.M, c.N, c.K, c.sigma,
+                e7, e8);
+  }
+}
+
 int main() {
   std::mt19937 rng(12345);
   try {
@@ -319,6 +483,7 @@ int main() {
     test_contractions(rng, 2, 30);
     test_contractions(rng, 3, 6);
     test_big_shapes();
+    test_ozaki(rng);
   } catch (const Error& e) {
     std::printf("FAIL: exception %d %s\n", e.code, e.what());
     return 2;
