@@ -62,8 +62,8 @@ struct OzSmem {
   static constexpr int kKoffB = kKoffA + OZ_KMAX * 4;       // int[64]
   static constexpr int kRowE = kKoffB + OZ_KMAX * 4;        // int[2][128]
   static constexpr int kColE = kRowE + 2 * OZ_TM * 4;       // int[64]
-  static constexpr int kBars = kColE + OZ_NMAX * 4;         // 2 mbarriers + tmem slot
-  static constexpr int kTotal = kBars + 32;
+  static constexpr int kBars = kColE + OZ_NMAX * 4;         // 1 + 8 + 8 mbarriers + tmem slot
+  static constexpr int kTotal = kBars + 17 * 8 + 16;
 };
 static_assert(OzSmem::kTotal <= 227 * 1024, "shared memory budget");
 
@@ -148,9 +148,14 @@ k_zgemm_ozaki(const double2* __restrict__ A, const double2* __restrict__ B,
   int* koffB = reinterpret_cast<int*>(smem + OzSmem::kKoffB);
   int* rowE = reinterpret_cast<int*>(smem + OzSmem::kRowE);     // [2][128] biased exponent fields
   int* colE = reinterpret_cast<int*>(smem + OzSmem::kColE);
-  uint64_t* ready = reinterpret_cast<uint64_t*>(smem + OzSmem::kBars);   // workers -> MMA
-  uint64_t* done = ready + 1;                                            // MMA -> workers
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
+  // mbarriers.  planes: the worker warps have written this tile's A planes (count 16).
+  // done[g]: the MMAs of accumulator group g have completed (tcgen05.commit).  freed[g]: every
+  // worker warp has read group g out of TMEM (count 16).  done / freed complete one phase per
+  // (tile, half), planes one per tile.
+  uint64_t* planes = reinterpret_cast<uint64_t*>(smem + OzSmem::kBars);
+  uint64_t* done = planes + 1;
+  uint64_t* freed = done + 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(freed + 8);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int K = (int)p.K, N = (int)p.N;
@@ -166,8 +171,11 @@ k_zgemm_ozaki(const double2* __restrict__ A, const double2* __restrict__ B,
   }
   if (tid < 2 * OZ_TM) rowE[tid] = 0;
   if (tid == 0) {
-    oz_mbar_init(ready, OZ_WORKERS / 32);
-    oz_mbar_init(done, 1);
+    oz_mbar_init(planes, OZ_WORKERS / 32);
+    for (int g = 0; g < 8; ++g) {
+      oz_mbar_init(&done[g], 1);
+      oz_mbar_init(&freed[g], OZ_WORKERS / 32);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   if (warp == 0) {
@@ -190,19 +198,25 @@ k_zgemm_ozaki(const double2* __restrict__ A, const double2* __restrict__ B,
       constexpr uint32_t IDESC = oz_idesc(OZ_TM, 32);
       const uint64_t a_base = oz_desc(oz_smem_u32(sA), A_LBO, SBO);
       const uint64_t b_base = oz_desc(oz_smem_u32(sB), B_LBO, SBO);
-      uint32_t it = 0;
-      for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+      uint32_t it = 0, tile_no = 0;
+      for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++tile_no) {
+        oz_mbar_wait(planes, tile_no & 1u);
         for (int h = 0; h < NH; ++h, ++it) {
-          oz_mbar_wait(ready, it & 1u);
-          asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-          // descriptor address fields are in 16-byte units; one K-step = two core matrices
-          oz::for_each_mma<G>(KS, [&](int accum, int a_plane, int b_plane, int ks, uint32_t acc) {
-            const uint64_t ad = a_base + (uint64_t)((a_plane * OZ_A_PLANE + ks * 2 * A_LBO) >> 4);
-            const uint64_t bd =
-                b_base + (uint64_t)((b_plane * OZ_B_PLANE + ks * 2 * B_LBO + h * 4 * SBO) >> 4);
-            oz_umma_i8(tmem_base + (uint32_t)(accum * 32), ad, bd, IDESC, acc);
-          });
-          oz_commit(done);
+#pragma unroll
+          for (int g = 0; g < G; ++g) {
+            // the accumulators of group g must have been drained by the previous (tile, half)
+            if (it > 0) oz_mbar_wait(&freed[g], (it - 1) & 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+            // descriptor address fields are in 16-byte units; one K-step = two core matrices
+            oz::for_each_mma_of_group(g, KS, [&](int accum, int a_plane, int b_plane, int ks,
+                                                 uint32_t acc) {
+              const uint64_t ad = a_base + (uint64_t)((a_plane * OZ_A_PLANE + ks * 2 * A_LBO) >> 4);
+              const uint64_t bd =
+                  b_base + (uint64_t)((b_plane * OZ_B_PLANE + ks * 2 * B_LBO + h * 4 * SBO) >> 4);
+              oz_umma_i8(tmem_base + (uint32_t)(accum * 32), ad, bd, IDESC, acc);
+            });
+            oz_commit(&done[g]);   // group g may be read while the next groups are computed
+          }
         }
       }
     }
@@ -251,7 +265,7 @@ k_zgemm_ozaki(const double2* __restrict__ A, const double2* __restrict__ B,
         for (int s = 0; s < OZ_S; ++s)
           oz_store(dst + (2 * OZ_S + s) * OZ_B_PLANE, pl[s]);
       }
-      // (made visible to the tensor core by the proxy fence before the first `ready` arrival)
+      // (made visible to the tensor core by the proxy fence before the first `planes` arrival)
     }
 
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;   // this warp's TMEM lanes
@@ -305,15 +319,12 @@ k_zgemm_ozaki(const double2* __restrict__ A, const double2* __restrict__ B,
       // output scale of this row: 2^(EA - 5) with |x| < 2^EA, EA = ea - 1022
       const double sa = oz::out_scale(ea);
 
-      for (int h = 0; h < NH; ++h, ++it) {
-        // h = 0: the planes are written; h = 1: this warp has drained the accumulators
-        asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
-        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
-        __syncwarp();
-        if (lane == 0) oz_mbar_arrive(ready);
-        oz_mbar_wait(done, it & 1u);
-        asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+      // the planes of this tile are written: generic-proxy stores -> visible to the tensor core
+      asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+      __syncwarp();
+      if (lane == 0) oz_mbar_arrive(planes);
 
+      for (int h = 0; h < NH; ++h, ++it) {
         const int n0 = h * 32 + cpart * 8;
         long long hr[8], hq[8];   // Horner sums over the groups, re / im
         double vr[8], vq[8];
@@ -331,9 +342,15 @@ k_zgemm_ozaki(const double2* __restrict__ A, const double2* __restrict__ B,
           }
           uint32_t r[8], q[8];
           const uint32_t col = tmem_base + lane_base + (uint32_t)((2 * g) * 32 + cpart * 8);
+          oz_mbar_wait(&done[g], it & 1u);
+          asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
           OZ_TMEM_LD8(r, col);
           OZ_TMEM_LD8(q, col + 32);
           asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+          // this warp is done with group g: the MMA warp may overwrite it (next half / tile)
+          asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+          __syncwarp();
+          if (lane == 0) oz_mbar_arrive(&freed[g]);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             hr[j] = hr[j] * 128 + (long long)(int)r[j];

@@ -129,27 +129,24 @@ OZ_HD uint32_t plane_off(int rows, int row, int chunk) {
   return (uint32_t)(chunk * rows * 16 + (row >> 3) * 128 + (row & 7) * 16);
 }
 
-// The MMA schedule of one (tile, 32-column half): calls
+// The MMA schedule of accumulator group g of one (tile, 32-column half): calls
 //     f(accumulator, a_plane, b_plane, ks, accumulate)
 // for every 128 x 32 x 32 MMA in issue order.  Accumulator 2g is Cr of group g, 2g + 1 is Ci.
 // A planes: [0, S) re digits, [S, 2S) im digits.  B planes: [0, S) re, [S, 2S) im,
 // [2S, 3S) digits of -im (Cr = Ar Br + Ai (-Bi), Ci = Ar Bi + Ai Br).
-template <int G, class F>
-OZ_HD void for_each_mma(int KS, F&& f) {
+template <class F>
+OZ_HD void for_each_mma_of_group(int g, int KS, F&& f) {
+  unsigned acc = 0;
 #pragma unroll
-  for (int g = 0; g < G; ++g) {
-    unsigned acc = 0;
-#pragma unroll
-    for (int s = 0; s < S; ++s) {
-      const int t = g - s;
-      if (t < 0 || t >= S) continue;
-      for (int ks = 0; ks < KS; ++ks) {
-        f(2 * g, s, t, ks, acc);
-        f(2 * g + 1, s, S + t, ks, acc);
-        f(2 * g, S + s, 2 * S + t, ks, 1u);
-        f(2 * g + 1, S + s, t, ks, 1u);
-        acc = 1u;
-      }
+  for (int s = 0; s < S; ++s) {
+    const int t = g - s;
+    if (t < 0 || t >= S) continue;
+    for (int ks = 0; ks < KS; ++ks) {
+      f(2 * g, s, t, ks, acc);
+      f(2 * g + 1, s, S + t, ks, acc);
+      f(2 * g, S + s, 2 * S + t, ks, 1u);
+      f(2 * g + 1, S + s, t, ks, 1u);
+      acc = 1u;
     }
   }
 }

@@ -39,4 +39,7 @@ timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_zg
 
 # 5. per-shape probe of the sweep-step GEMMs (A/B of the kernel variants)
 timeout 300 python tools/gemm_probe.py > $OUT/gemm_probe_$TAG.log 2>&1
+
+# 6. bring-up of the experimental INT8 tensor-core ZGEMM (staged, each stage under a timeout)
+timeout 1300 python tools/ozaki_probe.py > $OUT/ozaki_probe_$TAG.log 2>&1
 ls -la $OUT | tail -30
