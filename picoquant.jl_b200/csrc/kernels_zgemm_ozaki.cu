@@ -108,15 +108,21 @@ __host__ __device__ constexpr uint32_t oz_idesc(int M, int N) {
   return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) |
          ((uint32_t)(M >> 4) << 24);
 }
-__device__ __forceinline__ void oz_umma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
-                                           uint32_t idesc, uint32_t accumulate) {
+// The descriptors are passed as (low, high) words: only the 14-bit start-address field in the
+// low word changes from MMA to MMA, so the issuing thread does 32-bit adds of constants.
+__device__ __forceinline__ void oz_umma_i8(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi,
+                                           uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                           uint32_t accumulate) {
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n"
+      ".reg .b64 da, db;\n"
+      "mov.b64 da, {%1, %2};\n"
+      "mov.b64 db, {%3, %4};\n"
+      "setp.ne.b32 p, %6, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], da, db, %5, p;\n"
       "}\n" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
       : "memory");
 }
 __device__ __forceinline__ void oz_commit(uint64_t* bar) {
@@ -198,23 +204,29 @@ k_zgemm_ozaki(const double2* __restrict__ A, const double2* __restrict__ B,
       constexpr uint32_t IDESC = oz_idesc(OZ_TM, 32);
       const uint64_t a_base = oz_desc(oz_smem_u32(sA), A_LBO, SBO);
       const uint64_t b_base = oz_desc(oz_smem_u32(sB), B_LBO, SBO);
+      const uint32_t a_lo = (uint32_t)a_base, a_hi = (uint32_t)(a_base >> 32);
+      const uint32_t b_lo = (uint32_t)b_base, b_hi = (uint32_t)(b_base >> 32);
       uint32_t it = 0, tile_no = 0;
       for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++tile_no) {
         oz_mbar_wait(planes, tile_no & 1u);
         for (int h = 0; h < NH; ++h, ++it) {
+          const uint32_t bh_lo = b_lo + (uint32_t)((h * 4 * SBO) >> 4);   // rows 32 h .. of B
 #pragma unroll
           for (int g = 0; g < G; ++g) {
             // the accumulators of group g must have been drained by the previous (tile, half)
             if (it > 0) oz_mbar_wait(&freed[g], (it - 1) & 1u);
             asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
             // descriptor address fields are in 16-byte units; one K-step = two core matrices
-            oz::for_each_mma_of_group(g, KS, [&](int accum, int a_plane, int b_plane, int ks,
-                                                 uint32_t acc) {
-              const uint64_t ad = a_base + (uint64_t)((a_plane * OZ_A_PLANE + ks * 2 * A_LBO) >> 4);
-              const uint64_t bd =
-                  b_base + (uint64_t)((b_plane * OZ_B_PLANE + ks * 2 * B_LBO + h * 4 * SBO) >> 4);
-              oz_umma_i8(tmem_base + (uint32_t)(accum * 32), ad, bd, IDESC, acc);
-            });
+            auto mma = [&](int accum, int a_plane, int b_plane, int ks, uint32_t acc) {
+              oz_umma_i8(tmem_base + (uint32_t)(accum * 32),
+                         a_lo + (uint32_t)((a_plane * OZ_A_PLANE + ks * 2 * (int)A_LBO) >> 4), a_hi,
+                         bh_lo + (uint32_t)((b_plane * OZ_B_PLANE + ks * 2 * (int)B_LBO) >> 4), b_hi,
+                         IDESC, acc);
+            };
+            if (KS == 2)
+              oz::for_each_mma_of_group<2>(g, mma);
+            else
+              oz::for_each_mma_of_group<1>(g, mma);
             oz_commit(&done[g]);   // group g may be read while the next groups are computed
           }
         }

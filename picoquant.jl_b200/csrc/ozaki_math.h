@@ -134,13 +134,14 @@ OZ_HD uint32_t plane_off(int rows, int row, int chunk) {
 // for every 128 x 32 x 32 MMA in issue order.  Accumulator 2g is Cr of group g, 2g + 1 is Ci.
 // A planes: [0, S) re digits, [S, 2S) im digits.  B planes: [0, S) re, [S, 2S) im,
 // [2S, 3S) digits of -im (Cr = Ar Br + Ai (-Bi), Ci = Ar Bi + Ai Br).
-template <class F>
-OZ_HD void for_each_mma_of_group(int g, int KS, F&& f) {
+template <int KS, class F>
+OZ_HD void for_each_mma_of_group(int g, F&& f) {
   unsigned acc = 0;
 #pragma unroll
   for (int s = 0; s < S; ++s) {
     const int t = g - s;
     if (t < 0 || t >= S) continue;
+#pragma unroll
     for (int ks = 0; ks < KS; ++ks) {
       f(2 * g, s, t, ks, acc);
       f(2 * g + 1, s, S + t, ks, acc);

@@ -392,8 +392,7 @@ static double ozaki_tile_error(std::mt19937& rng, int Mrows, int N, int K, doubl
   for (int h = 0; h < NH; ++h) {
     std::vector<int32_t> acc((size_t)2 * G * TM * 32, 0);   // [accumulator][row][column]
     long long worst = 0;
-    for (int grp = 0; grp < G; ++grp)
-    oz::for_each_mma_of_group(grp, KS, [&](int accum, int a_plane, int b_plane, int ks, unsigned accumulate) {
+    auto mma = [&](int accum, int a_plane, int b_plane, int ks, unsigned accumulate) {
       const size_t ab = (size_t)a_plane * A_PLANE + (size_t)ks * 2 * A_LBO;
       const size_t bb = (size_t)b_plane * B_PLANE + (size_t)ks * 2 * B_LBO + (size_t)h * 4 * SBO;
       for (int r = 0; r < TM; ++r)
@@ -406,7 +405,13 @@ static double ozaki_tile_error(std::mt19937& rng, int Mrows, int N, int K, doubl
           worst = std::max(worst, std::llabs(v));
           a = (int32_t)v;
         }
-    });
+    };
+    for (int grp = 0; grp < G; ++grp) {
+      if (KS == 2)
+        oz::for_each_mma_of_group<2>(grp, mma);
+      else
+        oz::for_each_mma_of_group<1>(grp, mma);
+    }
     CHECK(worst < (1ll << 31), "int32 accumulator overflow: %lld", worst);
     for (int r = 0; r < Mrows; ++r)
       for (int c = 0; c < 32; ++c) {
