@@ -70,6 +70,9 @@ def parse_args():
     ap.add_argument("--lanes", type=int, default=4,
                     help="slices kept in flight per GPU (pq_program_run_slices)")
     ap.add_argument("--cpu-sample-slices", type=int, default=2)
+    ap.add_argument("--ozaki", type=int, default=0, choices=[0, 7, 8],
+                    help="EXPERIMENTAL: route the skinny ComplexF64 GEMM steps to the INT8 tensor-core "
+                         "Ozaki kernel with 7 / 8 accumulator groups (option zgemm_ozaki; default off)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
     a = ap.parse_args()
@@ -576,6 +579,8 @@ def main():
     mine = partitions_of_rank(a.slices, rank, world)
 
     b = B200Backend(dtype, device=local_rank)
+    if a.ozaki:
+        b.set_option("zgemm_ozaki", a.ozaki)
     if world > 1:
         ids = [B200Backend.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(ids, src=0)
@@ -822,7 +827,7 @@ def main():
                                                        if c == "ncon"),
                        "kernel_launches_per_slice": sc.program.launches,
                        "arena_bytes": sc.program.arena_bytes, "parallelism": "slices/%d" % world,
-                       "slices_in_flight_per_gpu": a.lanes,
+                       "slices_in_flight_per_gpu": a.lanes, "zgemm_ozaki": a.ozaki,
                        "l2": "inputs larger than L2: per-step intermediates of 2^24 elements "
                              "(256 MiB c128) stream through the 126 MB L2"},
             "amplitude_wall_ms": ms_per_step,
