@@ -213,6 +213,7 @@ struct FusedParams {
 };
 
 void init_kernels_ozaki();
+double run_ozaki_microbench(const Launch& L, const std::string& what);
 bool zgemm_ozaki_eligible(const ContractPlan& cp);
 void run_zgemm_ozaki(const Launch& L, const FusedParams& fp, int groups, const void* A,
                      const void* B, void* C);

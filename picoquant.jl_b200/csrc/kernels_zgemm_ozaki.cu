@@ -394,6 +394,127 @@ k_zgemm_ozaki(const double2* __restrict__ A, const double2* __restrict__ B,
   }
 }
 
+
+// ---------------------------------------------------------------------------
+// Bring-up aids (pq_microbench "umma_i8_selftest", "umma_i8_tops_n32", "umma_i8_tops_n64").
+//
+// Self-test: ONE 128 x 32 x 32 kind::i8 MMA on known int8 patterns laid out exactly like the
+// kernel's planes (plane_off, LBO = rows * 16, SBO = 128), read back with tcgen05.ld and
+// compared on the host with the integer dot products -- isolates the descriptor encodings
+// and the TMEM lane / column mapping from everything else.  Returns the number of wrong
+// entries (0 = pass).
+// ---------------------------------------------------------------------------
+__host__ __device__ inline int oz_pat_a(int r, int k) { return (r * 7 + k * 3) % 127 - 63; }
+__host__ __device__ inline int oz_pat_b(int c, int k) { return (c * 5 + k * 11 + 1) % 127 - 63; }
+
+__global__ void __launch_bounds__(128, 1) k_umma_i8_selftest(int* __restrict__ out) {
+  __shared__ __align__(1024) unsigned char sa[OZ_TM * 32];
+  __shared__ __align__(1024) unsigned char sb[32 * 32];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t slot;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int i = tid; i < OZ_TM * 32; i += 128) {
+    const int r = i >> 5, k = i & 31;
+    sa[oz::plane_off(OZ_TM, r, k >> 4) + (k & 15)] = (unsigned char)(signed char)oz_pat_a(r, k);
+  }
+  for (int i = tid; i < 32 * 32; i += 128) {
+    const int c = i >> 5, k = i & 31;
+    sb[oz::plane_off(32, c, k >> 4) + (k & 15)] = (unsigned char)(signed char)oz_pat_b(c, k);
+  }
+  if (tid == 0) {
+    oz_mbar_init(&bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(
+                     oz_smem_u32(&slot)),
+                 "r"(32u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+  const uint32_t tmem = slot;
+  if (tid == 0) {
+    const uint64_t ad = oz_desc(oz_smem_u32(sa), OZ_TM * 16, 128);
+    const uint64_t bd = oz_desc(oz_smem_u32(sb), 32 * 16, 128);
+    oz_umma_i8(tmem, (uint32_t)ad, (uint32_t)(ad >> 32), (uint32_t)bd, (uint32_t)(bd >> 32),
+               oz_idesc(OZ_TM, 32), 0u);
+    oz_commit(&bar);
+  }
+  oz_mbar_wait(&bar, 0u);
+  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+  const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+#pragma unroll
+  for (int c0 = 0; c0 < 32; c0 += 8) {
+    uint32_t r[8];
+    OZ_TMEM_LD8(r, tmem + lane_base + c0);
+    asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+#pragma unroll
+    for (int j = 0; j < 8; ++j) out[(warp * 32 + lane) * 32 + c0 + j] = (int)r[j];
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  if (warp == 0)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "r"(32u)
+                 : "memory");
+}
+
+// Issue-rate probe: every SM issues `iters` x 16 MMAs of 128 x NCOL x 32 on resident planes
+// (4 accumulators, values irrelevant).  Returns int8 TOPS (2 ops per MAC).
+template <int NCOL>
+__global__ void __launch_bounds__(128, 1) k_umma_i8_rate(int iters, int* __restrict__ sink) {
+  extern __shared__ __align__(1024) unsigned char smem[];   // A: 128 x 64, B: 64 x 64, zeroed
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t slot;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < (OZ_A_PLANE + OZ_B_PLANE) / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0x01010101u;
+  if (tid == 0) {
+    oz_mbar_init(&bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(
+                     oz_smem_u32(&slot)),
+                 "r"(256u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+  const uint32_t tmem = slot;
+  if (tid == 0) {
+    const uint64_t ad = oz_desc(oz_smem_u32(smem), OZ_TM * 16, 128);
+    const uint64_t bd = oz_desc(oz_smem_u32(smem + OZ_A_PLANE), OZ_NMAX * 16, 128);
+    constexpr uint32_t IDESC = oz_idesc(OZ_TM, NCOL);
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const uint32_t ks = (uint32_t)(j & 1) * ((2 * OZ_TM * 16) >> 4);
+        const uint32_t kb = (uint32_t)(j & 1) * ((2 * OZ_NMAX * 16) >> 4);
+        oz_umma_i8(tmem + (uint32_t)((j >> 2) * NCOL), (uint32_t)ad + ks, (uint32_t)(ad >> 32),
+                   (uint32_t)bd + kb, (uint32_t)(bd >> 32), IDESC, (it | (j & 3)) ? 1u : 0u);
+      }
+    }
+    oz_commit(&bar);
+  }
+  oz_mbar_wait(&bar, 0u);
+  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+  uint32_t r[8];
+  OZ_TMEM_LD8(r, tmem + ((uint32_t)(warp * 32) << 16));
+  asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+  if (r[0] == 0x7fffffffu) sink[blockIdx.x] = (int)r[1];   // keeps the loads alive
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  if (warp == 0)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "r"(256u)
+                 : "memory");
+}
+
 }  // namespace
 
 // The default path never depends on this experimental kernel: if its attributes cannot be set
@@ -426,6 +547,60 @@ void run_zgemm_ozaki(const Launch& L, const FusedParams& fp, int groups, const v
   else
     k_zgemm_ozaki<8><<<grid, OZ_THREADS, OzSmem::kTotal, L.stream>>>(
         (const double2*)A, (const double2*)B, (double2*)C, fp);
+}
+
+
+// pq_microbench back ends: "umma_i8_selftest" (wrong entries, 0 = pass), "umma_i8_tops_n32",
+// "umma_i8_tops_n64" (int8 TOPS at the kernel's MMA shape / at N = 64)
+double run_ozaki_microbench(const Launch& L, const std::string& what) {
+  if (what == "umma_i8_selftest") {
+    int* d = nullptr;
+    PQ_CUDA(cudaMalloc(&d, OZ_TM * 32 * sizeof(int)));
+    PQ_CUDA(cudaMemsetAsync(d, 0xff, OZ_TM * 32 * sizeof(int), L.stream));
+    k_umma_i8_selftest<<<1, 128, 0, L.stream>>>(d);
+    std::vector<int> got(OZ_TM * 32);
+    cudaError_t e = cudaMemcpyAsync(got.data(), d, got.size() * sizeof(int), cudaMemcpyDeviceToHost,
+                                    L.stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(L.stream);
+    cudaFree(d);
+    PQ_CUDA(e);
+    int wrong = 0;
+    for (int r = 0; r < OZ_TM; ++r)
+      for (int c = 0; c < 32; ++c) {
+        int want = 0;
+        for (int k = 0; k < 32; ++k) want += oz_pat_a(r, k) * oz_pat_b(c, k);
+        wrong += got[r * 32 + c] != want;
+      }
+    return wrong;
+  }
+  const bool n64 = what == "umma_i8_tops_n64";
+  PQ_REQUIRE(n64 || what == "umma_i8_tops_n32", PQ_ERR_INVALID, "unknown microbench: " + what);
+  const int iters = 4096, smem = OZ_A_PLANE + OZ_B_PLANE;
+  int* sink = nullptr;
+  PQ_CUDA(cudaMalloc(&sink, L.num_sms * sizeof(int)));
+  cudaEvent_t e0, e1;
+  PQ_CUDA(cudaEventCreate(&e0));
+  PQ_CUDA(cudaEventCreate(&e1));
+  float best = 1e30f;
+  for (int rep = 0; rep < 4; ++rep) {
+    PQ_CUDA(cudaEventRecord(e0, L.stream));
+    if (n64)
+      k_umma_i8_rate<64><<<L.num_sms, 128, smem, L.stream>>>(iters, sink);
+    else
+      k_umma_i8_rate<32><<<L.num_sms, 128, smem, L.stream>>>(iters, sink);
+    PQ_CUDA(cudaEventRecord(e1, L.stream));
+    PQ_CUDA(cudaEventSynchronize(e1));
+    float ms = 0;
+    PQ_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    if (rep > 0 && ms < best) best = ms;
+  }
+  cudaError_t e = cudaGetLastError();
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(sink);
+  PQ_CUDA(e);
+  const double macs = double(L.num_sms) * iters * 16.0 * OZ_TM * (n64 ? 64 : 32) * 32;
+  return 2.0 * macs / (best * 1e-3) / 1e12;
 }
 
 }  // namespace pq

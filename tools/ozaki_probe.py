@@ -7,6 +7,8 @@ hang, and a hung child must not hold the box:
 
     gpurun --timeout 900 -- 'python tools/ozaki_probe.py'
 
+  stage 0  pq_microbench("umma_i8_selftest"): one kind::i8 MMA on known patterns (descriptor
+           encodings, TMEM mapping), then the raw INT8 issue rate at N = 32 / 64
   stage 1  one tile, canonical layouts (M=128, N=K=64), then ragged M / N / K
   stage 2  the sweep-step shapes of the bench workload (gather fused), parity vs NumPy c128
   stage 3  timing of those shapes against the DMMA kernels (option off)
@@ -81,7 +83,16 @@ def child(stage):
     import picoquant_jl_b200  # noqa: F401
     from picoquant_jl_b200.host.b200_backend import B200Backend
     res = {}
-    if stage in ("1", "2"):
+    if stage == "0":
+        b = B200Backend(np.complex128)
+        res["selftest_wrong_entries"] = {"wrong": b.microbench("umma_i8_selftest")}
+        print("selftest", res["selftest_wrong_entries"], flush=True)
+        if res["selftest_wrong_entries"]["wrong"] == 0:
+            for w in ("umma_i8_tops_n32", "umma_i8_tops_n64"):
+                res[w] = {"tops": b.microbench(w)}
+                print(w, res[w], flush=True)
+        b.close()
+    elif stage in ("1", "2"):
         cases = SMALL if stage == "1" else SWEEP
         for name, (ad, ai, bd, bi) in cases.items():
             A, B = operands(ad, bd, 1)
@@ -150,7 +161,7 @@ def main():
         return 0
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
     summary, ok = {}, True
-    for stage, limit in (("1", 180), ("2", 300), ("3", 300), ("4", 420)):
+    for stage, limit in (("0", 120), ("1", 180), ("2", 300), ("3", 300), ("4", 420)):
         try:
             r = subprocess.run([sys.executable, os.path.abspath(__file__), "--child", stage],
                                capture_output=True, text=True, timeout=limit)
@@ -170,6 +181,8 @@ def main():
             if "rel_l2" in v and not v["rel_l2"] < 1e-11:
                 ok = False
             if "rel_err" in v and not v["rel_err"] < 1e-10:
+                ok = False
+            if "wrong" in v and v["wrong"] != 0:
                 ok = False
         if not ok:
             break
