@@ -70,9 +70,9 @@ def parse_args():
     ap.add_argument("--lanes", type=int, default=4,
                     help="slices kept in flight per GPU (pq_program_run_slices)")
     ap.add_argument("--cpu-sample-slices", type=int, default=2)
-    ap.add_argument("--ozaki", type=int, default=0, choices=[0, 7, 8],
+    ap.add_argument("--ozaki", type=int, default=0, choices=[0, 6, 7],
                     help="EXPERIMENTAL: route the skinny ComplexF64 GEMM steps to the INT8 tensor-core "
-                         "Ozaki kernel with 7 / 8 accumulator groups (option zgemm_ozaki; default off)")
+                         "Ozaki kernel with 6 / 7 accumulator groups (option zgemm_ozaki; default off)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
     a = ap.parse_args()

@@ -202,10 +202,10 @@ int pq_timer_end(pq_handle* h, double* ms);
  *                   products, 7 persistent skinny kernel where eligible
  *   "zgemm_skinny"  1 disables the persistent skinny ZGEMM
  *   "zgemm_3m"      1 four DMMAs per complex product instead of three (3M)
- *   "zgemm_ozaki"   EXPERIMENTAL, not yet validated on hardware: 7 or 8 routes the skinny
+ *   "zgemm_ozaki"   EXPERIMENTAL, not yet validated on hardware: 6 or 7 routes the skinny
  *                   ComplexF64 GEMM steps (K <= 64, N <= 64) to an INT8 tensor-core (tcgen05
- *                   kind::i8) Ozaki-scheme kernel keeping 7 / 8 accumulator groups (rel-L2
- *                   ~1e-13 / ~1e-14 per contraction); 0 (default) never launches it
+ *                   kind::i8) Ozaki-scheme kernel keeping 6 / 7 accumulator groups (rel-L2
+ *                   ~2e-13 / ~2e-14 per contraction); 0 (default) never launches it
  *   "zgemm_kfirst"  1 row-first gather order only
  *   "zgemm_stagger" ns of start delay per resident-CTA slot in the first wave (tile-per-CTA ZGEMM)
  * Every alternative computes the same contraction; the tests run them against each other. */

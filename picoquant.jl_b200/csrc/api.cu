@@ -589,8 +589,8 @@ extern "C" int pq_set_option(pq_handle* h, const char* key, int value) {
   else if (k == "zgemm_skinny") h->opt.zgemm_skinny = value;
   else if (k == "zgemm_3m") h->opt.zgemm_3m = value;
   else if (k == "zgemm_ozaki") {
-    if (value != 0 && value != 7 && value != 8) {
-      h->last_error = "zgemm_ozaki must be 0, 7 or 8";
+    if (value != 0 && value != 6 && value != 7) {
+      h->last_error = "zgemm_ozaki must be 0, 6 or 7";
       return PQ_ERR_INVALID;
     }
     h->opt.zgemm_ozaki = value;

@@ -120,7 +120,7 @@ struct Options {
   int zgemm_cfg = 0;  // fused ZGEMM: 0 auto, 1 = 64x64 (2 CTAs/SM), 2 = 64x32 (4 CTAs/SM), 3 = 128x8, 4 = 64x32 3M, 7 = persistent skinny where eligible
   int zgemm_3m = 0;       // persistent skinny ZGEMM: 0 = 3M (three DMMAs per complex product), 1 = 4M
   int zgemm_skinny = 0;   // persistent skinny fused ZGEMM: 0 auto, 1 off
-  int zgemm_ozaki = 0;    // EXPERIMENTAL int8 tensor-core ZGEMM (kernels_zgemm_ozaki.cu): 0 off, 7 / 8 = accumulator groups
+  int zgemm_ozaki = 0;    // EXPERIMENTAL int8 tensor-core ZGEMM (kernels_zgemm_ozaki.cu): 0 off, 6 / 7 = accumulator groups
   int zgemm_stagger = 0;  // ns of start delay per resident-CTA slot in the first wave (0 = off)
   int chain = 0;    // compiled programs: 0 = batch chains of tiny contractions into one launch, 1 = off
   int prio = 0;     // 0: small-grid graph nodes get the highest launch priority, 1: off

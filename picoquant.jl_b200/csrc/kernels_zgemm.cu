@@ -873,7 +873,7 @@ void run_zgemm_fused(const Launch& L, const ContractPlan& cp, const void* A, con
   bool akf = min_stride(cp.kA) < min_stride(cp.mA), bkf = min_stride(cp.kB) < min_stride(cp.nB);
   if (L.opt && L.opt->zgemm_kfirst == 1) akf = bkf = false;  // A/B check knob
   if (cfg == 3) akf = bkf = false;  // measured: no gain for the narrow tiles (HBM-bound)
-  // EXPERIMENTAL (off unless option "zgemm_ozaki" = 7 / 8): INT8 tensor-core Ozaki product
+  // EXPERIMENTAL (off unless option "zgemm_ozaki" = 6 / 7): INT8 tensor-core Ozaki product
   {
     const int oz = L.opt ? L.opt->zgemm_ozaki : 0;
     if (oz != 0 && zgemm_ozaki_eligible(cp)) {

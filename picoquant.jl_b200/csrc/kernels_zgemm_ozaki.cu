@@ -1,4 +1,4 @@
-// K2o (EXPERIMENTAL, opt-in: option "zgemm_ozaki" = 7 or 8; NOT yet run on hardware, see
+// K2o (EXPERIMENTAL, opt-in: option "zgemm_ozaki" = 6 or 7; NOT yet run on hardware, see
 // DESIGN.md section 2.1): ComplexF64 GEMM for the skinny sweep steps on the INT8 tensor cores
 // of sm_100a (tcgen05.mma kind::i8, int32 accumulators in TMEM) -- an Ozaki-scheme
 // ("error-free slicing") product.
@@ -13,31 +13,33 @@
 // tensor core replaced by an integer GEMM reading through the same LBO / SBO addressing).
 // Every row of A (all k, re and im together) gets one power-of-two scale 2^EA with
 // |x| < 2^EA; likewise every column n of B.  A real x of that row becomes the integer
-//     q = rint(x * 2^(47 - EA)),   |q| <= 2^47,
-// written in balanced base 128:  q = sum_{i<7} d_i 128^i,  d_i in [-64, 63]  (int8).
-// The digits come out of q + BIAS (BIAS = sum 64*128^i) as plain 7-bit fields, so there is no
-// carry chain.  With s counting digits from the most significant one, the product of digit
-// planes s of A and t of B has weight 128^(12 - s - t); all pairs with the same g = s + t are
-// summed EXACTLY by the tensor core in one int32 accumulator (|acc| < 2^23 for K <= 64), and
-// pairs with g >= G are dropped (G = 7: 28 pairs, rel-L2 ~1e-13 on well-scaled rows; G = 8:
-// 34 pairs, ~1e-14).  The complex product uses four real ones; the minus sign of
-// Cr = Ar Br - Ai Bi is carried by a third, negated set of B planes (B is tiny and resident).
-// Epilogue:  C = 2^(EA + EB - 10) * sum_g acc_g 2^(-7 g), evaluated as two int64 Horner sums
-// (g < 4 and g >= 4), two int64 -> f64 conversions and one FMA per real number.
+//     q = rint(x * 2^(46 - EA)),   |q| <= 2^46,
+// written in balanced base 256:  q = sum_{i<6} d_i 256^i,  d_i in [-128, 127]  (int8).
+// The digits are simply the bytes of q + BIAS (BIAS = sum 128*256^i) with the top bit flipped:
+// no carry chain, no bit-field shuffling.  With s counting digits from the most significant
+// one, the product of digit planes s of A and t of B has weight 256^(10 - s - t); all pairs
+// with the same g = s + t are summed EXACTLY by the tensor core in one int32 accumulator
+// (|acc| < 2^25 for K <= 64), and pairs with g >= G are dropped (G = 6: 21 pairs, rel-L2
+// ~2e-13 on well-scaled rows; G = 7: 26 pairs, ~2e-14).  The complex product uses four real
+// ones; the minus sign of Cr = Ar Br - Ai Bi is carried by a third, negated set of B planes
+// (B is tiny and resident).  Epilogue:  C = 2^(EA + EB - 12) * sum_g acc_g 256^-g, evaluated
+// as two int64 Horner sums (g < 3 and g >= 3), two int64 -> f64 conversions and one FMA per
+// real number.
 //
 // The kernel (same envelope as k_zgemm_skinny: K <= 64, N <= 64, gather straight from the
 // un-permuted operands).  One persistent CTA per SM, 16 worker warps + 1 MMA-issue warp:
-//   * B (K x N) is gathered, scaled and sliced into 3 x 7 resident int8 planes once per CTA;
+//   * B (K x N) is gathered, scaled and sliced into 3 x 6 resident int8 planes once per CTA;
 //   * a tile is 128 rows of A x all of K: worker thread (row, 16-k chunk) loads its 16 complex
 //     numbers, the row exponent is an atomicMax over the four chunk threads, and each thread
-//     writes one 16-byte core-matrix row per plane (7 re + 7 im planes, no-swizzle K-major
+//     writes one 16-byte core-matrix row per plane (6 re + 6 im planes, no-swizzle K-major
 //     UMMA layout, conflict-free STS.128);
 //   * the MMA warp issues, per 32-column half of N, G x (pairs) x 4 x (K/32) MMAs of shape
-//     128 x 32 x 32 into 2 G accumulators of 32 TMEM columns (G = 8 fills all 512 columns);
+//     128 x 32 x 32 into 2 G accumulators of 32 TMEM columns (G = 7: 448 of the 512 columns);
 //   * the worker warps drain TMEM (tcgen05.ld), combine, scale and store C[m + M n]
 //     (lane = row: 512-byte coalesced stores); the next tile of A is L2-prefetched meanwhile.
-// Phases of a tile are serialised (one set of A planes is all that fits beside B in 227 KB);
-// the expected bound is TMEM read bandwidth + slicing ALU work, ~2x under the DMMA time.
+// MMAs and TMEM drain are pipelined per accumulator group (mbarriers done[g] / freed[g]);
+// gather + slicing of a tile is serial with them (one set of A planes).  Expected bound: TMEM
+// read bandwidth + slicing ALU work, ~2x under the DMMA time -- to be measured.
 #include "common.h"
 #include "ozaki_math.h"
 
@@ -146,7 +148,7 @@ template <int G>
 __global__ void __launch_bounds__(OZ_THREADS, 1)
 k_zgemm_ozaki(const double2* __restrict__ A, const double2* __restrict__ B,
               double2* __restrict__ C, const FusedParams p) {
-  static_assert(G >= 5 && G <= 8, "2 * G * 32 accumulator columns must fit 512");
+  static_assert(G > oz::HI_GROUPS && G <= 8, "2 * G * 32 accumulator columns must fit 512");
   extern __shared__ __align__(1024) unsigned char smem[];
   unsigned char* sA = smem + OzSmem::kA;
   unsigned char* sB = smem + OzSmem::kB;
@@ -303,7 +305,7 @@ k_zgemm_ozaki(const double2* __restrict__ A, const double2* __restrict__ B,
       workers_barrier();
       const int ea = rowE[buf * OZ_TM + row];
       if (tid < OZ_TM) rowE[(buf ^ 1) * OZ_TM + tid] = 0;    // for the next tile (see header)
-      // ---- slice into the 7 + 7 planes of this tile ----
+      // ---- slice into the re and im digit planes of this tile ----
       if (chunk_on) {
         const double scale = oz::slice_scale(ea);
         oz::Word4 pl[OZ_S];
@@ -328,7 +330,7 @@ k_zgemm_ozaki(const double2* __restrict__ A, const double2* __restrict__ B,
           }
         }
       }
-      // output scale of this row: 2^(EA - 5) with |x| < 2^EA, EA = ea - 1022
+      // output scale of this row: 2^(EA - 6) with |x| < 2^EA, EA = ea - 1022
       const double sa = oz::out_scale(ea);
 
       // the planes of this tile are written: generic-proxy stores -> visible to the tensor core
@@ -339,16 +341,16 @@ k_zgemm_ozaki(const double2* __restrict__ A, const double2* __restrict__ B,
       for (int h = 0; h < NH; ++h, ++it) {
         const int n0 = h * 32 + cpart * 8;
         long long hr[8], hq[8];   // Horner sums over the groups, re / im
-        double vr[8], vq[8];
+        long long fr[8], fq[8];   // the finished first sums (groups 0 .. HI_GROUPS-1)
 #pragma unroll
         for (int j = 0; j < 8; ++j) hr[j] = hq[j] = 0;
 #pragma unroll
         for (int g = 0; g < G; ++g) {
-          if (g == 4) {   // groups 0..3 done: weight 2^-21 relative to group 0
+          if (g == oz::HI_GROUPS) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              vr[j] = (double)hr[j] * (1.0 / 2097152.0);
-              vq[j] = (double)hq[j] * (1.0 / 2097152.0);
+              fr[j] = hr[j];
+              fq[j] = hq[j];
               hr[j] = hq[j] = 0;
             }
           }
@@ -365,19 +367,18 @@ k_zgemm_ozaki(const double2* __restrict__ A, const double2* __restrict__ B,
           if (lane == 0) oz_mbar_arrive(&freed[g]);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            hr[j] = hr[j] * 128 + (long long)(int)r[j];
-            hq[j] = hq[j] * 128 + (long long)(int)q[j];
+            hr[j] = hr[j] * 256 + (long long)(int)r[j];
+            hq[j] = hq[j] * 256 + (long long)(int)q[j];
           }
         }
-        constexpr double LOW = 1.0 / (double)(1ull << (7 * (G - 1)));   // weight of the last group
         if (m < M) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const int n = n0 + j;
             if (n < N) {
               const double sc = sa * oz::out_scale(colE[n]);
-              const double re = fma((double)hr[j], LOW, vr[j]);
-              const double im = fma((double)hq[j], LOW, vq[j]);
+              const double re = oz::combine(fr[j], hr[j], G);
+              const double im = oz::combine(fq[j], hq[j], G);
               C[m + M * n] = make_double2(re * sc, im * sc);
             }
           }
@@ -522,30 +523,30 @@ __global__ void __launch_bounds__(128, 1) k_umma_i8_rate(int iters, int* __restr
 static bool g_ozaki_ready = false;
 
 void init_kernels_ozaki() {
+  cudaError_t e6 = cudaFuncSetAttribute(k_zgemm_ozaki<6>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        OzSmem::kTotal);
   cudaError_t e7 = cudaFuncSetAttribute(k_zgemm_ozaki<7>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         OzSmem::kTotal);
-  cudaError_t e8 = cudaFuncSetAttribute(k_zgemm_ozaki<8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        OzSmem::kTotal);
-  if (e7 != cudaSuccess || e8 != cudaSuccess) (void)cudaGetLastError();
-  g_ozaki_ready = (e7 == cudaSuccess && e8 == cudaSuccess);
+  if (e6 != cudaSuccess || e7 != cudaSuccess) (void)cudaGetLastError();
+  g_ozaki_ready = (e6 == cudaSuccess && e7 == cudaSuccess);
 }
 
 bool zgemm_ozaki_eligible(const ContractPlan& cp) {
   return cp.K >= 1 && cp.K <= OZ_KMAX && cp.N >= 1 && cp.N <= OZ_NMAX && cp.M >= 1;
 }
 
-// groups = 7 or 8 (option "zgemm_ozaki")
+// groups = 6 or 7 (option "zgemm_ozaki")
 void run_zgemm_ozaki(const Launch& L, const FusedParams& fp, int groups, const void* A,
                      const void* B, void* C) {
-  PQ_REQUIRE(groups == 7 || groups == 8, PQ_ERR_INVALID, "zgemm_ozaki must be 0, 7 or 8");
+  PQ_REQUIRE(groups == 6 || groups == 7, PQ_ERR_INVALID, "zgemm_ozaki must be 0, 6 or 7");
   PQ_REQUIRE(g_ozaki_ready, PQ_ERR_UNSUPPORTED, "zgemm_ozaki: kernel attributes could not be set");
   const long long tiles = (fp.M + OZ_TM - 1) / OZ_TM;
   const unsigned grid = (unsigned)(tiles < L.num_sms ? tiles : L.num_sms);
-  if (groups == 7)
-    k_zgemm_ozaki<7><<<grid, OZ_THREADS, OzSmem::kTotal, L.stream>>>(
+  if (groups == 6)
+    k_zgemm_ozaki<6><<<grid, OZ_THREADS, OzSmem::kTotal, L.stream>>>(
         (const double2*)A, (const double2*)B, (double2*)C, fp);
   else
-    k_zgemm_ozaki<8><<<grid, OZ_THREADS, OzSmem::kTotal, L.stream>>>(
+    k_zgemm_ozaki<7><<<grid, OZ_THREADS, OzSmem::kTotal, L.stream>>>(
         (const double2*)A, (const double2*)B, (double2*)C, fp);
 }
 

@@ -4,9 +4,10 @@
 // (the same role tile_math.h plays for the permute kernel).
 //
 // A real x of a row whose largest magnitude has biased exponent field `ef` (|x| < 2^(ef-1022))
-// becomes q = rint(x * 2^(QBITS - (ef - 1022))), |q| <= 2^QBITS, written in balanced base 128:
-// q = sum_i d_i 128^i with d_i in [-64, 63].  The digits are the 7-bit fields of q + BIAS minus
-// 64 (BIAS = sum_i 64 * 128^i), so no carries propagate.  Plane s holds digit 128^(S-1-s).
+// becomes q = rint(x * 2^(QBITS - (ef - 1022))), |q| <= 2^QBITS, written in balanced base 256:
+// q = sum_i d_i 256^i with d_i in [-128, 127] (int8).  The digits are the BYTES of q + BIAS
+// (BIAS = sum_i 128 * 256^i) with their top bit flipped, so there are no carries and no
+// bit-field shuffling.  Plane s holds digit 256^(S-1-s).
 #pragma once
 #include <stdint.h>
 
@@ -21,10 +22,12 @@
 namespace pq {
 namespace oz {
 
-constexpr int S = 7;                       // int8 digits per real number
-constexpr int QBITS = 7 * S - 2;           // |q| <= 2^47
-constexpr unsigned long long BIAS = 64ull * ((1ull << (7 * S)) - 1ull) / 127ull;
+constexpr int S = 6;                       // int8 digits per real number
+constexpr int QBITS = 8 * S - 2;           // |q| <= 2^46 (one bit of headroom below the bias)
+constexpr unsigned long long BIAS = 0x808080808080ull;   // sum_{i<S} 128 * 256^i
 constexpr int MIN_EF = 64;                 // rows below 2^-958 flush to zero
+constexpr int HI_GROUPS = 3;               // accumulator groups summed in the first Horner sum
+static_assert(S == 6, "BIAS, slice16 and the transposes are written for six digits");
 
 struct Word4 {
   uint32_t w[4];
@@ -41,13 +44,6 @@ OZ_HD uint32_t byte_perm(uint32_t a, uint32_t b, uint32_t sel) {
     r |= (uint32_t)((ab >> (8 * n)) & 0xFFu) << (8 * i);
   }
   return r;
-#endif
-}
-OZ_HD uint32_t funnel_r(uint32_t lo, uint32_t hi, int sh) {
-#ifdef __CUDA_ARCH__
-  return __funnelshift_r(lo, hi, sh);
-#else
-  return (uint32_t)(((((unsigned long long)hi) << 32) | lo) >> sh);
 #endif
 }
 OZ_HD long long d2ll_rn(double x) {
@@ -78,47 +74,35 @@ OZ_HD int abs_hi(double x) {
   return (int)((bits >> 32) & 0x7fffffffu);
 #endif
 }
-// slicing scale 2^(QBITS - (ef - 1022)) and output scale 2^((ef - 1022) - 5) of a row / column
+// slicing scale 2^(QBITS - (ef - 1022)) and output scale 2^((ef - 1022) - 6) of a row / column:
+// C = 2^(EA + EB - 2 QBITS) * 256^(2 (S - 1)) * sum_g acc_g 256^-g = 2^(EA - 6) 2^(EB - 6) * sum_g ...
 OZ_HD double slice_scale(int ef) { return ef >= MIN_EF ? pow2_field(QBITS + 2045 - ef) : 0.0; }
-OZ_HD double out_scale(int ef) { return ef >= MIN_EF ? pow2_field(ef - 4) : 0.0; }
-
-// 7-bit fields -> bytes: bits [7i, 7i+7) of t go to byte i (i < 4)
-OZ_HD uint32_t spread(uint32_t t) {
-  return (t & 0x7Fu) | ((t & 0x3F80u) << 1) | ((t & 0x1FC000u) << 2) | ((t & 0xFE00000u) << 3);
-}
-// field e in [0, 127] -> int8 digit e - 64, on four packed bytes
-OZ_HD uint32_t unbias(uint32_t p) {
-  p ^= 0x40404040u;
-  return p | ((p & 0x40404040u) << 1);
-}
+OZ_HD double out_scale(int ef) { return ef >= MIN_EF ? pow2_field(ef - 5) : 0.0; }
 
 // Slices 16 reals of one row (one 16-byte K chunk) into S planes: out[s] holds digit s
 // (s = 0 most significant) of the 16 numbers, byte j = number j.
 OZ_HD void slice16(const double* x, double scale, bool negate, Word4* out) {
 #pragma unroll
   for (int jg = 0; jg < 4; ++jg) {
-    uint32_t p0[4], p1[4];
+    uint32_t lo[4], hi[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       long long q = d2ll_rn(x[4 * jg + j] * scale);
       if (negate) q = -q;
-      const unsigned long long u = (unsigned long long)(q + (long long)BIAS);
-      const uint32_t lo = (uint32_t)u, hi = (uint32_t)(u >> 32);
-      p0[j] = unbias(spread(lo & 0x0FFFFFFFu));                   // digits 128^0 .. 128^3
-      p1[j] = unbias(spread(funnel_r(lo, hi, 28) & 0x1FFFFFu));   // digits 128^4 .. 128^6
+      const unsigned long long u = (unsigned long long)(q + (long long)BIAS) ^ BIAS;
+      lo[j] = (uint32_t)u;           // digits 256^0 .. 256^3
+      hi[j] = (uint32_t)(u >> 32);   // digits 256^4, 256^5 (upper half zero)
     }
     // 4 x 4 byte transposes: the word of plane i = byte i of the four numbers
-    const uint32_t t0 = byte_perm(p0[0], p0[1], 0x5140), t1 = byte_perm(p0[0], p0[1], 0x7362);
-    const uint32_t t2 = byte_perm(p0[2], p0[3], 0x5140), t3 = byte_perm(p0[2], p0[3], 0x7362);
-    out[6].w[jg] = byte_perm(t0, t2, 0x5410);   // 128^0 = least significant = plane 6
-    out[5].w[jg] = byte_perm(t0, t2, 0x7632);
-    out[4].w[jg] = byte_perm(t1, t3, 0x5410);
-    out[3].w[jg] = byte_perm(t1, t3, 0x7632);
-    const uint32_t v0 = byte_perm(p1[0], p1[1], 0x5140), v1 = byte_perm(p1[0], p1[1], 0x7362);
-    const uint32_t v2 = byte_perm(p1[2], p1[3], 0x5140), v3 = byte_perm(p1[2], p1[3], 0x7362);
-    out[2].w[jg] = byte_perm(v0, v2, 0x5410);
-    out[1].w[jg] = byte_perm(v0, v2, 0x7632);
-    out[0].w[jg] = byte_perm(v1, v3, 0x5410);
+    const uint32_t t0 = byte_perm(lo[0], lo[1], 0x5140), t1 = byte_perm(lo[0], lo[1], 0x7362);
+    const uint32_t t2 = byte_perm(lo[2], lo[3], 0x5140), t3 = byte_perm(lo[2], lo[3], 0x7362);
+    out[5].w[jg] = byte_perm(t0, t2, 0x5410);   // 256^0 = least significant = plane S - 1
+    out[4].w[jg] = byte_perm(t0, t2, 0x7632);
+    out[3].w[jg] = byte_perm(t1, t3, 0x5410);
+    out[2].w[jg] = byte_perm(t1, t3, 0x7632);
+    const uint32_t v0 = byte_perm(hi[0], hi[1], 0x5140), v2 = byte_perm(hi[2], hi[3], 0x5140);
+    out[1].w[jg] = byte_perm(v0, v2, 0x5410);
+    out[0].w[jg] = byte_perm(v0, v2, 0x7632);
   }
 }
 
@@ -152,14 +136,15 @@ OZ_HD void for_each_mma_of_group(int g, F&& f) {
   }
 }
 
-// value of sum_g acc_g 2^(-7 g) from the two Horner sums (groups 0..3 and 4..G-1)
+// value of sum_g acc_g 256^-g from the two Horner sums hi = sum_{g < HI_GROUPS} acc_g
+// 256^(HI_GROUPS-1-g) and lo = sum_{g >= HI_GROUPS} acc_g 256^(G-1-g)   (G > HI_GROUPS)
 OZ_HD double combine(long long hi, long long lo, int G) {
-  const double low = 1.0 / (double)(1ull << (7 * (G - 1)));
-  if (G <= 4) return (double)hi * low;   // (then `hi` holds groups 0..G-1)
+  const double whi = 1.0 / (double)(1ull << (8 * (HI_GROUPS - 1)));
+  const double wlo = 1.0 / (double)(1ull << (8 * (G - 1)));
 #ifdef __CUDA_ARCH__
-  return fma((double)lo, low, (double)hi * (1.0 / 2097152.0));
+  return fma((double)lo, wlo, (double)hi * whi);
 #else
-  return std::fma((double)lo, low, (double)hi * (1.0 / 2097152.0));
+  return std::fma((double)lo, wlo, (double)hi * whi);
 #endif
 }
 

@@ -381,8 +381,7 @@ static double ozaki_tile_error(std::mt19937& rng, int Mrows, int N, int K, doubl
       long long q = 0;
       for (int s = 0; s < oz::S; ++s) {
         const int d = plane_elem(sA, (size_t)s * A_PLANE, A_LBO, SBO, r, k);
-        CHECK(d >= -64 && d <= 64, "digit range %d", d);
-        q = q * 128 + d;
+        q = q * 256 + d;   // any int8 value is a legal balanced base-256 digit
       }
       const long long want = std::llrint(A[r + (size_t)Mrows * k].real() * oz::slice_scale(rowE[r]));
       CHECK(q == want, "digits of A[%d,%d]: %lld vs %lld", r, k, q, want);
@@ -421,12 +420,12 @@ static double ozaki_tile_error(std::mt19937& rng, int Mrows, int N, int K, doubl
         for (int gi = 0; gi < G; ++gi) {
           const long long ar = acc[((size_t)(2 * gi) * TM + r) * 32 + c];
           const long long aq = acc[((size_t)(2 * gi + 1) * TM + r) * 32 + c];
-          if (gi < 4) {
-            hr = hr * 128 + ar;
-            hq = hq * 128 + aq;
+          if (gi < oz::HI_GROUPS) {
+            hr = hr * 256 + ar;
+            hq = hq * 256 + aq;
           } else {
-            lr = lr * 128 + ar;
-            lq = lq * 128 + aq;
+            lr = lr * 256 + ar;
+            lq = lq * 256 + aq;
           }
         }
         const double sc = oz::out_scale(rowE[r]) * oz::out_scale(colE[n]);
@@ -452,18 +451,24 @@ static double ozaki_tile_error(std::mt19937& rng, int Mrows, int N, int K, doubl
 }
 
 static void test_ozaki(std::mt19937& rng) {
-  // bit tricks against plain arithmetic
-  for (int e = 0; e < 128; ++e) {
-    const uint32_t p = oz::unbias((uint32_t)e * 0x01010101u);
-    CHECK((int8_t)(p & 0xff) == e - 64 && (int8_t)(p >> 24) == e - 64, "unbias(%d)", e);
-  }
-  CHECK(oz::spread(0x0FFFFFFFu) == 0x7F7F7F7Fu && oz::spread(1u << 7) == 0x100u &&
-            oz::spread(1u << 27) == 0x40000000u, "spread");
   CHECK(oz::pow2_field(1023) == 1.0 && oz::pow2_field(1033) == 1024.0, "pow2_field");
-  CHECK(oz::BIAS == 283691315109952ull, "bias constant");
-  struct Case { int M, N, K; double sigma, sparsity, tol7, tol8; };
+  {  // bias constant and one hand-checked number: q = -1 -> digits (0,0,0,0,0,-1)
+    unsigned long long bias = 0;
+    for (int i = 0; i < oz::S; ++i) bias |= 128ull << (8 * i);
+    CHECK(oz::BIAS == bias, "bias constant");
+    double x[16] = {-1.0, 1.0, 128.0, -129.0};
+    oz::Word4 pl[oz::S];
+    oz::slice16(x, 1.0, false, pl);
+    auto digit = [&](int s, int j) { return (int)(int8_t)((pl[s].w[j / 4] >> (8 * (j % 4))) & 0xff); };
+    CHECK(digit(5, 0) == -1 && digit(4, 0) == 0 && digit(0, 0) == 0, "digits of -1");
+    CHECK(digit(5, 1) == 1 && digit(4, 1) == 0, "digits of 1");
+    CHECK(digit(5, 2) == -128 && digit(4, 2) == 1, "digits of 128 = 1*256 - 128");
+    CHECK(digit(5, 3) == 127 && digit(4, 3) == -1, "digits of -129 = -256 + 127");
+    CHECK(digit(5, 4) == 0 && digit(0, 15) == 0, "digits of 0");
+  }
+  struct Case { int M, N, K; double sigma, sparsity, tol6, tol7; };
   const Case cases[] = {
-      {128, 64, 64, 0.0, 0.0, 1e-12, 2e-13},   // the dominant sweep step's tile
+      {128, 64, 64, 0.0, 0.0, 1e-12, 2e-13},   // the dominant sweep step's tile (G = 6 / 7)
       {128, 64, 32, 0.0, 0.0, 1e-12, 2e-13},
       {100, 33, 40, 0.0, 0.5, 1e-12, 2e-13},   // ragged M, N, K; zeros
       {128, 32, 8, 0.0, 0.0, 1e-12, 2e-13},
@@ -471,12 +476,12 @@ static void test_ozaki(std::mt19937& rng) {
       {1, 1, 1, 0.0, 0.0, 1e-12, 2e-13},
   };
   for (const Case& c : cases) {
+    const double e6 = ozaki_tile_error<6>(rng, c.M, c.N, c.K, c.sigma, c.sparsity);
     const double e7 = ozaki_tile_error<7>(rng, c.M, c.N, c.K, c.sigma, c.sparsity);
-    const double e8 = ozaki_tile_error<8>(rng, c.M, c.N, c.K, c.sigma, c.sparsity);
+    CHECK(e6 < c.tol6, "ozaki G=6 M=%d N=%d K=%d: rel-L2 %.3e", c.M, c.N, c.K, e6);
     CHECK(e7 < c.tol7, "ozaki G=7 M=%d N=%d K=%d: rel-L2 %.3e", c.M, c.N, c.K, e7);
-    CHECK(e8 < c.tol8, "ozaki G=8 M=%d N=%d K=%d: rel-L2 %.3e", c.M, c.N, c.K, e8);
-    std::printf("ozaki M=%d N=%d K=%d sigma=%.0f: rel-L2 G=7 %.2e, G=8 %.2e\n", c.M, c.N, c.K, c.sigma,
-                e7, e8);
+    std::printf("ozaki M=%d N=%d K=%d sigma=%.0f: rel-L2 G=6 %.2e, G=7 %.2e\n", c.M, c.N, c.K, c.sigma,
+                e6, e7);
   }
 }
 

@@ -40,7 +40,7 @@ SHAPES = [
 ]
 
 
-@pytest.mark.parametrize("groups", [7, 8])
+@pytest.mark.parametrize("groups", [6, 7])
 @pytest.mark.parametrize("case", range(len(SHAPES)))
 def test_ozaki_contraction_matches_oracle(case, groups):
     ad, ai, bd, bi = SHAPES[case]
@@ -66,11 +66,11 @@ def test_ozaki_sliced_rqc_amplitude():
     rec = record_sliced_contraction(circ, 4, 1, plan_fn=lambda tn, s: sweep_plan(tn, 4, 4, sliced_bonds=s),
                                     output_config="0" * 16)
     amps = {}
-    for g in (0, 7, 8):
+    for g in (0, 6, 7):
         b = B200(zgemm_ozaki=g)
         sc = SlicedContraction(b, rec)
         sc.run([1, 2, 3, 4], "amp")
         amps[g] = complex(np.asarray(b.load_tensor_data("amp")).ravel()[0])
         b.close()
-    for g in (7, 8):
+    for g in (6, 7):
         assert abs(amps[g] - amps[0]) / abs(amps[0]) < 1e-10

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Bring-up probe for the EXPERIMENTAL int8 tensor-core ZGEMM (csrc/kernels_zgemm_ozaki.cu,
-option "zgemm_ozaki" = 7 / 8).  The kernel has been compiled and its arithmetic emulated on the
+option "zgemm_ozaki" = 6 / 7).  The kernel has been compiled and its arithmetic emulated on the
 host (csrc/test_lower.cpp: test_ozaki) but never run on a GPU, so this probe goes in stages and
 runs every stage in a child process under a timeout -- a wrong mbarrier phase shows up as a
 hang, and a hung child must not hold the box:
@@ -15,7 +15,7 @@ hang, and a hung child must not hold the box:
   stage 4  one slice of the bench workload as a compiled program, amplitude vs the oracle
 
 Writes gpurun_out/ozaki_probe.json.  Exit code 0 only if every stage that ran is within
-tolerance (1e-11 rel-L2 per contraction for G=7, 1e-10 for the amplitude).
+tolerance (1e-11 rel-L2 per contraction, 1e-10 for the amplitude).
 """
 import json
 import os
@@ -97,7 +97,7 @@ def child(stage):
         for name, (ad, ai, bd, bi) in cases.items():
             A, B = operands(ad, bd, 1)
             ref = reference(A, ai, B, bi)
-            for g in (7, 8):
+            for g in (6, 7):
                 b = B200Backend(np.complex128)
                 b.set_option("zgemm_ozaki", g)
                 b.set_option("fused", 0)
@@ -114,7 +114,7 @@ def child(stage):
     elif stage == "3":
         for name, (ad, ai, bd, bi) in SWEEP.items():
             A, B = operands(ad, bd, 2)
-            for label, g in (("dmma", 0), ("ozaki7", 7), ("ozaki8", 8)):
+            for label, g in (("dmma", 0), ("ozaki6", 6), ("ozaki7", 7)):
                 b = B200Backend(np.complex128)
                 b.set_option("zgemm_ozaki", g)
                 for rep in range(4):
@@ -138,7 +138,7 @@ def child(stage):
             rows, cols, depth, seed, slices = 7, 7, 24, 0, 64
         circ, rec, name = bench.build_workload(Args)
         ref = bench.run_cpu_slices(rec, np.complex128, [1, 2])
-        for g in (0, 7, 8):
+        for g in (0, 6, 7):
             b = B200Backend(np.complex128)
             b.set_option("zgemm_ozaki", g)
             sc = SlicedContraction(b, rec)
