@@ -40,6 +40,9 @@
 // MMAs and TMEM drain are pipelined per accumulator group (mbarriers done[g] / freed[g]);
 // gather + slicing of a tile is serial with them (one set of A planes).  Expected bound: TMEM
 // read bandwidth + slicing ALU work, ~2x under the DMMA time -- to be measured.
+#include <cstdio>
+#include <cstdlib>
+
 #include "common.h"
 #include "ozaki_math.h"
 
@@ -65,7 +68,7 @@ struct OzSmem {
   static constexpr int kRowE = kKoffB + OZ_KMAX * 4;        // int[2][128]
   static constexpr int kColE = kRowE + 2 * OZ_TM * 4;       // int[64]
   static constexpr int kBars = kColE + OZ_NMAX * 4;         // 1 + 8 + 8 mbarriers + tmem slot
-  static constexpr int kTotal = kBars + 17 * 8 + 16;
+  static constexpr int kTotal = kBars + 17 * 8 + 16;   // barriers, tmem slot, abort flag
 };
 static_assert(OzSmem::kTotal <= 227 * 1024, "shared memory budget");
 
@@ -78,18 +81,50 @@ __device__ __forceinline__ void oz_mbar_init(uint64_t* bar, int count) {
 __device__ __forceinline__ void oz_mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(oz_smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void oz_mbar_wait(uint64_t* bar, uint32_t parity) {
+// Watchdog for the bring-up phase: a wait that does not complete within ~2 s records WHICH
+// wait it was in g_oz_debug and raises a CTA-wide abort flag; every other wait of the CTA then
+// returns at once, so a wrong barrier phase ends as a finished kernel with a diagnosis
+// (pq_microbench "ozaki_debug") instead of a hung GPU.
+//   g_oz_debug = {flag, wait id, iteration, group, block, warp, -, -}
+__device__ int g_oz_debug[8];
+constexpr long long OZ_WAIT_LIMIT = 4000000000ll;   // clock64 ticks
+
+__device__ __forceinline__ bool oz_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
-      "WAIT_%=:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra DONE_%=;\n"
-      "bra WAIT_%=;\n"
-      "DONE_%=:\n"
-      "}\n" ::"r"(oz_smem_u32(bar)),
-      "r"(parity)
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(oz_smem_u32(bar)), "r"(parity)
       : "memory");
+  return ok != 0;
+}
+// wait ids: 1 planes (MMA warp), 2 freed[g] (MMA warp), 3 done[g] (workers), 4 probes
+__device__ __noinline__ void oz_wait_slow(uint64_t* bar, uint32_t parity, volatile int* abort_flag,
+                                          int id, int it, int g) {
+  const long long t0 = clock64();
+  while (!oz_try_wait(bar, parity)) {
+    if (*abort_flag) return;
+    if (clock64() - t0 > OZ_WAIT_LIMIT) {
+      *abort_flag = 1;
+      if (atomicCAS(&g_oz_debug[0], 0, 1) == 0) {
+        g_oz_debug[1] = id;
+        g_oz_debug[2] = it;
+        g_oz_debug[3] = g;
+        g_oz_debug[4] = (int)blockIdx.x;
+        g_oz_debug[5] = (int)(threadIdx.x >> 5);
+        __threadfence();
+      }
+      return;
+    }
+  }
+}
+__device__ __forceinline__ void oz_mbar_wait(uint64_t* bar, uint32_t parity, volatile int* abort_flag,
+                                             int id, int it, int g) {
+  if (!oz_try_wait(bar, parity)) oz_wait_slow(bar, parity, abort_flag, id, it, g);
 }
 
 // no-swizzle K-major shared-memory matrix descriptor: core matrix = 8 rows x 16 bytes
@@ -164,6 +199,7 @@ k_zgemm_ozaki(const double2* __restrict__ A, const double2* __restrict__ B,
   uint64_t* done = planes + 1;
   uint64_t* freed = done + 8;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(freed + 8);
+  volatile int* abort_flag = reinterpret_cast<volatile int*>(tmem_slot + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int K = (int)p.K, N = (int)p.N;
@@ -179,6 +215,7 @@ k_zgemm_ozaki(const double2* __restrict__ A, const double2* __restrict__ B,
   }
   if (tid < 2 * OZ_TM) rowE[tid] = 0;
   if (tid == 0) {
+    *abort_flag = 0;
     oz_mbar_init(planes, OZ_WORKERS / 32);
     for (int g = 0; g < 8; ++g) {
       oz_mbar_init(&done[g], 1);
@@ -210,13 +247,13 @@ k_zgemm_ozaki(const double2* __restrict__ A, const double2* __restrict__ B,
       const uint32_t b_lo = (uint32_t)b_base, b_hi = (uint32_t)(b_base >> 32);
       uint32_t it = 0, tile_no = 0;
       for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++tile_no) {
-        oz_mbar_wait(planes, tile_no & 1u);
+        oz_mbar_wait(planes, tile_no & 1u, abort_flag, 1, (int)it, -1);
         for (int h = 0; h < NH; ++h, ++it) {
           const uint32_t bh_lo = b_lo + (uint32_t)((h * 4 * SBO) >> 4);   // rows 32 h .. of B
 #pragma unroll
           for (int g = 0; g < G; ++g) {
             // the accumulators of group g must have been drained by the previous (tile, half)
-            if (it > 0) oz_mbar_wait(&freed[g], (it - 1) & 1u);
+            if (it > 0) oz_mbar_wait(&freed[g], (it - 1) & 1u, abort_flag, 2, (int)it, g);
             asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
             // descriptor address fields are in 16-byte units; one K-step = two core matrices
             auto mma = [&](int accum, int a_plane, int b_plane, int ks, uint32_t acc) {
@@ -356,7 +393,7 @@ k_zgemm_ozaki(const double2* __restrict__ A, const double2* __restrict__ B,
           }
           uint32_t r[8], q[8];
           const uint32_t col = tmem_base + lane_base + (uint32_t)((2 * g) * 32 + cpart * 8);
-          oz_mbar_wait(&done[g], it & 1u);
+          oz_mbar_wait(&done[g], it & 1u, abort_flag, 3, (int)it, g);
           asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
           OZ_TMEM_LD8(r, col);
           OZ_TMEM_LD8(q, col + 32);
@@ -413,6 +450,7 @@ __global__ void __launch_bounds__(128, 1) k_umma_i8_selftest(int* __restrict__ o
   __shared__ __align__(1024) unsigned char sb[32 * 32];
   __shared__ __align__(8) uint64_t bar;
   __shared__ uint32_t slot;
+  __shared__ int abort_flag;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   for (int i = tid; i < OZ_TM * 32; i += 128) {
     const int r = i >> 5, k = i & 31;
@@ -423,6 +461,7 @@ __global__ void __launch_bounds__(128, 1) k_umma_i8_selftest(int* __restrict__ o
     sb[oz::plane_off(32, c, k >> 4) + (k & 15)] = (unsigned char)(signed char)oz_pat_b(c, k);
   }
   if (tid == 0) {
+    abort_flag = 0;
     oz_mbar_init(&bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
@@ -445,7 +484,7 @@ __global__ void __launch_bounds__(128, 1) k_umma_i8_selftest(int* __restrict__ o
                oz_idesc(OZ_TM, 32), 0u);
     oz_commit(&bar);
   }
-  oz_mbar_wait(&bar, 0u);
+  oz_mbar_wait(&bar, 0u, &abort_flag, 4, 0, -1);
   asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
   const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
 #pragma unroll
@@ -470,9 +509,11 @@ __global__ void __launch_bounds__(128, 1) k_umma_i8_rate(int iters, int* __restr
   extern __shared__ __align__(1024) unsigned char smem[];   // A: 128 x 64, B: 64 x 64, zeroed
   __shared__ __align__(8) uint64_t bar;
   __shared__ uint32_t slot;
+  __shared__ int abort_flag;
   const int tid = threadIdx.x, warp = tid >> 5;
   for (int i = tid; i < (OZ_A_PLANE + OZ_B_PLANE) / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0x01010101u;
   if (tid == 0) {
+    abort_flag = 0;
     oz_mbar_init(&bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
@@ -503,7 +544,7 @@ __global__ void __launch_bounds__(128, 1) k_umma_i8_rate(int iters, int* __restr
     }
     oz_commit(&bar);
   }
-  oz_mbar_wait(&bar, 0u);
+  oz_mbar_wait(&bar, 0u, &abort_flag, 4, 0, -1);
   asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
   uint32_t r[8];
   OZ_TMEM_LD8(r, tmem + ((uint32_t)(warp * 32) << 16));
@@ -554,6 +595,19 @@ void run_zgemm_ozaki(const Launch& L, const FusedParams& fp, int groups, const v
 // pq_microbench back ends: "umma_i8_selftest" (wrong entries, 0 = pass), "umma_i8_tops_n32",
 // "umma_i8_tops_n64" (int8 TOPS at the kernel's MMA shape / at N = 64)
 double run_ozaki_microbench(const Launch& L, const std::string& what) {
+  if (what == "ozaki_debug") {   // 0 = no watchdog event since the last call; else the wait id
+    int rec[8] = {0};
+    PQ_CUDA(cudaStreamSynchronize(L.stream));
+    PQ_CUDA(cudaMemcpyFromSymbol(rec, g_oz_debug, sizeof(rec)));
+    if (rec[0]) {
+      std::fprintf(stderr, "ozaki watchdog: wait id %d (1 planes, 2 freed, 3 done, 4 probe) iteration %d "
+                           "group %d block %d warp %d\n", rec[1], rec[2], rec[3], rec[4], rec[5]);
+      int zero[8] = {0};
+      PQ_CUDA(cudaMemcpyToSymbol(g_oz_debug, zero, sizeof(zero)));
+      return rec[1];
+    }
+    return 0;
+  }
   if (what == "umma_i8_selftest") {
     int* d = nullptr;
     PQ_CUDA(cudaMalloc(&d, OZ_TM * 32 * sizeof(int)));
@@ -565,6 +619,12 @@ double run_ozaki_microbench(const Launch& L, const std::string& what) {
     if (e == cudaSuccess) e = cudaStreamSynchronize(L.stream);
     cudaFree(d);
     PQ_CUDA(e);
+    if (const char* path = std::getenv("PQ_OZAKI_DUMP")) {   // raw 128 x 32 int32, row-major
+      if (FILE* f = std::fopen(path, "wb")) {
+        std::fwrite(got.data(), sizeof(int), got.size(), f);
+        std::fclose(f);
+      }
+    }
     int wrong = 0;
     for (int r = 0; r < OZ_TM; ++r)
       for (int c = 0; c < 32; ++c) {

@@ -85,7 +85,9 @@ def child(stage):
     res = {}
     if stage == "0":
         b = B200Backend(np.complex128)
-        res["selftest_wrong_entries"] = {"wrong": b.microbench("umma_i8_selftest")}
+        os.environ.setdefault("PQ_OZAKI_DUMP", os.path.join(ROOT, "gpurun_out", "umma_i8_selftest.bin"))
+        res["selftest_wrong_entries"] = {"wrong": b.microbench("umma_i8_selftest"),
+                                         "watchdog": b.microbench("ozaki_debug")}
         print("selftest", res["selftest_wrong_entries"], flush=True)
         if res["selftest_wrong_entries"]["wrong"] == 0:
             for w in ("umma_i8_tops_n32", "umma_i8_tops_n64"):
@@ -108,8 +110,9 @@ def child(stage):
                 prof = b.profile_read()
                 got = np.asarray(b.load_tensor_data("C"))
                 err = float(np.linalg.norm(got.ravel() - ref.ravel()) / np.linalg.norm(ref.ravel()))
-                res["%s_g%d" % (name, g)] = {"rel_l2": err, "classes": sorted(prof)}
-                print(name, g, err, sorted(prof), flush=True)
+                dbg = b.microbench("ozaki_debug")   # != 0: a barrier wait timed out (see stderr)
+                res["%s_g%d" % (name, g)] = {"rel_l2": err, "classes": sorted(prof), "watchdog": dbg}
+                print(name, g, err, sorted(prof), "watchdog", dbg, flush=True)
                 b.close()
     elif stage == "3":
         for name, (ad, ai, bd, bi) in SWEEP.items():
@@ -149,7 +152,8 @@ def child(stage):
             ms = b.timer_end()
             got = b.load_tensor_data("s")
             err = float(abs(got - ref) / abs(ref))
-            res["slices_1_2_g%d" % g] = {"rel_err": err, "ms_per_slice": ms / 2}
+            res["slices_1_2_g%d" % g] = {"rel_err": err, "ms_per_slice": ms / 2,
+                                         "watchdog": b.microbench("ozaki_debug")}
             print("slices", g, err, ms / 2, flush=True)
             b.close()
     print("RESULT " + json.dumps(res), flush=True)
@@ -183,6 +187,8 @@ def main():
             if "rel_err" in v and not v["rel_err"] < 1e-10:
                 ok = False
             if "wrong" in v and v["wrong"] != 0:
+                ok = False
+            if v.get("watchdog"):
                 ok = False
         if not ok:
             break
