@@ -442,7 +442,7 @@ k_zgemm_ozaki(const double2* __restrict__ A, const double2* __restrict__ B,
 // and the TMEM lane / column mapping from everything else.  Returns the number of wrong
 // entries (0 = pass).
 // ---------------------------------------------------------------------------
-__host__ __device__ inline int oz_pat_a(int r, int k) { return (r * 7 + k * 3) % 127 - 63; }
+__host__ __device__ inline int oz_pat_a(int r, int k) { return (r * 7 + k * 3 + r / 64) % 127 - 63; }
 __host__ __device__ inline int oz_pat_b(int c, int k) { return (c * 5 + k * 11 + 1) % 127 - 63; }
 
 __global__ void __launch_bounds__(128, 1) k_umma_i8_selftest(int* __restrict__ out) {
