@@ -42,4 +42,16 @@ timeout 300 python tools/gemm_probe.py > $OUT/gemm_probe_$TAG.log 2>&1
 
 # 6. bring-up of the experimental INT8 tensor-core ZGEMM (staged, each stage under a timeout)
 timeout 1300 python tools/ozaki_probe.py > $OUT/ozaki_probe_$TAG.log 2>&1
+OZ_RC=$?
+echo "ozaki_probe rc=$OZ_RC" >> $OUT/ozaki_probe_$TAG.log
+if [ $OZ_RC -eq 0 ]; then
+  # 7. only after a green probe: gated parity tests, the headline with the INT8 kernel, its counters
+  PQ_TEST_OZAKI=1 timeout 600 python -m pytest tests/test_gpu_ozaki.py -q > $OUT/pytest_ozaki_$TAG.log 2>&1
+  for g in 6 7; do
+    timeout 600 python bench.py --ozaki $g > $OUT/bench_${TAG}_n1_ozaki$g.json 2> $OUT/bench_${TAG}_n1_ozaki$g.err
+  done
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_zgemm_ozaki -s 20 -c 3 \
+    -o $OUT/prof_${TAG}_ozaki -f \
+    python bench.py --ozaki 6 --steps 1 --warmup 1 --lanes 1 --no-cpu-baseline --no-profile > $OUT/ncu_full_${TAG}_ozaki.log 2>&1
+fi
 ls -la $OUT | tail -30
