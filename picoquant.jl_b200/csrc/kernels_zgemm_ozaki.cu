@@ -180,7 +180,7 @@ __device__ __forceinline__ void oz_store(unsigned char* dst, const oz::Word4& v)
 
 // G = number of accumulator groups kept (pairs of digit planes with s + t < G)
 template <int G>
-__global__ void __launch_bounds__(OZ_THREADS, 1)
+__global__ void __maxnreg__(120)
 k_zgemm_ozaki(const double2* __restrict__ A, const double2* __restrict__ B,
               double2* __restrict__ C, const FusedParams p) {
   static_assert(G > oz::HI_GROUPS && G <= 8, "2 * G * 32 accumulator columns must fit 512");
@@ -377,6 +377,17 @@ k_zgemm_ozaki(const double2* __restrict__ A, const double2* __restrict__ B,
 
       for (int h = 0; h < NH; ++h, ++it) {
         const int n0 = h * 32 + cpart * 8;
+        if (n0 >= N) {
+          // this warp's 8 columns lie beyond N (narrow steps): keep the barrier protocol in
+          // step, skip the TMEM loads and the arithmetic
+#pragma unroll 1
+          for (int g = 0; g < G; ++g) {
+            oz_mbar_wait(&done[g], it & 1u, abort_flag, 3, (int)it, g);
+            __syncwarp();
+            if (lane == 0) oz_mbar_arrive(&freed[g]);
+          }
+          continue;
+        }
         long long hr[8], hq[8];   // Horner sums over the groups, re / im
         long long fr[8], fq[8];   // the finished first sums (groups 0 .. HI_GROUPS-1)
 #pragma unroll
