@@ -73,7 +73,7 @@ def reference(A, ai, B, bi):
     out = sorted((x for x in ai + bi if x < 0), reverse=True)
     letters = {}
     for x in con + out:
-        letters[x] = chr(ord("a") + len(letters))
+        letters[x] = "abcdefghijklmnopqrstuvwxyzABCDEFGHIJKLMNOPQRSTUVWXYZ"[len(letters)]
     sub = "%s,%s->%s" % ("".join(letters[x] for x in ai), "".join(letters[x] for x in bi),
                          "".join(letters[x] for x in out))
     return np.einsum(sub, A, B, optimize=True)
