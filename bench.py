@@ -761,7 +761,32 @@ def main():
                 traffic = json.load(f).get(dom)
         except Exception:  # noqa: BLE001
             pass
-        if dom in ("gemm_tensor", "gemm_simt"):
+        if a.ozaki and dom == "gemm_tensor" and a.dtype == "c128":
+            # EXPERIMENTAL INT8 path: the class is judged against whichever roof it is closer
+            # to -- HBM (algorithmic operand + result bytes) or the INT8 tensor pipe, whose
+            # complex-flop equivalent is the measured kind::i8 issue rate divided by the int8
+            # MACs one complex MAC costs (4 real products x 21 / 26 digit-plane pairs)
+            pairs = 21 if a.ozaki == 6 else 26
+            tops = b.microbench("umma_i8_tops_n32")
+            peaks["umma_i8_tops_n32"] = tops
+            tensor_peak = tops * 8.0 / (2.0 * 4.0 * pairs)
+            f_t = kernels[dom]["achieved_tflops"] / tensor_peak
+            f_h = kernels[dom]["achieved_gbs"] / peaks["hbm_gbs"]
+            if f_h >= f_t:
+                roofline = {"kernel": dom, "bound": "hbm", "achieved": kernels[dom]["achieved_gbs"],
+                            "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": f_h, "traffic": None,
+                            "share_of_timed_slice": kernels[dom].get("share_of_timed_slice"),
+                            "peak_source": peaks["hbm_source"],
+                            "note": "INT8 Ozaki GEMM steps: algorithmic (MK + KN + MN) * 16 bytes / "
+                                    "event-timed device time; tensor-roof fraction %.3f" % f_t}
+            else:
+                roofline = {"kernel": dom, "bound": "tensor", "achieved": kernels[dom]["achieved_tflops"],
+                            "peak": tensor_peak, "unit": "TFLOP/s", "frac": f_t, "traffic": None,
+                            "share_of_timed_slice": kernels[dom].get("share_of_timed_slice"),
+                            "peak_source": "measured kind::i8 issue rate %.0f TOPS / %d int8 MACs per "
+                                           "complex MAC" % (tops, 4 * pairs),
+                            "note": "HBM-roof fraction %.3f" % f_h}
+        elif dom in ("gemm_tensor", "gemm_simt"):
             peak = peaks.get("cublas_zgemm_tflops") or peaks["fp64_dmma_probe_tflops"]
             ach = kernels[dom]["achieved_tflops"]
             roofline = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": peak,
