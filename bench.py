@@ -70,9 +70,10 @@ def parse_args():
     ap.add_argument("--lanes", type=int, default=4,
                     help="slices kept in flight per GPU (pq_program_run_slices)")
     ap.add_argument("--cpu-sample-slices", type=int, default=2)
-    ap.add_argument("--ozaki", type=int, default=0, choices=[0, 6, 7],
+    ap.add_argument("--ozaki", type=int, default=0, choices=[0, 3, 4, 6, 7],
                     help="EXPERIMENTAL: route the skinny ComplexF64 GEMM steps to the INT8 tensor-core "
-                         "Ozaki kernel with 6 / 7 accumulator groups (option zgemm_ozaki; default off)")
+                         "Ozaki kernel: 6 / 7 accumulator groups with --dtype c128 (option zgemm_ozaki), 3 / 4 with "
+                         "--dtype c64 (option cgemm_ozaki); default off")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
     a = ap.parse_args()
@@ -580,7 +581,9 @@ def main():
 
     b = B200Backend(dtype, device=local_rank)
     if a.ozaki:
-        b.set_option("zgemm_ozaki", a.ozaki)
+        if (a.dtype == "c128") != (a.ozaki in (6, 7)):
+            raise SystemExit("--ozaki 6|7 goes with --dtype c128, --ozaki 3|4 with --dtype c64")
+        b.set_option("zgemm_ozaki" if a.dtype == "c128" else "cgemm_ozaki", a.ozaki)
     if world > 1:
         ids = [B200Backend.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(ids, src=0)

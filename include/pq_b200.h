@@ -206,6 +206,9 @@ int pq_timer_end(pq_handle* h, double* ms);
  *                   ComplexF64 GEMM steps (K <= 64, N <= 64) to an INT8 tensor-core (tcgen05
  *                   kind::i8) Ozaki-scheme kernel keeping 6 / 7 accumulator groups (rel-L2
  *                   ~2e-13 / ~2e-14 per contraction); 0 (default) never launches it
+ *   "cgemm_ozaki"   EXPERIMENTAL ComplexF32 twin of zgemm_ozaki (4 digits per real): 4 accumulator
+ *                   groups (rel-L2 ~3e-8 per contraction; 3: ~2e-6, A/B only), gather fused
+ *                   (no K1 pass); 0 (default) never launches it
  *   "zgemm_kfirst"  1 row-first gather order only
  *   "zgemm_stagger" ns of start delay per resident-CTA slot in the first wave (tile-per-CTA ZGEMM)
  * Every alternative computes the same contraction; the tests run them against each other. */

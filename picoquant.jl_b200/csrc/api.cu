@@ -588,6 +588,13 @@ extern "C" int pq_set_option(pq_handle* h, const char* key, int value) {
   else if (k == "zgemm_stagger") h->opt.zgemm_stagger = value;
   else if (k == "zgemm_skinny") h->opt.zgemm_skinny = value;
   else if (k == "zgemm_3m") h->opt.zgemm_3m = value;
+  else if (k == "cgemm_ozaki") {
+    if (value != 0 && value != 3 && value != 4) {
+      h->last_error = "cgemm_ozaki must be 0, 3 or 4";
+      return PQ_ERR_INVALID;
+    }
+    h->opt.cgemm_ozaki = value;
+  }
   else if (k == "zgemm_ozaki") {
     if (value != 0 && value != 6 && value != 7) {
       h->last_error = "zgemm_ozaki must be 0, 6 or 7";

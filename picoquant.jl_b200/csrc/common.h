@@ -121,6 +121,7 @@ struct Options {
   int zgemm_3m = 0;       // persistent skinny ZGEMM: 0 = 3M (three DMMAs per complex product), 1 = 4M
   int zgemm_skinny = 0;   // persistent skinny fused ZGEMM: 0 auto, 1 off
   int zgemm_ozaki = 0;    // EXPERIMENTAL int8 tensor-core ZGEMM (kernels_zgemm_ozaki.cu): 0 off, 6 / 7 = accumulator groups
+  int cgemm_ozaki = 0;    // EXPERIMENTAL, ComplexF32 twin of zgemm_ozaki: 0 off, 3 / 4 = accumulator groups
   int zgemm_stagger = 0;  // ns of start delay per resident-CTA slot in the first wave (0 = off)
   int chain = 0;    // compiled programs: 0 = batch chains of tiny contractions into one launch, 1 = off
   int prio = 0;     // 0: small-grid graph nodes get the highest launch priority, 1: off
@@ -214,7 +215,12 @@ struct FusedParams {
 
 void init_kernels_ozaki();
 double run_ozaki_microbench(const Launch& L, const std::string& what);
-bool zgemm_ozaki_eligible(const ContractPlan& cp);
+// envelope of the INT8 Ozaki kernel: all of K and N resident per tile
+inline bool zgemm_ozaki_eligible(int64_t M, int64_t N, int64_t K) {
+  return K >= 1 && K <= 64 && N >= 1 && N <= 64 && M >= 1;
+}
+// ComplexF32 contraction with the gather fused, on the INT8 kernel (plan lowered with fused_gemm)
+void run_cgemm_ozaki_fused(const Launch& L, const ContractPlan& cp, const void* A, const void* B, void* C);
 void run_zgemm_ozaki(const Launch& L, const FusedParams& fp, int groups, const void* A,
                      const void* B, void* C);
 

@@ -632,7 +632,10 @@ static void run_contract_t(const Launch& L, const ContractPlan& p, const void* A
     }
     case CK_GEMM: {
       if (p.fused_gemm) {
-        run_zgemm_fused(L, p, A, B, C);
+        if (sizeof(R) == 8)
+          run_zgemm_fused(L, p, A, B, C);
+        else
+          run_cgemm_ozaki_fused(L, p, A, B, C);   // only lowered this way with option cgemm_ozaki
         break;
       }
       const void* Ap = A;

@@ -40,6 +40,12 @@
 // MMAs and TMEM drain are pipelined per accumulator group (mbarriers done[g] / freed[g]);
 // gather + slicing of a tile is serial with them (one set of A planes).  Expected bound: TMEM
 // read bandwidth + slicing ALU work, ~2x under the DMMA time -- to be measured.
+//
+// ComplexF32 twin (option "cgemm_ozaki" = 4): the same kernel with 4 digits per real
+// (q = rint(x * 2^(30 - E)), nothing of the float is lost), G = 4 groups = 10 plane pairs, all
+// 64 columns in one pass (2 * 4 * 64 = 512 TMEM columns), result rounded once to float:
+// rel-L2 ~3e-8 per contraction, and -- unlike the K1 + tcgen05 3xTF32 path -- the gather is
+// fused, so A is read once and nothing is materialised.
 #include <cstdio>
 #include <cstdlib>
 
@@ -51,26 +57,29 @@ namespace pq {
 namespace {
 
 constexpr int OZ_TM = 128;                 // rows per tile = UMMA M
-constexpr int OZ_S = oz::S;                // int8 digits per real number (ozaki_math.h)
 constexpr int OZ_WORKERS = 512;            // 16 worker warps: (row, 16-k chunk)
 constexpr int OZ_THREADS = OZ_WORKERS + 32;
 constexpr int OZ_KMAX = 64, OZ_NMAX = 64;
 constexpr int OZ_A_PLANE = OZ_TM * OZ_KMAX;     // bytes (int8)
 constexpr int OZ_B_PLANE = OZ_NMAX * OZ_KMAX;
-constexpr int OZ_A_BYTES = 2 * OZ_S * OZ_A_PLANE;   // re planes, then im planes
-constexpr int OZ_B_BYTES = 3 * OZ_S * OZ_B_PLANE;   // re, im, -im
 
+template <class Real> struct OzVec;
+template <> struct OzVec<double> { using type = double2; };
+template <> struct OzVec<float> { using type = float2; };
+
+// shared-memory layout for S digits per real: A planes (re, im), B planes (re, im, -im), tables
+template <int S>
 struct OzSmem {
   static constexpr int kA = 0;
-  static constexpr int kB = kA + OZ_A_BYTES;
-  static constexpr int kKoffA = kB + OZ_B_BYTES;            // int[64]
+  static constexpr int kB = kA + 2 * S * OZ_A_PLANE;
+  static constexpr int kKoffA = kB + 3 * S * OZ_B_PLANE;    // int[64]
   static constexpr int kKoffB = kKoffA + OZ_KMAX * 4;       // int[64]
   static constexpr int kRowE = kKoffB + OZ_KMAX * 4;        // int[2][128]
   static constexpr int kColE = kRowE + 2 * OZ_TM * 4;       // int[64]
-  static constexpr int kBars = kColE + OZ_NMAX * 4;         // 1 + 8 + 8 mbarriers + tmem slot
-  static constexpr int kTotal = kBars + 17 * 8 + 16;   // barriers, tmem slot, abort flag
+  static constexpr int kBars = kColE + OZ_NMAX * 4;         // 1 + 8 + 8 mbarriers
+  static constexpr int kTotal = kBars + 17 * 8 + 16;        // + tmem slot, abort flag
 };
-static_assert(OzSmem::kTotal <= 227 * 1024, "shared memory budget");
+static_assert(OzSmem<6>::kTotal <= 227 * 1024, "shared memory budget");
 
 __device__ __forceinline__ uint32_t oz_smem_u32(const void* p) {
   return (uint32_t)__cvta_generic_to_shared(p);
@@ -178,24 +187,32 @@ __device__ __forceinline__ void oz_store(unsigned char* dst, const oz::Word4& v)
   *reinterpret_cast<uint4*>(dst) = make_uint4(v.w[0], v.w[1], v.w[2], v.w[3]);
 }
 
-// G = number of accumulator groups kept (pairs of digit planes with s + t < G)
-template <int G>
+// Real = double (ComplexF64: 6 digits, NC = 32 columns per pass, G = 6 / 7 accumulator groups)
+// or float (ComplexF32: 4 digits, NC = 64, G = 3 / 4).  2 * G * NC accumulator columns <= 512.
+template <class Real, int G, int NC>
 __global__ void __maxnreg__(120)
-k_zgemm_ozaki(const double2* __restrict__ A, const double2* __restrict__ B,
-              double2* __restrict__ C, const FusedParams p) {
-  static_assert(G > oz::HI_GROUPS && G <= 8, "2 * G * 32 accumulator columns must fit 512");
+k_zgemm_ozaki(const typename OzVec<Real>::type* __restrict__ A,
+              const typename OzVec<Real>::type* __restrict__ B,
+              typename OzVec<Real>::type* __restrict__ C, const FusedParams p) {
+  using Tr = oz::Traits<Real>;
+  using V2 = typename OzVec<Real>::type;
+  using Sm = OzSmem<Tr::S>;
+  constexpr int S = Tr::S;
+  constexpr int CW = NC / 4;   // accumulator columns drained by one worker warp
+  static_assert(G >= oz::HI_GROUPS && 2 * G * NC <= 512, "accumulator columns must fit TMEM");
+  static_assert(NC == 32 || NC == 64, "one or two passes over N <= 64");
   extern __shared__ __align__(1024) unsigned char smem[];
-  unsigned char* sA = smem + OzSmem::kA;
-  unsigned char* sB = smem + OzSmem::kB;
-  int* koffA = reinterpret_cast<int*>(smem + OzSmem::kKoffA);
-  int* koffB = reinterpret_cast<int*>(smem + OzSmem::kKoffB);
-  int* rowE = reinterpret_cast<int*>(smem + OzSmem::kRowE);     // [2][128] biased exponent fields
-  int* colE = reinterpret_cast<int*>(smem + OzSmem::kColE);
+  unsigned char* sA = smem + Sm::kA;
+  unsigned char* sB = smem + Sm::kB;
+  int* koffA = reinterpret_cast<int*>(smem + Sm::kKoffA);
+  int* koffB = reinterpret_cast<int*>(smem + Sm::kKoffB);
+  int* rowE = reinterpret_cast<int*>(smem + Sm::kRowE);     // [2][128] biased exponent fields
+  int* colE = reinterpret_cast<int*>(smem + Sm::kColE);
   // mbarriers.  planes: the worker warps have written this tile's A planes (count 16).
   // done[g]: the MMAs of accumulator group g have completed (tcgen05.commit).  freed[g]: every
   // worker warp has read group g out of TMEM (count 16).  done / freed complete one phase per
-  // (tile, half), planes one per tile.
-  uint64_t* planes = reinterpret_cast<uint64_t*>(smem + OzSmem::kBars);
+  // (tile, column pass), planes one per tile.
+  uint64_t* planes = reinterpret_cast<uint64_t*>(smem + Sm::kBars);
   uint64_t* done = planes + 1;
   uint64_t* freed = done + 8;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(freed + 8);
@@ -205,7 +222,7 @@ k_zgemm_ozaki(const double2* __restrict__ A, const double2* __restrict__ B,
   const int K = (int)p.K, N = (int)p.N;
   const long long M = p.M;
   const int KS = (K + 31) / 32;              // UMMA k-steps (32 int8 each)
-  const int NH = N > 32 ? 2 : 1;             // 32-column halves of N
+  const int NH = (N + NC - 1) / NC;          // column passes over N
   const long long tiles = (M + OZ_TM - 1) / OZ_TM;
 
   if (tid < OZ_KMAX) {
@@ -240,7 +257,7 @@ k_zgemm_ozaki(const double2* __restrict__ A, const double2* __restrict__ B,
   if (warp == OZ_WORKERS / 32) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      constexpr uint32_t IDESC = oz_idesc(OZ_TM, 32);
+      constexpr uint32_t IDESC = oz_idesc(OZ_TM, NC);
       const uint64_t a_base = oz_desc(oz_smem_u32(sA), A_LBO, SBO);
       const uint64_t b_base = oz_desc(oz_smem_u32(sB), B_LBO, SBO);
       const uint32_t a_lo = (uint32_t)a_base, a_hi = (uint32_t)(a_base >> 32);
@@ -249,23 +266,23 @@ k_zgemm_ozaki(const double2* __restrict__ A, const double2* __restrict__ B,
       for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++tile_no) {
         oz_mbar_wait(planes, tile_no & 1u, abort_flag, 1, (int)it, -1);
         for (int h = 0; h < NH; ++h, ++it) {
-          const uint32_t bh_lo = b_lo + (uint32_t)((h * 4 * SBO) >> 4);   // rows 32 h .. of B
+          const uint32_t bh_lo = b_lo + (uint32_t)((h * (NC / 8) * SBO) >> 4);   // rows NC h .. of B
 #pragma unroll
           for (int g = 0; g < G; ++g) {
-            // the accumulators of group g must have been drained by the previous (tile, half)
+            // the accumulators of group g must have been drained by the previous (tile, pass)
             if (it > 0) oz_mbar_wait(&freed[g], (it - 1) & 1u, abort_flag, 2, (int)it, g);
             asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
             // descriptor address fields are in 16-byte units; one K-step = two core matrices
             auto mma = [&](int accum, int a_plane, int b_plane, int ks, uint32_t acc) {
-              oz_umma_i8(tmem_base + (uint32_t)(accum * 32),
+              oz_umma_i8(tmem_base + (uint32_t)(accum * NC),
                          a_lo + (uint32_t)((a_plane * OZ_A_PLANE + ks * 2 * (int)A_LBO) >> 4), a_hi,
                          bh_lo + (uint32_t)((b_plane * OZ_B_PLANE + ks * 2 * (int)B_LBO) >> 4), b_hi,
                          IDESC, acc);
             };
             if (KS == 2)
-              oz::for_each_mma_of_group<2>(g, mma);
+              oz::for_each_mma_of_group<S, 2>(g, mma);
             else
-              oz::for_each_mma_of_group<1>(g, mma);
+              oz::for_each_mma_of_group<S, 1>(g, mma);
             oz_commit(&done[g]);   // group g may be read while the next groups are computed
           }
         }
@@ -282,78 +299,76 @@ k_zgemm_ozaki(const double2* __restrict__ A, const double2* __restrict__ B,
     // ---- B: gathered, scaled per column n, sliced into re / im / -im planes, once ----
     {
       const int n = tid & (OZ_NMAX - 1), bchunk = (tid >> 6) & 3;
-      const bool mine = tid < 4 * OZ_NMAX && n < NH * 32 && bchunk * 16 < KS * 32;
-      double xr[16], xi[16];
+      const bool mine = tid < 4 * OZ_NMAX && n < NH * NC && bchunk * 16 < KS * 32;
+      Real xr[16], xi[16];
       int ef = 0;
       if (mine) {
         const long long rb = n < N ? map_offset(p.nB, n) : -1;
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           const int k = bchunk * 16 + j;
-          double2 v = make_double2(0.0, 0.0);
+          V2 v;
+          v.x = v.y = (Real)0;
           if (rb >= 0 && k < K) v = B[rb + koffB[k]];
           xr[j] = v.x;
           xi[j] = v.y;
-          ef = max(ef, max(oz::abs_hi(v.x), oz::abs_hi(v.y)));
+          ef = max(ef, max(Tr::key(v.x), Tr::key(v.y)));
         }
-        atomicMax(&colE[n], ef >> 20);
+        atomicMax(&colE[n], Tr::exp_field(ef));
       }
       workers_barrier();
       if (mine) {
-        const int e = colE[n];
-        const double scale = oz::slice_scale(e);
-        oz::Word4 pl[OZ_S];
+        const auto scale = Tr::slice_scale(colE[n]);
+        oz::Word4 pl[S];
         unsigned char* dst = sB + oz::plane_off(OZ_NMAX, n, bchunk);
-        oz::slice16(xr, scale, false, pl);
+        Tr::slice16(xr, scale, false, pl);
 #pragma unroll
-        for (int s = 0; s < OZ_S; ++s) oz_store(dst + s * OZ_B_PLANE, pl[s]);
-        oz::slice16(xi, scale, false, pl);
+        for (int s = 0; s < S; ++s) oz_store(dst + s * OZ_B_PLANE, pl[s]);
+        Tr::slice16(xi, scale, false, pl);
 #pragma unroll
-        for (int s = 0; s < OZ_S; ++s)
-          oz_store(dst + (OZ_S + s) * OZ_B_PLANE, pl[s]);
-        oz::slice16(xi, scale, true, pl);
+        for (int s = 0; s < S; ++s) oz_store(dst + (S + s) * OZ_B_PLANE, pl[s]);
+        Tr::slice16(xi, scale, true, pl);
 #pragma unroll
-        for (int s = 0; s < OZ_S; ++s)
-          oz_store(dst + (2 * OZ_S + s) * OZ_B_PLANE, pl[s]);
+        for (int s = 0; s < S; ++s) oz_store(dst + (2 * S + s) * OZ_B_PLANE, pl[s]);
       }
       // (made visible to the tensor core by the proxy fence before the first `planes` arrival)
     }
 
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;   // this warp's TMEM lanes
-    const int cpart = warp >> 2;                                    // 8 of the 32 columns
+    const int cpart = warp >> 2;                                    // CW of the NC columns
     uint32_t it = 0;
     int buf = 0;
     for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, buf ^= 1) {
       const long long m = tile * OZ_TM + row;
       const long long ra = m < M ? map_offset(p.mA, m) : -1;
       // ---- gather this thread's 16 complex numbers, row exponent ----
-      double xr[16], xi[16];
+      Real xr[16], xi[16];
       int ef = 0;
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
         const int k = chunk * 16 + j;
-        double2 v = make_double2(0.0, 0.0);
+        V2 v;
+        v.x = v.y = (Real)0;
         if (chunk_on && ra >= 0 && k < K) v = A[ra + koffA[k]];
         xr[j] = v.x;
         xi[j] = v.y;
-        ef = max(ef, max(oz::abs_hi(v.x), oz::abs_hi(v.y)));
+        ef = max(ef, max(Tr::key(v.x), Tr::key(v.y)));
       }
-      if (chunk_on) atomicMax(&rowE[buf * OZ_TM + row], ef >> 20);
+      if (chunk_on) atomicMax(&rowE[buf * OZ_TM + row], Tr::exp_field(ef));
       workers_barrier();
       const int ea = rowE[buf * OZ_TM + row];
       if (tid < OZ_TM) rowE[(buf ^ 1) * OZ_TM + tid] = 0;    // for the next tile (see header)
       // ---- slice into the re and im digit planes of this tile ----
       if (chunk_on) {
-        const double scale = oz::slice_scale(ea);
-        oz::Word4 pl[OZ_S];
+        const auto scale = Tr::slice_scale(ea);
+        oz::Word4 pl[S];
         unsigned char* dst = sA + oz::plane_off(OZ_TM, row, chunk);
-        oz::slice16(xr, scale, false, pl);
+        Tr::slice16(xr, scale, false, pl);
 #pragma unroll
-        for (int s = 0; s < OZ_S; ++s) oz_store(dst + s * OZ_A_PLANE, pl[s]);
-        oz::slice16(xi, scale, false, pl);
+        for (int s = 0; s < S; ++s) oz_store(dst + s * OZ_A_PLANE, pl[s]);
+        Tr::slice16(xi, scale, false, pl);
 #pragma unroll
-        for (int s = 0; s < OZ_S; ++s)
-          oz_store(dst + (OZ_S + s) * OZ_A_PLANE, pl[s]);
+        for (int s = 0; s < S; ++s) oz_store(dst + (S + s) * OZ_A_PLANE, pl[s]);
       }
       // L2 prefetch of the next tile's rows (registers are needed by the epilogue)
       {
@@ -367,8 +382,8 @@ k_zgemm_ozaki(const double2* __restrict__ A, const double2* __restrict__ B,
           }
         }
       }
-      // output scale of this row: 2^(EA - 6) with |x| < 2^EA, EA = ea - 1022
-      const double sa = oz::out_scale(ea);
+      // output scale of this row: 2^(EA - 6) with |x| < 2^EA
+      const double sa = Tr::out_scale(ea);
 
       // the planes of this tile are written: generic-proxy stores -> visible to the tensor core
       asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
@@ -376,9 +391,9 @@ k_zgemm_ozaki(const double2* __restrict__ A, const double2* __restrict__ B,
       if (lane == 0) oz_mbar_arrive(planes);
 
       for (int h = 0; h < NH; ++h, ++it) {
-        const int n0 = h * 32 + cpart * 8;
-        if (n0 >= N) {
-          // this warp's 8 columns lie beyond N (narrow steps): keep the barrier protocol in
+        const int nbase = h * NC + cpart * CW;
+        if (nbase >= N) {
+          // this warp's columns lie beyond N (narrow steps): keep the barrier protocol in
           // step, skip the TMEM loads and the arithmetic
 #pragma unroll 1
           for (int g = 0; g < G; ++g) {
@@ -388,46 +403,54 @@ k_zgemm_ozaki(const double2* __restrict__ A, const double2* __restrict__ B,
           }
           continue;
         }
-        long long hr[8], hq[8];   // Horner sums over the groups, re / im
-        long long fr[8], fq[8];   // the finished first sums (groups 0 .. HI_GROUPS-1)
+#pragma unroll 1
+        for (int cb = 0; cb < CW / 8; ++cb) {   // 8 columns at a time (register budget)
+          const int n0 = nbase + cb * 8;
+          long long hr[8], hq[8];   // Horner sums over the groups, re / im
+          long long fr[8], fq[8];   // the finished first sums (groups 0 .. HI_GROUPS-1)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) hr[j] = hq[j] = 0;
+          for (int j = 0; j < 8; ++j) hr[j] = hq[j] = fr[j] = fq[j] = 0;
 #pragma unroll
-        for (int g = 0; g < G; ++g) {
-          if (g == oz::HI_GROUPS) {
+          for (int g = 0; g < G; ++g) {
+            uint32_t r[8], q[8];
+            const uint32_t col = tmem_base + lane_base + (uint32_t)((2 * g) * NC + cpart * CW + cb * 8);
+            // (already complete on the later column blocks of this pass)
+            oz_mbar_wait(&done[g], it & 1u, abort_flag, 3, (int)it, g);
+            asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+            OZ_TMEM_LD8(r, col);
+            OZ_TMEM_LD8(q, col + NC);
+            asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+            if (cb == CW / 8 - 1) {
+              // this warp is done with group g: the MMA warp may overwrite it (next pass / tile)
+              asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+              __syncwarp();
+              if (lane == 0) oz_mbar_arrive(&freed[g]);
+            }
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              fr[j] = hr[j];
-              fq[j] = hq[j];
-              hr[j] = hq[j] = 0;
+              hr[j] = hr[j] * 256 + (long long)(int)r[j];
+              hq[j] = hq[j] * 256 + (long long)(int)q[j];
+            }
+            if (g == oz::HI_GROUPS - 1) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                fr[j] = hr[j];
+                fq[j] = hq[j];
+                hr[j] = hq[j] = 0;
+              }
             }
           }
-          uint32_t r[8], q[8];
-          const uint32_t col = tmem_base + lane_base + (uint32_t)((2 * g) * 32 + cpart * 8);
-          oz_mbar_wait(&done[g], it & 1u, abort_flag, 3, (int)it, g);
-          asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-          OZ_TMEM_LD8(r, col);
-          OZ_TMEM_LD8(q, col + 32);
-          asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
-          // this warp is done with group g: the MMA warp may overwrite it (next half / tile)
-          asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
-          __syncwarp();
-          if (lane == 0) oz_mbar_arrive(&freed[g]);
+          if (m < M) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            hr[j] = hr[j] * 256 + (long long)(int)r[j];
-            hq[j] = hq[j] * 256 + (long long)(int)q[j];
-          }
-        }
-        if (m < M) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int n = n0 + j;
-            if (n < N) {
-              const double sc = sa * oz::out_scale(colE[n]);
-              const double re = oz::combine(fr[j], hr[j], G);
-              const double im = oz::combine(fq[j], hq[j], G);
-              C[m + M * n] = make_double2(re * sc, im * sc);
+            for (int j = 0; j < 8; ++j) {
+              const int n = n0 + j;
+              if (n < N) {
+                const double sc = sa * Tr::out_scale(colE[n]);
+                V2 out;
+                out.x = (Real)(oz::combine(fr[j], hr[j], G) * sc);
+                out.y = (Real)(oz::combine(fq[j], hq[j], G) * sc);
+                C[m + M * n] = out;
+              }
             }
           }
         }
@@ -442,7 +465,6 @@ k_zgemm_ozaki(const double2* __restrict__ A, const double2* __restrict__ B,
                  : "memory");
   }
 }
-
 
 // ---------------------------------------------------------------------------
 // Bring-up aids (pq_microbench "umma_i8_selftest", "umma_i8_tops_n32", "umma_i8_tops_n64").
@@ -575,33 +597,69 @@ __global__ void __launch_bounds__(128, 1) k_umma_i8_rate(int iters, int* __restr
 static bool g_ozaki_ready = false;
 
 void init_kernels_ozaki() {
-  cudaError_t e6 = cudaFuncSetAttribute(k_zgemm_ozaki<6>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        OzSmem::kTotal);
-  cudaError_t e7 = cudaFuncSetAttribute(k_zgemm_ozaki<7>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        OzSmem::kTotal);
-  if (e6 != cudaSuccess || e7 != cudaSuccess) (void)cudaGetLastError();
-  g_ozaki_ready = (e6 == cudaSuccess && e7 == cudaSuccess);
+  cudaError_t e[4];
+  e[0] = cudaFuncSetAttribute(k_zgemm_ozaki<double, 6, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              OzSmem<6>::kTotal);
+  e[1] = cudaFuncSetAttribute(k_zgemm_ozaki<double, 7, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              OzSmem<6>::kTotal);
+  e[2] = cudaFuncSetAttribute(k_zgemm_ozaki<float, 3, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              OzSmem<4>::kTotal);
+  e[3] = cudaFuncSetAttribute(k_zgemm_ozaki<float, 4, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              OzSmem<4>::kTotal);
+  g_ozaki_ready = true;
+  for (cudaError_t x : e)
+    if (x != cudaSuccess) {
+      (void)cudaGetLastError();
+      g_ozaki_ready = false;
+    }
 }
 
-bool zgemm_ozaki_eligible(const ContractPlan& cp) {
-  return cp.K >= 1 && cp.K <= OZ_KMAX && cp.N >= 1 && cp.N <= OZ_NMAX && cp.M >= 1;
-}
-
-// groups = 6 or 7 (option "zgemm_ozaki")
+// ComplexF64: groups = 6 or 7 (option "zgemm_ozaki"); ComplexF32: groups = 3 or 4
+// (option "cgemm_ozaki").  The caller brackets the launch with L.begin / L.end.
 void run_zgemm_ozaki(const Launch& L, const FusedParams& fp, int groups, const void* A,
                      const void* B, void* C) {
-  PQ_REQUIRE(groups == 6 || groups == 7, PQ_ERR_INVALID, "zgemm_ozaki must be 0, 6 or 7");
-  PQ_REQUIRE(g_ozaki_ready, PQ_ERR_UNSUPPORTED, "zgemm_ozaki: kernel attributes could not be set");
+  PQ_REQUIRE(g_ozaki_ready, PQ_ERR_UNSUPPORTED, "ozaki GEMM: kernel attributes could not be set");
+  PQ_REQUIRE(zgemm_ozaki_eligible(fp.M, fp.N, fp.K), PQ_ERR_INVALID, "ozaki GEMM: K, N <= 64 only");
   const long long tiles = (fp.M + OZ_TM - 1) / OZ_TM;
   const unsigned grid = (unsigned)(tiles < L.num_sms ? tiles : L.num_sms);
-  if (groups == 6)
-    k_zgemm_ozaki<6><<<grid, OZ_THREADS, OzSmem::kTotal, L.stream>>>(
-        (const double2*)A, (const double2*)B, (double2*)C, fp);
-  else
-    k_zgemm_ozaki<7><<<grid, OZ_THREADS, OzSmem::kTotal, L.stream>>>(
-        (const double2*)A, (const double2*)B, (double2*)C, fp);
+  if (L.elem_size == 16) {
+    PQ_REQUIRE(groups == 6 || groups == 7, PQ_ERR_INVALID, "zgemm_ozaki must be 0, 6 or 7");
+    if (groups == 6)
+      k_zgemm_ozaki<double, 6, 32><<<grid, OZ_THREADS, OzSmem<6>::kTotal, L.stream>>>(
+          (const double2*)A, (const double2*)B, (double2*)C, fp);
+    else
+      k_zgemm_ozaki<double, 7, 32><<<grid, OZ_THREADS, OzSmem<6>::kTotal, L.stream>>>(
+          (const double2*)A, (const double2*)B, (double2*)C, fp);
+  } else {
+    PQ_REQUIRE(groups == 3 || groups == 4, PQ_ERR_INVALID, "cgemm_ozaki must be 0, 3 or 4");
+    if (groups == 3)
+      k_zgemm_ozaki<float, 3, 64><<<grid, OZ_THREADS, OzSmem<4>::kTotal, L.stream>>>(
+          (const float2*)A, (const float2*)B, (float2*)C, fp);
+    else
+      k_zgemm_ozaki<float, 4, 64><<<grid, OZ_THREADS, OzSmem<4>::kTotal, L.stream>>>(
+          (const float2*)A, (const float2*)B, (float2*)C, fp);
+  }
 }
 
+void run_cgemm_ozaki_fused(const Launch& L, const ContractPlan& cp, const void* A, const void* B,
+                           void* C) {
+  PQ_REQUIRE(L.elem_size == 8 && L.opt && L.opt->cgemm_ozaki != 0, PQ_ERR_INVALID,
+             "fused ComplexF32 GEMM plans exist only with option cgemm_ozaki");
+  FusedParams fp{};
+  fp.mA = cp.mA;
+  fp.kA = cp.kA;
+  fp.nB = cp.nB;
+  fp.kB = cp.kB;
+  fp.M = cp.M;
+  fp.N = cp.N;
+  fp.K = cp.K;
+  fp.num_sms = L.num_sms;
+  L.begin(KC_GEMM_TENSOR, double(cp.M * cp.K + cp.N * cp.K + cp.M * cp.N) * 8.0,
+          8.0 * double(cp.M) * double(cp.N) * double(cp.K));
+  run_zgemm_ozaki(L, fp, L.opt->cgemm_ozaki, A, B, C);
+  L.end();
+  PQ_CUDA(cudaGetLastError());
+}
 
 // pq_microbench back ends: "umma_i8_selftest" (wrong entries, 0 = pass), "umma_i8_tops_n32",
 // "umma_i8_tops_n64" (int8 TOPS at the kernel's MMA shape / at N = 64)

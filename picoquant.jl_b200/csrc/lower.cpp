@@ -324,6 +324,16 @@ ContractPlan lower_contract(const std::vector<int64_t>& a_dims, const std::vecto
     }
     P.fused_gemm = ka < (int64_t(1) << 31) && kb < (int64_t(1) << 31);
   }
+  if (P.kind == CK_GEMM && elem_size == 8 && opt.cgemm_ozaki != 0 && opt.fused == 0 &&
+      (opt.gemm == 0 || opt.gemm == 2) && zgemm_ozaki_eligible(M, N, K)) {
+    // EXPERIMENTAL: ComplexF32 skinny steps on the INT8 tensor-core kernel, gather fused
+    int64_t ka = 0, kb = 0;
+    for (int d = 0; d < P.kA.nd; ++d) {
+      ka += (P.kA.ext[d] - 1) * P.kA.str[d];
+      kb += (P.kB.ext[d] - 1) * P.kB.str[d];
+    }
+    P.fused_gemm = ka < (int64_t(1) << 31) && kb < (int64_t(1) << 31);
+  }
   if (P.kind == CK_GEMM && !P.fused_gemm) {
     std::vector<int> pa = a_open, pb = b_open;
     pa.insert(pa.end(), a_con.begin(), a_con.end());

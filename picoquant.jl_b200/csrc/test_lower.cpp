@@ -313,93 +313,96 @@ static void test_big_shapes() {
 
 
 // ---------------------------------------------------------------------------
-// INT8 Ozaki-scheme ZGEMM (kernels_zgemm_ozaki.cu): the kernel's own slicing, plane layout,
-// MMA schedule, recombination and scaling (ozaki_math.h) executed on the host, with the
-// tensor core replaced by an integer GEMM that reads its operands through the UMMA
-// no-swizzle K-major addressing (LBO / SBO), against a long double reference.
+// INT8 Ozaki-scheme complex GEMM (kernels_zgemm_ozaki.cu): the kernel's own slicing, plane
+// layout, MMA schedule, recombination and scaling (ozaki_math.h) executed on the host, with the
+// tensor core replaced by an integer GEMM that reads its operands through the UMMA no-swizzle
+// K-major addressing (LBO / SBO), against a long double reference.  Real = double (ComplexF64,
+// NC = 32 columns per pass) or float (ComplexF32, NC = 64).
 // ---------------------------------------------------------------------------
 static int8_t plane_elem(const std::vector<int8_t>& buf, size_t plane_base, int lbo, int sbo, int row,
                          int k) {
   return buf[plane_base + (size_t)(k / 16) * lbo + (size_t)(row / 8) * sbo + (row % 8) * 16 + k % 16];
 }
 
-template <int G>
+template <class Real, int G, int NC>
 static double ozaki_tile_error(std::mt19937& rng, int Mrows, int N, int K, double spread_sigma,
                                double sparsity) {
+  using Tr = oz::Traits<Real>;
+  typedef std::complex<Real> cr;
+  constexpr int S = Tr::S;
   const int TM = 128, NMAX = 64, KMAX = 64;
-  const int KS = (K + 31) / 32, NH = N > 32 ? 2 : 1;
+  const int KS = (K + 31) / 32, NH = (N + NC - 1) / NC;
   const int A_PLANE = TM * KMAX, B_PLANE = NMAX * KMAX, A_LBO = TM * 16, B_LBO = NMAX * 16, SBO = 128;
   std::normal_distribution<double> g(0.0, 1.0);
   std::uniform_real_distribution<double> u(0.0, 1.0);
   auto draw = [&]() {
-    if (u(rng) < sparsity) return 0.0;
-    return g(rng) * std::exp(spread_sigma * g(rng));
+    if (u(rng) < sparsity) return (Real)0;
+    return (Real)(g(rng) * std::exp(spread_sigma * g(rng)));
   };
-  std::vector<cd> A((size_t)Mrows * K), B((size_t)N * K);   // A[m + Mrows k], B[n + N k]
-  for (auto& x : A) x = cd(draw(), draw());
-  for (auto& x : B) x = cd(draw(), draw());
+  const Real tiny = sizeof(Real) == 8 ? (Real)1e-300 : (Real)1e-30;
+  std::vector<cr> A((size_t)Mrows * K), B((size_t)N * K);   // A[m + Mrows k], B[n + N k]
+  for (auto& x : A) x = cr(draw(), draw());
+  for (auto& x : B) x = cr(draw(), draw());
   if (Mrows > 3)
-    for (int k = 0; k < K; ++k) A[3 + (size_t)Mrows * k] = 0.0;   // an all-zero row
+    for (int k = 0; k < K; ++k) A[3 + (size_t)Mrows * k] = (Real)0;   // an all-zero row
   if (Mrows > 5)
-    for (int k = 0; k < K; ++k) A[5 + (size_t)Mrows * k] *= 1e-300;   // a tiny row (still normal)
+    for (int k = 0; k < K; ++k) A[5 + (size_t)Mrows * k] *= tiny;     // a tiny row (still normal)
 
-  std::vector<int8_t> sA((size_t)2 * oz::S * A_PLANE, 0), sB((size_t)3 * oz::S * B_PLANE, 0);
+  std::vector<int8_t> sA((size_t)2 * S * A_PLANE, 0), sB((size_t)3 * S * B_PLANE, 0);
   std::vector<int> rowE(TM, 0), colE(NMAX, 0);
   auto fill = [&](std::vector<int8_t>& planes, int plane_bytes, int rows_layout, int nplanesets,
-                  std::vector<int>& E, int row, const cd* src, size_t ld, bool valid) {
+                  std::vector<int>& E, int row, const cr* src, size_t ld, bool valid) {
     // exponent over the whole row, then the (row, chunk) work items of the kernel
     int ef = 0;
     for (int k = 0; k < K; ++k) {
-      const cd v = valid ? src[(size_t)k * ld] : cd(0, 0);
-      ef = std::max(ef, std::max(oz::abs_hi(v.real()), oz::abs_hi(v.imag())));
+      const cr v = valid ? src[(size_t)k * ld] : cr(0, 0);
+      ef = std::max(ef, std::max(Tr::key(v.real()), Tr::key(v.imag())));
     }
-    E[row] = ef >> 20;
-    const double scale = oz::slice_scale(E[row]);
+    E[row] = Tr::exp_field(ef);
+    const auto scale = Tr::slice_scale(E[row]);
     for (int chunk = 0; chunk * 16 < KS * 32; ++chunk) {
-      double xr[16], xi[16];
+      Real xr[16], xi[16];
       for (int j = 0; j < 16; ++j) {
         const int k = chunk * 16 + j;
-        const cd v = (valid && k < K) ? src[(size_t)k * ld] : cd(0, 0);
+        const cr v = (valid && k < K) ? src[(size_t)k * ld] : cr(0, 0);
         xr[j] = v.real();
         xi[j] = v.imag();
       }
       const uint32_t off = oz::plane_off(rows_layout, row, chunk);
-      oz::Word4 pl[oz::S];
+      oz::Word4 pl[S];
       for (int set = 0; set < nplanesets; ++set) {
-        oz::slice16(set == 0 ? xr : xi, scale, set == 2, pl);
-        for (int s = 0; s < oz::S; ++s)
-          std::memcpy(&planes[(size_t)(set * oz::S + s) * plane_bytes + off], pl[s].w, 16);
+        Tr::slice16(set == 0 ? xr : xi, scale, set == 2, pl);
+        for (int s = 0; s < S; ++s)
+          std::memcpy(&planes[(size_t)(set * S + s) * plane_bytes + off], pl[s].w, 16);
       }
     }
   };
-  for (int n = 0; n < NH * 32; ++n) fill(sB, B_PLANE, NMAX, 3, colE, n, &B[n < N ? n : 0], N, n < N);
+  for (int n = 0; n < NH * NC; ++n) fill(sB, B_PLANE, NMAX, 3, colE, n, &B[n < N ? n : 0], N, n < N);
   for (int r = 0; r < TM; ++r) fill(sA, A_PLANE, TM, 2, rowE, r, &A[r < Mrows ? r : 0], Mrows, r < Mrows);
 
-  // digits reconstruct q exactly and stay inside int8's balanced range
+  // the digits reconstruct q exactly (any int8 value is a legal balanced base-256 digit)
   for (int r = 0; r < std::min(Mrows, 8); ++r)
     for (int k = 0; k < K; ++k) {
       long long q = 0;
-      for (int s = 0; s < oz::S; ++s) {
-        const int d = plane_elem(sA, (size_t)s * A_PLANE, A_LBO, SBO, r, k);
-        q = q * 256 + d;   // any int8 value is a legal balanced base-256 digit
-      }
-      const long long want = std::llrint(A[r + (size_t)Mrows * k].real() * oz::slice_scale(rowE[r]));
+      for (int s = 0; s < S; ++s) q = q * 256 + plane_elem(sA, (size_t)s * A_PLANE, A_LBO, SBO, r, k);
+      const long long want =
+          std::llrint((double)A[r + (size_t)Mrows * k].real() * (double)Tr::slice_scale(rowE[r]));
       CHECK(q == want, "digits of A[%d,%d]: %lld vs %lld", r, k, q, want);
     }
 
-  std::vector<cd> C((size_t)Mrows * N);
+  std::vector<std::complex<double>> C((size_t)Mrows * N);
   for (int h = 0; h < NH; ++h) {
-    std::vector<int32_t> acc((size_t)2 * G * TM * 32, 0);   // [accumulator][row][column]
+    std::vector<int32_t> acc((size_t)2 * G * TM * NC, 0);   // [accumulator][row][column]
     long long worst = 0;
     auto mma = [&](int accum, int a_plane, int b_plane, int ks, unsigned accumulate) {
       const size_t ab = (size_t)a_plane * A_PLANE + (size_t)ks * 2 * A_LBO;
-      const size_t bb = (size_t)b_plane * B_PLANE + (size_t)ks * 2 * B_LBO + (size_t)h * 4 * SBO;
+      const size_t bb = (size_t)b_plane * B_PLANE + (size_t)ks * 2 * B_LBO + (size_t)h * (NC / 8) * SBO;
       for (int r = 0; r < TM; ++r)
-        for (int c = 0; c < 32; ++c) {
+        for (int c = 0; c < NC; ++c) {
           long long sum = 0;
           for (int k = 0; k < 32; ++k)
             sum += (int)plane_elem(sA, ab, A_LBO, SBO, r, k) * (int)plane_elem(sB, bb, B_LBO, SBO, c, k);
-          int32_t& a = acc[((size_t)accum * TM + r) * 32 + c];
+          int32_t& a = acc[((size_t)accum * TM + r) * NC + c];
           const long long v = (accumulate ? (long long)a : 0) + sum;
           worst = std::max(worst, std::llabs(v));
           a = (int32_t)v;
@@ -407,29 +410,28 @@ static double ozaki_tile_error(std::mt19937& rng, int Mrows, int N, int K, doubl
     };
     for (int grp = 0; grp < G; ++grp) {
       if (KS == 2)
-        oz::for_each_mma_of_group<2>(grp, mma);
+        oz::for_each_mma_of_group<S, 2>(grp, mma);
       else
-        oz::for_each_mma_of_group<1>(grp, mma);
+        oz::for_each_mma_of_group<S, 1>(grp, mma);
     }
     CHECK(worst < (1ll << 31), "int32 accumulator overflow: %lld", worst);
     for (int r = 0; r < Mrows; ++r)
-      for (int c = 0; c < 32; ++c) {
-        const int n = h * 32 + c;
+      for (int c = 0; c < NC; ++c) {
+        const int n = h * NC + c;
         if (n >= N) continue;
-        long long hr = 0, hq = 0, lr = 0, lq = 0;
+        long long hr = 0, hq = 0, fr = 0, fq = 0;   // as in the kernel's epilogue
         for (int gi = 0; gi < G; ++gi) {
-          const long long ar = acc[((size_t)(2 * gi) * TM + r) * 32 + c];
-          const long long aq = acc[((size_t)(2 * gi + 1) * TM + r) * 32 + c];
-          if (gi < oz::HI_GROUPS) {
-            hr = hr * 256 + ar;
-            hq = hq * 256 + aq;
-          } else {
-            lr = lr * 256 + ar;
-            lq = lq * 256 + aq;
+          hr = hr * 256 + acc[((size_t)(2 * gi) * TM + r) * NC + c];
+          hq = hq * 256 + acc[((size_t)(2 * gi + 1) * TM + r) * NC + c];
+          if (gi == oz::HI_GROUPS - 1) {
+            fr = hr;
+            fq = hq;
+            hr = hq = 0;
           }
         }
-        const double sc = oz::out_scale(rowE[r]) * oz::out_scale(colE[n]);
-        C[r + (size_t)Mrows * n] = cd(oz::combine(hr, lr, G) * sc, oz::combine(hq, lq, G) * sc);
+        const double sc = Tr::out_scale(rowE[r]) * Tr::out_scale(colE[n]);
+        const cr out((Real)(oz::combine(fr, hr, G) * sc), (Real)(oz::combine(fq, hq, G) * sc));
+        C[r + (size_t)Mrows * n] = std::complex<double>(out.real(), out.imag());
       }
   }
   long double num = 0, den = 0;
@@ -437,51 +439,102 @@ static double ozaki_tile_error(std::mt19937& rng, int Mrows, int N, int K, doubl
     for (int n = 0; n < N; ++n) {
       long double rr = 0, ri = 0;
       for (int k = 0; k < K; ++k) {
-        const cd a = A[r + (size_t)Mrows * k], b = B[n + (size_t)N * k];
+        const cr a = A[r + (size_t)Mrows * k], b = B[n + (size_t)N * k];
         rr += (long double)a.real() * b.real() - (long double)a.imag() * b.imag();
         ri += (long double)a.real() * b.imag() + (long double)a.imag() * b.real();
       }
-      const cd got = C[r + (size_t)Mrows * n];
-      if (r == 5) continue;   // the 1e-300 row: its products underflow, checked separately below
+      const std::complex<double> got = C[r + (size_t)Mrows * n];
+      if (r == 5) continue;   // the tiny row: its products underflow the result type
       num += (got.real() - rr) * (got.real() - rr) + (got.imag() - ri) * (got.imag() - ri);
       den += rr * rr + ri * ri;
-      if (r == 3) CHECK(got == cd(0, 0), "zero row must give exact zeros");
+      if (r == 3) CHECK(got == std::complex<double>(0, 0), "zero row must give exact zeros");
     }
   return (double)std::sqrt(num / den);
 }
 
-static void test_ozaki(std::mt19937& rng) {
-  CHECK(oz::pow2_field(1023) == 1.0 && oz::pow2_field(1033) == 1024.0, "pow2_field");
-  {  // bias constant and one hand-checked number: q = -1 -> digits (0,0,0,0,0,-1)
-    unsigned long long bias = 0;
-    for (int i = 0; i < oz::S; ++i) bias |= 128ull << (8 * i);
-    CHECK(oz::BIAS == bias, "bias constant");
-    double x[16] = {-1.0, 1.0, 128.0, -129.0};
-    oz::Word4 pl[oz::S];
-    oz::slice16(x, 1.0, false, pl);
-    auto digit = [&](int s, int j) { return (int)(int8_t)((pl[s].w[j / 4] >> (8 * (j % 4))) & 0xff); };
-    CHECK(digit(5, 0) == -1 && digit(4, 0) == 0 && digit(0, 0) == 0, "digits of -1");
-    CHECK(digit(5, 1) == 1 && digit(4, 1) == 0, "digits of 1");
-    CHECK(digit(5, 2) == -128 && digit(4, 2) == 1, "digits of 128 = 1*256 - 128");
-    CHECK(digit(5, 3) == 127 && digit(4, 3) == -1, "digits of -129 = -256 + 127");
-    CHECK(digit(5, 4) == 0 && digit(0, 15) == 0, "digits of 0");
+template <class Real>
+static void check_digits_by_hand() {
+  using Tr = oz::Traits<Real>;
+  constexpr int S = Tr::S;
+  unsigned long long bias = 0;
+  for (int i = 0; i < S; ++i) bias |= 128ull << (8 * i);
+  CHECK((unsigned long long)Tr::BIAS == bias, "bias constant");
+  Real x[16] = {-1, 1, 128, -129};
+  oz::Word4 pl[S];
+  Tr::slice16(x, (Real)1, false, pl);
+  auto digit = [&](int s, int j) { return (int)(int8_t)((pl[s].w[j / 4] >> (8 * (j % 4))) & 0xff); };
+  CHECK(digit(S - 1, 0) == -1 && digit(S - 2, 0) == 0 && digit(0, 0) == 0, "digits of -1");
+  CHECK(digit(S - 1, 1) == 1 && digit(S - 2, 1) == 0, "digits of 1");
+  CHECK(digit(S - 1, 2) == -128 && digit(S - 2, 2) == 1, "digits of 128 = 1*256 - 128");
+  CHECK(digit(S - 1, 3) == 127 && digit(S - 2, 3) == -1, "digits of -129 = -256 + 127");
+  CHECK(digit(S - 1, 4) == 0 && digit(0, 15) == 0, "digits of 0");
+  Tr::slice16(x, (Real)1, true, pl);
+  CHECK(digit(S - 1, 0) == 1 && digit(S - 1, 2) == -128 && digit(S - 2, 2) == 0 && digit(S - 2, 3) == 1,
+        "negated digits");
+}
+
+static void test_ozaki_lowering() {
+  // ComplexF32 GEMM-shaped steps are lowered with the gather fused only under option cgemm_ozaki
+  std::vector<int64_t> ad(20, 2), bd(12, 2);
+  std::vector<int32_t> ai, bi;
+  int o = 0, k = 0;
+  for (int i = 0; i < 20; ++i) {
+    if (i == 3 || i == 4 || i == 5 || i == 15 || i == 17 || i == 19) ai.push_back(++k);
+    else ai.push_back(-(++o));
   }
-  struct Case { int M, N, K; double sigma, sparsity, tol6, tol7; };
-  const Case cases[] = {
-      {128, 64, 64, 0.0, 0.0, 1e-12, 2e-13},   // the dominant sweep step's tile (G = 6 / 7)
+  for (int i = 6; i >= 1; --i) bi.push_back(i);
+  for (int j = 0; j < 6; ++j) bi.push_back(-(o + 1 + j));
+  Options opt;
+  ContractPlan P = lower_contract(ad, ai, bd, bi, 8, opt);
+  CHECK(P.kind == CK_GEMM && !P.fused_gemm && P.tempA_bytes > 0, "c64 default: materialised TTGT");
+  opt.cgemm_ozaki = 4;
+  P = lower_contract(ad, ai, bd, bi, 8, opt);
+  CHECK(P.kind == CK_GEMM && P.fused_gemm && P.tempA_bytes == 0 && P.M == (1 << 14) && P.N == 64 && P.K == 64,
+        "c64 with cgemm_ozaki: fused gather");
+  P = lower_contract(ad, ai, bd, bi, 16, opt);
+  CHECK(P.kind == CK_GEMM && P.fused_gemm, "c128 unaffected by cgemm_ozaki");
+  std::printf("ozaki lowering: ok\n");
+}
+
+static void test_ozaki(std::mt19937& rng) {
+  test_ozaki_lowering();
+  CHECK(oz::pow2_field(1023) == 1.0 && oz::pow2_field(1033) == 1024.0, "pow2_field");
+  CHECK(oz::pow2_field_f(127) == 1.0f && oz::pow2_field_f(137) == 1024.0f, "pow2_field_f");
+  CHECK(oz::Traits<float>::out_scale(126 + 6) == 1.0 && oz::Traits<double>::out_scale(1022 + 6) == 1.0,
+        "output scales");
+  check_digits_by_hand<double>();
+  check_digits_by_hand<float>();
+  struct Case { int M, N, K; double sigma, sparsity, tol_lo, tol_hi; };
+  const Case cases64[] = {   // ComplexF64: G = 6 / 7
+      {128, 64, 64, 0.0, 0.0, 1e-12, 2e-13},   // the dominant sweep step's tile
       {128, 64, 32, 0.0, 0.0, 1e-12, 2e-13},
       {100, 33, 40, 0.0, 0.5, 1e-12, 2e-13},   // ragged M, N, K; zeros
       {128, 32, 8, 0.0, 0.0, 1e-12, 2e-13},
       {77, 17, 64, 3.0, 0.0, 2e-10, 1e-11},    // log-normal magnitudes inside a row (sigma 3)
       {1, 1, 1, 0.0, 0.0, 1e-12, 2e-13},
   };
-  for (const Case& c : cases) {
-    const double e6 = ozaki_tile_error<6>(rng, c.M, c.N, c.K, c.sigma, c.sparsity);
-    const double e7 = ozaki_tile_error<7>(rng, c.M, c.N, c.K, c.sigma, c.sparsity);
-    CHECK(e6 < c.tol6, "ozaki G=6 M=%d N=%d K=%d: rel-L2 %.3e", c.M, c.N, c.K, e6);
-    CHECK(e7 < c.tol7, "ozaki G=7 M=%d N=%d K=%d: rel-L2 %.3e", c.M, c.N, c.K, e7);
-    std::printf("ozaki M=%d N=%d K=%d sigma=%.0f: rel-L2 G=6 %.2e, G=7 %.2e\n", c.M, c.N, c.K, c.sigma,
-                e6, e7);
+  for (const Case& c : cases64) {
+    const double e6 = ozaki_tile_error<double, 6, 32>(rng, c.M, c.N, c.K, c.sigma, c.sparsity);
+    const double e7 = ozaki_tile_error<double, 7, 32>(rng, c.M, c.N, c.K, c.sigma, c.sparsity);
+    CHECK(e6 < c.tol_lo, "ozaki c128 G=6 M=%d N=%d K=%d: rel-L2 %.3e", c.M, c.N, c.K, e6);
+    CHECK(e7 < c.tol_hi, "ozaki c128 G=7 M=%d N=%d K=%d: rel-L2 %.3e", c.M, c.N, c.K, e7);
+    std::printf("ozaki c128 M=%d N=%d K=%d sigma=%.0f: rel-L2 G=6 %.2e, G=7 %.2e\n", c.M, c.N, c.K,
+                c.sigma, e6, e7);
+  }
+  const Case cases32[] = {   // ComplexF32: G = 3 / 4; the tolerance of the backend is 1e-5
+      {128, 64, 64, 0.0, 0.0, 5e-6, 1e-7},   // G = 3 drops the 256^-3 group: coarse, for A/B only
+      {100, 33, 40, 0.0, 0.5, 5e-6, 1e-7},
+      {128, 8, 64, 0.0, 0.0, 5e-6, 1e-7},
+      {77, 17, 64, 2.0, 0.0, 5e-5, 5e-7},
+      {1, 1, 1, 0.0, 0.0, 5e-6, 1e-7},
+  };
+  for (const Case& c : cases32) {
+    const double e3 = ozaki_tile_error<float, 3, 64>(rng, c.M, c.N, c.K, c.sigma, c.sparsity);
+    const double e4 = ozaki_tile_error<float, 4, 64>(rng, c.M, c.N, c.K, c.sigma, c.sparsity);
+    CHECK(e3 < c.tol_lo, "ozaki c64 G=3 M=%d N=%d K=%d: rel-L2 %.3e", c.M, c.N, c.K, e3);
+    CHECK(e4 < c.tol_hi, "ozaki c64 G=4 M=%d N=%d K=%d: rel-L2 %.3e", c.M, c.N, c.K, e4);
+    std::printf("ozaki c64  M=%d N=%d K=%d sigma=%.0f: rel-L2 G=3 %.2e, G=4 %.2e\n", c.M, c.N, c.K,
+                c.sigma, e3, e4);
   }
 }
 

@@ -21,9 +21,9 @@ pytestmark = [pytest.mark.gpu,
                                  reason="experimental kernel: set PQ_TEST_OZAKI=1 after bring-up")]
 
 
-def B200(**opts):
+def B200(dtype=np.complex128, **opts):
     from picoquant_jl_b200.host.b200_backend import B200Backend
-    b = B200Backend(np.complex128)
+    b = B200Backend(dtype)
     for k, v in opts.items():
         b.set_option(k, v)
     return b
@@ -57,6 +57,26 @@ def test_ozaki_contraction_matches_oracle(case, groups):
     b.save_tensor_data("B", B)
     b.contract_tensors("A", ai, "B", bi, "C")
     assert rel_l2(b.load_tensor_data("C"), ref.load_tensor_data("C")) < 1e-11
+    b.close()
+
+
+@pytest.mark.parametrize("case", range(len(SHAPES)))
+def test_ozaki_c64_contraction_matches_f64_oracle(case):
+    """ComplexF32 twin (option cgemm_ozaki = 4): within 1e-5 of the ComplexF64 oracle downcast,
+    and no worse than 2e-6 on these well-scaled operands."""
+    ad, ai, bd, bi = SHAPES[case]
+    rng = np.random.default_rng(100 + case)
+    A = np.asarray((rng.standard_normal(ad) + 1j * rng.standard_normal(ad)).astype(np.complex64), order="F")
+    B = np.asarray((rng.standard_normal(bd) + 1j * rng.standard_normal(bd)).astype(np.complex64), order="F")
+    ref = OracleBackend(np.complex128)
+    ref.save_tensor_data("A", A.astype(np.complex128))
+    ref.save_tensor_data("B", B.astype(np.complex128))
+    ref.contract_tensors("A", ai, "B", bi, "C")
+    b = B200(np.complex64, cgemm_ozaki=4)
+    b.save_tensor_data("A", A)
+    b.save_tensor_data("B", B)
+    b.contract_tensors("A", ai, "B", bi, "C")
+    assert rel_l2(b.load_tensor_data("C"), ref.load_tensor_data("C")) < 2e-6
     b.close()
 
 

@@ -13,6 +13,8 @@ hang, and a hung child must not hold the box:
   stage 2  the sweep-step shapes of the bench workload (gather fused), parity vs NumPy c128
   stage 3  timing of those shapes against the DMMA kernels (option off)
   stage 4  one slice of the bench workload as a compiled program, amplitude vs the oracle
+  stage 5  the ComplexF32 twin (option cgemm_ozaki = 4): parity vs the c128 reference and timing
+           against the K1 + tcgen05 3xTF32 path
 
 Writes gpurun_out/ozaki_probe.json.  Exit code 0 only if every stage that ran is within
 tolerance (1e-11 rel-L2 per contraction, 1e-10 for the amplitude).
@@ -156,6 +158,28 @@ def child(stage):
                                          "watchdog": b.microbench("ozaki_debug")}
             print("slices", g, err, ms / 2, flush=True)
             b.close()
+    elif stage == "5":
+        for name, (ad, ai, bd, bi) in list(SMALL.items()) + list(SWEEP.items()):
+            A, B = operands(ad, bd, 3)
+            A, B = A.astype(np.complex64), B.astype(np.complex64)
+            ref = reference(A.astype(np.complex128), ai, B.astype(np.complex128), bi)
+            for label, g in (("tf32", 0), ("ozaki4", 4)):
+                b = B200Backend(np.complex64)
+                b.set_option("cgemm_ozaki", g)
+                for rep in range(3):
+                    b.save_tensor_data("A", A)
+                    b.save_tensor_data("B", B)
+                    if rep == 1:
+                        b.profile_enable(True)
+                    b.contract_tensors("A", ai, "B", bi, "C")
+                prof = b.profile_read()
+                ms = sum(r["ms"] for r in prof.values()) / 2
+                got = np.asarray(b.load_tensor_data("C"))
+                err = float(np.linalg.norm(got.ravel() - ref.ravel()) / np.linalg.norm(ref.ravel()))
+                res["%s_%s" % (name, label)] = {"rel_l2_c64": err, "ms": ms, "classes": sorted(prof),
+                                                "watchdog": b.microbench("ozaki_debug")}
+                print(name, label, res["%s_%s" % (name, label)], flush=True)
+                b.close()
     print("RESULT " + json.dumps(res), flush=True)
 
 
@@ -165,7 +189,7 @@ def main():
         return 0
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
     summary, ok = {}, True
-    for stage, limit in (("0", 120), ("1", 180), ("2", 300), ("3", 300), ("4", 420)):
+    for stage, limit in (("0", 120), ("1", 180), ("2", 300), ("3", 300), ("4", 420), ("5", 420)):
         try:
             r = subprocess.run([sys.executable, os.path.abspath(__file__), "--child", stage],
                                capture_output=True, text=True, timeout=limit)
@@ -185,6 +209,8 @@ def main():
             if "rel_l2" in v and not v["rel_l2"] < 1e-11:
                 ok = False
             if "rel_err" in v and not v["rel_err"] < 1e-10:
+                ok = False
+            if "rel_l2_c64" in v and not v["rel_l2_c64"] < 1e-5:
                 ok = False
             if "wrong" in v and v["wrong"] != 0:
                 ok = False
