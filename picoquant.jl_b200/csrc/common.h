@@ -219,6 +219,12 @@ double run_ozaki_microbench(const Launch& L, const std::string& what);
 inline bool zgemm_ozaki_eligible(int64_t M, int64_t N, int64_t K) {
   return K >= 1 && K <= 64 && N >= 1 && N <= 64 && M >= 1;
 }
+// long contractions (64 < K <= 8192) on canonical layouts; ws = (M + N) ints
+inline bool zgemm_ozaki_kloop_eligible(int64_t M, int64_t N, int64_t K) {
+  return K > 64 && K <= 8192 && M >= 1 && N >= 1 && M + N < (int64_t(1) << 30);
+}
+void run_zgemm_ozaki_kloop(const Launch& L, int groups, const void* A, const void* B, void* C,
+                           int64_t M, int64_t N, int64_t K, void* ws);
 // ComplexF32 contraction with the gather fused, on the INT8 kernel (plan lowered with fused_gemm)
 void run_cgemm_ozaki_fused(const Launch& L, const ContractPlan& cp, const void* A, const void* B, void* C);
 void run_zgemm_ozaki(const Launch& L, const FusedParams& fp, int groups, const void* A,

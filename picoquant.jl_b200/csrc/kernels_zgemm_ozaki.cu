@@ -41,6 +41,8 @@
 // gather + slicing of a tile is serial with them (one set of A planes).  Expected bound: TMEM
 // read bandwidth + slicing ALU work, ~2x under the DMMA time -- to be measured.
 //
+// Long contractions: k_zgemm_ozaki_kloop below (canonical layouts, K in chunks of 64).
+//
 // ComplexF32 twin (option "cgemm_ozaki" = 4): the same kernel with 4 digits per real
 // (q = rint(x * 2^(30 - E)), nothing of the float is lost), G = 4 groups = 10 plane pairs, all
 // 64 columns in one pass (2 * 4 * 64 = 512 TMEM columns), result rounded once to float:
@@ -467,6 +469,278 @@ k_zgemm_ozaki(const typename OzVec<Real>::type* __restrict__ A,
 }
 
 // ---------------------------------------------------------------------------
+// K2'o: the same product for LONG contractions on canonical layouts A[m + M k], B[n + N k]
+// (behind K1, where k_zgemm_dmma3m runs today): K is walked in chunks of 64 with the int32
+// accumulators staying in TMEM, so one CTA tile is 128 rows x NC columns x all of K.
+//   * the row / column scales must be the same for every chunk: k_oz_row_exponents computes
+//     them once per operand (max exponent field over the whole row) into the plan's workspace;
+//   * per chunk the workers load + slice 128 x 64 of A and NC x 64 of B (B is not resident
+//     here), wait until the MMAs of the previous chunk have consumed the planes
+//     (`consumed`, tcgen05.commit), write the planes and arrive on `planes`; the loads of the
+//     next chunk are already in flight while the tensor core works on the current one;
+//   * the MMA thread accumulates chunk after chunk; on the last chunk it commits group by
+//     group (`done[g]`) and the epilogue of the skinny kernel drains TMEM.
+// |acc| <= 2^14 * K * 12 bounds K to 8192 (int32); longer contractions stay on DMMA.
+// Tiles are rasterised in bands of 16 row tiles so that the CTAs of a wave share a band of A
+// and a few column blocks of B in L2.
+// ---------------------------------------------------------------------------
+constexpr long long OZ_KLOOP_MAXK = 8192;
+
+template <class Real>
+__global__ void __launch_bounds__(128)
+k_oz_row_exponents(const typename OzVec<Real>::type* __restrict__ X, long long R, long long K,
+                   int* __restrict__ E) {
+  using Tr = oz::Traits<Real>;
+  const long long r = (long long)blockIdx.x * 128 + threadIdx.x;
+  if (r >= R) return;
+  const long long per = (K + gridDim.y - 1) / gridDim.y;
+  const long long k0 = (long long)blockIdx.y * per, k1 = (k0 + per < K) ? k0 + per : K;
+  int key = 0;
+  for (long long k = k0; k < k1; ++k) {
+    const typename OzVec<Real>::type v = X[r + R * k];
+    key = max(key, max(Tr::key(v.x), Tr::key(v.y)));
+  }
+  atomicMax(&E[r], Tr::exp_field(key));   // E is zeroed by the launcher
+}
+
+template <class Real, int G, int NC>
+__global__ void __maxnreg__(120)
+k_zgemm_ozaki_kloop(const typename OzVec<Real>::type* __restrict__ A,
+                    const typename OzVec<Real>::type* __restrict__ B,
+                    typename OzVec<Real>::type* __restrict__ C, long long M, long long N, long long K,
+                    const int* __restrict__ expA, const int* __restrict__ expB) {
+  using Tr = oz::Traits<Real>;
+  using V2 = typename OzVec<Real>::type;
+  using Sm = OzSmem<Tr::S>;
+  constexpr int S = Tr::S;
+  constexpr int CW = NC / 4;
+  static_assert(G >= oz::HI_GROUPS && 2 * G * NC <= 512, "accumulator columns must fit TMEM");
+  extern __shared__ __align__(1024) unsigned char smem[];
+  unsigned char* sA = smem + Sm::kA;
+  unsigned char* sB = smem + Sm::kB;
+  // planes: this chunk's planes are written (count 16, one phase per chunk); consumed: the MMAs
+  // of a chunk have completed (commit, one phase per chunk); done[g] / freed[g]: as in the
+  // skinny kernel, one phase per tile
+  uint64_t* planes = reinterpret_cast<uint64_t*>(smem + Sm::kBars);
+  uint64_t* done = planes + 1;
+  uint64_t* freed = done + 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(freed + 8);
+  volatile int* abort_flag = reinterpret_cast<volatile int*>(tmem_slot + 1);
+  uint64_t* consumed = reinterpret_cast<uint64_t*>(smem + Sm::kRowE);   // (the row table is unused here)
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const long long tiles_m = (M + OZ_TM - 1) / OZ_TM, tiles_n = (N + NC - 1) / NC;
+  const long long tiles = tiles_m * tiles_n;
+  const long long chunks = (K + OZ_KMAX - 1) / OZ_KMAX;
+  constexpr long long BAND = 16;
+  auto tile_coords = [&](long long t, long long& mt, long long& nt) {
+    const long long band = t / (BAND * tiles_n), within = t - band * BAND * tiles_n;
+    const long long bm = (tiles_m - band * BAND) < BAND ? (tiles_m - band * BAND) : BAND;
+    nt = within / bm;
+    mt = band * BAND + within % bm;
+  };
+
+  if (tid == 0) {
+    *abort_flag = 0;
+    oz_mbar_init(planes, OZ_WORKERS / 32);
+    oz_mbar_init(consumed, 1);
+    for (int g = 0; g < 8; ++g) {
+      oz_mbar_init(&done[g], 1);
+      oz_mbar_init(&freed[g], OZ_WORKERS / 32);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(
+                     oz_smem_u32(tmem_slot)),
+                 "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  constexpr uint32_t A_LBO = OZ_TM * 16, B_LBO = OZ_NMAX * 16, SBO = 128;
+
+  if (warp == OZ_WORKERS / 32) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t IDESC = oz_idesc(OZ_TM, NC);
+      const uint64_t a_base = oz_desc(oz_smem_u32(sA), A_LBO, SBO);
+      const uint64_t b_base = oz_desc(oz_smem_u32(sB), B_LBO, SBO);
+      const uint32_t a_lo = (uint32_t)a_base, a_hi = (uint32_t)(a_base >> 32);
+      const uint32_t b_lo = (uint32_t)b_base, b_hi = (uint32_t)(b_base >> 32);
+      uint32_t it = 0, cc = 0;   // tiles / chunks done by this CTA
+      for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
+        for (long long c = 0; c < chunks; ++c, ++cc) {
+          const bool last = c == chunks - 1;
+          const int kleft = (int)((K - c * OZ_KMAX) < OZ_KMAX ? (K - c * OZ_KMAX) : OZ_KMAX);
+          const int KS = (kleft + 31) / 32;
+          oz_mbar_wait(planes, cc & 1u, abort_flag, 1, (int)cc, -1);
+          asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+#pragma unroll
+          for (int g = 0; g < G; ++g) {
+            if (c == 0 && it > 0) {   // the previous tile's epilogue must have drained group g
+              oz_mbar_wait(&freed[g], (it - 1) & 1u, abort_flag, 2, (int)it, g);
+              asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+            }
+            auto mma = [&](int accum, int a_plane, int b_plane, int ks, uint32_t acc) {
+              oz_umma_i8(tmem_base + (uint32_t)(accum * NC),
+                         a_lo + (uint32_t)((a_plane * OZ_A_PLANE + ks * 2 * (int)A_LBO) >> 4), a_hi,
+                         b_lo + (uint32_t)((b_plane * OZ_B_PLANE + ks * 2 * (int)B_LBO) >> 4), b_hi,
+                         IDESC, c > 0 ? 1u : acc);
+            };
+            if (KS == 2)
+              oz::for_each_mma_of_group<S, 2>(g, mma);
+            else
+              oz::for_each_mma_of_group<S, 1>(g, mma);
+            if (last) oz_commit(&done[g]);
+          }
+          oz_commit(consumed);   // the planes may be rewritten once these MMAs have completed
+        }
+      }
+    }
+  } else {
+    // ===================== workers =====================
+    const int row = tid & (OZ_TM - 1), chunk = tid >> 7;
+    const int bn = tid % NC, bchunk = tid / NC;            // B work item (threads < 4 * NC)
+    const bool b_mine = tid < 4 * NC;
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    const int cpart = warp >> 2;
+    uint32_t it = 0, cc = 0;
+    for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
+      long long mt, nt;
+      tile_coords(tile, mt, nt);
+      const long long m = mt * OZ_TM + row, n0 = nt * NC;
+      const long long nb = n0 + bn;
+      const int ea = m < M ? expA[m] : 0;
+      const int eb = (b_mine && nb < N) ? expB[nb] : 0;
+      const auto scale_a = Tr::slice_scale(ea);
+      const auto scale_b = Tr::slice_scale(eb);
+      for (long long c = 0; c < chunks; ++c, ++cc) {
+        const long long kbase = c * OZ_KMAX;
+        Real xr[16], xi[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const long long k = kbase + chunk * 16 + j;
+          V2 v;
+          v.x = v.y = (Real)0;
+          if (m < M && k < K) v = A[m + M * k];
+          xr[j] = v.x;
+          xi[j] = v.y;
+        }
+        // the MMAs of the previous chunk must be done with the planes
+        if (cc > 0) oz_mbar_wait(consumed, (cc - 1) & 1u, abort_flag, 5, (int)cc, -1);
+        {
+          oz::Word4 pl[S];
+          unsigned char* dst = sA + oz::plane_off(OZ_TM, row, chunk);
+          Tr::slice16(xr, scale_a, false, pl);
+#pragma unroll
+          for (int s = 0; s < S; ++s) oz_store(dst + s * OZ_A_PLANE, pl[s]);
+          Tr::slice16(xi, scale_a, false, pl);
+#pragma unroll
+          for (int s = 0; s < S; ++s) oz_store(dst + (S + s) * OZ_A_PLANE, pl[s]);
+        }
+        if (b_mine) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const long long k = kbase + bchunk * 16 + j;
+            V2 v;
+            v.x = v.y = (Real)0;
+            if (nb < N && k < K) v = B[nb + N * k];
+            xr[j] = v.x;
+            xi[j] = v.y;
+          }
+          oz::Word4 pl[S];
+          unsigned char* dst = sB + oz::plane_off(OZ_NMAX, bn, bchunk);
+          Tr::slice16(xr, scale_b, false, pl);
+#pragma unroll
+          for (int s = 0; s < S; ++s) oz_store(dst + s * OZ_B_PLANE, pl[s]);
+          Tr::slice16(xi, scale_b, false, pl);
+#pragma unroll
+          for (int s = 0; s < S; ++s) oz_store(dst + (S + s) * OZ_B_PLANE, pl[s]);
+          Tr::slice16(xi, scale_b, true, pl);
+#pragma unroll
+          for (int s = 0; s < S; ++s) oz_store(dst + (2 * S + s) * OZ_B_PLANE, pl[s]);
+        }
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+        __syncwarp();
+        if (lane == 0) oz_mbar_arrive(planes);
+      }
+
+      // ---- epilogue of the tile (as in the skinny kernel, one column pass) ----
+      const double sa = Tr::out_scale(ea);
+      const long long nbase = n0 + cpart * CW;
+      if (nbase >= N) {
+#pragma unroll 1
+        for (int g = 0; g < G; ++g) {
+          oz_mbar_wait(&done[g], it & 1u, abort_flag, 3, (int)it, g);
+          __syncwarp();
+          if (lane == 0) oz_mbar_arrive(&freed[g]);
+        }
+        continue;
+      }
+#pragma unroll 1
+      for (int cb = 0; cb < CW / 8; ++cb) {
+        long long hr[8], hq[8], fr[8], fq[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) hr[j] = hq[j] = fr[j] = fq[j] = 0;
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+          uint32_t r[8], q[8];
+          const uint32_t col = tmem_base + lane_base + (uint32_t)((2 * g) * NC + cpart * CW + cb * 8);
+          oz_mbar_wait(&done[g], it & 1u, abort_flag, 3, (int)it, g);
+          asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+          OZ_TMEM_LD8(r, col);
+          OZ_TMEM_LD8(q, col + NC);
+          asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+          if (cb == CW / 8 - 1) {
+            asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+            __syncwarp();
+            if (lane == 0) oz_mbar_arrive(&freed[g]);
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            hr[j] = hr[j] * 256 + (long long)(int)r[j];
+            hq[j] = hq[j] * 256 + (long long)(int)q[j];
+          }
+          if (g == oz::HI_GROUPS - 1) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              fr[j] = hr[j];
+              fq[j] = hq[j];
+              hr[j] = hq[j] = 0;
+            }
+          }
+        }
+        if (m < M) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const long long n = nbase + cb * 8 + j;
+            if (n < N) {
+              const double sc = sa * Tr::out_scale(__ldg(&expB[n]));
+              V2 out;
+              out.x = (Real)(oz::combine(fr[j], hr[j], G) * sc);
+              out.y = (Real)(oz::combine(fq[j], hq[j], G) * sc);
+              C[m + M * n] = out;
+            }
+          }
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base),
+                 "r"(512u)
+                 : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------
 // Bring-up aids (pq_microbench "umma_i8_selftest", "umma_i8_tops_n32", "umma_i8_tops_n64").
 //
 // Self-test: ONE 128 x 32 x 32 kind::i8 MMA on known int8 patterns laid out exactly like the
@@ -606,7 +880,21 @@ void init_kernels_ozaki() {
                               OzSmem<4>::kTotal);
   e[3] = cudaFuncSetAttribute(k_zgemm_ozaki<float, 4, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                               OzSmem<4>::kTotal);
+  cudaError_t f[4];
+  f[0] = cudaFuncSetAttribute(k_zgemm_ozaki_kloop<double, 6, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              OzSmem<6>::kTotal);
+  f[1] = cudaFuncSetAttribute(k_zgemm_ozaki_kloop<double, 7, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              OzSmem<6>::kTotal);
+  f[2] = cudaFuncSetAttribute(k_zgemm_ozaki_kloop<float, 3, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              OzSmem<4>::kTotal);
+  f[3] = cudaFuncSetAttribute(k_zgemm_ozaki_kloop<float, 4, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              OzSmem<4>::kTotal);
   g_ozaki_ready = true;
+  for (cudaError_t x : f)
+    if (x != cudaSuccess) {
+      (void)cudaGetLastError();
+      g_ozaki_ready = false;
+    }
   for (cudaError_t x : e)
     if (x != cudaSuccess) {
       (void)cudaGetLastError();
@@ -638,6 +926,47 @@ void run_zgemm_ozaki(const Launch& L, const FusedParams& fp, int groups, const v
     else
       k_zgemm_ozaki<float, 4, 64><<<grid, OZ_THREADS, OzSmem<4>::kTotal, L.stream>>>(
           (const float2*)A, (const float2*)B, (float2*)C, fp);
+  }
+}
+
+// Long contractions on canonical layouts A[m + M k], B[n + N k] (see k_zgemm_ozaki_kloop).
+// `ws` holds (M + N) ints for the row / column exponent fields (ContractPlan::ws_bytes).
+template <class Real, int G, int NC>
+static void launch_kloop(const Launch& L, const void* A, const void* B, void* C, int64_t M, int64_t N,
+                         int64_t K, int* expA, int* expB) {
+  using V2 = typename OzVec<Real>::type;
+  const long long tiles = ((M + OZ_TM - 1) / OZ_TM) * ((N + NC - 1) / NC);
+  const unsigned grid = (unsigned)(tiles < L.num_sms ? tiles : L.num_sms);
+  k_zgemm_ozaki_kloop<Real, G, NC><<<grid, OZ_THREADS, OzSmem<oz::Traits<Real>::S>::kTotal, L.stream>>>(
+      (const V2*)A, (const V2*)B, (V2*)C, M, N, K, expA, expB);
+}
+
+void run_zgemm_ozaki_kloop(const Launch& L, int groups, const void* A, const void* B, void* C,
+                           int64_t M, int64_t N, int64_t K, void* ws) {
+  PQ_REQUIRE(g_ozaki_ready, PQ_ERR_UNSUPPORTED, "ozaki GEMM: kernel attributes could not be set");
+  PQ_REQUIRE(ws != nullptr && zgemm_ozaki_kloop_eligible(M, N, K), PQ_ERR_INVALID,
+             "ozaki GEMM (long K): needs the plan's workspace and 64 < K <= 8192");
+  int* expA = static_cast<int*>(ws);
+  int* expB = expA + M;
+  PQ_CUDA(cudaMemsetAsync(ws, 0, size_t(M + N) * sizeof(int), L.stream));
+  const unsigned ksplit = (unsigned)(K >= 4096 ? 16 : K >= 1024 ? 4 : 1);
+  const dim3 ga((unsigned)((M + 127) / 128), ksplit), gb((unsigned)((N + 127) / 128), ksplit);
+  if (L.elem_size == 16) {
+    PQ_REQUIRE(groups == 6 || groups == 7, PQ_ERR_INVALID, "zgemm_ozaki must be 0, 6 or 7");
+    k_oz_row_exponents<double><<<ga, 128, 0, L.stream>>>((const double2*)A, M, K, expA);
+    k_oz_row_exponents<double><<<gb, 128, 0, L.stream>>>((const double2*)B, N, K, expB);
+    if (groups == 6)
+      launch_kloop<double, 6, 32>(L, A, B, C, M, N, K, expA, expB);
+    else
+      launch_kloop<double, 7, 32>(L, A, B, C, M, N, K, expA, expB);
+  } else {
+    PQ_REQUIRE(groups == 3 || groups == 4, PQ_ERR_INVALID, "cgemm_ozaki must be 0, 3 or 4");
+    k_oz_row_exponents<float><<<ga, 128, 0, L.stream>>>((const float2*)A, M, K, expA);
+    k_oz_row_exponents<float><<<gb, 128, 0, L.stream>>>((const float2*)B, N, K, expB);
+    if (groups == 3)
+      launch_kloop<float, 3, 64>(L, A, B, C, M, N, K, expA, expB);
+    else
+      launch_kloop<float, 4, 64>(L, A, B, C, M, N, K, expA, expB);
   }
 }
 

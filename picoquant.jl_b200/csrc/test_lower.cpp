@@ -350,20 +350,24 @@ static double ozaki_tile_error(std::mt19937& rng, int Mrows, int N, int K, doubl
 
   std::vector<int8_t> sA((size_t)2 * S * A_PLANE, 0), sB((size_t)3 * S * B_PLANE, 0);
   std::vector<int> rowE(TM, 0), colE(NMAX, 0);
-  auto fill = [&](std::vector<int8_t>& planes, int plane_bytes, int rows_layout, int nplanesets,
-                  std::vector<int>& E, int row, const cr* src, size_t ld, bool valid) {
-    // exponent over the whole row, then the (row, chunk) work items of the kernel
+  // exponent fields over the WHOLE row / column (the K-looped kernel computes them in a pre-pass;
+  // the skinny kernel, K <= 64, per tile -- the same thing there)
+  auto exponent = [&](const cr* src, size_t ld, bool valid) {
     int ef = 0;
     for (int k = 0; k < K; ++k) {
       const cr v = valid ? src[(size_t)k * ld] : cr(0, 0);
       ef = std::max(ef, std::max(Tr::key(v.real()), Tr::key(v.imag())));
     }
-    E[row] = Tr::exp_field(ef);
-    const auto scale = Tr::slice_scale(E[row]);
-    for (int chunk = 0; chunk * 16 < KS * 32; ++chunk) {
+    return Tr::exp_field(ef);
+  };
+  // the (row, 16-k chunk) work items of the kernel for the 64-k chunk starting at kbase
+  auto fill = [&](std::vector<int8_t>& planes, int plane_bytes, int rows_layout, int nplanesets, int ef,
+                  int row, const cr* src, size_t ld, bool valid, int kbase, int KSc) {
+    const auto scale = Tr::slice_scale(ef);
+    for (int chunk = 0; chunk * 16 < KSc * 32; ++chunk) {
       Real xr[16], xi[16];
       for (int j = 0; j < 16; ++j) {
-        const int k = chunk * 16 + j;
+        const int k = kbase + chunk * 16 + j;
         const cr v = (valid && k < K) ? src[(size_t)k * ld] : cr(0, 0);
         xr[j] = v.real();
         xi[j] = v.imag();
@@ -377,12 +381,22 @@ static double ozaki_tile_error(std::mt19937& rng, int Mrows, int N, int K, doubl
       }
     }
   };
-  for (int n = 0; n < NH * NC; ++n) fill(sB, B_PLANE, NMAX, 3, colE, n, &B[n < N ? n : 0], N, n < N);
-  for (int r = 0; r < TM; ++r) fill(sA, A_PLANE, TM, 2, rowE, r, &A[r < Mrows ? r : 0], Mrows, r < Mrows);
+  for (int n = 0; n < NH * NC; ++n) colE[n % NMAX] = 0;
+  std::vector<int> colEall(NH * NC, 0);
+  for (int n = 0; n < NH * NC; ++n) colEall[n] = exponent(&B[n < N ? n : 0], N, n < N);
+  for (int r = 0; r < TM; ++r) rowE[r] = exponent(&A[r < Mrows ? r : 0], Mrows, r < Mrows);
+  const int chunks = (K + KMAX - 1) / KMAX;
+  auto fill_chunk = [&](int c, int KSc) {
+    for (int n = 0; n < NH * NC; ++n)
+      fill(sB, B_PLANE, NMAX, 3, colEall[n], n % NMAX, &B[n < N ? n : 0], N, n < N, c * KMAX, KSc);
+    for (int r = 0; r < TM; ++r)
+      fill(sA, A_PLANE, TM, 2, rowE[r], r, &A[r < Mrows ? r : 0], Mrows, r < Mrows, c * KMAX, KSc);
+  };
+  fill_chunk(0, std::min(KS, 2));
 
   // the digits reconstruct q exactly (any int8 value is a legal balanced base-256 digit)
   for (int r = 0; r < std::min(Mrows, 8); ++r)
-    for (int k = 0; k < K; ++k) {
+    for (int k = 0; k < std::min(K, KMAX); ++k) {
       long long q = 0;
       for (int s = 0; s < S; ++s) q = q * 256 + plane_elem(sA, (size_t)s * A_PLANE, A_LBO, SBO, r, k);
       const long long want =
@@ -394,9 +408,11 @@ static double ozaki_tile_error(std::mt19937& rng, int Mrows, int N, int K, doubl
   for (int h = 0; h < NH; ++h) {
     std::vector<int32_t> acc((size_t)2 * G * TM * NC, 0);   // [accumulator][row][column]
     long long worst = 0;
+    int chunk_no = 0;
     auto mma = [&](int accum, int a_plane, int b_plane, int ks, unsigned accumulate) {
       const size_t ab = (size_t)a_plane * A_PLANE + (size_t)ks * 2 * A_LBO;
       const size_t bb = (size_t)b_plane * B_PLANE + (size_t)ks * 2 * B_LBO + (size_t)h * (NC / 8) * SBO;
+      if (chunk_no > 0) accumulate = 1u;   // k_zgemm_ozaki_kloop: later chunks always accumulate
       for (int r = 0; r < TM; ++r)
         for (int c = 0; c < NC; ++c) {
           long long sum = 0;
@@ -408,11 +424,15 @@ static double ozaki_tile_error(std::mt19937& rng, int Mrows, int N, int K, doubl
           a = (int32_t)v;
         }
     };
-    for (int grp = 0; grp < G; ++grp) {
-      if (KS == 2)
-        oz::for_each_mma_of_group<S, 2>(grp, mma);
-      else
-        oz::for_each_mma_of_group<S, 1>(grp, mma);
+    for (chunk_no = 0; chunk_no < chunks; ++chunk_no) {
+      const int kleft = std::min(K - chunk_no * KMAX, KMAX), KSc = (kleft + 31) / 32;
+      if (chunks > 1) fill_chunk(chunk_no, KSc);   // (one chunk: the planes are already filled)
+      for (int grp = 0; grp < G; ++grp) {
+        if (KSc == 2)
+          oz::for_each_mma_of_group<S, 2>(grp, mma);
+        else
+          oz::for_each_mma_of_group<S, 1>(grp, mma);
+      }
     }
     CHECK(worst < (1ll << 31), "int32 accumulator overflow: %lld", worst);
     for (int r = 0; r < Mrows; ++r)
@@ -429,7 +449,7 @@ static double ozaki_tile_error(std::mt19937& rng, int Mrows, int N, int K, doubl
             hr = hq = 0;
           }
         }
-        const double sc = Tr::out_scale(rowE[r]) * Tr::out_scale(colE[n]);
+        const double sc = Tr::out_scale(rowE[r]) * Tr::out_scale(colEall[n]);
         const cr out((Real)(oz::combine(fr, hr, G) * sc), (Real)(oz::combine(fq, hq, G) * sc));
         C[r + (size_t)Mrows * n] = std::complex<double>(out.real(), out.imag());
       }
@@ -493,6 +513,31 @@ static void test_ozaki_lowering() {
         "c64 with cgemm_ozaki: fused gather");
   P = lower_contract(ad, ai, bd, bi, 16, opt);
   CHECK(P.kind == CK_GEMM && P.fused_gemm, "c128 unaffected by cgemm_ozaki");
+  {  // long contraction (config-4 shape class): canonical TTGT + exponent workspace only with the option
+    std::vector<int64_t> a2 = {64, 4096, 32}, b2 = {4096, 48};
+    std::vector<int32_t> ai2 = {-1, 1, -2}, bi2 = {1, -3};
+    Options o2;
+    ContractPlan Q = lower_contract(a2, ai2, b2, bi2, 16, o2);
+    CHECK(Q.kind == CK_GEMM && !Q.fused_gemm && Q.ws_bytes == 0 && Q.K == 4096, "long K default");
+    o2.zgemm_ozaki = 6;
+    Q = lower_contract(a2, ai2, b2, bi2, 16, o2);
+    CHECK(Q.kind == CK_GEMM && !Q.fused_gemm && Q.ws_bytes == size_t(64 * 32 + 48) * 4, "long K with zgemm_ozaki");
+    Q = lower_contract(a2, ai2, b2, bi2, 8, o2);
+    CHECK(Q.ws_bytes == 0, "c64 needs cgemm_ozaki");
+    o2.cgemm_ozaki = 4;
+    Q = lower_contract(a2, ai2, b2, bi2, 8, o2);
+    CHECK(Q.ws_bytes == size_t(64 * 32 + 48) * 4, "long K with cgemm_ozaki");
+  }
+  {  // 64 < K <= 1024: fused DMMA by default, canonical + K-looped INT8 kernel with the option
+    std::vector<int64_t> a3 = {300, 200}, b3 = {70, 200};
+    std::vector<int32_t> ai3 = {-1, 1}, bi3 = {-2, 1};
+    Options o3;
+    ContractPlan Q = lower_contract(a3, ai3, b3, bi3, 16, o3);
+    CHECK(Q.kind == CK_GEMM && Q.fused_gemm && Q.ws_bytes == 0, "K = 200 default: fused DMMA");
+    o3.zgemm_ozaki = 7;
+    Q = lower_contract(a3, ai3, b3, bi3, 16, o3);
+    CHECK(Q.kind == CK_GEMM && !Q.fused_gemm && Q.ws_bytes == size_t(370) * 4, "K = 200 with zgemm_ozaki");
+  }
   std::printf("ozaki lowering: ok\n");
 }
 
@@ -520,6 +565,20 @@ static void test_ozaki(std::mt19937& rng) {
     CHECK(e7 < c.tol_hi, "ozaki c128 G=7 M=%d N=%d K=%d: rel-L2 %.3e", c.M, c.N, c.K, e7);
     std::printf("ozaki c128 M=%d N=%d K=%d sigma=%.0f: rel-L2 G=6 %.2e, G=7 %.2e\n", c.M, c.N, c.K,
                 c.sigma, e6, e7);
+  }
+  // long contractions (k_zgemm_ozaki_kloop): one column block, K walked in chunks of 64
+  const Case kloop64[] = {{128, 32, 200, 0.0, 0.0, 1e-12, 2e-13}, {50, 20, 1024, 0.0, 0.3, 1e-12, 2e-13},
+                          {128, 32, 65, 1.0, 0.0, 5e-12, 5e-13}};
+  for (const Case& c : kloop64) {
+    const double e6 = ozaki_tile_error<double, 6, 32>(rng, c.M, c.N, c.K, c.sigma, c.sparsity);
+    const double e7 = ozaki_tile_error<double, 7, 32>(rng, c.M, c.N, c.K, c.sigma, c.sparsity);
+    CHECK(e6 < c.tol_lo && e7 < c.tol_hi, "ozaki kloop c128 M=%d N=%d K=%d: %.3e %.3e", c.M, c.N, c.K, e6, e7);
+    std::printf("ozaki c128 kloop M=%d N=%d K=%d: rel-L2 G=6 %.2e, G=7 %.2e\n", c.M, c.N, c.K, e6, e7);
+  }
+  {
+    const double e4 = ozaki_tile_error<float, 4, 64>(rng, 128, 64, 300, 0.0, 0.0);
+    CHECK(e4 < 1e-7, "ozaki kloop c64 K=300: %.3e", e4);
+    std::printf("ozaki c64  kloop M=128 N=64 K=300: rel-L2 G=4 %.2e\n", e4);
   }
   const Case cases32[] = {   // ComplexF32: G = 3 / 4; the tolerance of the backend is 1e-5
       {128, 64, 64, 0.0, 0.0, 5e-6, 1e-7},   // G = 3 drops the 256^-3 group: coarse, for A/B only

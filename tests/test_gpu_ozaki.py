@@ -80,6 +80,38 @@ def test_ozaki_c64_contraction_matches_f64_oracle(case):
     b.close()
 
 
+LONG_K = [
+    # canonical TTGT + k_zgemm_ozaki_kloop: 64 < K <= 8192
+    ((300, 200), [-1, 1], (70, 200), [-2, 1]),
+    ((64, 1100, 8), [-1, 1, -2], (1100, 40), [1, -3]),
+    ((2,) * 19, [1, -1, 2, -2, 3, -3, 4, -4, 5, -5, 6, -6, 7, -7, 8, -8, 9, 10, 11], (2,) * 16,
+     [11, 10, 9, 8, 7, 6, 5, 4, 3, 2, 1, -9, -10, -11, -12, -13]),
+]
+
+
+@pytest.mark.parametrize("dtype,groups,tol", [(np.complex128, 6, 1e-11), (np.complex128, 7, 1e-11),
+                                             (np.complex64, 4, 2e-6)])
+@pytest.mark.parametrize("case", range(len(LONG_K)))
+def test_ozaki_long_contraction_matches_oracle(case, dtype, groups, tol):
+    ad, ai, bd, bi = LONG_K[case]
+    rng = np.random.default_rng(200 + case)
+    A = np.asarray((rng.standard_normal(ad) + 1j * rng.standard_normal(ad)).astype(dtype), order="F")
+    B = np.asarray((rng.standard_normal(bd) + 1j * rng.standard_normal(bd)).astype(dtype), order="F")
+    ref = OracleBackend(np.complex128)
+    ref.save_tensor_data("A", A.astype(np.complex128))
+    ref.save_tensor_data("B", B.astype(np.complex128))
+    ref.contract_tensors("A", ai, "B", bi, "C")
+    opt = "zgemm_ozaki" if dtype == np.complex128 else "cgemm_ozaki"
+    b = B200(dtype, **{opt: groups})
+    b.save_tensor_data("A", A)
+    b.save_tensor_data("B", B)
+    b.profile_enable(True)
+    b.contract_tensors("A", ai, "B", bi, "C")
+    assert "gemm_tensor" in b.profile_read()
+    assert rel_l2(b.load_tensor_data("C"), ref.load_tensor_data("C")) < tol
+    b.close()
+
+
 def test_ozaki_sliced_rqc_amplitude():
     """A sliced 4x4 depth-12 RQC amplitude with every eligible GEMM step on the INT8 kernel."""
     circ = create_RQC(4, 4, 12, seed=1)

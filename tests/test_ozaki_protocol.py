@@ -162,3 +162,116 @@ def test_model_catches_a_missing_wait():
                 run(seed, 3, 2, 6)
     finally:
         mma_thread = good
+
+
+# ---------------------------------------------------------------------------
+# k_zgemm_ozaki_kloop: K walked in chunks; planes rewritten per chunk behind `consumed`
+# ---------------------------------------------------------------------------
+def kloop_mma_thread(st, tiles, chunks, G):
+    it = cc = 0
+    for _ in range(tiles):
+        for c in range(chunks):
+            yield ("wait", st["planes"], cc & 1)
+            for g in range(G):
+                if c == 0 and it > 0:
+                    yield ("wait", st["freed"][g], (it - 1) & 1)
+                yield ("kissue", it, cc, c, g, c == chunks - 1)
+            yield ("kcommit_consumed", cc)
+            cc += 1
+        it += 1
+
+
+def kloop_worker(st, w, tiles, chunks, G):
+    it = cc = 0
+    for _ in range(tiles):
+        for c in range(chunks):
+            if cc > 0:
+                yield ("wait", st["consumed"], (cc - 1) & 1)
+            yield ("kslice", cc)
+            yield ("arrive", st["planes"])
+            cc += 1
+        for g in range(G):
+            yield ("wait", st["done"][g], it & 1)
+            yield ("read", it, g)
+            yield ("arrive", st["freed"][g])
+        it += 1
+
+
+def run_kloop(seed, tiles, chunks, G):
+    rng = random.Random(seed)
+    st = {"planes": MBar(NW), "consumed": MBar(1), "done": [MBar(1) for _ in range(G)],
+          "freed": [MBar(NW) for _ in range(G)]}
+    agents = {"mma": kloop_mma_thread(st, tiles, chunks, G)}
+    agents.update({w: kloop_worker(st, w, tiles, chunks, G) for w in range(NW)})
+    pending = {k: None for k in agents}
+    inflight = []            # FIFO of async tensor-core events: ("mma", it, cc, g, last) / ("consumed", cc)
+    mma_done_chunk = set()   # chunks whose MMAs have all completed
+    completed, issued, reads = {}, set(), {}
+    sliced = {}
+    live = set(agents)
+    steps = 0
+    while live or inflight:
+        steps += 1
+        assert steps < 10_000_000
+        choices = list(live) + (["tc"] if inflight else [])
+        rng.shuffle(choices)
+        progressed = False
+        for who in choices:
+            if who == "tc":
+                ev = inflight.pop(0)
+                if ev[0] == "mma":
+                    _, it, cc, g, last = ev
+                    if last:
+                        completed[(it, g)] = True
+                        st["done"][g].arrive()
+                else:
+                    mma_done_chunk.add(ev[1])
+                    st["consumed"].arrive()
+                progressed = True
+                break
+            act = pending[who]
+            if act is None:
+                try:
+                    act = next(agents[who])
+                except StopIteration:
+                    live.discard(who)
+                    progressed = True
+                    break
+            kind = act[0]
+            if kind == "wait":
+                if not act[1].test(act[2]):
+                    pending[who] = act
+                    continue
+            elif kind == "arrive":
+                act[1].arrive()
+            elif kind == "kslice":
+                cc = act[1]
+                assert cc == 0 or (cc - 1) in mma_done_chunk, "planes rewritten while the previous chunk is in use"
+                sliced.setdefault(cc, set()).add(who)
+            elif kind == "kissue":
+                _, it, cc, c, g, last = act
+                assert len(sliced.get(cc, ())) == NW, "MMA issued before all planes of the chunk were written"
+                assert not sliced.get(cc + 1), "MMA issued while the next chunk is being written"
+                if c == 0 and it > 0:
+                    assert len(reads.get((it - 1, g), ())) == NW, "accumulator overwritten before all warps read it"
+                if c == 0:
+                    issued.add((it, g))
+                inflight.append(("mma", it, cc, g, last))
+            elif kind == "kcommit_consumed":
+                inflight.append(("consumed", act[1]))
+            elif kind == "read":
+                _, it, g = act
+                assert completed.get((it, g)), "accumulator read before its MMAs completed"
+                assert (it + 1, g) not in issued, "accumulator read after the next tile started on it"
+                reads.setdefault((it, g), set()).add(who)
+            pending[who] = None
+            progressed = True
+            break
+        assert progressed, "deadlock: %r" % {k: v for k, v in pending.items() if v is not None}
+    assert len(completed) == tiles * G and all(len(v) == NW for v in reads.values())
+
+
+@pytest.mark.parametrize("tiles,chunks,G", [(1, 1, 6), (1, 4, 6), (3, 2, 7), (4, 3, 4), (2, 5, 6)])
+def test_kloop_protocol_random_interleavings(tiles, chunks, G):
+    for seed in range(30):
+        run_kloop(seed, tiles, chunks, G)

@@ -13,6 +13,8 @@ hang, and a hung child must not hold the box:
   stage 2  the sweep-step shapes of the bench workload (gather fused), parity vs NumPy c128
   stage 3  timing of those shapes against the DMMA kernels (option off)
   stage 4  one slice of the bench workload as a compiled program, amplitude vs the oracle
+  stage 6  long contractions (64 < K <= 8192, k_zgemm_ozaki_kloop behind K1): parity and timing
+           against the 3M DMMA kernel on the top shapes of BASELINE config 4
   stage 5  the ComplexF32 twin (option cgemm_ozaki = 4): parity vs the c128 reference and timing
            against the K1 + tcgen05 3xTF32 path
 
@@ -180,6 +182,31 @@ def child(stage):
                                                 "watchdog": b.microbench("ozaki_debug")}
                 print(name, label, res["%s_%s" % (name, label)], flush=True)
                 b.close()
+    elif stage == "6":
+        shapes = {"K200": ((300, 200), [-1, 1], (70, 200), [-2, 1]),
+                  "cfg4_top_M13_N13_K11": ((2 ** 13, 2 ** 11), [-1, 1], (2 ** 13, 2 ** 11), [-2, 1]),
+                  "cfg4_M12_N12_K8": ((2 ** 12, 2 ** 8), [-1, 1], (2 ** 12, 2 ** 8), [-2, 1])}
+        for name, (ad, ai, bd, bi) in shapes.items():
+            A, B = operands(ad, bd, 4)
+            ref = A @ B.T
+            for label, g in (("dmma", 0), ("ozaki6", 6)):
+                b = B200Backend(np.complex128)
+                b.set_option("zgemm_ozaki", g)
+                for rep in range(3):
+                    b.save_tensor_data("A", A)
+                    b.save_tensor_data("B", B)
+                    if rep == 1:
+                        b.profile_enable(True)
+                    b.contract_tensors("A", ai, "B", bi, "C")
+                prof = b.profile_read()
+                ms = sum(r["ms"] for r in prof.values()) / 2
+                got = np.asarray(b.load_tensor_data("C"))
+                err = float(np.linalg.norm(got - ref) / np.linalg.norm(ref))
+                res["%s_%s" % (name, label)] = {"rel_l2": err, "ms": ms,
+                                                "tflops": 8.0 * ad[0] * bd[0] * ad[1] / ms / 1e9,
+                                                "watchdog": b.microbench("ozaki_debug")}
+                print(name, label, res["%s_%s" % (name, label)], flush=True)
+                b.close()
     print("RESULT " + json.dumps(res), flush=True)
 
 
@@ -189,7 +216,7 @@ def main():
         return 0
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
     summary, ok = {}, True
-    for stage, limit in (("0", 120), ("1", 180), ("2", 300), ("3", 300), ("4", 420), ("5", 420)):
+    for stage, limit in (("0", 120), ("1", 180), ("2", 300), ("3", 300), ("4", 420), ("5", 420), ("6", 420)):
         try:
             r = subprocess.run([sys.executable, os.path.abspath(__file__), "--child", stage],
                                capture_output=True, text=True, timeout=limit)
