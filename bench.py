@@ -363,6 +363,11 @@ def config_arm(a):
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
     from picoquant_jl_b200.host.b200_backend import B200Backend
     b = B200Backend(dtype, device=0)
+    if a.ozaki:   # EXPERIMENTAL INT8 tensor-core GEMMs (off by default)
+        if (a.dtype == "c128") != (a.ozaki in (6, 7)):
+            raise SystemExit("--ozaki 6|7 goes with --dtype c128, --ozaki 3|4 with --dtype c64")
+        b.set_option("zgemm_ozaki" if a.dtype == "c128" else "cgemm_ozaki", a.ozaki)
+        cfg["ozaki_groups"] = a.ozaki
     for cmd, x in parse_dsl(w.text):
         if cmd == "tensor":
             b.save_tensor_data(x["key"], w.store.read(x["key"]))

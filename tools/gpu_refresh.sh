@@ -50,6 +50,8 @@ if [ $OZ_RC -eq 0 ]; then
   for g in 6 7; do
     timeout 600 python bench.py --ozaki $g > $OUT/bench_${TAG}_n1_ozaki$g.json 2> $OUT/bench_${TAG}_n1_ozaki$g.err
   done
+  timeout 600 python bench.py --workload rqc6x6 --ozaki 6 > $OUT/bench_${TAG}_rqc6x6_ozaki6.json 2> $OUT/bench_${TAG}_rqc6x6_ozaki6.err
+  timeout 600 python bench.py --workload rqc6x6 --dtype c64 --ozaki 4 > $OUT/bench_${TAG}_rqc6x6_c64_ozaki4.json 2> $OUT/bench_${TAG}_rqc6x6_c64_ozaki4.err
   timeout 600 python bench.py --dtype c64 --ozaki 4 > $OUT/bench_${TAG}_n1_c64_ozaki4.json 2> $OUT/bench_${TAG}_n1_c64_ozaki4.err
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_zgemm_ozaki -s 20 -c 3 \
     -o $OUT/prof_${TAG}_ozaki -f \
