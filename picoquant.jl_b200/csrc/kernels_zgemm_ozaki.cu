@@ -484,7 +484,6 @@ k_zgemm_ozaki(const typename OzVec<Real>::type* __restrict__ A,
 // Tiles are rasterised in bands of 16 row tiles so that the CTAs of a wave share a band of A
 // and a few column blocks of B in L2.
 // ---------------------------------------------------------------------------
-constexpr long long OZ_KLOOP_MAXK = 8192;
 
 template <class Real>
 __global__ void __launch_bounds__(128)
