@@ -326,7 +326,7 @@ static int8_t plane_elem(const std::vector<int8_t>& buf, size_t plane_base, int 
 
 template <class Real, int G, int NC>
 static double ozaki_tile_error(std::mt19937& rng, int Mrows, int N, int K, double spread_sigma,
-                               double sparsity) {
+                               double sparsity, double big = 1.0) {
   using Tr = oz::Traits<Real>;
   typedef std::complex<Real> cr;
   constexpr int S = Tr::S;
@@ -343,6 +343,12 @@ static double ozaki_tile_error(std::mt19937& rng, int Mrows, int N, int K, doubl
   std::vector<cr> A((size_t)Mrows * K), B((size_t)N * K);   // A[m + Mrows k], B[n + N k]
   for (auto& x : A) x = cr(draw(), draw());
   for (auto& x : B) x = cr(draw(), draw());
+  if (big != 1.0) {   // rows / columns of wildly different magnitude (exercises the scale range)
+    for (int r = 0; r < Mrows; ++r)
+      for (int k = 0; k < K; ++k) A[r + (size_t)Mrows * k] *= (Real)((r & 1) ? big : 1.0 / big);
+    for (int n = 0; n < N; ++n)
+      for (int k = 0; k < K; ++k) B[n + (size_t)N * k] *= (Real)((n & 1) ? 1.0 / big : big);
+  }
   if (Mrows > 3)
     for (int k = 0; k < K; ++k) A[3 + (size_t)Mrows * k] = (Real)0;   // an all-zero row
   if (Mrows > 5)
@@ -465,8 +471,10 @@ static double ozaki_tile_error(std::mt19937& rng, int Mrows, int N, int K, doubl
       }
       const std::complex<double> got = C[r + (size_t)Mrows * n];
       if (r == 5) continue;   // the tiny row: its products underflow the result type
-      num += (got.real() - rr) * (got.real() - rr) + (got.imag() - ri) * (got.imag() - ri);
-      den += rr * rr + ri * ri;
+      long double w = 1.0L;   // undo the row / column scaling so that every entry counts
+      if (big != 1.0) w = ((r & 1) ? 1.0L / big : (long double)big) * ((n & 1) ? (long double)big : 1.0L / big);
+      num += w * w * ((got.real() - rr) * (got.real() - rr) + (got.imag() - ri) * (got.imag() - ri));
+      den += w * w * (rr * rr + ri * ri);
       if (r == 3) CHECK(got == std::complex<double>(0, 0), "zero row must give exact zeros");
     }
   return (double)std::sqrt(num / den);
@@ -579,6 +587,12 @@ static void test_ozaki(std::mt19937& rng) {
     const double e4 = ozaki_tile_error<float, 4, 64>(rng, 128, 64, 300, 0.0, 0.0);
     CHECK(e4 < 1e-7, "ozaki kloop c64 K=300: %.3e", e4);
     std::printf("ozaki c64  kloop M=128 N=64 K=300: rel-L2 G=4 %.2e\n", e4);
+  }
+  {  // scale range: rows and columns 1e+-140 (double) / 1e+-15 (float) apart
+    const double e6 = ozaki_tile_error<double, 6, 32>(rng, 64, 48, 64, 0.0, 0.0, 1e140);
+    const double e4 = ozaki_tile_error<float, 4, 64>(rng, 64, 48, 64, 0.0, 0.0, 1e15);
+    CHECK(e6 < 1e-12 && e4 < 1e-7, "ozaki scale range: %.3e %.3e", e6, e4);
+    std::printf("ozaki scale range: c128 %.2e, c64 %.2e\n", e6, e4);
   }
   const Case cases32[] = {   // ComplexF32: G = 3 / 4; the tolerance of the backend is 1e-5
       {128, 64, 64, 0.0, 0.0, 5e-6, 1e-7},   // G = 3 drops the 256^-3 group: coarse, for A/B only
