@@ -663,6 +663,14 @@ k_zgemm_ozaki_kloop(const typename OzVec<Real>::type* __restrict__ A,
           Tr::slice16(xi, scale_b, true, pl);
 #pragma unroll
           for (int s = 0; s < S; ++s) oz_store(dst + (2 * S + s) * OZ_B_PLANE, pl[s]);
+          // B's loads sit behind the slicing of A (registers): pull the next chunk into L2 now
+          if (nb < N && c + 1 < chunks) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const long long k = kbase + OZ_KMAX + bchunk * 16 + j;
+              if (k < K) asm volatile("prefetch.global.L2 [%0];\n" ::"l"(B + nb + N * k));
+            }
+          }
         }
         asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
         __syncwarp();
