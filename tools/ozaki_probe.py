@@ -13,10 +13,10 @@ hang, and a hung child must not hold the box:
   stage 2  the sweep-step shapes of the bench workload (gather fused), parity vs NumPy c128
   stage 3  timing of those shapes against the DMMA kernels (option off)
   stage 4  one slice of the bench workload as a compiled program, amplitude vs the oracle
-  stage 6  long contractions (64 < K <= 8192, k_zgemm_ozaki_kloop behind K1): parity and timing
-           against the 3M DMMA kernel on the top shapes of BASELINE config 4
   stage 5  the ComplexF32 twin (option cgemm_ozaki = 4): parity vs the c128 reference and timing
            against the K1 + tcgen05 3xTF32 path
+  stage 6  long contractions (64 < K <= 8192, k_zgemm_ozaki_kloop behind K1): parity and timing
+           against the 3M DMMA kernel on the top shapes of BASELINE config 4
 
 Writes gpurun_out/ozaki_probe.json.  Exit code 0 only if every stage that ran is within
 tolerance (1e-11 rel-L2 per contraction, 1e-10 for the amplitude).
