@@ -114,7 +114,10 @@ struct Traits<double> {
   static OZ_HD double slice_scale(int ef) { return ef >= MIN_EF ? pow2_field(QBITS + 2045 - ef) : 0.0; }
   // output scale 2^(E - 6):  C = 2^(EA + EB - 2 QBITS) 256^(2 (S - 1)) sum_g acc_g 256^-g
   //                            = 2^(EA - 6) 2^(EB - 6) sum_g acc_g 256^-g
-  static OZ_HD double out_scale(int ef) { return ef >= MIN_EF ? pow2_field(ef - 5) : 0.0; }
+  // (a row holding an Inf or a NaN has the all-ones field: its results are NaN, as with DMMA)
+  static OZ_HD double out_scale(int ef) {
+    return ef >= 2047 ? pow2_field(2047) * 0.0 : ef >= MIN_EF ? pow2_field(ef - 5) : 0.0;
+  }
 
   // Slices 16 reals of one row (one 16-byte K chunk) into S planes: out[s] holds digit s
   // (s = 0 most significant) of the 16 numbers, byte j = number j.
@@ -157,7 +160,9 @@ struct Traits<float> {
   static OZ_HD float slice_scale(int ef) { return ef >= MIN_EF ? pow2_field_f(QBITS + 253 - ef) : 0.0f; }
   // output scale 2^(E - 6) (the same formula as for double: 2 QBITS - 16 (S - 1) = 12), kept in
   // double so that the product of a row and a column scale cannot under- or overflow
-  static OZ_HD double out_scale(int ef) { return ef >= MIN_EF ? pow2_field(ef + 891) : 0.0; }
+  static OZ_HD double out_scale(int ef) {
+    return ef >= 255 ? pow2_field(2047) * 0.0 : ef >= MIN_EF ? pow2_field(ef + 891) : 0.0;
+  }
 
   static OZ_HD void slice16(const float* x, float scale, bool negate, Word4* out) {
 #pragma unroll

@@ -6,6 +6,7 @@
 #include <complex>
 #include <cstdio>
 #include <cstdlib>
+#include <limits>
 #include <numeric>
 #include <random>
 
@@ -555,6 +556,15 @@ static void test_ozaki(std::mt19937& rng) {
   CHECK(oz::pow2_field_f(127) == 1.0f && oz::pow2_field_f(137) == 1024.0f, "pow2_field_f");
   CHECK(oz::Traits<float>::out_scale(126 + 6) == 1.0 && oz::Traits<double>::out_scale(1022 + 6) == 1.0,
         "output scales");
+  {  // Inf / NaN in a row poison that row's results instead of producing finite garbage
+    const double inf = std::numeric_limits<double>::infinity();
+    using Td = oz::Traits<double>;
+    using Tf = oz::Traits<float>;
+    CHECK(Td::exp_field(Td::key(inf)) == 2047 && Td::exp_field(Td::key(std::nan(""))) == 2047, "inf key");
+    CHECK(Tf::exp_field(Tf::key((float)inf)) == 255, "inf key (float)");
+    CHECK(std::isnan(Td::out_scale(2047)) && std::isnan(Tf::out_scale(255)), "NaN output scale");
+    CHECK(Td::out_scale(2046) > 0 && std::isfinite(Td::out_scale(2046)) && Tf::out_scale(254) > 0, "largest finite rows");
+  }
   check_digits_by_hand<double>();
   check_digits_by_hand<float>();
   struct Case { int M, N, K; double sigma, sparsity, tol_lo, tol_hi; };
