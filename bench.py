@@ -836,6 +836,18 @@ def main():
                "kind": "port", "sample": "%d of %d slices (%.1f s), NumPy/OpenBLAS oracle"
                                          % (len(sample), a.slices, dt),
                "amplitude_wall_s_extrapolated": dt / len(sample) * a.slices}
+        # one slice on a single BLAS thread, for context; never fatal
+        try:
+            from threadpoolctl import threadpool_limits
+            with threadpool_limits(limits=1):
+                t0 = time.perf_counter()
+                run_cpu_slices(rec, dtype, [1])
+                dt1 = time.perf_counter() - t0
+            cpu["single_thread"] = {"value": 8.0 * macs / dt1 / 1e12, "unit": UNIT, "cores": 1,
+                                    "sample": "1 of %d slices (%.1f s)" % (a.slices, dt1)}
+            use_all_host_threads()
+        except Exception as e:  # noqa: BLE001
+            cpu["single_thread"] = {"error": repr(e)}
         # cheap parity guard: device partial sum of the same slices vs the ComplexF64 oracle
         b.delete_tensor("check_sum")
         sc.run(sample, "check_sum")
