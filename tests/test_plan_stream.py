@@ -4,6 +4,7 @@ reference code emits (hand-derived from src/layer2.jl:132-405,
 src/layer2/slicing.jl and src/backends/dsl.jl:113-214)."""
 import logging
 
+import numpy as np
 import pytest
 
 from picoquant_jl_b200.host import (DSLBackend, TensorNetworkCircuit, add_gate, add_input,
@@ -111,3 +112,31 @@ def test_multi_index_partition_quirk_single_partition(caplog):
     with caplog.at_level(logging.ERROR):
         assert multi_index_partition((2, 2), 1, 1) == (1, 1)
     assert "must match" in caplog.text
+
+
+def test_multi_index_partition_is_a_bijection_property():
+    """Property (hypothesis): for bond dims whose prefix product hits P exactly, the P partition
+    ids map one-to-one onto the multi-indices of that prefix, first bond fastest -- the
+    size-independent form of slicing.jl:12-26 that the sharded slice loop relies on."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=200, deadline=None)
+    @given(st.lists(st.integers(min_value=2, max_value=5), min_size=1, max_size=5),
+           st.lists(st.integers(min_value=2, max_value=4), min_size=1, max_size=3))
+    def check(prefix, tail):
+        dims = tuple(prefix + tail)         # the reference never inspects the last dim: keep a tail
+        P = int(np.prod(prefix))
+        seen = set()
+        for p in range(1, P + 1):
+            v = multi_index_partition(dims, P, p)
+            assert len(v) == len(prefix)
+            assert all(1 <= b <= d for b, d in zip(v, prefix))
+            flat, stride = 0, 1
+            for b, d in zip(v, prefix):
+                flat += (b - 1) * stride
+                stride *= d
+            assert flat == p - 1            # column-major unravel
+            seen.add(v)
+        assert len(seen) == P
+
+    check()
