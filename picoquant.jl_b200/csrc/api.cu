@@ -197,9 +197,10 @@ extern "C" int pq_save_tensor(pq_handle* h, const char* label, int rank, const i
   auto old = h->tensors.find(label);
   if (old != h->tensors.end() && old->second.buf && !old->second.buf->external &&
       old->second.buf->bytes == size_t(n) * h->elem_size &&
-      old->second.buf.use_count() - old->second.buf->pins == 1)
+      old->second.buf.use_count() - old->second.buf->pins == 1) {
     t.buf = old->second.buf;
-  else
+    t.buf->gen += 1;
+  } else
     t.buf = std::make_shared<Buffer>(size_t(n) * h->elem_size, h->stream);
   bool direct = (h->dtype == PQ_C128 && host_dtype == PQ_HOST_C128) ||
                 (h->dtype == PQ_C64 && host_dtype == PQ_HOST_C64);

@@ -13,6 +13,7 @@ struct Buffer {
   cudaStream_t stream = nullptr;
   bool external = false;  // memory owned by somebody else (program arenas)
   int pins = 0;           // compiled programs bound to this buffer (leaf tensors)
+  uint64_t gen = 0;       // bumped by every in-place re-save (programs re-run their invariant part)
   Buffer(size_t n, cudaStream_t s);
   Buffer(void* p, size_t n) : ptr(p), bytes(n), external(true) {}
   ~Buffer();

@@ -192,7 +192,7 @@ __device__ __forceinline__ void oz_store(unsigned char* dst, const oz::Word4& v)
 // Real = double (ComplexF64: 6 digits, NC = 32 columns per pass, G = 6 / 7 accumulator groups)
 // or float (ComplexF32: 4 digits, NC = 64, G = 3 / 4).  2 * G * NC accumulator columns <= 512.
 template <class Real, int G, int NC>
-__global__ void __maxnreg__(120)
+__global__ void __maxnreg__(96)
 k_zgemm_ozaki(const typename OzVec<Real>::type* __restrict__ A,
               const typename OzVec<Real>::type* __restrict__ B,
               typename OzVec<Real>::type* __restrict__ C, const FusedParams p) {
@@ -503,7 +503,7 @@ k_oz_row_exponents(const typename OzVec<Real>::type* __restrict__ X, long long R
 }
 
 template <class Real, int G, int NC>
-__global__ void __maxnreg__(120)
+__global__ void __maxnreg__(96)
 k_zgemm_ozaki_kloop(const typename OzVec<Real>::type* __restrict__ A,
                     const typename OzVec<Real>::type* __restrict__ B,
                     typename OzVec<Real>::type* __restrict__ C, long long M, long long N, long long K,

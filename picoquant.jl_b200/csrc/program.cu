@@ -184,6 +184,10 @@ struct pq_program {
   int device = 0;
   // leaf tensors the program is bound to: (store key, pinned buffer)
   std::vector<std::pair<std::string, std::shared_ptr<Buffer>>> leaves;
+  // what each leaf looked like when the program was compiled / last prepared: an in-place
+  // re-save bumps Buffer::gen (hoisted invariant tensors are then stale), and must keep dims
+  std::vector<uint64_t> leaf_gen;
+  std::vector<std::vector<int64_t>> leaf_dims;
   // dependency DAG for multi-stream capture: deps[j] = earlier steps j must wait for
   std::vector<std::vector<int>> deps;
   // chains of tiny contractions that one CTA executes back to back; chains with the same
@@ -734,6 +738,8 @@ extern "C" int pq_program_compile(pq_handle* h, const char* tl_text, pq_program*
         s.bytes = t.buf->bytes;
         t.buf->pins += 1;
         p->leaves.emplace_back(tok[2], t.buf);
+        p->leaf_gen.push_back(t.buf->gen);
+        p->leaf_dims.push_back(t.dims);
         drop(tok[1]);
         syms[tok[1]] = s;
       } else if (cmd == "del") {
@@ -978,11 +984,36 @@ extern "C" int pq_program_hoist_stats(const pq_program* p, int64_t* macs_invaria
 
 static void check_leaves(pq_handle* h, pq_program* p) {
   PQ_REQUIRE(p->device == h->device, PQ_ERR_INVALID, "program belongs to another device");
-  for (auto& l : p->leaves) {
+  for (size_t i = 0; i < p->leaves.size(); ++i) {
+    auto& l = p->leaves[i];
     auto it = h->tensors.find(l.first);
     PQ_REQUIRE(it != h->tensors.end() && it->second.buf.get() == l.second.get(), PQ_ERR_INVALID,
                "tensor '" + l.first + "' was deleted or rebound since the program was compiled; "
                "recompile the program");
+    PQ_REQUIRE(it->second.dims == p->leaf_dims[i], PQ_ERR_SHAPE,
+               "tensor '" + l.first + "' changed shape since the program was compiled; "
+               "recompile the program");
+    if (l.second->gen != p->leaf_gen[i]) {  // re-saved in place: hoisted tensors are stale
+      p->leaf_gen[i] = l.second->gen;
+      p->prepared = false;
+    }
+  }
+}
+
+// Per-slice view parameters come from the caller: the same bounds the compile-time defaults
+// and pq_view get (the reference raises BoundsError, src/layer1.jl:191-194), checked on the
+// host before anything is uploaded -- k_view itself does not check.
+static void check_starts(const pq_program* p, const int32_t* view_starts, int nslices) {
+  if (!view_starts || p->nviews == 0) return;
+  for (const Step& s : p->steps) {
+    if (s.kind != ST_VIEW) continue;
+    for (int i = 0; i < nslices; ++i) {
+      const int64_t st = view_starts[size_t(i) * p->nviews + s.view_slot];
+      PQ_REQUIRE(st >= 1 && st + s.nsel - 1 <= s.ext, PQ_ERR_INVALID,
+                 "view start " + std::to_string(st) + " (slice " + std::to_string(i) + ", view " +
+                     std::to_string(s.view_slot) + ") outside [1, " +
+                     std::to_string(s.ext - s.nsel + 1) + "]");
+    }
   }
 }
 
@@ -1007,10 +1038,14 @@ extern "C" int pq_program_prepare(pq_handle* h, pq_program* p) {
 // Publishes the `save` results of one run of `lane` in the handle's store and, optionally,
 // adds them to `accumulate_into` -- on the handle's stream.
 static void publish_saves(pq_handle* h, pq_program* p, Launch& L, int lane,
-                          const char* accumulate_into) {
+                          const char* accumulate_into, bool split = false) {
+  PQ_REQUIRE(!accumulate_into || p->nsaves <= 1, PQ_ERR_UNSUPPORTED,
+             "accumulate_into needs a program with a single `save` (it has " +
+                 std::to_string(p->nsaves) + ")");
   for (Step& s : p->steps) {
     if (s.kind != ST_SAVE) continue;
-    const std::shared_ptr<Buffer>& out = p->lanes[lane].outs[s.save_slot];
+    // with hoisting a slice-invariant `save` ran once, in phase 0, into lane 0's buffer
+    const std::shared_ptr<Buffer>& out = p->lanes[(split && !s.dep) ? 0 : lane].outs[s.save_slot];
     Tensor t;
     t.dims = s.dims;
     t.buf = out;
@@ -1072,6 +1107,7 @@ extern "C" int pq_program_run(pq_handle* h, pq_program* p, const int32_t* view_s
     check_leaves(h, p);
     if (view_starts)
       PQ_REQUIRE(nviews == p->nviews, PQ_ERR_INVALID, "pq_program_run: wrong number of view starts");
+    check_starts(p, view_starts, 1);
     run_one(h, p, view_starts, accumulate_into);
   } catch (const Error& e) {
     h->last_error = e.what();
@@ -1101,6 +1137,7 @@ extern "C" int pq_program_run_slices(pq_handle* h, pq_program* p, const int32_t*
       PQ_REQUIRE(nviews == p->nviews, PQ_ERR_INVALID,
                  "pq_program_run_slices: wrong number of view starts");
     if (nslices == 0) return PQ_OK;
+    check_starts(p, view_starts, nslices);
     const bool eager = h->profile || h->opt.graph == 1;
     if (nlanes > pq_program::MAX_LANES) nlanes = pq_program::MAX_LANES;
     if (nlanes > nslices) nlanes = nslices;
@@ -1151,7 +1188,7 @@ extern "C" int pq_program_run_slices(pq_handle* h, pq_program* p, const int32_t*
       PQ_CUDA(cudaEventRecord(m.done_ev, m.stream));
       // join: publish / accumulate in slice order on the handle's stream
       PQ_CUDA(cudaStreamWaitEvent(h->stream, m.done_ev, 0));
-      publish_saves(h, p, L, lane, accumulate_into);
+      publish_saves(h, p, L, lane, accumulate_into, split);
       PQ_CUDA(cudaEventRecord(m.acc_ev, h->stream));
     }
     h->note_tensor(p->max_elems);
