@@ -62,6 +62,15 @@ const char* pq_version(void);
 int pq_save_tensor(pq_handle* h, const char* label, int rank, const int64_t* dims,
                    const void* host, int host_dtype);
 
+/* The same for a whole network's worth of tensors in one call: save_tensor_data is called once
+ * per node while a network is built (src/layer3.jl:195,226,277,308) and again on every rank of
+ * the sliced flow (examples/dist_slicing_example.jl:22-27) -- O(#gates) uploads of <= 16 elements.
+ * `dims_flat` holds the extents of tensor 0, then of tensor 1, ... (sum of ranks entries).  One
+ * pinned staging block, one host->device copy, one scatter launch; per-tensor semantics are
+ * exactly pq_save_tensor's. */
+int pq_save_tensors(pq_handle* h, int n, const char* const* labels, const int* ranks,
+                    const int64_t* dims_flat, const void* const* hosts, const int* host_dtypes);
+
 /* size(load_tensor_data(...)) without the copy; PQ_ERR_NOT_FOUND mirrors `nothing`
  * (interactive.jl:44-49).  `dims` must hold PQ_MAX_RANK entries. */
 int pq_tensor_info(pq_handle* h, const char* label, int* rank, int64_t* dims);

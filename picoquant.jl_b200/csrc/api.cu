@@ -139,6 +139,9 @@ extern "C" int pq_destroy(pq_handle* h) {
     cudaEventDestroy(h->timer0);
     cudaEventDestroy(h->timer1);
   }
+  if (h->stage_host) cudaFreeHost(h->stage_host);
+  if (h->stage_dev) cudaFree(h->stage_dev);
+  if (h->stage_ev) cudaEventDestroy(h->stage_ev);
   cudaStreamSynchronize(h->stream);
   cudaStreamDestroy(h->stream);
   delete h;
@@ -221,6 +224,91 @@ extern "C" int pq_save_tensor(pq_handle* h, const char* label, int rank, const i
   }
   h->note_tensor(n);
   h->tensors[label] = std::move(t);
+  PQ_CATCH(h)
+}
+
+// Batched save_tensor_data: the O(#gates) tiny uploads of a network (interactive.jl:32-36 called
+// once per node from src/layer3.jl:195,226,277,308; re-done per rank in
+// examples/dist_slicing_example.jl:22-27) as ONE pinned staging block, ONE host->device copy and
+// ONE scatter launch.  Same per-tensor semantics as pq_save_tensor (convert to the backend
+// dtype, in-place update of a uniquely held buffer of the same size, rebind otherwise).
+extern "C" int pq_save_tensors(pq_handle* h, int n, const char* const* labels, const int* ranks,
+                               const int64_t* dims_flat, const void* const* hosts,
+                               const int* host_dtypes) {
+  if (!h) return PQ_ERR_INVALID;
+  PQ_TRY(h)
+  PQ_REQUIRE(n >= 0 && (n == 0 || (labels && ranks && hosts && host_dtypes)), PQ_ERR_INVALID,
+             "pq_save_tensors: bad arguments");
+  if (n == 0) return PQ_OK;
+  set_device(h);
+  // validate everything before touching the store
+  std::vector<int64_t> numel(n);
+  std::vector<size_t> dim_at(n), off(n);
+  size_t pos = 0, bytes = 0;
+  const size_t table_bytes = (size_t(n) * sizeof(ScatterItem) + 255) & ~size_t(255);
+  for (int i = 0; i < n; ++i) {
+    PQ_REQUIRE(labels[i] && hosts[i] && ranks[i] >= 0 && ranks[i] <= PQ_MAX_RANK &&
+                   (ranks[i] == 0 || dims_flat),
+               PQ_ERR_INVALID, "pq_save_tensors: bad arguments for tensor " + std::to_string(i));
+    PQ_REQUIRE(host_dtypes[i] >= PQ_HOST_F32 && host_dtypes[i] <= PQ_HOST_C128, PQ_ERR_INVALID,
+               "bad host dtype");
+    dim_at[i] = pos;
+    int64_t m = 1;
+    for (int d = 0; d < ranks[i]; ++d) {
+      PQ_REQUIRE(dims_flat[pos + d] >= 1, PQ_ERR_INVALID, "extents must be >= 1");
+      m *= dims_flat[pos + d];
+    }
+    pos += ranks[i];
+    numel[i] = m;
+    off[i] = table_bytes + bytes;
+    bytes += (size_t(m) * h->elem_size + 15) & ~size_t(15);
+  }
+  const size_t total = table_bytes + bytes;
+  if (h->stage_busy) PQ_CUDA(cudaEventSynchronize(h->stage_ev));   // previous batch still copying
+  if (total > h->stage_cap) {
+    if (h->stage_host) PQ_CUDA(cudaFreeHost(h->stage_host));
+    if (h->stage_dev) PQ_CUDA(cudaFree(h->stage_dev));
+    h->stage_host = h->stage_dev = nullptr;
+    h->stage_cap = 0;
+    const size_t cap = total * 2;
+    PQ_CUDA(cudaMallocHost(&h->stage_host, cap));
+    PQ_CUDA(cudaMalloc(&h->stage_dev, cap));
+    h->stage_cap = cap;
+  }
+  if (!h->stage_ev) PQ_CUDA(cudaEventCreateWithFlags(&h->stage_ev, cudaEventDisableTiming));
+  ScatterItem* table = reinterpret_cast<ScatterItem*>(h->stage_host);
+  for (int i = 0; i < n; ++i) {
+    Tensor t;
+    t.dims.assign(dims_flat + dim_at[i], dims_flat + dim_at[i] + ranks[i]);
+    const size_t nb = size_t(numel[i]) * h->elem_size;
+    auto old = h->tensors.find(labels[i]);
+    if (old != h->tensors.end() && old->second.buf && !old->second.buf->external &&
+        old->second.buf->bytes == nb && old->second.buf.use_count() - old->second.buf->pins == 1) {
+      t.buf = old->second.buf;
+      t.buf->gen += 1;
+    } else {
+      t.buf = std::make_shared<Buffer>(nb, h->stream);
+    }
+    unsigned char* dst = h->stage_host + off[i];
+    const bool direct = (h->dtype == PQ_C128 && host_dtypes[i] == PQ_HOST_C128) ||
+                        (h->dtype == PQ_C64 && host_dtypes[i] == PQ_HOST_C64);
+    if (direct)
+      memcpy(dst, hosts[i], nb);
+    else if (h->dtype == PQ_C128)
+      convert_host<double>(hosts[i], host_dtypes[i], (double*)dst, numel[i]);
+    else
+      convert_host<float>(hosts[i], host_dtypes[i], (float*)dst, numel[i]);
+    table[i].dst = t.buf->ptr;
+    table[i].src_off = off[i];
+    table[i].words = nb / 8;
+    h->note_tensor(numel[i]);
+    h->tensors[labels[i]] = std::move(t);
+  }
+  PQ_CUDA(cudaMemcpyAsync(h->stage_dev, h->stage_host, total, cudaMemcpyHostToDevice, h->stream));
+  PQ_CUDA(cudaEventRecord(h->stage_ev, h->stream));
+  h->stage_busy = true;
+  Launch L = h->launch_ctx();
+  run_scatter(L, h->stage_dev, reinterpret_cast<const ScatterItem*>(h->stage_dev), n, double(bytes));
   PQ_CATCH(h)
 }
 

@@ -237,6 +237,15 @@ void init_kernels_cgemm();
 void run_view(const Launch& L, const void* in, void* out, int64_t inner, int64_t ext_in,
               int64_t nsel, int64_t outer, int start0, const int32_t* start_dev);
 void run_accumulate(const Launch& L, void* dst, const void* src, int64_t n);
+// pq_save_tensors: `table` (device) holds n ScatterItem; item i copies `words` 8-byte words from
+// the staging block at `src_off` to `dst`
+struct ScatterItem {
+  void* dst;
+  unsigned long long src_off;
+  unsigned long long words;
+};
+void run_scatter(const Launch& L, const unsigned char* stage_dev, const ScatterItem* table, int n,
+                 double bytes);
 double run_microbench(const Launch& L, const std::string& what);
 
 // gemm back ends on canonical layouts A'[m + M k], B''[n + N k], C[m + M n]

@@ -52,6 +52,12 @@ struct pq_handle {
   double prof_flops[PQ_NUM_KERNEL_CLASSES] = {0};
   pq::Comm* comm = nullptr;
   cudaEvent_t timer0 = nullptr, timer1 = nullptr;
+  // pq_save_tensors: one pinned staging block (table + packed data) and its device twin
+  unsigned char* stage_host = nullptr;
+  unsigned char* stage_dev = nullptr;
+  size_t stage_cap = 0;
+  cudaEvent_t stage_ev = nullptr;
+  bool stage_busy = false;
 
   pq::Launch launch_ctx();
   pq::Tensor& get(const std::string& label);

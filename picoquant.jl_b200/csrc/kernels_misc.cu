@@ -66,6 +66,24 @@ void run_accumulate(const Launch& L, void* dst, const void* src, int64_t n) {
   PQ_CUDA(cudaGetLastError());
 }
 
+// one CTA per tensor of a pq_save_tensors batch: staging block -> the tensor's own buffer
+__global__ void __launch_bounds__(128) k_scatter(const unsigned char* __restrict__ stage,
+                                                 const ScatterItem* __restrict__ table) {
+  const ScatterItem it = table[blockIdx.x];
+  const uint2* src = reinterpret_cast<const uint2*>(stage + it.src_off);
+  uint2* dst = reinterpret_cast<uint2*>(it.dst);
+  for (unsigned long long i = threadIdx.x; i < it.words; i += blockDim.x) dst[i] = src[i];
+}
+
+void run_scatter(const Launch& L, const unsigned char* stage_dev, const ScatterItem* table, int n,
+                 double bytes) {
+  if (n <= 0) return;
+  L.begin(KC_COPY, 2.0 * bytes, 0);
+  k_scatter<<<(unsigned)n, 128, 0, L.stream>>>(stage_dev, table);
+  L.end();
+  PQ_CUDA(cudaGetLastError());
+}
+
 __global__ void __launch_bounds__(256) k_copy16(const uint4* __restrict__ in, uint4* __restrict__ out,
                                                 long long n) {
   const long long stride = (long long)gridDim.x * blockDim.x;
@@ -74,7 +92,7 @@ __global__ void __launch_bounds__(256) k_copy16(const uint4* __restrict__ in, ui
 }
 
 double run_microbench(const Launch& L, const std::string& what) {
-  if (what.rfind("umma_i8_", 0) == 0 || what == "ozaki_debug") return run_ozaki_microbench(L, what);
+  if (what.rfind("umma_i8_", 0) == 0 || what.rfind("ozaki_", 0) == 0) return run_ozaki_microbench(L, what);
   if (what == "dmma_tflops") return run_fp64_probe(L, true);
   if (what.rfind("dmma_tflops_w", 0) == 0) return run_fp64_probe(L, true, std::stoi(what.substr(13)));
   if (what == "dfma_tflops") return run_fp64_probe(L, false);

@@ -98,6 +98,13 @@ __device__ __forceinline__ void oz_mbar_arrive(uint64_t* bar) {
 // (pq_microbench "ozaki_debug") instead of a hung GPU.
 //   g_oz_debug = {flag, wait id, iteration, group, block, warp, -, -}
 __device__ int g_oz_debug[8];
+// Phase trace of block 0 (template parameter TR; off in the product instantiations): clock64
+// stamps per tile, see tools/ozaki_trace.py for the event numbering.
+__device__ long long g_oz_trace[16 * 64];
+#define OZ_TRACE(tile_no, ev)                                                             \
+  do {                                                                                    \
+    if (TR && blockIdx.x == 0 && (tile_no) < 16) g_oz_trace[(tile_no) * 64 + (ev)] = clock64(); \
+  } while (0)
 constexpr long long OZ_WAIT_LIMIT = 4000000000ll;   // clock64 ticks
 
 __device__ __forceinline__ bool oz_try_wait(uint64_t* bar, uint32_t parity) {
@@ -191,7 +198,7 @@ __device__ __forceinline__ void oz_store(unsigned char* dst, const oz::Word4& v)
 
 // Real = double (ComplexF64: 6 digits, NC = 32 columns per pass, G = 6 / 7 accumulator groups)
 // or float (ComplexF32: 4 digits, NC = 64, G = 3 / 4).  2 * G * NC accumulator columns <= 512.
-template <class Real, int G, int NC>
+template <class Real, int G, int NC, bool TR = false>
 __global__ void __maxnreg__(96)
 k_zgemm_ozaki(const typename OzVec<Real>::type* __restrict__ A,
               const typename OzVec<Real>::type* __restrict__ B,
@@ -267,6 +274,7 @@ k_zgemm_ozaki(const typename OzVec<Real>::type* __restrict__ A,
       uint32_t it = 0, tile_no = 0;
       for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++tile_no) {
         oz_mbar_wait(planes, tile_no & 1u, abort_flag, 1, (int)it, -1);
+        OZ_TRACE(tile_no, 48);
         for (int h = 0; h < NH; ++h, ++it) {
           const uint32_t bh_lo = b_lo + (uint32_t)((h * (NC / 8) * SBO) >> 4);   // rows NC h .. of B
 #pragma unroll
@@ -286,6 +294,7 @@ k_zgemm_ozaki(const typename OzVec<Real>::type* __restrict__ A,
             else
               oz::for_each_mma_of_group<S, 1>(g, mma);
             oz_commit(&done[g]);   // group g may be read while the next groups are computed
+            OZ_TRACE(tile_no, 49 + h * 7 + g);
           }
         }
       }
@@ -340,8 +349,10 @@ k_zgemm_ozaki(const typename OzVec<Real>::type* __restrict__ A,
     const int cpart = warp >> 2;                                    // CW of the NC columns
     uint32_t it = 0;
     int buf = 0;
-    for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, buf ^= 1) {
+    uint32_t tno = 0;
+    for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, buf ^= 1, ++tno) {
       const long long m = tile * OZ_TM + row;
+      if (tid == 0) OZ_TRACE(tno, 0);
       const long long ra = m < M ? map_offset(p.mA, m) : -1;
       // ---- gather this thread's 16 complex numbers, row exponent ----
       Real xr[16], xi[16];
@@ -357,7 +368,9 @@ k_zgemm_ozaki(const typename OzVec<Real>::type* __restrict__ A,
         ef = max(ef, max(Tr::key(v.x), Tr::key(v.y)));
       }
       if (chunk_on) atomicMax(&rowE[buf * OZ_TM + row], Tr::exp_field(ef));
+      if (tid == 0) OZ_TRACE(tno, 1);
       workers_barrier();
+      if (tid == 0) OZ_TRACE(tno, 2);
       const int ea = rowE[buf * OZ_TM + row];
       if (tid < OZ_TM) rowE[(buf ^ 1) * OZ_TM + tid] = 0;    // for the next tile (see header)
       // ---- slice into the re and im digit planes of this tile ----
@@ -372,6 +385,7 @@ k_zgemm_ozaki(const typename OzVec<Real>::type* __restrict__ A,
 #pragma unroll
         for (int s = 0; s < S; ++s) oz_store(dst + (S + s) * OZ_A_PLANE, pl[s]);
       }
+      if (tid == 0) OZ_TRACE(tno, 3);
       // L2 prefetch of the next tile's rows (registers are needed by the epilogue)
       {
         const long long mn = m + (long long)gridDim.x * OZ_TM;
@@ -391,6 +405,7 @@ k_zgemm_ozaki(const typename OzVec<Real>::type* __restrict__ A,
       asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
       __syncwarp();
       if (lane == 0) oz_mbar_arrive(planes);
+      if (tid == 0) OZ_TRACE(tno, 4);
 
       for (int h = 0; h < NH; ++h, ++it) {
         const int nbase = h * NC + cpart * CW;
@@ -418,10 +433,12 @@ k_zgemm_ozaki(const typename OzVec<Real>::type* __restrict__ A,
             const uint32_t col = tmem_base + lane_base + (uint32_t)((2 * g) * NC + cpart * CW + cb * 8);
             // (already complete on the later column blocks of this pass)
             oz_mbar_wait(&done[g], it & 1u, abort_flag, 3, (int)it, g);
+            if (tid == 0 && cb == 0) OZ_TRACE(tno, 5 + h * 16 + g);
             asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
             OZ_TMEM_LD8(r, col);
             OZ_TMEM_LD8(q, col + NC);
             asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+            if (tid == 0 && cb == 0) OZ_TRACE(tno, 13 + h * 16 + g);
             if (cb == CW / 8 - 1) {
               // this warp is done with group g: the MMA warp may overwrite it (next pass / tile)
               asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
@@ -456,6 +473,7 @@ k_zgemm_ozaki(const typename OzVec<Real>::type* __restrict__ A,
             }
           }
         }
+        if (tid == 0) OZ_TRACE(tno, 40 + h);
       }
     }
   }
@@ -919,7 +937,12 @@ void run_zgemm_ozaki(const Launch& L, const FusedParams& fp, int groups, const v
   const unsigned grid = (unsigned)(tiles < L.num_sms ? tiles : L.num_sms);
   if (L.elem_size == 16) {
     PQ_REQUIRE(groups == 6 || groups == 7, PQ_ERR_INVALID, "zgemm_ozaki must be 0, 6 or 7");
-    if (groups == 6)
+    if (groups == 6 && std::getenv("PQ_OZAKI_TRACE")) {
+      cudaFuncSetAttribute(k_zgemm_ozaki<double, 6, 32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           OzSmem<6>::kTotal);
+      k_zgemm_ozaki<double, 6, 32, true><<<grid, OZ_THREADS, OzSmem<6>::kTotal, L.stream>>>(
+          (const double2*)A, (const double2*)B, (double2*)C, fp);
+    } else if (groups == 6)
       k_zgemm_ozaki<double, 6, 32><<<grid, OZ_THREADS, OzSmem<6>::kTotal, L.stream>>>(
           (const double2*)A, (const double2*)B, (double2*)C, fp);
     else
@@ -1011,6 +1034,17 @@ double run_ozaki_microbench(const Launch& L, const std::string& what) {
       PQ_CUDA(cudaMemcpyToSymbol(g_oz_debug, zero, sizeof(zero)));
       return rec[1];
     }
+    return 0;
+  }
+  if (what == "ozaki_trace") {   // dumps block 0's phase stamps to $PQ_OZAKI_TRACE
+    std::vector<long long> tr(16 * 64);
+    PQ_CUDA(cudaStreamSynchronize(L.stream));
+    PQ_CUDA(cudaMemcpyFromSymbol(tr.data(), g_oz_trace, tr.size() * sizeof(long long)));
+    if (const char* path = std::getenv("PQ_OZAKI_TRACE"))
+      if (FILE* f = std::fopen(path, "wb")) {
+        std::fwrite(tr.data(), sizeof(long long), tr.size(), f);
+        std::fclose(f);
+      }
     return 0;
   }
   if (what == "umma_i8_selftest") {

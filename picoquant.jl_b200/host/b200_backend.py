@@ -42,7 +42,7 @@ ABI_SYMBOLS = [
     "pq_reset_counters", "pq_profile_enable", "pq_profile_read", "pq_kernel_class_name",
     "pq_set_option", "pq_microbench", "pq_timer_begin", "pq_timer_end",
     "pq_program_set_hoist", "pq_program_prepare", "pq_program_hoist_stats",
-    "pq_program_run_slices", "pq_decompose",
+    "pq_program_run_slices", "pq_decompose", "pq_save_tensors",
 ]
 
 _lib = None
@@ -72,6 +72,8 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
     lib.pq_create.argtypes = [c_int, c_int, POINTER(c_void_p)]
     lib.pq_destroy.argtypes = [c_void_p]
     lib.pq_save_tensor.argtypes = [c_void_p, c_char_p, c_int, i64p, c_void_p, c_int]
+    lib.pq_save_tensors.argtypes = [c_void_p, c_int, POINTER(c_char_p), POINTER(c_int), i64p,
+                                    POINTER(c_void_p), POINTER(c_int)]
     lib.pq_tensor_info.argtypes = [c_void_p, c_char_p, POINTER(c_int), i64p]
     lib.pq_load_tensor.argtypes = [c_void_p, c_char_p, c_void_p, c_int]
     lib.pq_contract.argtypes = [c_void_p, c_char_p, i32p, c_int, c_char_p, i32p, c_int, c_char_p]
@@ -253,6 +255,38 @@ class B200Backend(AbstractBackend):
         args = (self._h, tensor_label.encode(), arr.ndim, dims, arr.ctypes.data_as(c_void_p),
                 _HOST_DTYPES[arr.dtype], arr)
         return args, arr.size * self.dtype.itemsize
+
+    def prepare_save_batch(self, items):
+        """Pre-marshals ``pq_save_tensors`` for ``[(label, array), ...]`` (the gate tensors of
+        a network, uploaded again for every amplitude): returns ``(args, nbytes)``; the host
+        arrays are kept alive by the tuple."""
+        arrs, labels = [], []
+        for label, data in items:
+            arr = np.asarray(data)
+            if arr.dtype not in _HOST_DTYPES:
+                arr = arr.astype(np.complex128 if np.iscomplexobj(arr) else np.float64)
+            arr = np.array(arr, order="F", copy=True) if not arr.flags.f_contiguous else arr
+            arrs.append(arr)
+            labels.append(label.encode())
+        n = len(arrs)
+        flat = [d for a in arrs for d in a.shape]
+        args = (self._h, n, (c_char_p * max(1, n))(*labels),
+                (c_int * max(1, n))(*[a.ndim for a in arrs]),
+                (c_int64 * max(1, len(flat)))(*flat),
+                (c_void_p * max(1, n))(*[a.ctypes.data for a in arrs]),
+                (c_int * max(1, n))(*[_HOST_DTYPES[a.dtype] for a in arrs]), arrs, labels)
+        return args, sum(a.size for a in arrs) * self.dtype.itemsize
+
+    def save_prepared_batch(self, args):
+        rc = self.lib.pq_save_tensors(*args[:7])
+        if rc != 0:
+            self._check(rc)
+
+    def save_tensors(self, items):
+        """``save_tensor_data`` for many tensors in one call (one staging copy, one H2D,
+        one scatter launch): ``items`` = ``[(label, array), ...]``."""
+        args, _ = self.prepare_save_batch(list(items))
+        self.save_prepared_batch(args)
 
     def save_prepared(self, args):
         rc = self.lib.pq_save_tensor(*args[:6])

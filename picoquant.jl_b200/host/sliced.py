@@ -127,20 +127,18 @@ class SlicedContraction:
 
     def upload(self) -> int:
         """Host -> device copy of every leaf tensor named by a ``tensor``
-        command (the HDF5 file of the reference DSL flow), one ``pq_save_tensor``
-        per tensor from the host arrays.  Returns the bytes copied.  The ctypes
-        argument tuples are prepared once; the copies themselves happen on
+        command (the HDF5 file of the reference DSL flow; the per-rank re-upload of
+        examples/dist_slicing_example.jl:22-27) through ONE ``pq_save_tensors`` call:
+        the host arrays are packed into a pinned staging block, copied with a single
+        H2D transfer and scattered by one launch.  Returns the bytes copied.  The
+        ctypes argument arrays are prepared once; the packing and the copy happen on
         every call."""
         if self._upload_args is None:
-            self._upload_args = []
-            for cmd, a in parse_dsl(self.rec.text):
-                if cmd == "tensor":
-                    self._upload_args.append(self.backend.prepare_save(
-                        a["key"], self.rec.store.read(a["key"])))
-        nbytes = 0
-        for args, n in self._upload_args:
-            self.backend.save_prepared(args)
-            nbytes += n
+            items = [(a["key"], self.rec.store.read(a["key"]))
+                     for cmd, a in parse_dsl(self.rec.text) if cmd == "tensor"]
+            self._upload_args = self.backend.prepare_save_batch(items)
+        args, nbytes = self._upload_args
+        self.backend.save_prepared_batch(args)
         return nbytes
 
     def run(self, partitions: Sequence[int], accumulate_into: str = "partial_sum",

@@ -63,6 +63,27 @@ function save_tensor_data(backend::B200Backend, tensor_label::Symbol,
                             host_code(eltype(data))))
 end
 
+# Batched form of save_tensor_data (one staging copy, one host->device transfer, one launch)
+# for the O(#gates) tiny node tensors of a network -- e.g. the per-rank upload of
+# examples/dist_slicing_example.jl:22-27:
+#     save_tensors(backend, [(:node_1, data1), (:node_2, data2), ...])
+function save_tensors(backend::B200Backend, items::Vector{<:Tuple{Symbol,AbstractArray}})
+    arrays = [eltype(d) <: Union{Float32,Float64,ComplexF32,ComplexF64} ? Array(d) :
+              Array{ComplexF64}(d) for (_, d) in items]
+    labels = [String(l) for (l, _) in items]
+    ranks = Cint[ndims(a) for a in arrays]
+    dims = Int64[s for a in arrays for s in size(a)]
+    codes = Cint[host_code(eltype(a)) for a in arrays]
+    GC.@preserve arrays labels begin
+        ptrs = Ptr{Cvoid}[Ptr{Cvoid}(pointer(a)) for a in arrays]
+        cstrs = Cstring[Base.unsafe_convert(Cstring, l) for l in labels]
+        pq_check(backend, ccall((:pq_save_tensors, libpq_b200), Cint,
+                                (Ptr{Cvoid}, Cint, Ptr{Cstring}, Ptr{Cint}, Ptr{Int64},
+                                 Ptr{Ptr{Cvoid}}, Ptr{Cint}),
+                                backend.handle, length(arrays), cstrs, ranks, dims, ptrs, codes))
+    end
+end
+
 # src/backends/interactive.jl:44-49 (returns `nothing` when absent)
 function load_tensor_data(backend::B200Backend{T}, tensor_label::Symbol) where {T}
     rank = Ref{Cint}(0)

@@ -64,3 +64,29 @@ def test_product_path_does_not_import_the_oracle():
                 with open(os.path.join(base, name)) as f:
                     text = f.read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", text, re.M), name
+
+
+def _build_abi_smoke():
+    import subprocess
+    here = os.path.dirname(os.path.abspath(__file__))
+    subprocess.run(["make", "-C", here, "abi_smoke"], check=True, capture_output=True)
+    return os.path.join(here, "abi_smoke")
+
+
+def test_pure_c_driver_builds_and_links():
+    """tests/abi_smoke.c (C99, no Python / C++ in the caller) compiles against include/pq_b200.h
+    and links libpq_b200.so; without a GPU it must stop at pq_create with exit code 2."""
+    import subprocess
+    exe = _build_abi_smoke()
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode in (0, 2), (r.returncode, r.stdout, r.stderr)
+
+
+@pytest.mark.gpu
+def test_pure_c_driver_runs_on_gpu():
+    """The foreign-host call sequence (create -> save -> save_tensors -> contract -> info ->
+    save_output -> load -> permute -> delete) from plain C, checked against a scalar loop."""
+    import subprocess
+    exe = _build_abi_smoke()
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "abi_smoke ok" in r.stdout, (r.returncode, r.stdout, r.stderr)

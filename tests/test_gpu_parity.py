@@ -855,3 +855,65 @@ def test_qft_26_uniform_c64():
     assert abs(np.linalg.norm(psi.astype(np.complex128)) - 1.0) < 1e-4
     assert np.max(np.abs(psi - 2 ** (-n / 2))) < 1e-5 * 2 ** (-n / 2) * 50
     assert b.counters()["n_contract"] == 389
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_batched_save_matches_single_saves(dtype):
+    """pq_save_tensors (one staging block, one H2D, one scatter launch) must leave the store in
+    exactly the state n pq_save_tensor calls do: bit-identical data, conversion to the backend
+    dtype, in-place update of bound leaves (a compiled program sees the new values), rebinding
+    on a size change, rank-0 tensors."""
+    rng = np.random.default_rng(77)
+    items = [("g%d" % i, rand_tensor(rng, shp, np.complex128))
+             for i, shp in enumerate([(2, 2), (2, 2, 2, 2), (2,), (4, 2, 2), (3, 5), (1,), (2, 2, 4)])]
+    items.append(("real64", np.asfortranarray(rng.standard_normal((2, 3)))))
+    items.append(("real32", np.asfortranarray(rng.standard_normal((4,)).astype(np.float32))))
+    items.append(("scalar", np.array(1.5 - 2j)))
+    items.append(("c64src", rand_tensor(rng, (2, 2), np.complex64)))
+    a, b = B200(dtype), B200(dtype)
+    for label, arr in items:
+        a.save_tensor_data(label, arr)
+    b.save_tensors(items)
+    for label, arr in items:
+        x, y = a.load_tensor_data(label), b.load_tensor_data(label)
+        assert x.shape == y.shape == np.asarray(arr).shape
+        assert x.tobytes() == y.tobytes(), label
+    # a program bound to the leaves sees a batched in-place re-save
+    text = "tensor A g0\ntensor B g3\nncon C A -1,1 B 1,-2,-3\nsave C out result\n".replace("g3", "g6")
+    items2 = dict(items)
+    b.save_tensor_data("g6", rand_tensor(rng, (2, 3, 2), np.complex128))
+    prog = b.compile_program(text)
+    prog.run()
+    new_a, new_b = rand_tensor(rng, (2, 2), np.complex128), rand_tensor(rng, (2, 3, 2), np.complex128)
+    b.save_tensors([("g0", new_a), ("g6", new_b)])
+    prog.run()
+    ref = layer1.contract_tensors((new_a, new_b), ([-1, 1], [1, -2, -3]))
+    assert rel_l2(b.load_tensor_data("result"), ref) < TOL[np.dtype(dtype)]
+    # a size change rebinds the label: the program must refuse to run on stale shapes
+    from picoquant_jl_b200.host.b200_backend import B200Error
+    b.save_tensors([("g0", rand_tensor(rng, (3, 3), np.complex128))])
+    with pytest.raises(B200Error):
+        prog.run()
+    assert items2["g0"].shape == (2, 2)
+    # bad arguments leave an error, not a crash
+    with pytest.raises(B200Error):
+        b.save_tensors([("bad", np.zeros((0, 2)))])
+
+
+def test_program_view_starts_are_bounds_checked():
+    """Caller-supplied per-slice view starts outside [1, ext - nsel + 1] must be rejected on the
+    host (BoundsError in the reference, src/layer1.jl:191-194), for run and run_slices."""
+    from picoquant_jl_b200.host.b200_backend import B200Error
+    b = B200(np.complex128)
+    rng = np.random.default_rng(3)
+    b.save_tensor_data("t", rand_tensor(rng, (2, 4, 2), np.complex128))
+    prog = b.compile_program("tensor A t\nview V A 2 2\nsave V out result\n")
+    prog.run([3])
+    assert b.load_tensor_data("result").shape == (2, 1, 2)
+    for bad in ([0], [5], [-1]):
+        with pytest.raises(B200Error):
+            prog.run(bad)
+    with pytest.raises(B200Error):
+        prog.run_slices([[1], [9]], "acc", 2)
+    prog.run_slices([[1], [4]], "acc", 2)
+    assert b.load_tensor_data("acc").shape == (2, 1, 2)
