@@ -188,11 +188,22 @@ int pq_reset_counters(pq_handle* h);
 /* Per-kernel-class CUDA-event timing on the handle's stream (eager mode only).
  * Classes: see pq_kernel_class_name.  Each record accumulates device time, launch
  * count, algorithmic bytes and real flops. */
-#define PQ_NUM_KERNEL_CLASSES 13
+#define PQ_NUM_KERNEL_CLASSES 15
 int pq_profile_enable(pq_handle* h, int on);
 int pq_profile_read(pq_handle* h, double* ms, int64_t* launches, double* bytes,
                     double* flops); /* arrays of PQ_NUM_KERNEL_CLASSES */
 const char* pq_kernel_class_name(int cls);
+
+/* The same per-class figures measured INSIDE the graph replays of pq_program_run_slices
+ * (same lanes, same parallel branches as the timed run): a profiling instance of every
+ * (lane, round) graph carries event-record nodes around each kernel node.  Per class:
+ * `busy_ms` = length of the union of its kernels' [start, end] intervals (concurrent kernels
+ * are not counted twice, so busy_ms <= wall_ms), `sum_ms` = plain sum of durations, launches,
+ * algorithmic bytes and real flops; `wall_ms` = first kernel start to last kernel end.
+ * nslices <= 16 * nlanes.  Results are NOT accumulated anywhere (measurement only). */
+int pq_program_profile_slices(pq_handle* h, pq_program* p, const int32_t* view_starts, int nslices,
+                              int nviews, int nlanes, double* busy_ms, double* sum_ms,
+                              int64_t* launches, double* bytes, double* flops, double* wall_ms);
 
 /* Device-side stopwatch on the handle's stream (CUDA events): `pq_timer_begin` records
  * the start event; `pq_timer_end` records the stop event, waits for it and returns the

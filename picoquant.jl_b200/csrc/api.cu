@@ -29,12 +29,18 @@ void Launch::begin(int cls, double bytes, double flops) const {
     cur.flops = flops;
     cudaEventCreate(&cur.e0);
     cudaEventCreate(&cur.e1);
-    cudaEventRecord(cur.e0, stream);
+    if (external)
+      cudaEventRecordWithFlags(cur.e0, stream, cudaEventRecordExternal);
+    else
+      cudaEventRecord(cur.e0, stream);
   }
 }
 void Launch::end() const {
   if (profile && prof) {
-    cudaEventRecord(cur.e1, stream);
+    if (external)
+      cudaEventRecordWithFlags(cur.e1, stream, cudaEventRecordExternal);
+    else
+      cudaEventRecord(cur.e1, stream);
     prof->push_back(cur);
   }
 }
@@ -636,7 +642,7 @@ extern "C" const char* pq_kernel_class_name(int cls) {
   static const char* names[PQ_NUM_KERNEL_CLASSES] = {
       "permute_tiled", "permute_generic", "contract_small", "contract_direct", "contract_dot",
       "gemm_simt",     "gemm_tensor",     "view",           "accumulate",      "copy",
-      "allreduce",     "svd",             "other"};
+      "allreduce",     "svd",             "other",          "contract_chain",  "gemm_int8"};
   return (cls >= 0 && cls < PQ_NUM_KERNEL_CLASSES) ? names[cls] : "?";
 }
 

@@ -102,9 +102,11 @@ enum KClass {
   KC_COPY = 9,
   KC_ALLREDUCE = 10,
   KC_SVD = 11,
-  KC_OTHER = 12
+  KC_OTHER = 12,
+  KC_CONTRACT_CHAIN = 13,  // k_contract_chain: a group of chains of tiny contractions
+  KC_GEMM_INT8 = 14        // k_zgemm_ozaki*: GEMM-shaped steps on the INT8 tensor pipe (tcgen05 kind::i8)
 };
-static_assert(KC_OTHER + 1 == PQ_NUM_KERNEL_CLASSES, "class count");
+static_assert(KC_GEMM_INT8 + 1 == PQ_NUM_KERNEL_CLASSES, "class count");
 
 struct ProfRecord {
   cudaEvent_t e0, e1;
@@ -134,8 +136,10 @@ struct Launch {
   int elem_size = 16;   // 8 (c64) or 16 (c128)
   int num_sms = 148;
   int64_t* launch_counter = nullptr;
-  // profiling (eager only)
+  // profiling: eager launches record plain events; while a profiling graph is captured
+  // (`external`), the events become event-record NODES of the graph (cudaEventRecordExternal)
   bool profile = false;
+  bool external = false;
   std::vector<ProfRecord>* prof = nullptr;
   mutable ProfRecord cur{};
   void begin(int cls, double bytes, double flops) const;
@@ -200,7 +204,8 @@ struct ChainRange {  // items [begin, begin + count) are executed in order by on
 };
 // false when the plan does not fit a ChainItem (too many fused dims, sizes beyond int)
 bool chain_item_from_plan(const ContractPlan& p, ChainItem& it);
-void run_chains(const Launch& L, const ChainItem* d_items, const ChainRange* d_ranges, int nchains);
+void run_chains(const Launch& L, const ChainItem* d_items, const ChainRange* d_ranges, int nchains,
+                double bytes = 0, double flops = 0);
 
 // operands of the gather-fused ZGEMM kernels (kernels_zgemm.cu, kernels_zgemm_ozaki.cu):
 // C[m + M n] = sum_k A[mA(m) + kA(k)] * B[nB(n) + kB(k)]

@@ -347,9 +347,10 @@ bool chain_item_from_plan(const ContractPlan& p, ChainItem& it) {
   return true;
 }
 
-void run_chains(const Launch& L, const ChainItem* d_items, const ChainRange* d_ranges, int nchains) {
+void run_chains(const Launch& L, const ChainItem* d_items, const ChainRange* d_ranges, int nchains,
+                double bytes, double flops) {
   if (nchains <= 0) return;
-  L.begin(KC_CONTRACT_SMALL, 0, 0);
+  L.begin(KC_CONTRACT_CHAIN, bytes, flops);
   if (L.elem_size == 16)
     k_contract_chain<double><<<nchains, CHAIN_THREADS, 0, L.stream>>>(d_items, d_ranges);
   else
@@ -652,7 +653,7 @@ static void run_contract_t(const Launch& L, const ContractPlan& p, const void* A
       const int oz = L.opt ? (sizeof(R) == 8 ? L.opt->zgemm_ozaki : L.opt->cgemm_ozaki) : 0;
       if (tensor && oz != 0 && ws != nullptr && zgemm_ozaki_kloop_eligible(p.M, p.N, p.K)) {
         // EXPERIMENTAL (options zgemm_ozaki / cgemm_ozaki): INT8 tensor-core product, K in chunks
-        L.begin(KC_GEMM_TENSOR, double(p.M * p.K + p.N * p.K + p.M * p.N) * sizeof(R) * 2,
+        L.begin(KC_GEMM_INT8, double(p.M * p.K + p.N * p.K + p.M * p.N) * sizeof(R) * 2,
                 8.0 * double(p.M) * double(p.N) * double(p.K));
         run_zgemm_ozaki_kloop(L, oz, Ap, Bp, C, p.M, p.N, p.K, ws);
         L.end();

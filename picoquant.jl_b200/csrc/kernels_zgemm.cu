@@ -877,7 +877,7 @@ void run_zgemm_fused(const Launch& L, const ContractPlan& cp, const void* A, con
   {
     const int oz = L.opt ? L.opt->zgemm_ozaki : 0;
     if (oz != 0 && zgemm_ozaki_eligible(cp.M, cp.N, cp.K)) {
-      L.begin(KC_GEMM_TENSOR, bytes, flops);
+      L.begin(KC_GEMM_INT8, bytes, flops);
       run_zgemm_ozaki(L, fp, oz, A, B, C);
       L.end();
       PQ_CUDA(cudaGetLastError());

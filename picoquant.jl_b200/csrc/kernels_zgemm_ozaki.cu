@@ -1013,7 +1013,7 @@ void run_cgemm_ozaki_fused(const Launch& L, const ContractPlan& cp, const void* 
   fp.N = cp.N;
   fp.K = cp.K;
   fp.num_sms = L.num_sms;
-  L.begin(KC_GEMM_TENSOR, double(cp.M * cp.K + cp.N * cp.K + cp.M * cp.N) * 8.0,
+  L.begin(KC_GEMM_INT8, double(cp.M * cp.K + cp.N * cp.K + cp.M * cp.N) * 8.0,
           8.0 * double(cp.M) * double(cp.N) * double(cp.K));
   run_zgemm_ozaki(L, fp, L.opt->cgemm_ozaki, A, B, C);
   L.end();

@@ -485,7 +485,14 @@ static void issue_steps_dag(pq_handle* h, pq_program* p, Launch& L0, int phase, 
     const long long me = counter++;
     if (g >= 0) {
       const pq_program::ChainGroup& G = p->groups[g];
-      run_chains(L, items + G.item_base, p->d_ranges + G.range_base, (int)G.ranges.size());
+      double gbytes = 0, gflops = 0;
+      for (int m : G.steps) {
+        const ContractPlan& c = p->steps[m].cp;
+        gbytes += double(c.M * c.K + c.N * c.K + c.M * c.N) * h->elem_size;
+        gflops += 8.0 * double(c.M) * double(c.N) * double(c.K);
+      }
+      run_chains(L, items + G.item_base, p->d_ranges + G.range_base, (int)G.ranges.size(), gbytes,
+                 gflops);
       // one event for the group: every member maps to it
       PQ_CUDA(cudaEventRecord(p->step_ev[G.first], streams[best]));
       for (int m : G.steps) {
@@ -561,8 +568,15 @@ static void prioritise_small_nodes(cudaGraph_t graph, int num_sms) {
 
 // Executes one phase of the program on the handle's stream: eagerly (profiling / option
 // graph=1) or by launching its CUDA graph, captured on first use.
+// A profiling instance of one graph: the same capture with event-record nodes around every
+// kernel node (pq_program_profile_slices).
+struct ProfCapture {
+  cudaGraphExec_t exec = nullptr;
+  std::vector<ProfRecord> recs;
+};
+
 static void run_phase(pq_handle* h, pq_program* p, Launch& L, int phase, int lane = 0,
-                      cudaStream_t on = nullptr) {
+                      cudaStream_t on = nullptr, ProfCapture* pc = nullptr) {
   // phase -1 = the whole stream as ONE graph (no hoisting): invariant and dependent chains
   // then share the parallel branches
   const int slot = phase < 0 ? 2 : phase;
@@ -576,7 +590,8 @@ static void run_phase(pq_handle* h, pq_program* p, Launch& L, int phase, int lan
   if (eager) {
     issue_steps(h, p, L, phase, w);
   } else {
-    if (!m.exec2[slot]) {
+    cudaGraphExec_t& exec = pc ? pc->exec : m.exec2[slot];
+    if (!exec) {
       // graphs are captured on the handle's stream (nothing executes) and may be launched
       // on any stream
       Launch LC = L;
@@ -584,7 +599,12 @@ static void run_phase(pq_handle* h, pq_program* p, Launch& L, int phase, int lan
       int64_t captured = 0;
       LC.launch_counter = &captured;
       LC.profile = false;
-      if (h->opt.graph != 2) upload_chain_items(h, p, slot, w);
+      if (pc) {   // event-record nodes around every kernel node
+        LC.profile = true;
+        LC.external = true;
+        LC.prof = &pc->recs;
+      }
+      if (h->opt.graph != 2 && !m.chain_items[slot]) upload_chain_items(h, p, slot, w);
       cudaGraph_t graph = nullptr;
       PQ_CUDA(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
       try {
@@ -599,12 +619,12 @@ static void run_phase(pq_handle* h, pq_program* p, Launch& L, int phase, int lan
       }
       PQ_CUDA(cudaStreamEndCapture(h->stream, &graph));
       if (h->opt.prio == 0) prioritise_small_nodes(graph, h->num_sms);
-      cudaError_t e = cudaGraphInstantiate(&m.exec2[slot], graph, 0);
+      cudaError_t e = cudaGraphInstantiate(&exec, graph, 0);
       cudaGraphDestroy(graph);
       PQ_CUDA(e);
       m.graph_launches[slot] = captured;
     }
-    PQ_CUDA(cudaGraphLaunch(m.exec2[slot], on ? on : h->stream));
+    PQ_CUDA(cudaGraphLaunch(exec, on ? on : h->stream));
     h->launches += m.graph_launches[slot];
   }
   h->n_contract += phase < 0 ? p->ncontract : p->ncontract2[phase];
@@ -1200,6 +1220,143 @@ extern "C" int pq_program_run_slices(pq_handle* h, pq_program* p, const int32_t*
     return PQ_ERR_INVALID;
   }
   return PQ_OK;
+}
+
+// Per-class timing measured inside the graph replays (see include/pq_b200.h).  Same launch
+// structure as pq_program_run_slices -- lanes on their own streams, one graph per slice with
+// its parallel branches -- but every (lane, round) uses a profiling instance of the graph whose
+// kernel nodes are bracketed by event-record nodes.  Nothing is published or accumulated.
+extern "C" int pq_program_profile_slices(pq_handle* h, pq_program* p, const int32_t* view_starts,
+                                         int nslices, int nviews, int nlanes, double* busy_ms,
+                                         double* sum_ms, int64_t* launches, double* bytes,
+                                         double* flops, double* wall_ms) {
+  if (!h || !p || nslices <= 0) return PQ_ERR_INVALID;
+  std::vector<std::vector<ProfCapture>> caps;   // [lane][round]
+  cudaEvent_t base = nullptr;
+  int rc = PQ_OK;
+  try {
+    PQ_CUDA(cudaSetDevice(h->device));
+    check_leaves(h, p);
+    PQ_REQUIRE(!(h->profile || h->opt.graph == 1), PQ_ERR_INVALID,
+               "pq_program_profile_slices measures graph replays: not available in eager mode");
+    if (view_starts)
+      PQ_REQUIRE(nviews == p->nviews, PQ_ERR_INVALID,
+                 "pq_program_profile_slices: wrong number of view starts");
+    check_starts(p, view_starts, nslices);
+    if (nlanes < 1) nlanes = 1;
+    if (nlanes > pq_program::MAX_LANES) nlanes = pq_program::MAX_LANES;
+    if (nlanes > nslices) nlanes = nslices;
+    PQ_REQUIRE(nslices <= 16 * nlanes, PQ_ERR_INVALID, "pq_program_profile_slices: too many slices");
+    ensure_lanes(h, p, nlanes);
+    const int rounds = (nslices + nlanes - 1) / nlanes;
+    caps.resize(nlanes);
+    for (auto& c : caps) c.resize(rounds);
+    const bool params = view_starts && p->nviews > 0;
+    int32_t* d_table = nullptr;
+    if (params) {
+      const size_t n = size_t(nslices) * p->nviews;
+      PQ_CUDA(cudaMalloc(&d_table, sizeof(int32_t) * n));
+      cudaError_t e = cudaMemcpy(d_table, view_starts, sizeof(int32_t) * n, cudaMemcpyHostToDevice);
+      if (e != cudaSuccess) {
+        cudaFree(d_table);
+        PQ_CUDA(e);
+      }
+    }
+    Launch L = h->launch_ctx();
+    int64_t dummy = 0;
+    L.launch_counter = &dummy;   // a measurement pass does not count as product launches
+    const int64_t nc0 = h->n_contract, macs0 = h->macs, l0 = h->launches;
+    const bool split = p->hoist;
+    if (split && !p->prepared) {
+      run_phase(h, p, L, 0);
+      p->prepared = true;
+    }
+    // pass 0 captures + instantiates every profiling instance (host-bound: the lanes do not
+    // overlap yet); pass 1 launches them back to back like the timed run and is the one the
+    // events keep
+    PQ_CUDA(cudaEventCreate(&base));
+    for (int pass = 0; pass < 2; ++pass) {
+      PQ_CUDA(cudaStreamSynchronize(h->stream));
+      PQ_CUDA(cudaEventRecord(base, h->stream));
+      PQ_CUDA(cudaEventRecord(p->batch_ev, h->stream));
+      for (int l = 0; l < nlanes; ++l)
+        PQ_CUDA(cudaStreamWaitEvent(p->lanes[l].stream, p->batch_ev, 0));
+      for (int s = 0; s < nslices; ++s) {
+        const int lane = s % nlanes, round = s / nlanes;
+        LaneMem& m = p->lanes[lane];
+        if (params)
+          PQ_CUDA(cudaMemcpyAsync(m.d_starts, d_table + size_t(s) * p->nviews,
+                                  sizeof(int32_t) * p->nviews, cudaMemcpyDeviceToDevice, m.stream));
+        run_phase(h, p, L, split ? 1 : -1, lane, m.stream, &caps[lane][round]);
+      }
+      for (int l = 0; l < nlanes; ++l) PQ_CUDA(cudaStreamSynchronize(p->lanes[l].stream));
+    }
+    if (d_table) cudaFree(d_table);
+    h->n_contract = nc0;
+    h->macs = macs0;
+    h->launches = l0;
+    // intervals relative to `base`
+    struct Iv {
+      float a, b;
+    };
+    std::vector<std::vector<Iv>> iv(PQ_NUM_KERNEL_CLASSES);
+    float first = 1e30f, last = 0;
+    for (int c = 0; c < PQ_NUM_KERNEL_CLASSES; ++c) {
+      if (busy_ms) busy_ms[c] = 0;
+      if (sum_ms) sum_ms[c] = 0;
+      if (launches) launches[c] = 0;
+      if (bytes) bytes[c] = 0;
+      if (flops) flops[c] = 0;
+    }
+    for (auto& lane : caps)
+      for (auto& cap : lane)
+        for (auto& r : cap.recs) {
+          float a = 0, b = 0;
+          PQ_CUDA(cudaEventElapsedTime(&a, base, r.e0));
+          PQ_CUDA(cudaEventElapsedTime(&b, base, r.e1));
+          iv[r.cls].push_back({a, b});
+          if (a < first) first = a;
+          if (b > last) last = b;
+          if (sum_ms) sum_ms[r.cls] += double(b - a);
+          if (launches) launches[r.cls] += 1;
+          if (bytes) bytes[r.cls] += r.bytes;
+          if (flops) flops[r.cls] += r.flops;
+        }
+    for (int c = 0; c < PQ_NUM_KERNEL_CLASSES; ++c) {
+      auto& v = iv[c];
+      std::sort(v.begin(), v.end(), [](const Iv& x, const Iv& y) { return x.a < y.a; });
+      double busy = 0;
+      float ca = 0, cb = -1;
+      for (const Iv& x : v) {
+        if (cb < 0 || x.a > cb) {
+          if (cb >= 0) busy += double(cb - ca);
+          ca = x.a;
+          cb = x.b;
+        } else if (x.b > cb) {
+          cb = x.b;
+        }
+      }
+      if (cb >= 0) busy += double(cb - ca);
+      if (busy_ms) busy_ms[c] = busy;
+    }
+    if (wall_ms) *wall_ms = last > first ? double(last - first) : 0.0;
+  } catch (const Error& e) {
+    h->last_error = e.what();
+    rc = e.code;
+  } catch (const std::exception& e) {
+    h->last_error = e.what();
+    rc = PQ_ERR_INVALID;
+  }
+  for (auto& lane : caps)
+    for (auto& cap : lane) {
+      if (cap.exec) cudaGraphExecDestroy(cap.exec);
+      for (auto& r : cap.recs) {
+        cudaEventDestroy(r.e0);
+        cudaEventDestroy(r.e1);
+      }
+    }
+  if (base) cudaEventDestroy(base);
+  return rc;
 }
 
 extern "C" int pq_program_destroy(pq_handle* h, pq_program* p) {

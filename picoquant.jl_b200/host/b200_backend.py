@@ -27,7 +27,7 @@ LIB_PATH = os.path.join(os.path.dirname(_HERE), "csrc", "libpq_b200.so")
 PQ_C64, PQ_C128 = 0, 1
 PQ_HOST_F32, PQ_HOST_F64, PQ_HOST_C64, PQ_HOST_C128 = 0, 1, 2, 3
 PQ_MAX_RANK = 64
-PQ_NUM_KERNEL_CLASSES = 13
+PQ_NUM_KERNEL_CLASSES = 15
 
 _STATUS = {-1: "PQ_ERR_INVALID", -2: "PQ_ERR_NOT_FOUND", -3: "PQ_ERR_SHAPE", -4: "PQ_ERR_CUDA",
            -5: "PQ_ERR_NCCL", -6: "PQ_ERR_PARSE", -7: "PQ_ERR_UNSUPPORTED"}
@@ -42,7 +42,7 @@ ABI_SYMBOLS = [
     "pq_reset_counters", "pq_profile_enable", "pq_profile_read", "pq_kernel_class_name",
     "pq_set_option", "pq_microbench", "pq_timer_begin", "pq_timer_end",
     "pq_program_set_hoist", "pq_program_prepare", "pq_program_hoist_stats",
-    "pq_program_run_slices", "pq_decompose", "pq_save_tensors",
+    "pq_program_run_slices", "pq_decompose", "pq_save_tensors", "pq_program_profile_slices",
 ]
 
 _lib = None
@@ -93,6 +93,9 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
     lib.pq_program_num_views.argtypes = [c_void_p]
     lib.pq_program_run.argtypes = [c_void_p, c_void_p, i32p, c_int, c_char_p]
     lib.pq_program_run_slices.argtypes = [c_void_p, c_void_p, i32p, c_int, c_int, c_char_p, c_int]
+    dp = POINTER(c_double)
+    lib.pq_program_profile_slices.argtypes = [c_void_p, c_void_p, i32p, c_int, c_int, c_int, dp, dp,
+                                              i64p, dp, dp, dp]
     lib.pq_program_destroy.argtypes = [c_void_p, c_void_p]
     lib.pq_program_stats.argtypes = [c_void_p, i64p, i64p, i64p]
     lib.pq_program_set_hoist.argtypes = [c_void_p, c_int]
@@ -170,6 +173,31 @@ class Program:
         acc = accumulate_into.encode() if accumulate_into else None
         b._check(b.lib.pq_program_run_slices(b._h, self._p, flat if nv else None, n, nv, acc,
                                              int(lanes)))
+
+    def profile_slices(self, view_starts: Sequence[Sequence[int]], lanes: int = 1) -> dict:
+        """Per-kernel-class timing measured INSIDE the graph replays of the slice loop
+        (``pq_program_profile_slices``): same lanes and parallel branches as ``run_slices``,
+        with event-record nodes around every kernel node.  Returns ``{"wall_ms": ..,
+        "classes": {name: {busy_ms, sum_ms, launches, bytes, flops}}}``; ``busy_ms`` is the
+        union of the class's kernel intervals (<= wall_ms)."""
+        b = self.backend
+        n = len(view_starts)
+        nv = len(view_starts[0]) if n else 0
+        flat = _i32([v for row in view_starts for v in row])
+        k = PQ_NUM_KERNEL_CLASSES
+        busy, tot = (c_double * k)(), (c_double * k)()
+        la = (c_int64 * k)()
+        by, fl = (c_double * k)(), (c_double * k)()
+        wall = c_double()
+        b._check(b.lib.pq_program_profile_slices(b._h, self._p, flat if nv else None, n, nv,
+                                                 int(lanes), busy, tot, la, by, fl, byref(wall)))
+        classes = {}
+        for i in range(k):
+            if la[i]:
+                classes[b.lib.pq_kernel_class_name(i).decode()] = {
+                    "busy_ms": busy[i], "sum_ms": tot[i], "launches": la[i], "bytes": by[i],
+                    "flops": fl[i]}
+        return {"wall_ms": wall.value, "classes": classes}
 
     def close(self) -> None:
         if self._p:

@@ -107,7 +107,7 @@ def test_ozaki_long_contraction_matches_oracle(case, dtype, groups, tol):
     b.save_tensor_data("B", B)
     b.profile_enable(True)
     b.contract_tensors("A", ai, "B", bi, "C")
-    assert "gemm_tensor" in b.profile_read()
+    assert "gemm_int8" in b.profile_read()
     assert rel_l2(b.load_tensor_data("C"), ref.load_tensor_data("C")) < tol
     b.close()
 
