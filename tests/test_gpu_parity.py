@@ -846,6 +846,58 @@ def test_qft_20_closed_form(dtype):
     assert rel_l2(switch_endianness(psi), ref_be) < tol
 
 
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_qft_26_closed_form(dtype):
+    """config 3 at full size (2^26 amplitudes) with a NON-trivial basis input, so every cu1
+    phase matters: the closed form of test/algorithms_tests.jl:39-82 (normalised inverse DFT
+    in big-endian indexing), rel-L2 at 1x the north-star tolerance, both element types."""
+    n = 26
+    tol = TOL[np.dtype(dtype)]
+    circ = create_qft_circuit(n)
+    x_le = 0b10110011100011110001101101
+    cfg = "".join("1" if (x_le >> q) & 1 else "0" for q in range(n))
+    x_be = int(cfg, 2)
+    b = B200(dtype)
+    psi = statevector(circ, b, input_config=cfg)
+    assert psi.shape == (2 ** n,) and b.counters()["n_contract"] == 389
+    b.close()
+    psi_be = switch_endianness(psi)
+    del psi
+    num = den = 0.0
+    step = 2 ** 22   # closed form in blocks (keeps the host footprint small)
+    for k0 in range(0, 2 ** n, step):
+        k = np.arange(k0, k0 + step, dtype=np.int64)
+        ref = np.exp(2j * np.pi * ((x_be * k) % (2 ** n)) / 2 ** n) * 2 ** (-n / 2)
+        d = psi_be[k0:k0 + step].astype(np.complex128) - ref
+        num += float(np.vdot(d, d).real)
+        den += float(np.vdot(ref, ref).real)
+    assert np.sqrt(num / den) < tol, np.sqrt(num / den)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_config5_rqc_7x7_d24_slices_vs_oracle(dtype):
+    """BASELINE config 5 at full size (the bench workload): 7x7 depth-24 RQC, decomposed,
+    P = 64 slices, sweep plan.  The device partial sum of four slices (first, two middle,
+    last; two lanes, like the timed loop) against the ComplexF64 oracle interpreting the
+    same command streams, at 1x the tolerance (test/layer2_tests.jl:419-455 at scale)."""
+    tol = TOL[np.dtype(dtype)]
+    circ = create_RQC(7, 7, 24, seed=0)
+    n = circ.n_qubits
+
+    def plan_fn(tn, sliced):
+        return sweep_plan(tn, 7, 7, sliced_bonds=sliced)
+
+    rec = record_sliced_contraction(circ, 64, 1, plan_fn=plan_fn, output_config="0" * n)
+    sample = [1, 22, 43, 64]
+    ref = oracle_sliced_amplitude(rec, sample)
+    b = B200(dtype)
+    sc = SlicedContraction(b, rec)
+    sc.run(sample, lanes=2)
+    got = sc.result()
+    assert close(got, ref, tol), (got, ref, abs(complex(got) - ref) / abs(ref))
+    b.close()
+
+
 def test_qft_26_uniform_c64():
     """config 3 at full size (2^26 amplitudes, ComplexF32): uniform superposition."""
     n = 26
