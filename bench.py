@@ -75,6 +75,8 @@ def parse_args():
                     help="EXPERIMENTAL: route the skinny ComplexF64 GEMM steps to the INT8 tensor-core "
                          "Ozaki kernel: 6 / 7 accumulator groups with --dtype c128 (option zgemm_ozaki), 3 / 4 with "
                          "--dtype c64 (option cgemm_ozaki); default off")
+    ap.add_argument("--no-int8", action="store_true",
+                    help="option ozaki_auto = 0: keep the skinny GEMM steps on DMMA / tcgen05 3xTF32 (A/B)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
     a = ap.parse_args()
@@ -364,7 +366,10 @@ def config_arm(a):
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
     from picoquant_jl_b200.host.b200_backend import B200Backend
     b = B200Backend(dtype, device=0)
-    if a.ozaki:   # EXPERIMENTAL INT8 tensor-core GEMMs (off by default)
+    if a.no_int8:
+        b.set_option("ozaki_auto", 0)
+        cfg["ozaki_auto"] = 0
+    if a.ozaki:   # forced INT8 tensor-core GEMMs (incl. the experimental K-looped kernel)
         if (a.dtype == "c128") != (a.ozaki in (6, 7)):
             raise SystemExit("--ozaki 6|7 goes with --dtype c128, --ozaki 3|4 with --dtype c64")
         b.set_option("zgemm_ozaki" if a.dtype == "c128" else "cgemm_ozaki", a.ozaki)
@@ -586,6 +591,8 @@ def main():
     mine = partitions_of_rank(a.slices, rank, world)
 
     b = B200Backend(dtype, device=local_rank)
+    if a.no_int8:
+        b.set_option("ozaki_auto", 0)
     if a.ozaki:
         if (a.dtype == "c128") != (a.ozaki in (6, 7)):
             raise SystemExit("--ozaki 6|7 goes with --dtype c128, --ozaki 3|4 with --dtype c64")
@@ -777,13 +784,13 @@ def main():
             # (algorithmic operand + result bytes) or the INT8 tensor pipe, whose complex-flop
             # equivalent is the measured kind::i8 issue rate over the int8 MACs one complex MAC
             # costs (4 real products x digit-plane pairs)
-            pairs = {6: 21, 7: 26, 3: 6, 4: 10}.get(oz_groups, 21)
+            pairs = {6: 21, 7: 26, 3: 6, 4: 10}.get(oz_groups, 21 if a.dtype == "c128" else 10)
             tops = b.microbench("umma_i8_tops_n64")
             peaks["umma_i8_tops_n64"] = tops
             tensor_peak = tops * 8.0 / (2.0 * 4.0 * pairs)
             f_t = kernels[dom]["achieved_tflops"] / tensor_peak
             f_h = kernels[dom]["achieved_gbs"] / peaks["hbm_gbs"]
-            common = {"kernel": "gemm_int8 (k_zgemm_ozaki)", "traffic": traffic, "traffic_source": traffic_src,
+            common = {"kernel": "gemm_int8 (k_ozaki_t, tcgen05.mma kind::i8)", "traffic": traffic, "traffic_source": traffic_src,
                       "share_of_timed_slice": share, "frac_hbm": f_h, "frac_int8_pipe": f_t,
                       "achieved_tflops_algorithmic": kernels[dom]["achieved_tflops"]}
             if f_h >= f_t:
@@ -883,7 +890,7 @@ def main():
                                                        if c == "ncon"),
                        "kernel_launches_per_slice": sc.program.launches,
                        "arena_bytes": sc.program.arena_bytes, "parallelism": "slices/%d" % world,
-                       "slices_in_flight_per_gpu": a.lanes, "zgemm_ozaki": a.ozaki,
+                       "slices_in_flight_per_gpu": a.lanes, "zgemm_ozaki": a.ozaki, "ozaki_auto": 0 if a.no_int8 else 1,
                        "l2": "inputs larger than L2: per-step intermediates of 2^24 elements "
                              "(256 MiB c128) stream through the 126 MB L2"},
             "amplitude_wall_ms": ms_per_step,

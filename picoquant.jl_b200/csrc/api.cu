@@ -126,6 +126,7 @@ extern "C" int pq_create(int device, int dtype, pq_handle** out) {
     init_kernels();
     init_kernels_cgemm();
     init_kernels_ozaki();
+    init_kernels_ozaki_t();
   } catch (const std::exception&) {
     delete h;
     return PQ_ERR_CUDA;
@@ -697,6 +698,8 @@ extern "C" int pq_set_option(pq_handle* h, const char* key, int value) {
     }
     h->opt.zgemm_ozaki = value;
   }
+  else if (k == "ozaki_gen") h->opt.ozaki_gen = value;
+  else if (k == "ozaki_auto") h->opt.ozaki_auto = value;
   else if (k == "zgemm_cfg") h->opt.zgemm_cfg = value;
   else if (k == "zgemm_kfirst") h->opt.zgemm_kfirst = value;
   else {

@@ -124,6 +124,8 @@ struct Options {
   int zgemm_skinny = 0;   // persistent skinny fused ZGEMM: 0 auto, 1 off
   int zgemm_ozaki = 0;    // EXPERIMENTAL int8 tensor-core ZGEMM (kernels_zgemm_ozaki.cu): 0 off, 6 / 7 = accumulator groups
   int cgemm_ozaki = 0;    // EXPERIMENTAL, ComplexF32 twin of zgemm_ozaki: 0 off, 3 / 4 = accumulator groups
+  int ozaki_gen = 0;      // which INT8 kernel serves K, N <= 64 at 6 / 4 groups: 0 = k_ozaki_t (second generation), 1 = k_zgemm_ozaki
+  int ozaki_auto = 1;     // 1 (default): GEMM-shaped steps inside ozaki_t_preferred() run on k_ozaki_t (INT8 tensor cores); 0: never unless forced by zgemm_ozaki / cgemm_ozaki
   int zgemm_stagger = 0;  // ns of start delay per resident-CTA slot in the first wave (0 = off)
   int chain = 0;    // compiled programs: 0 = batch chains of tiny contractions into one launch, 1 = off
   int prio = 0;     // 0: small-grid graph nodes get the highest launch priority, 1: off
@@ -220,9 +222,24 @@ struct FusedParams {
 
 void init_kernels_ozaki();
 double run_ozaki_microbench(const Launch& L, const std::string& what);
+// second-generation kernel (kernels_zgemm_ozaki2.cu): transposed, K-concatenated, warp-specialised
+void init_kernels_ozaki_t();
+double run_ozaki_t_microbench(const Launch& L, const std::string& what);
+void run_zgemm_ozaki_t(const Launch& L, const FusedParams& fp, const void* A, const void* B, void* C);
 // envelope of the INT8 Ozaki kernel: all of K and N resident per tile
 inline bool zgemm_ozaki_eligible(int64_t M, int64_t N, int64_t K) {
   return K >= 1 && K <= 64 && N >= 1 && N <= 64 && M >= 1;
+}
+// Default policy (option ozaki_auto): which GEMM-shaped steps run on k_ozaki_t, from the
+// per-shape timings on B200 (profiles/ozaki_t_probe_r02.json).  ComplexF64: the steps the FP64
+// tensor pipe bounds (K >= 32 with N >= 32: 167 vs 267 us at M = 2^18, N = K = 64); the
+// HBM-bound K <= 16 steps stay on the persistent DMMA kernel (81 vs 108 us).  ComplexF32: every
+// skinny step (the alternative is a K1 permute + tcgen05 3xTF32 on canonical layouts: 109 vs
+// 245 us, and 4.5e-8 instead of 3.4e-7 relative error).
+inline bool ozaki_t_preferred(int elem_size, int64_t M, int64_t N, int64_t K) {
+  if (!zgemm_ozaki_eligible(M, N, K) || M < 4096) return false;
+  if (elem_size == 16) return K >= 32 && N >= 32;
+  return N > 16 || K > 16;
 }
 // long contractions (64 < K <= 8192) on canonical layouts; ws = (M + N) ints
 inline bool zgemm_ozaki_kloop_eligible(int64_t M, int64_t N, int64_t K) {

@@ -875,7 +875,10 @@ void run_zgemm_fused(const Launch& L, const ContractPlan& cp, const void* A, con
   if (cfg == 3) akf = bkf = false;  // measured: no gain for the narrow tiles (HBM-bound)
   // EXPERIMENTAL (off unless option "zgemm_ozaki" = 6 / 7): INT8 tensor-core Ozaki product
   {
-    const int oz = L.opt ? L.opt->zgemm_ozaki : 0;
+    int oz = L.opt ? L.opt->zgemm_ozaki : 0;
+    if (oz == 0 && (L.opt == nullptr || (L.opt->ozaki_auto != 0 && L.opt->zgemm_cfg == 0 && L.opt->zgemm_skinny == 0)) &&
+        ozaki_t_preferred(16, cp.M, cp.N, cp.K))
+      oz = 6;   // default policy: k_ozaki_t
     if (oz != 0 && zgemm_ozaki_eligible(cp.M, cp.N, cp.K)) {
       L.begin(KC_GEMM_INT8, bytes, flops);
       run_zgemm_ozaki(L, fp, oz, A, B, C);

@@ -933,6 +933,10 @@ void run_zgemm_ozaki(const Launch& L, const FusedParams& fp, int groups, const v
                      const void* B, void* C) {
   PQ_REQUIRE(g_ozaki_ready, PQ_ERR_UNSUPPORTED, "ozaki GEMM: kernel attributes could not be set");
   PQ_REQUIRE(zgemm_ozaki_eligible(fp.M, fp.N, fp.K), PQ_ERR_INVALID, "ozaki GEMM: K, N <= 64 only");
+  if ((L.opt == nullptr || L.opt->ozaki_gen == 0) && groups == (L.elem_size == 16 ? 6 : 4)) {
+    run_zgemm_ozaki_t(L, fp, A, B, C);   // second-generation kernel (kernels_zgemm_ozaki2.cu)
+    return;
+  }
   const long long tiles = (fp.M + OZ_TM - 1) / OZ_TM;
   const unsigned grid = (unsigned)(tiles < L.num_sms ? tiles : L.num_sms);
   if (L.elem_size == 16) {
@@ -1002,8 +1006,8 @@ void run_zgemm_ozaki_kloop(const Launch& L, int groups, const void* A, const voi
 
 void run_cgemm_ozaki_fused(const Launch& L, const ContractPlan& cp, const void* A, const void* B,
                            void* C) {
-  PQ_REQUIRE(L.elem_size == 8 && L.opt && L.opt->cgemm_ozaki != 0, PQ_ERR_INVALID,
-             "fused ComplexF32 GEMM plans exist only with option cgemm_ozaki");
+  PQ_REQUIRE(L.elem_size == 8, PQ_ERR_INVALID, "fused ComplexF32 GEMM plans run on the INT8 kernel only");
+  const int groups = (L.opt && L.opt->cgemm_ozaki != 0) ? L.opt->cgemm_ozaki : 4;
   FusedParams fp{};
   fp.mA = cp.mA;
   fp.kA = cp.kA;
@@ -1015,7 +1019,7 @@ void run_cgemm_ozaki_fused(const Launch& L, const ContractPlan& cp, const void* 
   fp.num_sms = L.num_sms;
   L.begin(KC_GEMM_INT8, double(cp.M * cp.K + cp.N * cp.K + cp.M * cp.N) * 8.0,
           8.0 * double(cp.M) * double(cp.N) * double(cp.K));
-  run_zgemm_ozaki(L, fp, L.opt->cgemm_ozaki, A, B, C);
+  run_zgemm_ozaki(L, fp, groups, A, B, C);
   L.end();
   PQ_CUDA(cudaGetLastError());
 }

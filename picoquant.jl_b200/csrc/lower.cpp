@@ -327,9 +327,10 @@ ContractPlan lower_contract(const std::vector<int64_t>& a_dims, const std::vecto
     // go through canonical layouts to the K-looped INT8 kernel instead of the fused DMMA GEMM
     if (opt.zgemm_ozaki != 0 && zgemm_ozaki_kloop_eligible(M, N, K)) P.fused_gemm = false;
   }
-  if (P.kind == CK_GEMM && elem_size == 8 && opt.cgemm_ozaki != 0 && opt.fused == 0 &&
-      (opt.gemm == 0 || opt.gemm == 2) && zgemm_ozaki_eligible(M, N, K)) {
-    // EXPERIMENTAL: ComplexF32 skinny steps on the INT8 tensor-core kernel, gather fused
+  if (P.kind == CK_GEMM && elem_size == 8 && opt.fused == 0 && (opt.gemm == 0 || opt.gemm == 2) &&
+      ((opt.cgemm_ozaki != 0 && zgemm_ozaki_eligible(M, N, K)) ||
+       (opt.cgemm_ozaki == 0 && opt.ozaki_auto != 0 && ozaki_t_preferred(8, M, N, K)))) {
+    // ComplexF32 skinny steps on the INT8 tensor-core kernel, gather fused (no K1 pass)
     int64_t ka = 0, kb = 0;
     for (int d = 0; d < P.kA.nd; ++d) {
       ka += (P.kA.ext[d] - 1) * P.kA.str[d];

@@ -481,6 +481,196 @@ static double ozaki_tile_error(std::mt19937& rng, int Mrows, int N, int K, doubl
   return (double)std::sqrt(num / den);
 }
 
+// Second-generation kernel (kernels_zgemm_ozaki2.cu: k_ozaki_t): W = resident B planes (128 rows,
+// rows 2n / 2n+1 = Cr / Ci of column n, contraction [re half | im half]), X = a 64-row tile of
+// A; the same host-side execution of the kernel's own arithmetic (ozaki_math.h, namespace ot).
+// constant != 0: every entry of A and B is (constant, constant) -- the largest accumulator sums.
+template <class Real>
+static double ozaki_t_tile_error(std::mt19937& rng, int Mrows, int N, int K, double spread_sigma,
+                                 double sparsity, double big = 1.0, double constant = 0.0) {
+  using Tr = oz::Traits<Real>;
+  namespace ot = oz::ot;
+  typedef std::complex<Real> cr;
+  constexpr int S = Tr::S, G = Tr::S;
+  const int KC = (K + 15) / 16;
+  std::normal_distribution<double> g(0.0, 1.0);
+  std::uniform_real_distribution<double> u(0.0, 1.0);
+  auto draw = [&]() {
+    if (constant != 0.0) return (Real)constant;
+    if (u(rng) < sparsity) return (Real)0;
+    return (Real)(g(rng) * std::exp(spread_sigma * g(rng)));
+  };
+  const Real tiny = sizeof(Real) == 8 ? (Real)1e-300 : (Real)1e-30;
+  std::vector<cr> A((size_t)Mrows * K), B((size_t)N * K);   // A[m + Mrows k], B[n + N k]
+  for (auto& x : A) x = cr(draw(), draw());
+  for (auto& x : B) x = cr(draw(), draw());
+  if (big != 1.0) {
+    for (int r = 0; r < Mrows; ++r)
+      for (int k = 0; k < K; ++k) A[r + (size_t)Mrows * k] *= (Real)((r & 1) ? big : 1.0 / big);
+    for (int n = 0; n < N; ++n)
+      for (int k = 0; k < K; ++k) B[n + (size_t)N * k] *= (Real)((n & 1) ? 1.0 / big : big);
+  }
+  if (Mrows > 3 && constant == 0.0)
+    for (int k = 0; k < K; ++k) A[3 + (size_t)Mrows * k] = (Real)0;
+  if (Mrows > 5 && constant == 0.0)
+    for (int k = 0; k < K; ++k) A[5 + (size_t)Mrows * k] *= tiny;
+
+  std::vector<unsigned char> sW((size_t)S * ot::W_PLANE, 0xAB), sX((size_t)S * ot::X_PLANE, 0xCD);
+  std::vector<int> rowE(ot::ROWS, 0), colE(64, 0);
+  // the kernel's work items: (row or column, 16-k chunk), exponent = max over the chunks
+  auto gather = [&](const cr* src, size_t ld, bool valid, int c, Real* xr, Real* xi) {
+    int key = 0;
+    for (int i = 0; i < 16; ++i) {
+      const int k = c * 16 + i;
+      const cr v = (valid && k < K) ? src[(size_t)k * ld] : cr(0, 0);
+      xr[i] = v.real();
+      xi[i] = v.imag();
+      key = std::max(key, std::max(Tr::key(v.real()), Tr::key(v.imag())));
+    }
+    return key;
+  };
+  Real xr[16], xi[16];
+  for (int n = 0; n < 64; ++n) {
+    int key = 0;
+    for (int c = 0; c < 4; ++c) key = std::max(key, gather(&B[n < N ? n : 0], N, n < N && c < KC, c, xr, xi));
+    colE[n] = Tr::exp_field(key);
+    if (sizeof(Real) == 8) colE[n] = ot::field_clamp(colE[n]);   // OtScale<double>::col_field
+    for (int c = 0; c < KC; ++c) {
+      gather(&B[n < N ? n : 0], N, n < N, c, xr, xi);
+      ot::w_item<Real>(sW.data(), n, c, KC, xr, xi, Tr::slice_scale(colE[n]));
+    }
+  }
+  for (int j = 0; j < ot::ROWS; ++j) {
+    int key = 0;
+    for (int c = 0; c < 4; ++c)
+      key = std::max(key, gather(&A[j < Mrows ? j : 0], Mrows, j < Mrows && c < KC, c, xr, xi));
+    rowE[j] = Tr::exp_field(key);
+    if (sizeof(Real) == 8) rowE[j] = ot::field_clamp(rowE[j]);   // OtScale<double>::row_field
+    for (int c = 0; c < KC; ++c) {
+      gather(&A[j < Mrows ? j : 0], Mrows, j < Mrows, c, xr, xi);
+      ot::x_item<Real>(sX.data(), j, c, KC, xr, xi, Tr::slice_scale(rowE[j]));
+    }
+  }
+  auto elem = [&](const std::vector<unsigned char>& buf, size_t base, int lbo, int row, int k) {
+    return (int)(int8_t)buf[base + (size_t)(k / 16) * lbo + (size_t)(row / 8) * ot::SBO + (row % 8) * 16 + k % 16];
+  };
+  // the digits of X reconstruct q exactly, re half and im half
+  for (int j = 0; j < std::min(Mrows, 8); ++j)
+    for (int k = 0; k < K; ++k) {
+      long long qr = 0, qi = 0;
+      for (int s = 0; s < S; ++s) {
+        qr = qr * 256 + elem(sX, (size_t)s * ot::X_PLANE, ot::X_LBO, j, k);
+        qi = qi * 256 + elem(sX, (size_t)s * ot::X_PLANE, ot::X_LBO, j, KC * 16 + k);
+      }
+      const double sc = (double)Tr::slice_scale(rowE[j]);
+      CHECK(qr == std::llrint((double)A[j + (size_t)Mrows * k].real() * sc) &&
+                qi == std::llrint((double)A[j + (size_t)Mrows * k].imag() * sc),
+            "ozaki_t digits of A[%d,%d]", j, k);
+    }
+  // MMA schedule: D[group][W row][tile row], int32 with an overflow watch
+  std::vector<int32_t> acc((size_t)G * ot::WROWS * ot::ROWS, 0);
+  long long worst = 0;
+  int mmas = 0;
+  for (int grp = 0; grp < G; ++grp)
+    ot::for_each_mma_of_group<S>(grp, KC, [&](int wp, int xp, int ks, unsigned accumulate) {
+      ++mmas;
+      const size_t wb = (size_t)wp * ot::W_PLANE + (size_t)ks * 2 * ot::W_LBO;
+      const size_t xb = (size_t)xp * ot::X_PLANE + (size_t)ks * 2 * ot::X_LBO;
+      for (int l = 0; l < ot::WROWS; ++l)
+        for (int j = 0; j < ot::ROWS; ++j) {
+          long long sum = 0;
+          for (int k = 0; k < 32; ++k) sum += elem(sW, wb, ot::W_LBO, l, k) * elem(sX, xb, ot::X_LBO, j, k);
+          int32_t& a = acc[((size_t)grp * ot::WROWS + l) * ot::ROWS + j];
+          const long long v = (accumulate ? (long long)a : 0) + sum;
+          worst = std::max(worst, std::llabs(v));
+          a = (int32_t)v;
+        }
+    });
+  CHECK(mmas == (S * (S + 1) / 2) * KC, "ozaki_t MMA count %d", mmas);
+  CHECK(worst < (1ll << 31), "ozaki_t int32 accumulator overflow: %lld", worst);
+  std::vector<std::complex<double>> C((size_t)Mrows * N);
+  for (int n = 0; n < N; ++n)
+    for (int j = 0; j < Mrows; ++j) {
+      double out[2];
+      for (int part = 0; part < 2; ++part) {
+        int r[G];
+        long long exact = 0;
+        for (int grp = 0; grp < G; ++grp) {
+          r[grp] = acc[((size_t)grp * ot::WROWS + ot::w_row(n, part)) * ot::ROWS + j];
+          exact = exact * 256 + r[grp];
+        }
+        // the int32 pair sums inside combine() must not wrap
+        CHECK(std::llabs((long long)r[0] * 256 + r[1]) < (1ll << 31) &&
+                  std::llabs((long long)r[2] * 256 + r[3]) < (1ll << 31),
+              "ozaki_t pair sum overflow");
+        const long long v = ot::combine<G>(r);
+        CHECK(v == exact, "ozaki_t combine: %lld vs %lld", v, exact);
+        const double want = (double)v * (Tr::out_scale(colE[n]) * ot::group_weight<G>() * Tr::out_scale(rowE[j]));
+        if (sizeof(Real) == 8) {   // OtScale<double>::apply: both scales inside the conversion, two DADDs
+          using Td = oz::Traits<double>;
+          const bool dead = colE[n] < Td::MIN_EF || colE[n] >= 2047;
+          const ot::DoubleMagic m = ot::double_magic(dead ? 0 : Td::out_exp(colE[n]) - 8 * (G - 1), colE[n] >= 2047);
+          CHECK(ot::to_double_scaled(v, ot::double_magic(0, false), 0) == (double)v, "ozaki_t to_double(%lld)", v);
+          out[part] = ot::to_double_scaled(v, m, ot::row_word(rowE[j]));
+          // identical to the plain product (flushed rows / columns have v == 0)
+          CHECK(out[part] == want || (v == 0 && out[part] == 0.0), "ozaki_t double scaling: %g vs %g", out[part], want);
+        } else {                   // OtScale<float>::apply: FP32 only, row scale first
+          using Tf = oz::Traits<float>;
+          const float f = (ot::combine_f32(r) * Tf::out_scale_f(rowE[j], 0)) * Tf::out_scale_f(colE[n], -8 * (G - 1));
+          out[part] = (double)f;
+          // within one ulp of the correctly rounded result
+          CHECK(std::fabs(out[part] - want) <= std::fabs(want) * 1.2e-7 + 1e-44, "ozaki_t float scaling: %g vs %g", out[part], want);
+        }
+      }
+      C[j + (size_t)Mrows * n] = std::complex<double>(out[0], out[1]);
+    }
+  long double num = 0, den = 0;
+  for (int r = 0; r < Mrows; ++r)
+    for (int n = 0; n < N; ++n) {
+      long double rr = 0, ri = 0;
+      for (int k = 0; k < K; ++k) {
+        const cr a = A[r + (size_t)Mrows * k], b = B[n + (size_t)N * k];
+        rr += (long double)a.real() * b.real() - (long double)a.imag() * b.imag();
+        ri += (long double)a.real() * b.imag() + (long double)a.imag() * b.real();
+      }
+      const std::complex<double> got = C[r + (size_t)Mrows * n];
+      if (r == 5 && constant == 0.0) continue;
+      long double w = 1.0L;
+      if (big != 1.0) w = ((r & 1) ? 1.0L / big : (long double)big) * ((n & 1) ? (long double)big : 1.0L / big);
+      num += w * w * ((got.real() - rr) * (got.real() - rr) + (got.imag() - ri) * (got.imag() - ri));
+      den += w * w * (rr * rr + ri * ri);
+      if (r == 3 && constant == 0.0) CHECK(got == std::complex<double>(0, 0), "ozaki_t: zero row must give exact zeros");
+    }
+  return (double)std::sqrt(num / den);
+}
+
+static void test_ozaki_t(std::mt19937& rng) {
+  struct Case { int M, N, K; double sigma, sparsity, tol64, tol32; };
+  const Case cases[] = {
+      {64, 64, 64, 0.0, 0.0, 1e-12, 1e-7}, {64, 64, 64, 3.0, 0.0, 5e-11, 5e-7}, {50, 33, 40, 0.0, 0.3, 1e-12, 1e-7},
+      {64, 64, 32, 0.0, 0.0, 1e-12, 1e-7}, {64, 64, 8, 0.0, 0.0, 1e-12, 1e-7},  {17, 5, 1, 0.0, 0.0, 1e-12, 1e-7},
+      {64, 32, 17, 1.0, 0.5, 5e-12, 2e-7}, {64, 64, 48, 0.0, 0.0, 1e-12, 1e-7},
+  };
+  for (const Case& c : cases) {
+    const double e64 = ozaki_t_tile_error<double>(rng, c.M, c.N, c.K, c.sigma, c.sparsity);
+    const double e32 = ozaki_t_tile_error<float>(rng, c.M, c.N, c.K, c.sigma, c.sparsity);
+    CHECK(e64 < c.tol64, "ozaki_t c128 M=%d N=%d K=%d: rel-L2 %.3e", c.M, c.N, c.K, e64);
+    CHECK(e32 < c.tol32, "ozaki_t c64 M=%d N=%d K=%d: rel-L2 %.3e", c.M, c.N, c.K, e32);
+    std::printf("ozaki_t M=%d N=%d K=%d sigma=%.0f: rel-L2 c128 %.2e, c64 %.2e\n", c.M, c.N, c.K, c.sigma, e64, e32);
+  }
+  {
+    const double e64 = ozaki_t_tile_error<double>(rng, 64, 48, 64, 0.0, 0.0, 1e140);
+    const double e32 = ozaki_t_tile_error<float>(rng, 64, 48, 64, 0.0, 0.0, 1e15);
+    CHECK(e64 < 1e-12 && e32 < 1e-7, "ozaki_t scale range: %.3e %.3e", e64, e32);
+  }
+  for (double cst : {1.0, 1.9999999, -1.0, 1.0000001}) {   // largest sums: every product has the same sign
+    const double e64 = ozaki_t_tile_error<double>(rng, 64, 64, 64, 0.0, 0.0, 1.0, cst);
+    const double e32 = ozaki_t_tile_error<float>(rng, 64, 64, 64, 0.0, 0.0, 1.0, cst);
+    CHECK(e64 < 1e-12 && e32 < 1e-7, "ozaki_t constant %.7f: %.3e %.3e", cst, e64, e32);
+  }
+  std::printf("ozaki_t (second-generation kernel arithmetic): ok\n");
+}
+
 template <class Real>
 static void check_digits_by_hand() {
   using Tr = oz::Traits<Real>;
@@ -515,7 +705,21 @@ static void test_ozaki_lowering() {
   for (int j = 0; j < 6; ++j) bi.push_back(-(o + 1 + j));
   Options opt;
   ContractPlan P = lower_contract(ad, ai, bd, bi, 8, opt);
-  CHECK(P.kind == CK_GEMM && !P.fused_gemm && P.tempA_bytes > 0, "c64 default: materialised TTGT");
+  CHECK(P.kind == CK_GEMM && P.fused_gemm && P.tempA_bytes == 0, "c64 default (ozaki_auto): gather fused, k_ozaki_t");
+  opt.ozaki_auto = 0;
+  P = lower_contract(ad, ai, bd, bi, 8, opt);
+  CHECK(P.kind == CK_GEMM && !P.fused_gemm && P.tempA_bytes > 0, "c64 with ozaki_auto = 0: materialised TTGT");
+  {   // below the policy's envelope (M < 4096) the materialised path stays
+    std::vector<int64_t> as(12, 2);
+    std::vector<int32_t> ais = {-1, -2, -3, 1, 2, 3, -4, -5, -6, 4, 5, 6};
+    Options od;
+    ContractPlan Q = lower_contract(as, ais, bd, bi, 8, od);
+    CHECK(Q.kind == CK_GEMM && !Q.fused_gemm && Q.M == 64, "c64 default, small M: materialised TTGT");
+    CHECK(ozaki_t_preferred(16, 1 << 18, 64, 64) && !ozaki_t_preferred(16, 1 << 18, 64, 8) &&
+              !ozaki_t_preferred(16, 1 << 18, 8, 64) && ozaki_t_preferred(8, 1 << 18, 64, 8) &&
+              !ozaki_t_preferred(8, 1 << 18, 65, 8) && !ozaki_t_preferred(16, 1000, 64, 64),
+          "ozaki_t_preferred envelope");
+  }
   opt.cgemm_ozaki = 4;
   P = lower_contract(ad, ai, bd, bi, 8, opt);
   CHECK(P.kind == CK_GEMM && P.fused_gemm && P.tempA_bytes == 0 && P.M == (1 << 14) && P.N == 64 && P.K == 64,
@@ -631,6 +835,7 @@ int main() {
     test_contractions(rng, 3, 6);
     test_big_shapes();
     test_ozaki(rng);
+    test_ozaki_t(rng);
   } catch (const Error& e) {
     std::printf("FAIL: exception %d %s\n", e.code, e.what());
     return 2;

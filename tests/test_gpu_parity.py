@@ -260,7 +260,9 @@ def test_persistent_skinny_zgemm_shapes(kfirst):
         B = rand_tensor(rng, tuple(bd), np.complex128)
         ref = layer1.contract_tensors((A, B), (ai, bi))
         outs = []
-        for opts in (dict(zgemm_kfirst=kfirst), dict(zgemm_skinny=1)):
+        # (ozaki_auto=0: this test is about the DMMA kernels; by default K >= 32, N >= 32
+        # steps of this size run on the INT8 kernel, see test_default_policy_int8_kernel)
+        for opts in (dict(zgemm_kfirst=kfirst, ozaki_auto=0), dict(zgemm_skinny=1)):
             b = B200(np.complex128, **opts)
             b.save_tensor_data("A", A)
             b.save_tensor_data("B", B)
@@ -387,6 +389,84 @@ def test_plan_independence_rqc_4x5(dtype):
     for v in vals:
         assert abs(v - sim) / abs(sim) < 100 * tol, (vals, sim)
     assert abs(vals[0] - vals[1]) / abs(sim) < 2 * tol
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_default_policy_int8_kernel(dtype):
+    """Default kernel choice (option ozaki_auto, csrc/common.h: ozaki_t_preferred): the skinny
+    GEMM-shaped sweep steps run on the INT8 tensor-core kernel k_ozaki_t with the gather fused
+    (one launch, class gemm_int8, no permute kernels) and meet the north-star tolerance at 1x;
+    shapes outside the policy keep their DMMA / fused small-operand kernels.  Ragged M / N / K,
+    contracted axes scattered over A, K first, narrow N, odd M (scalar store path)."""
+    rng = np.random.default_rng(77)
+    tol = TOL[np.dtype(dtype)]
+    c128 = np.dtype(dtype) == np.complex128
+    cases = [
+        # M = 2^16, N = K = 64, contracted axes scattered
+        ((2,) * 22, [-1, -2, -3, 1, 2, 3] + [-(i + 4) for i in range(10)] + [4, -14, 5, -15, 6, -16],
+         (2,) * 12, [6, 5, 4, 3, 2, 1] + [-(20 + i) for i in range(6)], True),
+        # low bits contracted, N = 32
+        ((2,) * 22, [1, 2, 3] + [-(i + 1) for i in range(16)] + [4, 5, 6],
+         (2,) * 11, [6, 5, 4, 3, 2, 1] + [-(20 + i) for i in range(5)], True),
+        ((40017, 35), [-1, 1], (35, 33), [1, -2], True),          # ragged everything, odd M
+        ((7, 5, 38000), [1, 2, -1], (5, 17, 7), [2, -2, 1], not c128),   # K = 35 first, N = 17: c64 only
+        ((3, 50000), [1, -1], (3, 64), [1, -2], not c128),        # K = 3: HBM-bound, DMMA kernel in c128
+        ((2000, 64), [-1, 1], (64, 64), [1, -2], False),          # M < 4096: outside the envelope
+    ]
+    for ad, ai, bd, bi, int8 in cases:
+        A = rand_tensor(rng, tuple(ad), dtype)
+        B = rand_tensor(rng, tuple(bd), dtype)
+        ref = layer1.contract_tensors((A.astype(np.complex128), B.astype(np.complex128)), (ai, bi))
+        b = B200(dtype)
+        b.save_tensor_data("A", A)
+        b.save_tensor_data("B", B)
+        b.profile_enable(True)
+        b.contract_tensors("A", ai, "B", bi, "C")
+        prof = b.profile_read()
+        b.profile_enable(False)
+        if int8:
+            assert set(prof) == {"gemm_int8"}, (ad, prof)
+        else:
+            assert "gemm_int8" not in prof, (ad, prof)
+        got = b.load_tensor_data("C")
+        assert got.shape == ref.shape
+        assert rel_l2(got, ref) < tol, (ad, ai, rel_l2(got, ref))
+        assert b.microbench("ozaki_t_debug") == 0   # no mbarrier watchdog event
+        b.close()
+
+
+def test_int8_kernel_special_values():
+    """k_ozaki_t on rows / columns the slicing treats specially: an all-zero row gives exact
+    zeros, rows 1e+-140 apart keep their relative accuracy (one power-of-two scale per row and
+    column), a row holding an Inf or a NaN gives NaN in that row only (as DMMA would)."""
+    rng = np.random.default_rng(5)
+    M, N, K = 8192, 64, 64
+    A = rand_tensor(rng, (M, K), np.complex128)
+    B = rand_tensor(rng, (K, N), np.complex128)
+    A[3, :] = 0
+    A[10, :] *= 1e140
+    A[11, :] *= 1e-140
+    B[:, 5] *= 1e-120
+    B[:, 6] *= 1e120
+    A[20, 7] = np.inf
+    A[21, 9] = np.nan
+    b = B200(np.complex128)
+    b.save_tensor_data("A", A)
+    b.save_tensor_data("B", B)
+    b.profile_enable(True)
+    b.contract_tensors("A", [-1, 1], "B", [1, -2], "C")
+    assert set(b.profile_read()) == {"gemm_int8"}
+    got = np.asarray(b.load_tensor_data("C"))
+    with np.errstate(all="ignore"):
+        ref = A @ B
+    assert np.all(got[3] == 0)
+    assert np.all(np.isnan(got[20])) and np.all(np.isnan(got[21]))
+    ok = np.ones(M, bool)
+    ok[[20, 21]] = False
+    # every row and column judged at its own scale
+    err = np.abs(got[ok] - ref[ok]) / (np.linalg.norm(A[ok], axis=1)[:, None] * np.linalg.norm(B, axis=0)[None, :] + 1e-300)
+    assert err.max() < 1e-11, err.max()
+    b.close()
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
