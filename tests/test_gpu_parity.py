@@ -286,7 +286,7 @@ def test_narrow_n_zgemm_shapes(cfg):
     the boundary): lowered to the fused DMMA GEMM with 128x8 tiles instead of the
     small-operand kernel; ragged M / N / K, both gather orders."""
     rng = np.random.default_rng(41)
-    b = B200(np.complex128, zgemm_cfg=cfg)
+    b = B200(np.complex128, zgemm_cfg=cfg, ozaki_auto=0)   # (the DMMA kernels; the default policy has its own test)
     shapes = [
         ((2,) * 19, [1, 2, 3] + [-(i + 1) for i in range(13)] + [4, 5, 6],
          (2,) * 9, [6, 5, 4, 3, 2, 1] + [-(20 + i) for i in range(3)]),        # M=2^13 N=8 K=64
@@ -317,7 +317,7 @@ def test_fused_ttgt_zgemm_shapes(cfg):
     """The persistent fused-TTGT ZGEMM (operands gathered inside the GEMM, no permuted
     temporaries): ragged tiles, K tails, several tiles per CTA, low-address contracted axes."""
     rng = np.random.default_rng(29)
-    b = B200(np.complex128, zgemm_cfg=cfg)
+    b = B200(np.complex128, zgemm_cfg=cfg, ozaki_auto=0)   # (the DMMA kernels; the default policy has its own test)
     shapes = list(GEMM_SHAPES) + [
         ((2,) * 20, [1, 2, 3] + [-(i + 1) for i in range(14)] + [4, 5, 6],
          (2,) * 12, [6, 5, 4, 3, 2, 1] + [-(20 + i) for i in range(6)]),       # M=2^14 N=64 K=64
