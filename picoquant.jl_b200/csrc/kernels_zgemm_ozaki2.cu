@@ -81,6 +81,7 @@ __device__ __forceinline__ void ot_mbar_arrive(uint64_t* bar) {
 //   wait ids: 1 full (MMA), 2 freed (MMA), 3 done (epilogue), 4 empty (producers)
 __device__ int g_ot_debug[8];
 __device__ long long g_ot_trace[32 * 32];   // block 0: [tile < 32][event]
+__device__ long long g_ot_block_ns[2 * 160];   // TR: globaltimer at the start / end of every block
 #define OT_TRACE(tile_no, ev)                                                                   \
   do {                                                                                          \
     if (TR && blockIdx.x == 0 && (tile_no) < 32) g_ot_trace[(tile_no) * 32 + (ev)] = clock64(); \
@@ -219,8 +220,8 @@ __device__ __forceinline__ constexpr int ot_issue_order(int i) {
 // Output scaling, kept lean in ISSUE SLOTS and FP64 instructions (the epilogue's two scarce
 // resources: ncu showed ~80 instructions per real number for an integer-only version, and the
 // DADD / DMULs of the first versions waiting on the FP64 pipe for a third of the epilogue's
-// time).  ComplexF64: both scales ride in the exponent fields of the magic constants of the
-// int64 -> double conversion (ot::to_double_scaled: two DADDs, no multiplication).
+// time).  ComplexF64: both scales ride in the exponent field of the magic constant of the
+// integer -> double conversion (ot::to_double51_scaled: ONE DADD, no multiplication).
 // ComplexF32: int32 -> float conversions, one FFMA, two FMULs (row scale first).
 template <class Real> struct OtScale;
 template <> struct OtScale<double> {
@@ -237,7 +238,8 @@ template <> struct OtScale<double> {
   }
   template <int G>
   static __device__ __forceinline__ double apply(const int* rr, const col_type& c, row_type sr) {
-    return ot::to_double_scaled(ot::combine<G>(rr), c, sr);
+    static_assert(G == 6, "ComplexF64: six digits, six groups");
+    return ot::to_double51_scaled(ot::combine51(rr), c, sr);
   }
 };
 template <> struct OtScale<float> {
@@ -333,6 +335,11 @@ k_ozaki_t(const typename OtVec<Real>::type* __restrict__ A, const typename OtVec
   // (the shuffle makes the warp index provably warp-uniform: the role branches below are then
   // convergent for ptxas, and the MMA warp's descriptor arithmetic runs on the uniform datapath)
   const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
+  if (TR && tid == 0 && blockIdx.x < 160) {
+    unsigned long long ns;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
+    g_ot_block_ns[2 * blockIdx.x] = (long long)ns;
+  }
   const int K = (int)p.K, N = (int)p.N;
   const long long M = p.M;
   const int KC = (K + 15) / 16;   // 16-k chunks per half = MMA k-steps
@@ -394,29 +401,20 @@ k_ozaki_t(const typename OtVec<Real>::type* __restrict__ A, const typename OtVec
 
   if (warp < OT_PW) {
     // ===================== producers =====================
+    // thread = (tile row j, 16-k chunk c).  The gather of a tile is one batch of 16 loads per
+    // thread; the row offset of the NEXT tile is computed behind the issued loads (its chain of
+    // constant-bank reads cost ~1000 clocks per tile at the top of the loop).  ComplexF32
+    // (32 data registers per batch) keeps TWO batches in flight: the loads of tile t + 1 are
+    // issued before tile t is sliced.  ComplexF64 (64 registers) has room for one; an L2
+    // prefetch of the next tile was tried and changed nothing (pq: PQ_OT_PF experiment).
     const int j = warp * 8 + (lane & 7), c = lane >> 3;
     const bool on = c < KC;
-    uint32_t t = 0;
-    for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++t) {
-      const uint32_t stage = t & 1u, use = t >> 1;
+    constexpr bool TWO = sizeof(Real) == 4;
+    auto row_offset = [&](long long tile) -> long long {
       const long long m = tile * ot::ROWS + j;
-      const long long ra = m < M ? map_offset(p.mA, m) : -1;
-      if (tid == 0) OT_TRACE(t, 0);
-      // the next tile of this CTA goes to L2 now: a thread has registers for ONE tile's loads,
-      // and with those alone in flight the gather ran at 65 % duty (2.9 us per 64 KB burst)
-      {
-        const long long mn = m + (long long)gridDim.x * ot::ROWS;
-        if (on && mn < M) {
-          const long long rn = map_offset(p.mA, mn);
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const int k = c * 16 + i;
-            if (k < K) asm volatile("prefetch.global.L2 [%0];\n" ::"l"(A + rn + koffA[k]));
-          }
-        }
-      }
-      Real xr[16], xi[16];
-      int key = 0;
+      return (tile < tiles && m < M) ? map_offset(p.mA, m) : -1;
+    };
+    auto issue = [&](Real (&xr)[16], Real (&xi)[16], long long ra) {
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
         const int k = c * 16 + i;
@@ -425,8 +423,13 @@ k_ozaki_t(const typename OtVec<Real>::type* __restrict__ A, const typename OtVec
         if (on && ra >= 0 && k < K) v = A[ra + koffA[k]];
         xr[i] = v.x;
         xi[i] = v.y;
-        key = max(key, max(Tr::key(v.x), Tr::key(v.y)));
       }
+    };
+    auto finish = [&](const Real (&xr)[16], const Real (&xi)[16], uint32_t t) {
+      const uint32_t stage = t & 1u, use = t >> 1;
+      int key = 0;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) key = max(key, max(Tr::key(xr[i]), Tr::key(xi[i])));
       key = max(key, __shfl_xor_sync(0xffffffffu, key, 8));
       key = max(key, __shfl_xor_sync(0xffffffffu, key, 16));
       const int ea = Sc::row_field(Tr::exp_field(key));
@@ -441,6 +444,37 @@ k_ozaki_t(const typename OtVec<Real>::type* __restrict__ A, const typename OtVec
       __syncwarp();
       if (lane == 0) ot_mbar_arrive(&full[stage]);
       if (tid == 0) OT_TRACE(t, 3);
+    };
+    const long long step = gridDim.x;
+    long long tile = blockIdx.x;
+    uint32_t t = 0;
+    Real xa_r[16], xa_i[16];
+    if constexpr (TWO) {
+      Real xb_r[16], xb_i[16];
+      long long ra = row_offset(tile);
+      issue(xa_r, xa_i, ra);
+      ra = row_offset(tile + step);
+      while (tile < tiles) {
+        if (tid == 0) OT_TRACE(t, 0);
+        issue(xb_r, xb_i, ra);               // tile + step (zeros beyond the last tile)
+        ra = row_offset(tile + 2 * step);
+        finish(xa_r, xa_i, t);
+        tile += step, ++t;
+        if (tile >= tiles) break;
+        if (tid == 0) OT_TRACE(t, 0);
+        issue(xa_r, xa_i, ra);
+        ra = row_offset(tile + 2 * step);
+        finish(xb_r, xb_i, t);
+        tile += step, ++t;
+      }
+    } else {
+      long long ra = row_offset(tile);
+      for (; tile < tiles; tile += step, ++t) {
+        if (tid == 0) OT_TRACE(t, 0);
+        issue(xa_r, xa_i, ra);
+        ra = row_offset(tile + step);        // behind the loads of this tile
+        finish(xa_r, xa_i, t);
+      }
     }
   } else if (warp == OT_PW + OT_EW) {
     // ===================== MMA issuer =====================
@@ -572,10 +606,20 @@ k_ozaki_t(const typename OtVec<Real>::type* __restrict__ A, const typename OtVec
         if (b + 2 < 8) wait_ld();
       }
       if (tid == OT_PW * 32) OT_TRACE(t, 18);
+      if (TR && tid == OT_PW * 32 && blockIdx.x == 0 && t < 32) {   // wall clock beside the SM clock
+        unsigned long long ns;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
+        g_ot_trace[t * 32 + 19] = (long long)ns;
+      }
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
   __syncthreads();
+  if (TR && tid == 0 && blockIdx.x < 160) {
+    unsigned long long ns;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
+    g_ot_block_ns[2 * blockIdx.x + 1] = (long long)ns;
+  }
   if (warp == 0) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(512u)
                  : "memory");
@@ -798,20 +842,21 @@ void run_zgemm_ozaki_t(const Launch& L, const FusedParams& fp, const void* A, co
   const long long tiles = (fp.M + ot::ROWS - 1) / ot::ROWS;
   const unsigned grid = (unsigned)(tiles < L.num_sms ? tiles : L.num_sms);
   const bool trace = std::getenv("PQ_OZAKI_TRACE") != nullptr;
+  const FusedParams& fq = fp;
   if (L.elem_size == 16) {
     if (trace)
       k_ozaki_t<double, true><<<grid, OT_THREADS, OtSmem<6>::kTotal, L.stream>>>(
-          (const double2*)A, (const double2*)B, (double2*)C, fp);
+          (const double2*)A, (const double2*)B, (double2*)C, fq);
     else
       k_ozaki_t<double><<<grid, OT_THREADS, OtSmem<6>::kTotal, L.stream>>>(
-          (const double2*)A, (const double2*)B, (double2*)C, fp);
+          (const double2*)A, (const double2*)B, (double2*)C, fq);
   } else {
     if (trace)
       k_ozaki_t<float, true><<<grid, OT_THREADS, OtSmem<4>::kTotal, L.stream>>>(
-          (const float2*)A, (const float2*)B, (float2*)C, fp);
+          (const float2*)A, (const float2*)B, (float2*)C, fq);
     else
       k_ozaki_t<float><<<grid, OT_THREADS, OtSmem<4>::kTotal, L.stream>>>(
-          (const float2*)A, (const float2*)B, (float2*)C, fp);
+          (const float2*)A, (const float2*)B, (float2*)C, fq);
   }
 }
 
@@ -882,6 +927,20 @@ double run_ozaki_t_microbench(const Launch& L, const std::string& what) {
   std::vector<long long> tr(32 * 32);
   PQ_CUDA(cudaStreamSynchronize(L.stream));
   PQ_CUDA(cudaMemcpyFromSymbol(tr.data(), g_ot_trace, tr.size() * sizeof(long long)));
+  {
+    std::vector<long long> bn(2 * 160);
+    PQ_CUDA(cudaMemcpyFromSymbol(bn.data(), g_ot_block_ns, bn.size() * sizeof(long long)));
+    long long first = 0, last = 0, dmin = 1ll << 60, dmax = 0;
+    for (int b = 0; b < L.num_sms && b < 160; ++b) {
+      if (bn[2 * b] == 0) continue;
+      if (first == 0 || bn[2 * b] < first) first = bn[2 * b];
+      if (bn[2 * b + 1] > last) last = bn[2 * b + 1];
+      dmin = std::min(dmin, bn[2 * b + 1] - bn[2 * b]);
+      dmax = std::max(dmax, bn[2 * b + 1] - bn[2 * b]);
+    }
+    std::fprintf(stderr, "ozaki_t blocks: first start -> last end %.1f us, block lifetime min %.1f max %.1f us\n",
+                 (last - first) / 1e3, dmin / 1e3, dmax / 1e3);
+  }
   if (const char* path = std::getenv("PQ_OZAKI_TRACE"))
     if (FILE* f = std::fopen(path, "wb")) {
       std::fwrite(tr.data(), sizeof(long long), tr.size(), f);

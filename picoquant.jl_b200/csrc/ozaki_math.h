@@ -416,6 +416,30 @@ OZ_HD double to_double_scaled(long long v, const DoubleMagic& m, int rw) {
   const double off = bits_double(((unsigned long long)w1 << 32) | 0x80100000u);
   return (dhi - off) + dlo;
 }
+// ONE DADD per real number (ComplexF64, 6 groups): V has up to 62 bits, the magic-number
+// conversion takes 51.  The low 11 bits of V weigh about as much as the groups the scheme
+// drops anyway (sum_{g >= 6} r_g 256^(5-g): ~2^9 for random digits), so V is first rounded to
+// V' = round(V / 2^11), |V'| < 2^51 -- from the group sums, int32 up to two widening
+// multiply-adds -- and V' 2^(11 + e) is one conversion:
+//     bits(1.5 2^52 2^(11 + e)) + V'  =  bits of  2^(11 + e) (1.5 2^52 + V').
+// FP64 instructions are the scarcest resource of this kernel (they share hardware with the
+// running MMA stream: measured, the epilogue's drain time halves when its DADDs are removed).
+constexpr int V_DROP = 11;
+OZ_HD long long combine51(const int* r) {   // V' = round(sum_g r_g 256^(5-g) / 2^11), G = 6
+  const int p01 = r[0] * 256 + r[1], p23 = r[2] * 256 + r[3];
+  const int s45 = r[4] * 32 + ((r[5] + 4) >> 3);    // (r4 256 + r5) / 8, |r4| < 2^24
+  const int t45 = (s45 + 128) >> 8;                 // ... / 2^11, rounded
+  return (long long)p01 * 2097152ll + ((long long)p23 * 32ll + (long long)t45);
+}
+OZ_HD double to_double51_scaled(long long v51, const DoubleMagic& m, int rw) {
+  const bool nan = rw == ROW_NAN || m.nan_column;
+  // magic = 1.5 * 2^52 * 2^(11 + e): high word (0x433 + 11 + e) << 20 | 0x80000, low word 0
+  const unsigned wm = (unsigned)(m.k_lo + rw) + ((unsigned)V_DROP << 20) + 0x80000u;
+  const double magic = bits_double((unsigned long long)wm << 32);
+  const double y = bits_double(((unsigned long long)wm << 32) + (unsigned long long)v51);
+  const double d = y - magic;
+  return nan ? bits_double(0x7ff8000000000000ull) : d;
+}
 // ComplexF32 result: V = p01 2^16 + p23 rounded to float through two int32 -> float
 // conversions and one FMA (within one ulp of V; no 64-bit conversion)
 OZ_HD float combine_f32(const int* r) {

@@ -611,9 +611,15 @@ static double ozaki_t_tile_error(std::mt19937& rng, int Mrows, int N, int K, dou
           const bool dead = colE[n] < Td::MIN_EF || colE[n] >= 2047;
           const ot::DoubleMagic m = ot::double_magic(dead ? 0 : Td::out_exp(colE[n]) - 8 * (G - 1), colE[n] >= 2047);
           CHECK(ot::to_double_scaled(v, ot::double_magic(0, false), 0) == (double)v, "ozaki_t to_double(%lld)", v);
-          out[part] = ot::to_double_scaled(v, m, ot::row_word(rowE[j]));
-          // identical to the plain product (flushed rows / columns have v == 0)
-          CHECK(out[part] == want || (v == 0 && out[part] == 0.0), "ozaki_t double scaling: %g vs %g", out[part], want);
+          // the two-DADD conversion of the full 62-bit V: identical to the plain product
+          const double full = ot::to_double_scaled(v, m, ot::row_word(rowE[j]));
+          CHECK(full == want || (v == 0 && full == 0.0), "ozaki_t double scaling: %g vs %g", full, want);
+          // the kernel's one-DADD conversion of V' = round(V / 2^11): within 2^11 units of V
+          const long long v51 = ot::combine51(r);
+          CHECK(std::llabs(v51) < (1ll << 51) && std::llabs(v51 * 2048 - v) <= 1300, "ozaki_t combine51: %lld vs %lld", v51 * 2048, v);
+          out[part] = ot::to_double51_scaled(v51, m, ot::row_word(rowE[j]));
+          const double unit = std::fabs(Tr::out_scale(colE[n]) * ot::group_weight<G>() * Tr::out_scale(rowE[j]));
+          CHECK(std::fabs(out[part] - want) <= 1300.0 * unit + std::fabs(want) * 3e-16, "ozaki_t 51-bit conversion: %g vs %g", out[part], want);
         } else {                   // OtScale<float>::apply: FP32 only, row scale first
           using Tf = oz::Traits<float>;
           const float f = (ot::combine_f32(r) * Tf::out_scale_f(rowE[j], 0)) * Tf::out_scale_f(colE[n], -8 * (G - 1));

@@ -33,3 +33,10 @@ for label, a, b in (("P: load latency (P0 -> P1)", 0, 1), ("P: wait for the stag
     else:
         d = tr[2:ntiles, b] - tr[2:ntiles, a]
     print("%-40s mean %.0f clk" % (label, d.mean()))
+
+n = int((tr[:, 18] > 0).sum())
+if n > 2 and tr[0, 19] > 0:
+    clk = tr[n - 1, 18] - tr[0, 18]
+    ns = tr[n - 1, 19] - tr[0, 19]
+    print("SM clock during the kernel (clock64 / globaltimer over tiles 0..%d): %.0f MHz; block 0 lifetime %.1f us"
+          % (n - 1, 1e3 * clk / ns, (tr[n - 1, 19] - tr[0, 19]) / 1e3))
