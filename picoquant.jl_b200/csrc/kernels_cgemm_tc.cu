@@ -80,22 +80,28 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N, bool neg_a) {
          | ((uint32_t)(M >> 4) << 24);   // m_dim
 }
 
+// whole-warp form: every lane executes the (uniform) surrounding code, one elected lane issues
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
                                           uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n"
-      ".reg .pred p;\n"
+      ".reg .pred p, q;\n"
+      "elect.sync _|q, 0xffffffff;\n"
       "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
       "}\n" ::"r"(tmem_d),
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
 
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(
-                   smem_u32(bar))
-               : "memory");
+  asm volatile(
+      "{\n"
+      ".reg .pred q;\n"
+      "elect.sync _|q, 0xffffffff;\n"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n"
+      "}\n" ::"r"(smem_u32(bar))
+      : "memory");
 }
 
 // hi part of the split: x rounded to TF32 (10 explicit mantissa bits), done with one integer
@@ -248,7 +254,11 @@ k_cgemm_tcgen05(const float2* __restrict__ A, const float2* __restrict__ B, floa
   uint64_t* drained = chunk_done + 2;       // [2] set folded into the sums (count 128)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(drained + 2);
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // (warp index through a shuffle: provably warp-uniform, so the role branches are convergent for
+  // ptxas and the MMA warp's descriptor arithmetic runs on the uniform datapath -- with `if (lane ==
+  // 0)` around the issue loop every UTCHMMA was wrapped in an ELECT / BRA.U.ANY loop behind four
+  // R2URs, ~17 instructions per MMA on a scheduler shared with two loader warps)
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
   // Rasterisation: consecutive CTAs walk GROUP_M m-tiles x all n-tiles, so one wave of CTAs
   // re-uses a band of A (GROUP_M*128 rows) and a few column tiles of B out of L2 instead of
   // streaming all of A once per wave (2.16 GB -> ~0.5 GB of DRAM traffic at 4096^3).
@@ -291,8 +301,8 @@ k_cgemm_tcgen05(const float2* __restrict__ A, const float2* __restrict__ B, floa
   constexpr uint32_t A_LBO = TM * 16, B_LBO = BN * 16, SBO = 128;
 
   if (warp == 8) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (all 32 lanes, uniform; one elected lane issues) =====
+    {
       for (long long kt = 0; kt < KT; ++kt) {
         const int s = (int)(kt % NSTAGE);
         const long long chunk = kt / STAGES_PER_CHUNK;
