@@ -71,10 +71,10 @@ def parse_args():
     ap.add_argument("--lanes", type=int, default=4,
                     help="slices kept in flight per GPU (pq_program_run_slices)")
     ap.add_argument("--cpu-sample-slices", type=int, default=2)
-    ap.add_argument("--ozaki", type=int, default=0, choices=[0, 3, 4, 6, 7],
-                    help="EXPERIMENTAL: route the skinny ComplexF64 GEMM steps to the INT8 tensor-core "
-                         "Ozaki kernel: 6 / 7 accumulator groups with --dtype c128 (option zgemm_ozaki), 3 / 4 with "
-                         "--dtype c64 (option cgemm_ozaki); default off")
+    ap.add_argument("--ozaki", type=int, default=0, choices=[0, 4, 6],
+                    help="force every eligible GEMM step (K, N <= 64) onto the INT8 tensor-core kernel: 6 with "
+                         "--dtype c128 (option zgemm_ozaki), 4 with --dtype c64 (option cgemm_ozaki); default: "
+                         "the library's own policy (ozaki_auto)")
     ap.add_argument("--no-int8", action="store_true",
                     help="option ozaki_auto = 0: keep the skinny GEMM steps on DMMA / tcgen05 3xTF32 (A/B)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -370,8 +370,8 @@ def config_arm(a):
         b.set_option("ozaki_auto", 0)
         cfg["ozaki_auto"] = 0
     if a.ozaki:   # forced INT8 tensor-core GEMMs (incl. the experimental K-looped kernel)
-        if (a.dtype == "c128") != (a.ozaki in (6, 7)):
-            raise SystemExit("--ozaki 6|7 goes with --dtype c128, --ozaki 3|4 with --dtype c64")
+        if (a.dtype == "c128") != (a.ozaki == 6):
+            raise SystemExit("--ozaki 6 goes with --dtype c128, --ozaki 4 with --dtype c64")
         b.set_option("zgemm_ozaki" if a.dtype == "c128" else "cgemm_ozaki", a.ozaki)
         cfg["ozaki_groups"] = a.ozaki
     for cmd, x in parse_dsl(w.text):
@@ -594,8 +594,8 @@ def main():
     if a.no_int8:
         b.set_option("ozaki_auto", 0)
     if a.ozaki:
-        if (a.dtype == "c128") != (a.ozaki in (6, 7)):
-            raise SystemExit("--ozaki 6|7 goes with --dtype c128, --ozaki 3|4 with --dtype c64")
+        if (a.dtype == "c128") != (a.ozaki == 6):
+            raise SystemExit("--ozaki 6 goes with --dtype c128, --ozaki 4 with --dtype c64")
         b.set_option("zgemm_ozaki" if a.dtype == "c128" else "cgemm_ozaki", a.ozaki)
     if world > 1:
         ids = [B200Backend.comm_unique_id() if rank == 0 else None]
@@ -784,7 +784,7 @@ def main():
             # (algorithmic operand + result bytes) or the INT8 tensor pipe, whose complex-flop
             # equivalent is the measured kind::i8 issue rate over the int8 MACs one complex MAC
             # costs (4 real products x digit-plane pairs)
-            pairs = {6: 21, 7: 26, 3: 6, 4: 10}.get(oz_groups, 21 if a.dtype == "c128" else 10)
+            pairs = 21 if a.dtype == "c128" else 10   # digit-plane pairs: 6 / 4 accumulator groups
             tops = b.microbench("umma_i8_tops_n64")
             peaks["umma_i8_tops_n64"] = tops
             tensor_peak = tops * 8.0 / (2.0 * 4.0 * pairs)

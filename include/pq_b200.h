@@ -222,13 +222,14 @@ int pq_timer_end(pq_handle* h, double* ms);
  *                   products, 7 persistent skinny kernel where eligible
  *   "zgemm_skinny"  1 disables the persistent skinny ZGEMM
  *   "zgemm_3m"      1 four DMMAs per complex product instead of three (3M)
- *   "zgemm_ozaki"   EXPERIMENTAL, not yet validated on hardware: 6 or 7 routes the skinny
- *                   ComplexF64 GEMM steps (K <= 64, N <= 64) to an INT8 tensor-core (tcgen05
- *                   kind::i8) Ozaki-scheme kernel keeping 6 / 7 accumulator groups (rel-L2
- *                   ~2e-13 / ~2e-14 per contraction); 0 (default) never launches it
- *   "cgemm_ozaki"   EXPERIMENTAL ComplexF32 twin of zgemm_ozaki (4 digits per real): 4 accumulator
- *                   groups (rel-L2 ~3e-8 per contraction; 3: ~2e-6, A/B only), gather fused
- *                   (no K1 pass); 0 (default) never launches it
+ *   "ozaki_auto"    default 1: GEMM-shaped steps with K <= 64, N <= 64 and M >= 4096 run on the INT8
+ *                   tensor-core kernel k_ozaki_t (tcgen05.mma kind::i8, Ozaki-scheme slicing into
+ *                   int8 digits, exact int32 accumulation; rel-L2 ~3e-13 per ComplexF64 and ~3e-8
+ *                   per ComplexF32 contraction) where it is the faster kernel: ComplexF64 with
+ *                   K >= 32 and N >= 32, ComplexF32 with N > 16 or K > 16.  0 keeps those steps
+ *                   on DMMA / K1 + tcgen05 3xTF32
+ *   "zgemm_ozaki"   6 forces every eligible ComplexF64 step (K <= 64, N <= 64) onto k_ozaki_t
+ *   "cgemm_ozaki"   4 forces every eligible ComplexF32 step onto k_ozaki_t (gather fused, no K1 pass)
  *   "zgemm_kfirst"  1 row-first gather order only
  *   "zgemm_stagger" ns of start delay per resident-CTA slot in the first wave (tile-per-CTA ZGEMM)
  * Every alternative computes the same contraction; the tests run them against each other. */

@@ -125,7 +125,6 @@ extern "C" int pq_create(int device, int dtype, pq_handle** out) {
     PQ_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold));
     init_kernels();
     init_kernels_cgemm();
-    init_kernels_ozaki();
     init_kernels_ozaki_t();
   } catch (const std::exception&) {
     delete h;
@@ -685,20 +684,19 @@ extern "C" int pq_set_option(pq_handle* h, const char* key, int value) {
   else if (k == "zgemm_skinny") h->opt.zgemm_skinny = value;
   else if (k == "zgemm_3m") h->opt.zgemm_3m = value;
   else if (k == "cgemm_ozaki") {
-    if (value != 0 && value != 3 && value != 4) {
-      h->last_error = "cgemm_ozaki must be 0, 3 or 4";
+    if (value != 0 && value != 4) {
+      h->last_error = "cgemm_ozaki must be 0 or 4";
       return PQ_ERR_INVALID;
     }
     h->opt.cgemm_ozaki = value;
   }
   else if (k == "zgemm_ozaki") {
-    if (value != 0 && value != 6 && value != 7) {
-      h->last_error = "zgemm_ozaki must be 0, 6 or 7";
+    if (value != 0 && value != 6) {
+      h->last_error = "zgemm_ozaki must be 0 or 6";
       return PQ_ERR_INVALID;
     }
     h->opt.zgemm_ozaki = value;
   }
-  else if (k == "ozaki_gen") h->opt.ozaki_gen = value;
   else if (k == "ozaki_auto") h->opt.ozaki_auto = value;
   else if (k == "zgemm_cfg") h->opt.zgemm_cfg = value;
   else if (k == "zgemm_kfirst") h->opt.zgemm_kfirst = value;

@@ -104,7 +104,7 @@ enum KClass {
   KC_SVD = 11,
   KC_OTHER = 12,
   KC_CONTRACT_CHAIN = 13,  // k_contract_chain: a group of chains of tiny contractions
-  KC_GEMM_INT8 = 14        // k_zgemm_ozaki*: GEMM-shaped steps on the INT8 tensor pipe (tcgen05 kind::i8)
+  KC_GEMM_INT8 = 14        // k_ozaki_t: GEMM-shaped steps on the INT8 tensor pipe (tcgen05 kind::i8)
 };
 static_assert(KC_GEMM_INT8 + 1 == PQ_NUM_KERNEL_CLASSES, "class count");
 
@@ -122,10 +122,9 @@ struct Options {
   int zgemm_cfg = 0;  // fused ZGEMM: 0 auto, 1 = 64x64 (2 CTAs/SM), 2 = 64x32 (4 CTAs/SM), 3 = 128x8, 4 = 64x32 3M, 7 = persistent skinny where eligible
   int zgemm_3m = 0;       // persistent skinny ZGEMM: 0 = 3M (three DMMAs per complex product), 1 = 4M
   int zgemm_skinny = 0;   // persistent skinny fused ZGEMM: 0 auto, 1 off
-  int zgemm_ozaki = 0;    // EXPERIMENTAL int8 tensor-core ZGEMM (kernels_zgemm_ozaki.cu): 0 off, 6 / 7 = accumulator groups
-  int cgemm_ozaki = 0;    // EXPERIMENTAL, ComplexF32 twin of zgemm_ozaki: 0 off, 3 / 4 = accumulator groups
-  int ozaki_gen = 0;      // which INT8 kernel serves K, N <= 64 at 6 / 4 groups: 0 = k_ozaki_t (second generation), 1 = k_zgemm_ozaki
-  int ozaki_auto = 1;     // 1 (default): GEMM-shaped steps inside ozaki_t_preferred() run on k_ozaki_t (INT8 tensor cores); 0: never unless forced by zgemm_ozaki / cgemm_ozaki
+  int zgemm_ozaki = 0;    // 6: force the INT8 tensor-core kernel k_ozaki_t for every eligible ComplexF64 step (K, N <= 64)
+  int cgemm_ozaki = 0;    // 4: the same for ComplexF32
+  int ozaki_auto = 1;     // 1 (default): GEMM-shaped steps inside ozaki_t_preferred() run on k_ozaki_t; 0: only when forced
   int zgemm_stagger = 0;  // ns of start delay per resident-CTA slot in the first wave (0 = off)
   int chain = 0;    // compiled programs: 0 = batch chains of tiny contractions into one launch, 1 = off
   int prio = 0;     // 0: small-grid graph nodes get the highest launch priority, 1: off
@@ -209,7 +208,7 @@ bool chain_item_from_plan(const ContractPlan& p, ChainItem& it);
 void run_chains(const Launch& L, const ChainItem* d_items, const ChainRange* d_ranges, int nchains,
                 double bytes = 0, double flops = 0);
 
-// operands of the gather-fused ZGEMM kernels (kernels_zgemm.cu, kernels_zgemm_ozaki.cu):
+// operands of the gather-fused GEMM kernels (kernels_zgemm.cu, kernels_zgemm_ozaki2.cu):
 // C[m + M n] = sum_k A[mA(m) + kA(k)] * B[nB(n) + kB(k)]
 struct FusedParams {
   IdxMap mA, kA, nB, kB;
@@ -220,37 +219,27 @@ struct FusedParams {
   int stagger_ns, first_wave, num_sms;
 };
 
-void init_kernels_ozaki();
-double run_ozaki_microbench(const Launch& L, const std::string& what);
-// second-generation kernel (kernels_zgemm_ozaki2.cu): transposed, K-concatenated, warp-specialised
+// INT8 tensor-core complex GEMM for the skinny sweep steps (kernels_zgemm_ozaki2.cu: k_ozaki_t)
 void init_kernels_ozaki_t();
 double run_ozaki_t_microbench(const Launch& L, const std::string& what);
 void run_zgemm_ozaki_t(const Launch& L, const FusedParams& fp, const void* A, const void* B, void* C);
-// envelope of the INT8 Ozaki kernel: all of K and N resident per tile
+// envelope of the kernel: all of K and N resident per tile
 inline bool zgemm_ozaki_eligible(int64_t M, int64_t N, int64_t K) {
   return K >= 1 && K <= 64 && N >= 1 && N <= 64 && M >= 1;
 }
 // Default policy (option ozaki_auto): which GEMM-shaped steps run on k_ozaki_t, from the
 // per-shape timings on B200 (profiles/ozaki_t_probe_r02.json).  ComplexF64: the steps the FP64
-// tensor pipe bounds (K >= 32 with N >= 32: 167 vs 267 us at M = 2^18, N = K = 64); the
+// tensor pipe bounds (K >= 32 with N >= 32: 155 vs 267 us at M = 2^18, N = K = 64); the
 // HBM-bound K <= 16 steps stay on the persistent DMMA kernel (81 vs 108 us).  ComplexF32: every
-// skinny step (the alternative is a K1 permute + tcgen05 3xTF32 on canonical layouts: 109 vs
+// skinny step (the alternative is a K1 permute + tcgen05 3xTF32 on canonical layouts: 77 vs
 // 245 us, and 4.5e-8 instead of 3.4e-7 relative error).
 inline bool ozaki_t_preferred(int elem_size, int64_t M, int64_t N, int64_t K) {
   if (!zgemm_ozaki_eligible(M, N, K) || M < 4096) return false;
   if (elem_size == 16) return K >= 32 && N >= 32;
   return N > 16 || K > 16;
 }
-// long contractions (64 < K <= 8192) on canonical layouts; ws = (M + N) ints
-inline bool zgemm_ozaki_kloop_eligible(int64_t M, int64_t N, int64_t K) {
-  return K > 64 && K <= 8192 && M >= 1 && N >= 1 && M + N < (int64_t(1) << 30);
-}
-void run_zgemm_ozaki_kloop(const Launch& L, int groups, const void* A, const void* B, void* C,
-                           int64_t M, int64_t N, int64_t K, void* ws);
 // ComplexF32 contraction with the gather fused, on the INT8 kernel (plan lowered with fused_gemm)
 void run_cgemm_ozaki_fused(const Launch& L, const ContractPlan& cp, const void* A, const void* B, void* C);
-void run_zgemm_ozaki(const Launch& L, const FusedParams& fp, int groups, const void* A,
-                     const void* B, void* C);
 
 void init_kernels();
 void init_kernels_cgemm();

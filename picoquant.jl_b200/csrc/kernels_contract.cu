@@ -636,7 +636,7 @@ static void run_contract_t(const Launch& L, const ContractPlan& p, const void* A
         if (sizeof(R) == 8)
           run_zgemm_fused(L, p, A, B, C);
         else
-          run_cgemm_ozaki_fused(L, p, A, B, C);   // only lowered this way with option cgemm_ozaki
+          run_cgemm_ozaki_fused(L, p, A, B, C);   // ComplexF32 skinny steps: k_ozaki_t, gather fused
         break;
       }
       const void* Ap = A;
@@ -650,14 +650,7 @@ static void run_contract_t(const Launch& L, const ContractPlan& p, const void* A
         Bp = tempB;
       }
       const bool tensor = (L.opt == nullptr || L.opt->gemm != 1);
-      const int oz = L.opt ? (sizeof(R) == 8 ? L.opt->zgemm_ozaki : L.opt->cgemm_ozaki) : 0;
-      if (tensor && oz != 0 && ws != nullptr && zgemm_ozaki_kloop_eligible(p.M, p.N, p.K)) {
-        // EXPERIMENTAL (options zgemm_ozaki / cgemm_ozaki): INT8 tensor-core product, K in chunks
-        L.begin(KC_GEMM_INT8, double(p.M * p.K + p.N * p.K + p.M * p.N) * sizeof(R) * 2,
-                8.0 * double(p.M) * double(p.N) * double(p.K));
-        run_zgemm_ozaki_kloop(L, oz, Ap, Bp, C, p.M, p.N, p.K, ws);
-        L.end();
-      } else if (tensor && sizeof(R) == 8)
+      if (tensor && sizeof(R) == 8)
         run_zgemm_dmma(L, Ap, Bp, C, p.M, p.N, p.K);      // FP64 DMMA
       else if (tensor)
         run_cgemm_tcgen05(L, Ap, Bp, C, p.M, p.N, p.K);   // tcgen05, 3xTF32

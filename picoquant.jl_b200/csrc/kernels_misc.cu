@@ -92,8 +92,7 @@ __global__ void __launch_bounds__(256) k_copy16(const uint4* __restrict__ in, ui
 }
 
 double run_microbench(const Launch& L, const std::string& what) {
-  if (what.rfind("ozaki_t_", 0) == 0) return run_ozaki_t_microbench(L, what);
-  if (what.rfind("umma_i8_", 0) == 0 || what.rfind("ozaki_", 0) == 0) return run_ozaki_microbench(L, what);
+  if (what.rfind("ozaki_t_", 0) == 0 || what.rfind("umma_i8_", 0) == 0) return run_ozaki_t_microbench(L, what);
   if (what == "dmma_tflops") return run_fp64_probe(L, true);
   if (what.rfind("dmma_tflops_w", 0) == 0) return run_fp64_probe(L, true, std::stoi(what.substr(13)));
   if (what == "dfma_tflops") return run_fp64_probe(L, false);

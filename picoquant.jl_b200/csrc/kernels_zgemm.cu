@@ -873,7 +873,7 @@ void run_zgemm_fused(const Launch& L, const ContractPlan& cp, const void* A, con
   bool akf = min_stride(cp.kA) < min_stride(cp.mA), bkf = min_stride(cp.kB) < min_stride(cp.nB);
   if (L.opt && L.opt->zgemm_kfirst == 1) akf = bkf = false;  // A/B check knob
   if (cfg == 3) akf = bkf = false;  // measured: no gain for the narrow tiles (HBM-bound)
-  // EXPERIMENTAL (off unless option "zgemm_ozaki" = 6 / 7): INT8 tensor-core Ozaki product
+  // INT8 tensor-core Ozaki product (default policy ozaki_t_preferred, or forced by zgemm_ozaki = 6)
   {
     int oz = L.opt ? L.opt->zgemm_ozaki : 0;
     if (oz == 0 && (L.opt == nullptr || (L.opt->ozaki_auto != 0 && L.opt->zgemm_cfg == 0 && L.opt->zgemm_skinny == 0)) &&
@@ -881,7 +881,7 @@ void run_zgemm_fused(const Launch& L, const ContractPlan& cp, const void* A, con
       oz = 6;   // default policy: k_ozaki_t
     if (oz != 0 && zgemm_ozaki_eligible(cp.M, cp.N, cp.K)) {
       L.begin(KC_GEMM_INT8, bytes, flops);
-      run_zgemm_ozaki(L, fp, oz, A, B, C);
+      run_zgemm_ozaki_t(L, fp, A, B, C);
       L.end();
       PQ_CUDA(cudaGetLastError());
       return;

@@ -1,12 +1,15 @@
 // K2t: second-generation INT8 tensor-core complex GEMM for the skinny sweep steps
 // (K <= 64, N <= 64, gather fused) -- "transposed, K-concatenated, warp-specialised".
 //
-// Same arithmetic as kernels_zgemm_ozaki.cu (Ozaki-scheme slicing into balanced base-256 int8
-// digits, exact int32 sums of equal-weight digit-plane products on tcgen05.mma kind::i8, see
-// ozaki_math.h), different mapping onto the SM -- the first kernel ran its phases (gather,
-// slice, MMA, TMEM drain) one after the other on a 128-row tile and measured 282 us on the
-// dominant step against 261 us for DMMA (ncu: long-scoreboard stalls on the gather, tensor
-// pipe 15 % active).  Here:
+// The arithmetic (ozaki_math.h; executed on the host by test_lower.cpp: test_ozaki_t): an
+// Ozaki-scheme product.  Every row of A (all k, re and im) gets one power-of-two scale, every
+// column of B likewise; a real x of a row becomes q = rint(x 2^(46 - E)), written in balanced
+// base 256 as six int8 digits (ComplexF32: four digits of a 30-bit q); products of digit planes
+// with equal weight are summed EXACTLY by tcgen05.mma kind::i8 in one int32 accumulator group,
+// pairs beyond the sixth (fourth) group are dropped (rel-L2 ~2.5e-13 / 2.7e-8 per contraction).
+// A first kernel with this arithmetic ran its phases (gather, slice, MMA, TMEM drain) one after
+// the other on 128-row tiles with A as the M-side operand and measured 282 us on the dominant
+// step against 261 us for DMMA (profiles/ozaki_probe_r02_first.json; removed).  Here:
 //
 //  * B is the RESIDENT M-side operand: W = 128 rows, row 2n = [Br(.,n) | -Bi(.,n)], row 2n+1 =
 //    [Bi(.,n) | Br(.,n)] (contraction length 2K: the four real products of a complex one are
@@ -814,6 +817,133 @@ __global__ void __launch_bounds__(512, 1) k_ot_ldtm_rate(long long* __restrict__
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(slot), "r"(512u) : "memory");
 }
 
+constexpr int OT_SELF_M = 128, OT_SELF_N = 64;                       // probe tiles: 128 x 64 (k) and 64 x 64 (k) int8 planes
+constexpr int OT_SELF_A_PLANE = OT_SELF_M * 64, OT_SELF_B_PLANE = OT_SELF_N * 64;
+// ---------------------------------------------------------------------------
+// Bring-up aids (pq_microbench "umma_i8_selftest", "umma_i8_tops_n32", "umma_i8_tops_n64").
+//
+// Self-test: ONE 128 x 32 x 32 kind::i8 MMA on known int8 patterns laid out exactly like the
+// kernel's planes (plane_off, LBO = rows * 16, SBO = 128), read back with tcgen05.ld and
+// compared on the host with the integer dot products -- isolates the descriptor encodings
+// and the TMEM lane / column mapping from everything else.  Returns the number of wrong
+// entries (0 = pass).
+// ---------------------------------------------------------------------------
+__host__ __device__ inline int ot_pat_a(int r, int k) { return (r * 7 + k * 3 + r / 64) % 127 - 63; }
+__host__ __device__ inline int ot_pat_b(int c, int k) { return (c * 5 + k * 11 + 1) % 127 - 63; }
+
+__global__ void __launch_bounds__(128, 1) k_umma_i8_selftest(int* __restrict__ out) {
+  __shared__ __align__(1024) unsigned char sa[OT_SELF_M * 32];
+  __shared__ __align__(1024) unsigned char sb[32 * 32];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t slot;
+  __shared__ int abort_flag;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int i = tid; i < OT_SELF_M * 32; i += 128) {
+    const int r = i >> 5, k = i & 31;
+    sa[oz::plane_off(OT_SELF_M, r, k >> 4) + (k & 15)] = (unsigned char)(signed char)ot_pat_a(r, k);
+  }
+  for (int i = tid; i < 32 * 32; i += 128) {
+    const int c = i >> 5, k = i & 31;
+    sb[oz::plane_off(32, c, k >> 4) + (k & 15)] = (unsigned char)(signed char)ot_pat_b(c, k);
+  }
+  if (tid == 0) {
+    abort_flag = 0;
+    ot_mbar_init(&bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(
+                     ot_smem_u32(&slot)),
+                 "r"(32u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+  const uint32_t tmem = slot;
+  if (tid == 0) {
+    const uint64_t ad = ot_desc(ot_smem_u32(sa), OT_SELF_M * 16, 128);
+    const uint64_t bd = ot_desc(ot_smem_u32(sb), 32 * 16, 128);
+    ot_umma_i8(tmem, (uint32_t)ad, (uint32_t)(ad >> 32), (uint32_t)bd, (uint32_t)(bd >> 32),
+               ot_idesc(OT_SELF_M, 32), 0u);
+    ot_commit(&bar);
+  }
+  ot_wait(&bar, 0u, &abort_flag, 4, 0, -1);
+  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+  const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+#pragma unroll
+  for (int c0 = 0; c0 < 32; c0 += 8) {
+    uint32_t r[8];
+    OT_TMEM_LD8(r, tmem + lane_base + c0);
+    asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+#pragma unroll
+    for (int j = 0; j < 8; ++j) out[(warp * 32 + lane) * 32 + c0 + j] = (int)r[j];
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  if (warp == 0)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "r"(32u)
+                 : "memory");
+}
+
+// Issue-rate probe: every SM issues `iters` x 16 MMAs of 128 x NCOL x 32 on resident planes
+// (4 accumulators, values irrelevant).  Returns int8 TOPS (2 ops per MAC).
+template <int NCOL>
+__global__ void __launch_bounds__(128, 1) k_umma_i8_rate(int iters, int* __restrict__ sink) {
+  extern __shared__ __align__(1024) unsigned char smem[];   // A: 128 x 64, B: 64 x 64, zeroed
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t slot;
+  __shared__ int abort_flag;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < (OT_SELF_A_PLANE + OT_SELF_B_PLANE) / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0x01010101u;
+  if (tid == 0) {
+    abort_flag = 0;
+    ot_mbar_init(&bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(
+                     ot_smem_u32(&slot)),
+                 "r"(256u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+  const uint32_t tmem = slot;
+  if (tid == 0) {
+    const uint64_t ad = ot_desc(ot_smem_u32(smem), OT_SELF_M * 16, 128);
+    const uint64_t bd = ot_desc(ot_smem_u32(smem + OT_SELF_A_PLANE), OT_SELF_N * 16, 128);
+    constexpr uint32_t IDESC = ot_idesc(OT_SELF_M, NCOL);
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const uint32_t ks = (uint32_t)(j & 1) * ((2 * OT_SELF_M * 16) >> 4);
+        const uint32_t kb = (uint32_t)(j & 1) * ((2 * OT_SELF_N * 16) >> 4);
+        ot_umma_i8(tmem + (uint32_t)((j >> 2) * NCOL), (uint32_t)ad + ks, (uint32_t)(ad >> 32),
+                   (uint32_t)bd + kb, (uint32_t)(bd >> 32), IDESC, (it | (j & 3)) ? 1u : 0u);
+      }
+    }
+    ot_commit(&bar);
+  }
+  ot_wait(&bar, 0u, &abort_flag, 4, 0, -1);
+  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+  uint32_t r[8];
+  OT_TMEM_LD8(r, tmem + ((uint32_t)(warp * 32) << 16));
+  asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+  if (r[0] == 0x7fffffffu) sink[blockIdx.x] = (int)r[1];   // keeps the loads alive
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  if (warp == 0)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "r"(256u)
+                 : "memory");
+}
+
+
 }  // namespace
 
 static bool g_ozaki_t_ready = false;
@@ -860,6 +990,26 @@ void run_zgemm_ozaki_t(const Launch& L, const FusedParams& fp, const void* A, co
   }
 }
 
+// ComplexF32 contraction with the gather fused (plans lowered with fused_gemm, see lower.cpp)
+void run_cgemm_ozaki_fused(const Launch& L, const ContractPlan& cp, const void* A, const void* B,
+                           void* C) {
+  PQ_REQUIRE(L.elem_size == 8, PQ_ERR_INVALID, "fused ComplexF32 GEMM plans run on the INT8 kernel only");
+  FusedParams fp{};
+  fp.mA = cp.mA;
+  fp.kA = cp.kA;
+  fp.nB = cp.nB;
+  fp.kB = cp.kB;
+  fp.M = cp.M;
+  fp.N = cp.N;
+  fp.K = cp.K;
+  fp.num_sms = L.num_sms;
+  L.begin(KC_GEMM_INT8, double(cp.M * cp.K + cp.N * cp.K + cp.M * cp.N) * 8.0,
+          8.0 * double(cp.M) * double(cp.N) * double(cp.K));
+  run_zgemm_ozaki_t(L, fp, A, B, C);
+  L.end();
+  PQ_CUDA(cudaGetLastError());
+}
+
 // pq_microbench back ends of this kernel: "ozaki_t_debug" (watchdog record, 0 = none),
 // "ozaki_t_trace" (block 0's phase stamps -> $PQ_OZAKI_TRACE)
 double run_ozaki_t_microbench(const Launch& L, const std::string& what) {
@@ -875,6 +1025,63 @@ double run_ozaki_t_microbench(const Launch& L, const std::string& what) {
       return rec[1];
     }
     return 0;
+  }
+  if (what.rfind("umma_i8_", 0) == 0) {
+  if (what == "umma_i8_selftest") {
+      int* d = nullptr;
+      PQ_CUDA(cudaMalloc(&d, OT_SELF_M * 32 * sizeof(int)));
+      PQ_CUDA(cudaMemsetAsync(d, 0xff, OT_SELF_M * 32 * sizeof(int), L.stream));
+      k_umma_i8_selftest<<<1, 128, 0, L.stream>>>(d);
+      std::vector<int> got(OT_SELF_M * 32);
+      cudaError_t e = cudaMemcpyAsync(got.data(), d, got.size() * sizeof(int), cudaMemcpyDeviceToHost,
+                                      L.stream);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(L.stream);
+      cudaFree(d);
+      PQ_CUDA(e);
+      if (const char* path = std::getenv("PQ_OZAKI_DUMP")) {   // raw 128 x 32 int32, row-major
+        if (FILE* f = std::fopen(path, "wb")) {
+          std::fwrite(got.data(), sizeof(int), got.size(), f);
+          std::fclose(f);
+        }
+      }
+      int wrong = 0;
+      for (int r = 0; r < OT_SELF_M; ++r)
+        for (int c = 0; c < 32; ++c) {
+          int want = 0;
+          for (int k = 0; k < 32; ++k) want += ot_pat_a(r, k) * ot_pat_b(c, k);
+          wrong += got[r * 32 + c] != want;
+        }
+      return wrong;
+    }
+    const bool n64 = what == "umma_i8_tops_n64";
+    PQ_REQUIRE(n64 || what == "umma_i8_tops_n32", PQ_ERR_INVALID, "unknown microbench: " + what);
+    const int iters = 4096, smem = OT_SELF_A_PLANE + OT_SELF_B_PLANE;
+    int* sink = nullptr;
+    PQ_CUDA(cudaMalloc(&sink, L.num_sms * sizeof(int)));
+    cudaEvent_t e0, e1;
+    PQ_CUDA(cudaEventCreate(&e0));
+    PQ_CUDA(cudaEventCreate(&e1));
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; ++rep) {
+      PQ_CUDA(cudaEventRecord(e0, L.stream));
+      if (n64)
+        k_umma_i8_rate<64><<<L.num_sms, 128, smem, L.stream>>>(iters, sink);
+      else
+        k_umma_i8_rate<32><<<L.num_sms, 128, smem, L.stream>>>(iters, sink);
+      PQ_CUDA(cudaEventRecord(e1, L.stream));
+      PQ_CUDA(cudaEventSynchronize(e1));
+      float ms = 0;
+      PQ_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+      if (rep > 0 && ms < best) best = ms;
+    }
+    cudaError_t e = cudaGetLastError();
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(sink);
+    PQ_CUDA(e);
+    const double macs = double(L.num_sms) * iters * 16.0 * OT_SELF_M * (n64 ? 64 : 32) * 32;
+    return 2.0 * macs / (best * 1e-3) / 1e12;
+  
   }
   if (what.rfind("ozaki_t_ldtm_", 0) == 0) {   // TMEM read bytes per SM clock
     int W = 8, warps = 8;

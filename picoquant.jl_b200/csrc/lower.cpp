@@ -323,9 +323,6 @@ ContractPlan lower_contract(const std::vector<int64_t>& a_dims, const std::vecto
       kb += (P.kB.ext[d] - 1) * P.kB.str[d];
     }
     P.fused_gemm = ka < (int64_t(1) << 31) && kb < (int64_t(1) << 31);
-    // EXPERIMENTAL: with zgemm_ozaki on, contractions longer than the skinny INT8 kernel's K <= 64
-    // go through canonical layouts to the K-looped INT8 kernel instead of the fused DMMA GEMM
-    if (opt.zgemm_ozaki != 0 && zgemm_ozaki_kloop_eligible(M, N, K)) P.fused_gemm = false;
   }
   if (P.kind == CK_GEMM && elem_size == 8 && opt.fused == 0 && (opt.gemm == 0 || opt.gemm == 2) &&
       ((opt.cgemm_ozaki != 0 && zgemm_ozaki_eligible(M, N, K)) ||
@@ -346,10 +343,6 @@ ContractPlan lower_contract(const std::vector<int64_t>& a_dims, const std::vecto
     P.permB = lower_permute(b_dims, pb, elem_size, opt);
     if (!P.permA.identity) P.tempA_bytes = size_t(M) * K * elem_size;
     if (!P.permB.identity) P.tempB_bytes = size_t(N) * K * elem_size;
-    // EXPERIMENTAL INT8 product for long contractions: row / column exponent tables
-    if ((elem_size == 16 ? opt.zgemm_ozaki : opt.cgemm_ozaki) != 0 && opt.gemm != 1 &&
-        zgemm_ozaki_kloop_eligible(M, N, K))
-      P.ws_bytes = size_t(M + N) * sizeof(int);
   }
   return P;
 }

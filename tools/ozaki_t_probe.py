@@ -1,12 +1,12 @@
 #!/usr/bin/env python
-"""Probe of the second-generation INT8 kernel (csrc/kernels_zgemm_ozaki2.cu, k_ozaki_t; options
-zgemm_ozaki = 6 / cgemm_ozaki = 4 with ozaki_gen = 0).  Every stage runs in a child process
+"""Probe of the INT8 tensor-core kernel (csrc/kernels_zgemm_ozaki2.cu, k_ozaki_t; forced by options
+zgemm_ozaki = 6 / cgemm_ozaki = 4, default under the ozaki_auto policy).  Every stage runs in a child process
 under a timeout (a wrong mbarrier phase must not hold the box):
 
   stage p  parity, both element types: one tile, ragged, many tiles, narrow N, short K, the
            sweep-step shapes of the bench workload (vs NumPy complex128)
-  stage t  timing of the sweep-step shapes: k_ozaki_t vs the first-generation kernel
-           (ozaki_gen = 1) vs the default path (DMMA / K1 + tcgen05 3xTF32)
+  stage t  timing of the sweep-step shapes: k_ozaki_t (forced) vs the other path (ozaki_auto = 0:
+           DMMA / K1 + tcgen05 3xTF32)
   stage r  phase trace of block 0 on the dominant step (PQ_OZAKI_TRACE) -> gpurun_out/ozaki_t_trace_*.bin
   stage s  one slice pair of the bench workload, amplitude vs the oracle, ms per slice
 
@@ -22,8 +22,57 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tools"))
-from ozaki_probe import SMALL, SWEEP, case, operands, reference  # noqa: E402
+
+
+def case(rank_a, con_pos, nb_open=6):
+    ai, o, k = [], 0, 0
+    for i in range(rank_a):
+        if i in con_pos:
+            k += 1
+            ai.append(k)
+        else:
+            o += 1
+            ai.append(-o)
+    nk = len(con_pos)
+    bi = list(range(nk, 0, -1)) + [-(o + 1 + j) for j in range(nb_open)]
+    return (2,) * rank_a, ai, (2,) * (nk + nb_open), bi
+
+
+SMALL = {
+    "tile_128x64x64": ((128, 64), [-1, 1], (64, 64), [-2, 1]),          # canonical A[m,k], B[n,k]
+    "ragged_100x33x40": ((100, 40), [-1, 1], (33, 40), [-2, 1]),
+    "two_tiles_200x64x64": ((200, 64), [-1, 1], (64, 64), [-2, 1]),
+    "many_tiles_40000x17x8": ((40000, 8), [-1, 1], (17, 8), [-2, 1]),
+    "k_first_64x300x24": ((64, 300), [1, -1], (64, 24), [1, -2]),       # contracted axis fastest
+}
+SWEEP = {
+    "con_3_4_5_18_20_22": case(24, [3, 4, 5, 18, 20, 22]),
+    "con_0_1_2_19_21_23": case(24, [0, 1, 2, 19, 21, 23]),
+    "con_tail_18_23": case(24, [18, 19, 20, 21, 22, 23]),
+    "M17_K6": case(23, [3, 4, 5, 18, 20, 22]),
+    "M18_K5": case(23, [3, 4, 18, 20, 22]),
+    "M18_K3_N6": case(21, [18, 19, 20]),
+    "M17_N5_K6": case(23, [3, 4, 5, 18, 20, 22], nb_open=5),
+}
+
+
+def operands(ad, bd, seed):
+    rng = np.random.default_rng(seed)
+    A = (rng.standard_normal(int(np.prod(ad))) + 1j * rng.standard_normal(int(np.prod(ad))))
+    B = (rng.standard_normal(int(np.prod(bd))) + 1j * rng.standard_normal(int(np.prod(bd))))
+    return A.reshape(ad, order="F"), B.reshape(bd, order="F")
+
+
+def reference(A, ai, B, bi):
+    con = sorted(x for x in ai if x > 0)
+    out = sorted((x for x in ai + bi if x < 0), reverse=True)
+    letters = {}
+    for x in con + out:
+        letters[x] = "abcdefghijklmnopqrstuvwxyzABCDEFGHIJKLMNOPQRSTUVWXYZ"[len(letters)]
+    sub = "%s,%s->%s" % ("".join(letters[x] for x in ai), "".join(letters[x] for x in bi),
+                         "".join(letters[x] for x in out))
+    return np.einsum(sub, A, B, optimize=True)
+
 
 OUT = os.path.join(ROOT, "gpurun_out", "ozaki_t_probe.json")
 EXTRA = {
@@ -65,10 +114,10 @@ def child(stage):
         for name, (ad, ai, bd, bi) in SWEEP.items():
             A, B = operands(ad, bd, 2)
             for dt, (npdt, opt, g, tol) in DT.items():
-                for label, val, gen in (("default", 0, 0), ("gen1", g, 1), ("gen2", g, 0)):
+                for label, val in (("other", 0), ("int8", g)):
                     b = B200Backend(npdt)
                     b.set_option(opt, val)
-                    b.set_option("ozaki_gen", gen)
+                    b.set_option("ozaki_auto", 0)
                     for rep in range(5):
                         b.save_tensor_data("A", A.astype(npdt))
                         b.save_tensor_data("B", B.astype(npdt))
@@ -107,9 +156,10 @@ def child(stage):
         sample = [1, 2]
         ref = complex(np.asarray(bench.run_cpu_slices(rec, np.complex128, sample)).reshape(-1)[0])
         for dt, (npdt, opt, g, tol) in DT.items():
-            for label, val in (("default", 0), ("gen2", g)):
+            for label, val in (("other", 0), ("int8", g)):
                 b = B200Backend(npdt)
                 b.set_option(opt, val)
+                b.set_option("ozaki_auto", 0)
                 sc = SlicedContraction(b, rec)
                 sc.run(sample, lanes=2)
                 b.sync()
