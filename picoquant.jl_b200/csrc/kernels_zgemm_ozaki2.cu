@@ -532,11 +532,12 @@ k_ozaki_t(const typename OtVec<Real>::type* __restrict__ A, const typename OtVec
     const int ch = (warp - OT_PW) >> 2;     // which 32 of the 64 tile rows
     const int jt = 2 * (lane & 3);          // this thread's row pair inside a block
     typename Sc::col_type sb[2];
-    int ncol[2];
+    V2* cbase[2];   // column n of C (null: n beyond N)
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-      ncol[h] = 16 * q + 8 * h + (lane >> 2);
-      sb[h] = Sc::template col_load<G>(colS[ncol[h]]);
+      const int n = 16 * q + 8 * h + (lane >> 2);
+      sb[h] = Sc::template col_load<G>(colS[n]);
+      cbase[h] = n < N ? C + M * (long long)n : nullptr;
     }
     const uint32_t lane_addr = tmem_base + ((uint32_t)(32 * q) << 16);
     const bool wide = (M & 1) == 0 && (reinterpret_cast<uintptr_t>(C) & 31) == 0;
@@ -561,8 +562,10 @@ k_ozaki_t(const typename OtVec<Real>::type* __restrict__ A, const typename OtVec
         }
       };
       auto wait_ld = [&]() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory"); };
-      auto process = [&](const uint32_t (&r)[G][4], int b) {
-        const int h = b & 1, j0 = 32 * ch + 8 * (b >> 1) + jt;
+      // full tiles of an even-M, 32-byte aligned C (the sweep steps): one unchecked wide store
+      const bool fast = wide && (tile + 1) * ot::ROWS <= M;
+      auto process = [&](const uint32_t (&r)[G][4], int h, int cg) {   // lanes half h, 8-row group cg
+        const int j0 = 32 * ch + 8 * cg + jt;
         Real v[4];   // re(m), re(m + 1), im(m), im(m + 1)
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -571,11 +574,12 @@ k_ozaki_t(const typename OtVec<Real>::type* __restrict__ A, const typename OtVec
           for (int g = 0; g < G; ++g) rr[g] = (int)r[g][i];
           v[i] = Sc::template apply<G>(rr, sb[h], rs[j0 + (i & 1)]);
         }
+        const Real re[2] = {v[0], v[1]}, im[2] = {v[2], v[3]};
         const long long m0 = tile * ot::ROWS + j0;
-        const int n = ncol[h];
-        if (n < N && m0 < M) {
-          V2* dst = C + m0 + M * (long long)n;
-          const Real re[2] = {v[0], v[1]}, im[2] = {v[2], v[3]};
+        if (fast) {
+          if (cbase[h] != nullptr) ot_store2(cbase[h] + m0, re, im, true);
+        } else if (cbase[h] != nullptr && m0 < M) {
+          V2* dst = cbase[h] + m0;
           if (m0 + 1 < M) {
             ot_store2(dst, re, im, wide);
           } else {
@@ -591,7 +595,7 @@ k_ozaki_t(const typename OtVec<Real>::type* __restrict__ A, const typename OtVec
 #pragma unroll 1
       for (int b = 0; b < 8; b += 2) {
         load(rb, b + 1, false);
-        process(ra, b);
+        process(ra, 0, b >> 1);
         wait_ld();
         if (b + 2 < 8) {
           load(ra, b + 2, false);
@@ -605,7 +609,7 @@ k_ozaki_t(const typename OtVec<Real>::type* __restrict__ A, const typename OtVec
               ot_mbar_arrive(&freed[(ot_dbuf<G>(g) ? (t & 1u) : 0u) * 8 + g]);
           }
         }
-        process(rb, b + 1);
+        process(rb, 1, b >> 1);
         if (b + 2 < 8) wait_ld();
       }
       if (tid == OT_PW * 32) OT_TRACE(t, 18);
