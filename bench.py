@@ -435,12 +435,18 @@ def config_arm(a):
             e1.record()
             torch.cuda.synchronize()
             best = min(best, e0.elapsed_time(e1))
-        peak = 8.0 * 4096 ** 3 / (best * 1e-3) / 1e12
+        lib = 8.0 * 4096 ** 3 / (best * 1e-3) / 1e12
         ach = kernels[dom]["achieved_tflops"]
+        if a.dtype == "c128":
+            peak, src = lib, "cuBLAS ZGEMM 4096^3 measured in this run (the FP64 DMMA pipe)"
+        else:
+            peak = tf32_split_peak_tflops()
+            src = ("TF32 tensor pipe / 3: cuBLAS TF32 SGEMM 8192^3 measured in this run, divided by the 3 pipe "
+                   "flops a 3xTF32 split product spends per algorithmic flop")
         roofline = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": peak,
-                    "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
-                    "peak_source": "cuBLAS %s 4096^3 measured in this run"
-                                   % ("ZGEMM" if a.dtype == "c128" else "CGEMM")}
+                    "unit": "TFLOP/s", "frac": ach / peak, "traffic": None, "peak_source": src,
+                    "library_gemm_tflops": lib,
+                    "library_gemm": "cuBLAS %s 4096^3" % ("ZGEMM" if a.dtype == "c128" else "CGEMM")}
     else:
         # whole-stream figure: algorithmic bytes of every step / device time of the replay
         ach = costs["bytes"] / (ms * 1e-3) / 1e9
@@ -548,6 +554,31 @@ class ClockSampler:
 # ---------------------------------------------------------------------------
 _REAL_STDOUT = None
 
+
+
+def tf32_split_peak_tflops():
+    """Roofline denominator of the ComplexF32 tcgen05 GEMM: the TF32 tensor-pipe rate
+    measured on this box (cuBLAS SGEMM with TF32 inputs, 8192^3) divided by 3 -- a complex
+    product costs 12 TF32 MMAs (hi*hi + hi*lo + lo*hi for each of its four real products) against
+    4 on exact inputs, so 3 pipe flops are spent per algorithmic flop."""
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        n = 8192
+        x = torch.randn(n, n, dtype=torch.float32, device="cuda")
+        y = torch.randn(n, n, dtype=torch.float32, device="cuda")
+        torch.matmul(x, y)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        best = 1e30
+        for _ in range(3):
+            e0.record()
+            torch.matmul(x, y)
+            e1.record()
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        return 2.0 * n ** 3 / (best * 1e-3) / 1e12 / 3.0
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
 
 def emit(line: dict) -> None:
     """Prints the ONE JSON line on the real stdout (native libraries such as NCCL write
@@ -806,6 +837,8 @@ def main():
                                             "complex MAC" % (tops, 4 * pairs))
         elif dom in GEMM_CLASSES:
             peak = peaks.get("cublas_zgemm_tflops") or peaks["fp64_dmma_probe_tflops"]
+            if a.dtype == "c64":
+                peaks["tf32_pipe_over_3_tflops"] = peak = tf32_split_peak_tflops()
             ach = kernels[dom]["achieved_tflops"]
             roofline = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": peak,
                         "unit": "TFLOP/s", "frac": ach / peak, "traffic": traffic,
@@ -816,11 +849,12 @@ def main():
                                  "same figure against the DMMA issue probe x 8/6" if a.dtype == "c128" else
                                  "achieved = algorithmic 8*M*N*K flops / in-graph busy time "
                                  "(tcgen05 3xTF32: 12 TF32 MMAs per complex product)"),
-                        "peak_source": "cuBLAS %s 4096^3 measured in this run "
-                                       "(MEASURED_PEAKS.json has no FP64 / complex figure); the "
-                                       "same library reaches %s TFLOP/s on the dominant skinny "
-                                       "shape" % ("ZGEMM" if a.dtype == "c128" else "CGEMM",
-                                                  peaks.get("cublas_zgemm_skinny_tflops"))}
+                        "peak_source": ("cuBLAS ZGEMM 4096^3 measured in this run "
+                                        "(MEASURED_PEAKS.json has no FP64 / complex figure); the "
+                                        "same library reaches %s TFLOP/s on the dominant skinny "
+                                        "shape" % peaks.get("cublas_zgemm_skinny_tflops")) if a.dtype == "c128" else
+                                       ("TF32 tensor pipe / 3 (cuBLAS TF32 SGEMM 8192^3 measured in this run; "
+                                        "cuBLAS CGEMM 4096^3 reaches %s TFLOP/s)" % peaks.get("cublas_zgemm_tflops"))}
             if a.dtype == "c128":
                 roofline["frac_of_3m_pipe"] = ach / (peaks["fp64_dmma_probe_tflops"] * 8.0 / 6.0)
         else:

@@ -17,8 +17,10 @@ rep = sys.argv[3] if len(sys.argv) > 3 else None
 out_dir = os.path.join(ROOT, "profiles")
 os.makedirs(out_dir, exist_ok=True)
 
-with open(launches) as f:
-    lines = [l for l in f if not l.startswith("==")]
+lines = []
+if launches != "-":
+    with open(launches) as f:
+        lines = [l for l in f if not l.startswith("==")]
 agg = collections.defaultdict(lambda: [0, 0.0])
 for row in csv.DictReader(lines):
     if row.get("Metric Name") != "gpu__time_duration.sum":
@@ -28,7 +30,7 @@ for row in csv.DictReader(lines):
     v = {"ns": v / 1e3, "us": v, "ms": v * 1e3}.get(row["Metric Unit"], v)
     agg[name][0] += 1
     agg[name][1] += v
-tot = sum(v[1] for v in agg.values())
+tot = sum(v[1] for v in agg.values()) or 1.0
 md = ["# ncu launch list summary (%s)" % tag, "",
       "Source: `%s` (`ncu --metrics gpu__time_duration.sum --clock-control none`; per-launch "
       "times are cold-cache and serialised: compare SHARES, not absolutes)." % os.path.basename(launches),
@@ -51,7 +53,24 @@ if rep:
             "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread",
             "launch__grid_size", "launch__block_size", "launch__occupancy_limit_registers",
             "launch__occupancy_limit_shared_mem",
-            "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "lts__t_bytes.sum"]
+            "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "lts__t_bytes.sum",
+            "sm__inst_executed_pipe_tensor_subpipe_imma.avg.pct_of_peak_sustained_active",
+            "sm__inst_executed_pipe_tensor_subpipe_hmma.avg.pct_of_peak_sustained_active",
+            "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
+            "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
+            "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active",
+            "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active",
+            "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
+            "sm__inst_executed_pipe_tmem.avg.pct_of_peak_sustained_active",
+            "sm__inst_executed_pipe_uniform.avg.pct_of_peak_sustained_active",
+            "smsp__issue_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum",
+            "lts__t_sector_hit_rate.pct",
+            "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+            "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
+            "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
+            "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
+            "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
+            "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio"]
     md += ["# ncu --set full, selected counters per captured launch", "",
            "Source: `%s`." % os.path.basename(rep), ""]
     min_us = float(os.environ.get("NCU_MIN_US", "0"))   # skip short launches in the detail part

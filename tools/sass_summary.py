@@ -39,8 +39,8 @@ with open(out_path, "w") as f:
     f.write("# library totals: " + ", ".join("%s %d" % (w, total[w]) for w in WATCH if total[w]) + "\n\n")
     for fn in order:
         c = counts[fn]
-        name = re.sub(r"\(.*", "", demangle(fn)).replace("void ", "")
-        name = re.sub(r"pq::\(anonymous namespace\)::|pq::", "", name)
+        name = demangle(fn).replace("(anonymous namespace)::", "")
+        name = re.sub(r"\(.*", "", name).replace("void ", "").replace("pq::", "")
         hits = ", ".join("%s %d" % (w, c[w]) for w in WATCH if c[w])
         f.write("%-72s %6d instr  %s\n" % (name[:72], c["_instructions"], hits))
 print(open(out_path).read()[:3000])
