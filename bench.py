@@ -97,6 +97,19 @@ def build_workload(a):
     return circ, rec, name
 
 
+def workload_config(a, name, rec, macs):
+    """The `config` object of the JSON line: the WORKLOAD only, identical for the GPU arm and the
+    reference (CPU) arm so that the driver can compare them; how an arm executes it goes into
+    its own `run` object."""
+    itemsize = 16 if a.dtype == "c128" else 8
+    return {"workload": name, "baseline_config": 5, "slices": a.slices, "plan": "sweep (harness planner)",
+            "complex_macs_per_slice": macs,
+            "contract_calls_per_slice": sum(1 for c, _ in parse_dsl(rec.text) if c == "ncon"),
+            "largest_intermediate_elems": 1 << 24,
+            "l2": "inputs larger than L2: per-step intermediates of 2^24 elements (%d MiB) stream "
+                  "through the 126 MB L2" % ((itemsize << 24) >> 20)}
+
+
 def slice_macs(rec):
     """Complex MACs of one slice on DATA extents (sliced bonds have extent 1)."""
     shapes, macs = {}, 0
@@ -150,6 +163,17 @@ def use_all_host_threads():
         return n
 
 
+def host_cpu_model():
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("model name"):
+                    return "%s x %d" % (line.split(":", 1)[1].strip(), os.cpu_count() or 1)
+    except OSError:
+        pass
+    return "unknown x %d" % (os.cpu_count() or 1)
+
+
 def cpu_threads():
     try:
         from threadpoolctl import threadpool_info
@@ -178,10 +202,12 @@ def reference_arm(a):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus,
         "steps": a.steps, "warmup": a.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": a.dtype, "data": "synthetic",
-        "config": {"workload": name, "slices": a.slices, "plan": "sweep",
-                   "note": "reference CPU path restated in NumPy/OpenBLAS (the Julia reference "
-                           "cannot run here); each step contracts ONE of the %d slices; a full "
-                           "amplitude costs %d x this" % (a.slices, a.slices)},
+        "config": workload_config(a, name, rec, macs),
+        "run": {"note": "reference CPU path restated in NumPy/OpenBLAS (the Julia reference cannot run "
+                        "here); each step contracts ONE of the %d slices -- a bounded sample of the "
+                        "workload, the metric is a rate; a full amplitude costs %d x this"
+                        % (a.slices, a.slices),
+                "slices_per_step": per_step, "host_cpu": host_cpu_model()},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cpu_threads(), "kind": "port",
                          "sample": "1 slice of %d per step" % a.slices},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -918,15 +944,12 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": a.dtype, "data": "synthetic",
-            "config": {"workload": name, "slices": a.slices, "slices_per_gpu": len(mine),
-                       "plan": "sweep (harness planner)", "complex_macs_per_slice": macs,
-                       "contract_calls_per_slice": sum(1 for c, _ in parse_dsl(rec.text)
-                                                       if c == "ncon"),
-                       "kernel_launches_per_slice": sc.program.launches,
-                       "arena_bytes": sc.program.arena_bytes, "parallelism": "slices/%d" % world,
-                       "slices_in_flight_per_gpu": a.lanes, "zgemm_ozaki": a.ozaki, "ozaki_auto": 0 if a.no_int8 else 1,
-                       "l2": "inputs larger than L2: per-step intermediates of 2^24 elements "
-                             "(256 MiB c128) stream through the 126 MB L2"},
+            "config": workload_config(a, name, rec, macs),
+            "run": {"slices_per_step": a.slices, "slices_per_gpu": len(mine),
+                    "kernel_launches_per_slice": sc.program.launches,
+                    "arena_bytes": sc.program.arena_bytes, "parallelism": "slices/%d" % world,
+                    "slices_in_flight_per_gpu": a.lanes, "zgemm_ozaki": a.ozaki,
+                    "ozaki_auto": 0 if a.no_int8 else 1, "host_cpu": host_cpu_model()},
             "amplitude_wall_ms": ms_per_step,
             "amplitude": [float(np.real(amplitude)), float(np.imag(amplitude))],
             "complex_mac_per_s": macs * a.slices / (ms_per_step * 1e-3),
