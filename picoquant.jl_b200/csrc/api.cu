@@ -357,6 +357,7 @@ extern "C" int pq_load_tensor(pq_handle* h, const char* label, void* host_out, i
       for (int64_t i = 0; i < 2 * n; ++i) d[i] = (double)s[i];
     }
   }
+  ozaki_t_check_watchdog();   // the stream is idle here
   PQ_CATCH(h)
 }
 
@@ -556,6 +557,7 @@ extern "C" int pq_sync(pq_handle* h) {
   set_device(h);
   PQ_CUDA(cudaStreamSynchronize(h->stream));
   PQ_CUDA(cudaGetLastError());
+  ozaki_t_check_watchdog();
   PQ_CATCH(h)
 }
 

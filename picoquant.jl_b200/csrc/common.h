@@ -223,6 +223,7 @@ struct FusedParams {
 void init_kernels_ozaki_t();
 double run_ozaki_t_microbench(const Launch& L, const std::string& what);
 void run_zgemm_ozaki_t(const Launch& L, const FusedParams& fp, const void* A, const void* B, void* C);
+void ozaki_t_check_watchdog();   // throws PQ_ERR_CUDA if a k_ozaki_t launch hit its mbarrier watchdog (call on an idle stream)
 // envelope of the kernel: all of K and N resident per tile
 inline bool zgemm_ozaki_eligible(int64_t M, int64_t N, int64_t K) {
   return K >= 1 && K <= 64 && N >= 1 && N <= 64 && M >= 1;

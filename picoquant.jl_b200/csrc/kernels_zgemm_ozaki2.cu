@@ -951,6 +951,7 @@ __global__ void __launch_bounds__(128, 1) k_umma_i8_rate(int iters, int* __restr
 }  // namespace
 
 static bool g_ozaki_t_ready = false;
+static bool g_ozaki_t_launched = false;   // any k_ozaki_t launch in this process (see ozaki_t_check_watchdog)
 
 void init_kernels_ozaki_t() {
   cudaError_t e[4];
@@ -977,6 +978,7 @@ void run_zgemm_ozaki_t(const Launch& L, const FusedParams& fp, const void* A, co
   const unsigned grid = (unsigned)(tiles < L.num_sms ? tiles : L.num_sms);
   const bool trace = std::getenv("PQ_OZAKI_TRACE") != nullptr;
   const FusedParams& fq = fp;
+  g_ozaki_t_launched = true;
   if (L.elem_size == 16) {
     if (trace)
       k_ozaki_t<double, true><<<grid, OT_THREADS, OtSmem<6>::kTotal, L.stream>>>(
@@ -1012,6 +1014,23 @@ void run_cgemm_ozaki_fused(const Launch& L, const ContractPlan& cp, const void* 
   run_zgemm_ozaki_t(L, fp, A, B, C);
   L.end();
   PQ_CUDA(cudaGetLastError());
+}
+
+// Sync points of the library (pq_sync, pq_load_tensor) call this once the stream is idle: a
+// watchdog event means a k_ozaki_t CTA gave up on an mbarrier wait and its results are garbage --
+// that must surface as an error, not as numbers.  `launched` keeps the check off the path of
+// handles that never ran the kernel.
+void ozaki_t_check_watchdog() {
+  if (!g_ozaki_t_launched) return;
+  int rec[8] = {0};
+  PQ_CUDA(cudaMemcpyFromSymbol(rec, g_ot_debug, sizeof(rec)));
+  if (rec[0] == 0) return;
+  int zero[8] = {0};
+  PQ_CUDA(cudaMemcpyToSymbol(g_ot_debug, zero, sizeof(zero)));
+  char msg[200];
+  std::snprintf(msg, sizeof(msg), "k_ozaki_t watchdog: wait id %d (1 full, 2 freed, 3 done, 4 empty) tile %d group %d "
+                "block %d warp %d never completed; results of that launch are invalid", rec[1], rec[2], rec[3], rec[4], rec[5]);
+  throw Error(PQ_ERR_CUDA, msg);
 }
 
 // pq_microbench back ends of this kernel: "ozaki_t_debug" (watchdog record, 0 = none),
