@@ -1,5 +1,6 @@
 // Small data-movement kernels: K7 slice copy (view_tensor!, reference
 // src/layer1.jl:191-194), slice-partial accumulation, and the bandwidth probe.
+#include <cstdio>
 #include "common.h"
 
 namespace pq {
@@ -91,7 +92,78 @@ __global__ void __launch_bounds__(256) k_copy16(const uint4* __restrict__ in, ui
     out[i] = in[i];
 }
 
+// Memory-system probe for the sweep-step access pattern (pq_microbench "stream_<mode>_<ctas>"): a
+// pure copy of 2^24 16-byte elements in 64 KB tiles, with the READ side laid out like the A operand
+// of the dominant sweep step (mode bit 0: 8 runs of 8 KB per tile, 4 / 16 / 64 MB apart; else one
+// contiguous 64 KB block) and the WRITE side like its result C[m + M n] (mode bit 1: 64 runs of
+// 1 KB per tile, 4 MB apart; else contiguous).  `ctas` resident CTAs per SM x 256 threads x 16
+// loads of 16 bytes in flight.  Returns GB/s (read + write).
+__global__ void __launch_bounds__(256)
+k_stream_probe(const uint4* __restrict__ in, uint4* __restrict__ out, int mode) {
+  const long long tiles = 4096;
+  for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    // tile bits 0..8 -> element bits 9..17, tile bits 9, 10, 11 -> element bits 19, 21, 23
+    const long long rbase = ((tile & 511) << 9) | (((tile >> 9) & 1) << 19) | (((tile >> 10) & 1) << 21) |
+                            (((tile >> 11) & 1) << 23);
+    uint4 v[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int u = threadIdx.x + 256 * i;   // 16-byte unit of the tile
+      long long src;
+      if (mode & 1) {
+        const int run = u >> 9, within = u & 511;   // run bits 0, 1, 2 -> element bits 18, 20, 22
+        src = rbase + within + ((long long)(run & 1) << 18) + ((long long)((run >> 1) & 1) << 20) +
+              ((long long)((run >> 2) & 1) << 22);
+      } else {
+        src = tile * 4096 + u;
+      }
+      v[i] = in[src];
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int u = threadIdx.x + 256 * i;
+      long long dst;
+      if (mode & 2) {
+        const int n = u >> 6, row = u & 63;
+        dst = tile * 64 + row + ((long long)n << 18);
+      } else {
+        dst = tile * 4096 + u;
+      }
+      out[dst] = v[i];
+    }
+  }
+}
+
 double run_microbench(const Launch& L, const std::string& what) {
+  if (what.rfind("stream_", 0) == 0) {
+    int mode = 0, ctas = 2;
+    std::sscanf(what.c_str() + 7, "%d_%d", &mode, &ctas);
+    const long long n = 1LL << 24;
+    uint4 *a = nullptr, *b = nullptr;
+    PQ_CUDA(cudaMalloc(&a, n * 16));
+    PQ_CUDA(cudaMalloc(&b, n * 16));
+    PQ_CUDA(cudaMemsetAsync(a, 1, n * 16, L.stream));
+    cudaEvent_t e0, e1;
+    PQ_CUDA(cudaEventCreate(&e0));
+    PQ_CUDA(cudaEventCreate(&e1));
+    float best = 1e30f;
+    for (int rep = 0; rep < 6; ++rep) {
+      PQ_CUDA(cudaEventRecord(e0, L.stream));
+      k_stream_probe<<<L.num_sms * ctas, 256, 0, L.stream>>>(a, b, mode);
+      PQ_CUDA(cudaEventRecord(e1, L.stream));
+      PQ_CUDA(cudaEventSynchronize(e1));
+      float ms = 0;
+      PQ_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+      if (rep > 0 && ms < best) best = ms;
+    }
+    cudaError_t err = cudaGetLastError();
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(a);
+    cudaFree(b);
+    PQ_CUDA(err);
+    return 2.0 * double(n) * 16.0 / (best * 1e-3) / 1e9;
+  }
   if (what.rfind("ozaki_t_", 0) == 0 || what.rfind("umma_i8_", 0) == 0) return run_ozaki_t_microbench(L, what);
   if (what == "dmma_tflops") return run_fp64_probe(L, true);
   if (what.rfind("dmma_tflops_w", 0) == 0) return run_fp64_probe(L, true, std::stoi(what.substr(13)));

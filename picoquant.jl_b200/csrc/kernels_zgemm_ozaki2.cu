@@ -595,12 +595,11 @@ k_ozaki_t(const typename OtVec<Real>::type* __restrict__ A, const typename OtVec
 #pragma unroll 1
       for (int b = 0; b < 8; b += 2) {
         load(rb, b + 1, false);
-        process(ra, 0, b >> 1);
-        wait_ld();
-        if (b + 2 < 8) {
-          load(ra, b + 2, false);
-        } else {
-          // every accumulator of the tile has been read by this warp: the MMA warp may overwrite
+        if (b + 2 == 8) {
+          // the last loads of the tile: release the accumulators BEFORE the last two blocks are
+          // recombined, so that the MMAs of the next tile's single-buffered groups (1900 clocks)
+          // run under that work instead of after it
+          wait_ld();
           asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
           __syncwarp();
           if (lane == 0) {
@@ -608,9 +607,15 @@ k_ozaki_t(const typename OtVec<Real>::type* __restrict__ A, const typename OtVec
             for (int g = 0; g < G; ++g)
               ot_mbar_arrive(&freed[(ot_dbuf<G>(g) ? (t & 1u) : 0u) * 8 + g]);
           }
+          process(ra, 0, b >> 1);
+          process(rb, 1, b >> 1);
+        } else {
+          process(ra, 0, b >> 1);
+          wait_ld();
+          load(ra, b + 2, false);
+          process(rb, 1, b >> 1);
+          wait_ld();
         }
-        process(rb, 1, b >> 1);
-        if (b + 2 < 8) wait_ld();
       }
       if (tid == OT_PW * 32) OT_TRACE(t, 18);
       if (TR && tid == OT_PW * 32 && blockIdx.x == 0 && t < 32) {   // wall clock beside the SM clock
