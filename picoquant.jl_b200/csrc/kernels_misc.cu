@@ -110,7 +110,13 @@ k_stream_probe(const uint4* __restrict__ in, uint4* __restrict__ out, int mode) 
     for (int i = 0; i < 16; ++i) {
       const int u = threadIdx.x + 256 * i;   // 16-byte unit of the tile
       long long src;
-      if (mode & 1) {
+      if (mode & 4) {
+        // the producers' own lane mapping: thread = (tile row j, 16-k chunk c), load i reads k = 16 c + i:
+        // a warp instruction touches 4 separate 128-byte pieces (8 rows x 16 bytes each)
+        const int j = (threadIdx.x >> 5) * 8 + (threadIdx.x & 7), c = (threadIdx.x & 31) >> 3, k = 16 * c + i;
+        src = rbase + (j & 7) + ((long long)(k & 7) << 3) + ((long long)(j >> 3) << 6) + ((long long)((k >> 3) & 1) << 18) +
+              ((long long)((k >> 4) & 1) << 20) + ((long long)((k >> 5) & 1) << 22);
+      } else if (mode & 1) {
         const int run = u >> 9, within = u & 511;   // run bits 0, 1, 2 -> element bits 18, 20, 22
         src = rbase + within + ((long long)(run & 1) << 18) + ((long long)((run >> 1) & 1) << 20) +
               ((long long)((run >> 2) & 1) << 22);

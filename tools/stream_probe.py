@@ -9,11 +9,11 @@ sys.path.insert(0, ROOT)
 import picoquant_jl_b200  # noqa
 from picoquant_jl_b200.host.b200_backend import B200Backend
 b = B200Backend(np.complex128)
-names = {0: "contiguous reads, contiguous writes", 1: "gathered reads (8 x 8 KB), contiguous writes",
+names = {7: "gathered reads in the producers' lane order (4 x 128 B per warp instruction), scattered writes", 0: "contiguous reads, contiguous writes", 1: "gathered reads (8 x 8 KB), contiguous writes",
          2: "contiguous reads, scattered writes (64 x 1 KB, 4 MB apart)", 3: "gathered reads, scattered writes (the sweep step)"}
 res = {"copy_gbs": b.microbench("copy_gbs")}
 print("plain copy: %.0f GB/s" % res["copy_gbs"])
-for mode in (0, 1, 2, 3):
+for mode in (0, 1, 2, 3, 7):
     for ctas in (1, 2, 4, 8):
         k = "stream_%d_%d" % (mode, ctas)
         res[k] = b.microbench(k)
