@@ -587,6 +587,7 @@ def tf32_split_peak_tflops():
     measured on this box (cuBLAS SGEMM with TF32 inputs, 8192^3) divided by 3 -- a complex
     product costs 12 TF32 MMAs (hi*hi + hi*lo + lo*hi for each of its four real products) against
     4 on exact inputs, so 3 pipe flops are spent per algorithmic flop."""
+    import torch
     old = torch.backends.cuda.matmul.allow_tf32
     torch.backends.cuda.matmul.allow_tf32 = True
     try:

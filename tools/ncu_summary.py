@@ -31,13 +31,14 @@ for row in csv.DictReader(lines):
     agg[name][0] += 1
     agg[name][1] += v
 tot = sum(v[1] for v in agg.values()) or 1.0
-md = ["# ncu launch list summary (%s)" % tag, "",
-      "Source: `%s` (`ncu --metrics gpu__time_duration.sum --clock-control none`; per-launch "
-      "times are cold-cache and serialised: compare SHARES, not absolutes)." % os.path.basename(launches),
-      "", "| kernel | launches | total us | avg us | share |", "|---|---:|---:|---:|---:|"]
-for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
-    md.append("| `%s` | %d | %.1f | %.2f | %.3f |" % (k, v[0], v[1], v[1] / v[0], v[1] / tot))
-md.append("")
+md = ["# ncu summary (%s)" % tag, ""]
+if agg:
+    md += ["Launch list: `%s` (`ncu --metrics gpu__time_duration.sum --clock-control none`; per-launch "
+           "times are cold-cache and serialised: compare SHARES, not absolutes)." % os.path.basename(launches),
+           "", "| kernel | launches | total us | avg us | share |", "|---|---:|---:|---:|---:|"]
+    for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+        md.append("| `%s` | %d | %.1f | %.2f | %.3f |" % (k, v[0], v[1], v[1] / v[0], v[1] / tot))
+    md.append("")
 
 if rep:
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True,
