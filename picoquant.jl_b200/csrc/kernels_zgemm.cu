@@ -482,6 +482,111 @@ k_zgemm_fused_t(const double2* __restrict__ A, const double2* __restrict__ B,
 }
 
 // ---------------------------------------------------------------------------
+// Thin-N fused TTGT ZGEMM: N <= 16, K <= 64, M huge (a site tensor with one open bond of 8
+// absorbed into the boundary: per row of A, 1 KB in and 128 B out -- a stream).  No shared-
+// memory staging of A at all: the m8n8k4 DMMA's A fragment is one element per lane (row
+// lane / 4, k lane % 4), so a warp owns 8 rows per step and fetches its fragments of all K
+// straight from the un-permuted tensor with K / 4 independent 16-byte loads per lane (8 KB in
+// flight per warp, 16 warps per SM), then runs the 4 * K / 4 DMMAs against B in shared memory
+// (K x N, gathered once per CTA).  C[m + M n]: 8 lanes x 16 B contiguous per column.
+//
+// What decides the speed of such a gather is how many 128-byte lines a QUARTER warp (8 lanes,
+// one L1 tag pass) touches per load -- measured on M = 2^18, N = 8, K = 64 (ncu durations):
+//     1 line  57 us (tiled kernel, rows fastest)     2 lines 56 us (this kernel, k fastest)
+//     4 lines 70 us (this kernel, rows fastest, fragment order)     8 lines 92 us (tiled, k fastest)
+// So the load order follows the operand: KF (a contracted axis is the fastest of A): lane ->
+// (row lane / 4, k lane % 4), the fragment order itself, 4 x 16 B contiguous per row; otherwise
+// lane -> (row lane % 8, k lane / 8), 8 x 16 B contiguous per k, and the 8 x 4 lane grid is
+// transposed into fragment order with two 64-bit shuffles per load.  Loads and DMMAs are
+// volatile asm, i.e. kept in program order: all loads of a step are in flight before the first
+// DMMA waits on one (left to itself the compiler re-uses fragment registers and issues the
+// loads in dependent batches between the DMMAs).  A half-step software pipeline (loads of the
+// next half of K in flight under the DMMAs of this one) measured the same and was dropped.
+// Replaces the 128 x 8 tile-per-CTA configuration of k_zgemm_fused_t on these steps.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ double2 thin_load(const double2* ptr, bool pred) {
+  double2 v;
+  asm volatile(
+      "{\n .reg .pred q;\n setp.ne.b32 q, %3, 0;\n mov.f64 %0, 0d0000000000000000;\n"
+      " mov.f64 %1, 0d0000000000000000;\n @q ld.global.nc.v2.f64 {%0, %1}, [%2];\n}\n"
+      : "=d"(v.x), "=d"(v.y)
+      : "l"(ptr), "r"((int)pred));
+  return v;
+}
+
+template <int KS, int NB, bool KF>   // K <= 4 KS, N <= 8 NB; KF: load in fragment order
+__global__ void __launch_bounds__(256, 2)
+k_zgemm_thin(const double2* __restrict__ A, const double2* __restrict__ B,
+             double2* __restrict__ C, const FusedParams p) {
+  constexpr int KP = 4 * KS, NP = 8 * NB;
+  __shared__ __align__(16) double2 sB[KP][NP];
+  __shared__ int koffA[KP];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int frow = lane >> 2, fk = lane & 3;                     // fragment order
+  const int lrow = KF ? frow : (lane & 7), lk = KF ? fk : (lane >> 3);   // load order
+  const int src = frow + 8 * fk;   // !KF: the lane that loaded this lane's fragment
+  const long long M = p.M;
+  const int N = (int)p.N, K = (int)p.K;
+
+  for (int k = tid; k < KP; k += 256) koffA[k] = k < K ? (int)map_offset(p.kA, k) : -1;
+  for (int i = tid; i < KP * NP; i += 256) {
+    const int k = i / NP, n = i % NP;
+    sB[k][n] = (k < K && n < N) ? B[map_offset(p.nB, n) + map_offset(p.kB, k)] : make_double2(0.0, 0.0);
+  }
+  __syncthreads();
+  int ko[KS];
+#pragma unroll
+  for (int ks = 0; ks < KS; ++ks) ko[ks] = koffA[4 * ks + lk];
+
+  const long long blocks = (M + 7) / 8, stride = (long long)gridDim.x * 8;
+  long long blk = (long long)blockIdx.x * 8 + warp;
+  bool lvalid = blk < blocks && blk * 8 + lrow < M;
+  long long ra = lvalid ? map_offset(p.mA, blk * 8 + lrow) : 0;
+  while (blk < blocks) {
+    const long long m = blk * 8 + frow;
+    double2 a[KS];
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) a[ks] = thin_load(A + ra + ko[ks], lvalid && ko[ks] >= 0);
+    // the row offset of the warp's next step, behind the loads
+    const long long nblk = blk + stride;
+    const bool nvalid = nblk < blocks && nblk * 8 + lrow < M;
+    const long long nra = nvalid ? map_offset(p.mA, nblk * 8 + lrow) : 0;
+    double cr[NB][2], ci[NB][2];
+#pragma unroll
+    for (int y = 0; y < NB; ++y) cr[y][0] = cr[y][1] = ci[y][0] = ci[y][1] = 0.0;
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+      double ax = a[ks].x, ay = a[ks].y;
+      if (!KF) {
+        ax = __shfl_sync(0xffffffffu, ax, src);
+        ay = __shfl_sync(0xffffffffu, ay, src);
+      }
+      const double nay = -ay;
+#pragma unroll
+      for (int y = 0; y < NB; ++y) {
+        const double2 b = sB[4 * ks + fk][8 * y + frow];
+        dmma(cr[y][0], cr[y][1], ax, b.x);
+        dmma(ci[y][0], ci[y][1], ax, b.y);
+        dmma(cr[y][0], cr[y][1], nay, b.y);
+        dmma(ci[y][0], ci[y][1], ay, b.x);
+      }
+    }
+    if (m < M) {
+#pragma unroll
+      for (int y = 0; y < NB; ++y)
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const int n = 8 * y + 2 * fk + c;
+          if (n < N) C[m + M * n] = make_double2(cr[y][c], ci[y][c]);
+        }
+    }
+    blk = nblk;
+    lvalid = nvalid;
+    ra = nra;
+  }
+}
+
+// ---------------------------------------------------------------------------
 // Persistent fused TTGT ZGEMM for the skinny sweep steps (K <= 64, 16 < N <= 64, M huge).
 //
 // Measured on the tile-per-CTA kernel above (M = 2^18, N = K = 64): with the DMMAs removed
@@ -784,6 +889,20 @@ static void launch_fused(int cfg, const Launch& L, const FusedParams& fp, const 
   }
 }
 
+template <bool KF>
+static void launch_thin(const Launch& L, const FusedParams& fp, const void* A, const void* B, void* C) {
+  const unsigned grid = (unsigned)(2 * L.num_sms);
+  const double2 *a = (const double2*)A, *b = (const double2*)B;
+  double2* c = (double2*)C;
+  if (fp.K <= 32) {
+    if (fp.N <= 8) k_zgemm_thin<8, 1, KF><<<grid, 256, 0, L.stream>>>(a, b, c, fp);
+    else k_zgemm_thin<8, 2, KF><<<grid, 256, 0, L.stream>>>(a, b, c, fp);
+  } else {
+    if (fp.N <= 8) k_zgemm_thin<16, 1, KF><<<grid, 256, 0, L.stream>>>(a, b, c, fp);
+    else k_zgemm_thin<16, 2, KF><<<grid, 256, 0, L.stream>>>(a, b, c, fp);
+  }
+}
+
 constexpr int SK_NG = 2, SK_S = 2;   // measured: four groups / deeper rings are not faster
 
 template <int TBN, bool AKF>
@@ -882,6 +1001,28 @@ void run_zgemm_fused(const Launch& L, const ContractPlan& cp, const void* A, con
     if (oz != 0 && zgemm_ozaki_eligible(cp.M, cp.N, cp.K)) {
       L.begin(KC_GEMM_INT8, bytes, flops);
       run_zgemm_ozaki_t(L, fp, A, B, C);
+      L.end();
+      PQ_CUDA(cudaGetLastError());
+      return;
+    }
+  }
+  // thin N, a contracted axis fastest in A: fragments straight from the un-permuted tensor
+  // (k_zgemm_thin, 58 us against 93 us of the tiled kernel on M = 2^18, N = 8, K = 64); with an
+  // open axis fastest the tiled kernel's row-first gather already touches one line per quarter
+  // warp and stays ahead (58 vs 61 us).  Options: an explicit zgemm_cfg or zgemm_thin = 1 keep
+  // the tiled kernel, zgemm_thin = 2 / 3 force k_zgemm_thin with the k-first / rows-first order.
+  {
+    const int thin = L.opt ? L.opt->zgemm_thin : 0;
+    PQ_REQUIRE(thin >= 0 && thin <= 3, PQ_ERR_INVALID, "zgemm_thin must be 0..3");
+    const bool k_fastest = min_stride(cp.kA) < min_stride(cp.mA);
+    if ((L.opt ? L.opt->zgemm_cfg : 0) == 0 && cp.N <= 16 && cp.K <= 64 &&
+        (thin >= 2 || (thin == 0 && k_fastest))) {
+      const bool kf = thin == 2 || (thin == 0 && k_fastest);
+      L.begin(KC_GEMM_TENSOR, bytes, flops);
+      if (kf)
+        launch_thin<true>(L, fp, A, B, C);
+      else
+        launch_thin<false>(L, fp, A, B, C);
       L.end();
       PQ_CUDA(cudaGetLastError());
       return;

@@ -341,6 +341,53 @@ def test_fused_ttgt_zgemm_shapes(cfg):
         assert rel_l2(got, ref) < 1e-10, (ad, ai, rel_l2(got, ref))
 
 
+@pytest.mark.parametrize("thin", [0, 1, 2, 3])
+def test_thin_n_zgemm(thin):
+    """ComplexF64 steps with one short open bond on the small side (N <= 16, K <= 64):
+    k_zgemm_thin (DMMA fragments loaded straight from the un-permuted operand; option zgemm_thin
+    2 / 3 force its k-first / rows-first load order, 0 is the policy, 1 the tiled kernel it
+    replaced).  Contracted axes lowest / highest / scattered in A, N = 8 and 16, K = 32 and 64,
+    ragged M, N and K, more 8-row steps than resident warps."""
+    rng = np.random.default_rng(61 + thin)
+    b = B200(np.complex128, zgemm_thin=thin, ozaki_auto=0)
+
+    def case(rank_a, con, nb_open):
+        ai, o, k = [], 0, 0
+        for i in range(rank_a):
+            if i in con:
+                k += 1
+                ai.append(k)
+            else:
+                o += 1
+                ai.append(-o)
+        bi = list(range(len(con), 0, -1)) + [-(o + 1 + j) for j in range(nb_open)]
+        return (2,) * rank_a, ai, (2,) * (len(con) + nb_open), bi
+
+    shapes = [
+        case(20, [0, 1, 2, 15, 17, 19], 3),      # contracted axes lowest: k-first policy, K = 64, N = 8
+        case(20, [3, 4, 5, 14, 16, 18], 3),      # open axes lowest
+        case(19, [0, 1, 16, 17, 18], 4),         # K = 32, N = 16
+        case(22, [1, 3, 5, 7, 9, 11], 3),        # 2^16 rows: several steps per warp
+        ((4099, 37), [-1, 1], (37, 11), [1, -2]),                 # ragged M, N, K (rows fastest)
+        ((53, 5001), [1, -1], (53, 13), [1, -2]),                 # ragged, contracted axis fastest
+        ((8, 4100, 8), [1, -1, 2], (8, 8, 9), [2, 1, -2]),        # two contracted axes around the open one
+    ]
+    for ad, ai, bd, bi in shapes:
+        A = rand_tensor(rng, tuple(ad), np.complex128)
+        B = rand_tensor(rng, tuple(bd), np.complex128)
+        b.save_tensor_data("A", A)
+        b.save_tensor_data("B", B)
+        b.profile_enable(True)
+        b.contract_tensors("A", ai, "B", bi, "C")
+        prof = b.profile_read()
+        b.profile_enable(False)
+        assert set(prof) == {"gemm_tensor"}, (ad, prof)
+        got = b.load_tensor_data("C")
+        ref = layer1.contract_tensors((A, B), (ai, bi))
+        assert got.shape == ref.shape
+        assert rel_l2(got, ref) < 1e-13, (thin, ad, ai, rel_l2(got, ref))
+
+
 @pytest.mark.parametrize("K", [8, 40, 255, 256, 257, 513, 4096])
 def test_tcgen05_cgemm_accuracy_over_k(K):
     """ComplexF32 GEMM on tcgen05 with 3xTF32 splitting and K-chunked fp32 folding: the

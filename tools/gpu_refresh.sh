@@ -54,4 +54,7 @@ timeout 120 python tools/ozaki_t_ldtm.py > $OUT/ozaki_t_ldtm_$TAG.log 2>&1
 timeout 300 python tools/slice_breakdown.py > $OUT/slice_breakdown_${TAG}_c128.txt 2>&1
 timeout 300 python tools/slice_breakdown.py c64 > $OUT/slice_breakdown_${TAG}_c64.txt 2>&1
 timeout 300 python tools/cgemm_probe.py > $OUT/cgemm_probe_$TAG.log 2>&1
+# thin-N DMMA kernel against the tiled one: kernel durations from an ncu launch list
+timeout 500 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $OUT/thin_launches_$TAG.csv \
+  -k regex:k_zgemm python tools/thin_probe.py > $OUT/thin_probe_$TAG.log 2>&1
 ls -la $OUT | tail -40
