@@ -156,6 +156,19 @@ __device__ __forceinline__ void ot_umma_i8(uint32_t tmem_d, uint32_t a_lo, uint3
       "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// A operand (the M side) from tensor memory: lane = row, 8 columns = the 32 int8 of one k-step
+__device__ __forceinline__ void ot_umma_i8_ts_elect(uint32_t tmem_d, uint32_t tmem_a, uint64_t b_desc,
+                                                    uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p, q;\n"
+      "elect.sync _|q, 0xffffffff;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "@q tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // Whole-warp variants: every lane executes the (uniform) surrounding code, one elected lane
 // issues.  With `if (lane == 0)` around the issue loop ptxas cannot prove uniformity: it wraps
 // every UTCIMMA in an ELECT / BRA.U.ANY loop and moves each descriptor through R2UR, ~17
@@ -209,16 +222,21 @@ __device__ __forceinline__ void ot_commit(uint64_t* bar) {
 // groups of columns double-buffer groups 4 and 5 -- the longest ones (20 + 24 of the 84 MMAs
 // of a tile), issued FIRST, so that the tensor core has ~2100 clocks of work on the next tile
 // while the epilogue still drains groups 0..3 of the current one.
-template <int G>
-__device__ __forceinline__ constexpr bool ot_dbuf(int g) { return G == 4 || g >= 4; }
-template <int G>
+// WT > 0 (ComplexF64 only): the spare 128 columns hold digit planes 0..WT-1 of W instead (8
+// columns per plane and k-step, lane = W row), the A operand of the TS form of the MMA -- no
+// double buffering then; groups in natural order.
+template <int G, int WT>
+__device__ __forceinline__ constexpr bool ot_dbuf(int g) { return G == 4 || (WT == 0 && g >= 4); }
+template <int G, int WT>
 __device__ __forceinline__ uint32_t ot_acc_col(int g, uint32_t buf) {
-  return G == 4 ? (uint32_t)(64 * g) + 256u * buf : (g < 4 ? (uint32_t)(64 * g) : 256u + 64u * (uint32_t)(g - 4) + 128u * buf);
+  return G == 4 ? (uint32_t)(64 * g) + 256u * buf
+                : (g < 4 || WT > 0 ? (uint32_t)(64 * g) : 256u + 64u * (uint32_t)(g - 4) + 128u * buf);
 }
-template <int G>
+template <int G, int WT>
 __device__ __forceinline__ constexpr int ot_issue_order(int i) {
-  return G == 4 ? i : (i == 0 ? 5 : i == 1 ? 4 : i - 2);
+  return (G == 4 || WT > 0) ? i : (i == 0 ? 5 : i == 1 ? 4 : i - 2);
 }
+__device__ __forceinline__ constexpr uint32_t ot_w_col(int wp, int ks) { return 384u + (uint32_t)((wp * 4 + ks) * 8); }
 
 // Output scaling, kept lean in ISSUE SLOTS and FP64 instructions (the epilogue's two scarce
 // resources: ncu showed ~80 instructions per real number for an integer-only version, and the
@@ -307,7 +325,7 @@ __device__ __forceinline__ void ot_store4(float2* dst, const double* re, const d
   }
 }
 
-template <class Real, bool TR = false>
+template <class Real, bool TR = false, int WT = 0>
 __global__ void __maxnreg__(96)
 k_ozaki_t(const typename OtVec<Real>::type* __restrict__ A, const typename OtVec<Real>::type* __restrict__ B,
           typename OtVec<Real>::type* __restrict__ C, const FusedParams p) {
@@ -316,6 +334,7 @@ k_ozaki_t(const typename OtVec<Real>::type* __restrict__ A, const typename OtVec
   using Sm = OtSmem<Tr::S>;
   constexpr int S = Tr::S, G = Tr::S;
   static_assert(G == 4 || G == 6, "accumulator placement (ot_acc_col) is written for 4 or 6 groups");
+  static_assert(WT == 0 || (G == 6 && WT <= 4), "W planes in tensor memory: ComplexF64 only, at most 4 planes (128 columns)");
   extern __shared__ __align__(1024) unsigned char smem[];
   unsigned char* sW = smem + Sm::kW;
   unsigned char* sX = smem + Sm::kX;
@@ -401,6 +420,28 @@ k_ozaki_t(const typename OtVec<Real>::type* __restrict__ A, const typename OtVec
     asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
   }
   __syncthreads();
+  if constexpr (WT > 0) {
+    // digit planes 0..WT-1 of W into tensor memory: lane = W row, 8 columns = the 32 digits of one
+    // k-step (two 16-byte chunks of the row).  Epilogue warp w writes the lanes of its quadrant.
+    if (warp >= OT_PW && warp < OT_PW + 4) {
+      const int r = 32 * (warp & 3) + lane;
+#pragma unroll
+      for (int wp = 0; wp < WT; ++wp)
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          const uint4 lo = *reinterpret_cast<const uint4*>(sW + wp * ot::W_PLANE + oz::plane_off(ot::WROWS, r, 2 * ks));
+          const uint4 hi = *reinterpret_cast<const uint4*>(sW + wp * ot::W_PLANE + oz::plane_off(ot::WROWS, r, 2 * ks + 1));
+          asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n" ::"r"(
+                           tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + ot_w_col(wp, ks)),
+                       "r"(lo.x), "r"(lo.y), "r"(lo.z), "r"(lo.w), "r"(hi.x), "r"(hi.y), "r"(hi.z), "r"(hi.w)
+                       : "memory");
+        }
+      asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+  }
 
   if (warp < OT_PW) {
     // ===================== producers =====================
@@ -494,14 +535,14 @@ k_ozaki_t(const typename OtVec<Real>::type* __restrict__ A, const typename OtVec
       const uint64_t xs = x_base + (uint64_t)((stage * (S * ot::X_PLANE)) >> 4);
 #pragma unroll
       for (int gi = 0; gi < G; ++gi) {
-        const int g = ot_issue_order<G>(gi);
-        const uint32_t buf = ot_dbuf<G>(g) ? (t & 1u) : 0u, u = ot_dbuf<G>(g) ? (t >> 1) : t;
+        const int g = ot_issue_order<G, WT>(gi);
+        const uint32_t buf = ot_dbuf<G, WT>(g) ? (t & 1u) : 0u, u = ot_dbuf<G, WT>(g) ? (t >> 1) : t;
         // the epilogue must have drained this accumulator (its previous use)
         if (u > 0) {
           ot_wait(&freed[buf * 8 + g], (u - 1) & 1u, abort_flag, 2, (int)t, g);
           asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
         }
-        const uint32_t acc_addr = tmem_base + ot_acc_col<G>(g, buf);
+        const uint32_t acc_addr = tmem_base + ot_acc_col<G, WT>(g, buf);
         uint32_t acc = 0;
 #pragma unroll
         for (int sp = 0; sp < S; ++sp) {
@@ -510,8 +551,12 @@ k_ozaki_t(const typename OtVec<Real>::type* __restrict__ A, const typename OtVec
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) {
             if (ks < KC) {
-              ot_umma_i8_elect(acc_addr, w_base + (uint64_t)((wp * ot::W_PLANE + ks * 2 * ot::W_LBO) >> 4),
-                               xs + (uint64_t)((sp * ot::X_PLANE + ks * 2 * ot::X_LBO) >> 4), IDESC, acc);
+              if (WT > 0 && wp < WT)
+                ot_umma_i8_ts_elect(acc_addr, tmem_base + ot_w_col(wp, ks),
+                                    xs + (uint64_t)((sp * ot::X_PLANE + ks * 2 * ot::X_LBO) >> 4), IDESC, acc);
+              else
+                ot_umma_i8_elect(acc_addr, w_base + (uint64_t)((wp * ot::W_PLANE + ks * 2 * ot::W_LBO) >> 4),
+                                 xs + (uint64_t)((sp * ot::X_PLANE + ks * 2 * ot::X_LBO) >> 4), IDESC, acc);
               acc = 1u;
             }
           }
@@ -552,13 +597,13 @@ k_ozaki_t(const typename OtVec<Real>::type* __restrict__ A, const typename OtVec
         const uint32_t la = lane_addr + ((uint32_t)(16 * (b & 1)) << 16) + col0;
 #pragma unroll
         for (int g = 0; g < G; ++g) {
-          const uint32_t buf = ot_dbuf<G>(g) ? (t & 1u) : 0u, u = ot_dbuf<G>(g) ? (t >> 1) : t;
+          const uint32_t buf = ot_dbuf<G, WT>(g) ? (t & 1u) : 0u, u = ot_dbuf<G, WT>(g) ? (t >> 1) : t;
           if (first) {
             ot_wait(&done[buf * 8 + g], u & 1u, abort_flag, 3, (int)t, g);
             asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
             if (tid == OT_PW * 32 && (g == 0 || g == G - 1)) OT_TRACE(t, g == 0 ? 16 : 17);
           }
-          OT_TMEM_LD_16x256(r[g], la + ot_acc_col<G>(g, buf));
+          OT_TMEM_LD_16x256(r[g], la + (ot_acc_col<G, WT>(g, buf)));
         }
       };
       auto wait_ld = [&]() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory"); };
@@ -605,7 +650,7 @@ k_ozaki_t(const typename OtVec<Real>::type* __restrict__ A, const typename OtVec
           if (lane == 0) {
 #pragma unroll
             for (int g = 0; g < G; ++g)
-              ot_mbar_arrive(&freed[(ot_dbuf<G>(g) ? (t & 1u) : 0u) * 8 + g]);
+              ot_mbar_arrive(&freed[(ot_dbuf<G, WT>(g) ? (t & 1u) : 0u) * 8 + g]);
           }
           process(ra, 0, b >> 1);
           process(rb, 1, b >> 1);
@@ -646,15 +691,24 @@ k_ozaki_t(const typename OtVec<Real>::type* __restrict__ A, const typename OtVec
 // reports SM clocks per MMA.  mode bits: 1 = every MMA reads the SAME W / X slices (operand
 // reuse), 2 = operand-major order (consecutive MMAs rotate over the accumulators instead of
 // chaining into one), 4 = the 16 idle warps poll the final mbarrier with one lane per warp
-// instead of all 32, 8 = no idle warps at all (they exit), 16 = N = 128 tiles (two X planes side by side).
+// instead of all 32, 8 = no idle warps at all (they exit), 16 = N = 128 tiles (two X planes side by side),
+// 32 / 64 / 128 = an arithmetic loop beside the MMA stream, 256 = the W operand from TENSOR memory
+// (TS form; accumulators 0..3 only, W in columns 384..511), 512 = the eight producer warps stream
+// 64 KB batches from global memory beside the MMA stream like the kernel's producers (16 loads of
+// 16 bytes per thread, one batch in flight; their clocks per batch in out[148 + block]),
+// 1024 = no MMAs at all (the load stream alone).
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(OT_THREADS, 1) k_ot_mma_rate(int iters, int mode, long long* __restrict__ out) {
+template <bool TS>
+__global__ void __launch_bounds__(OT_THREADS, 1) k_ot_mma_rate(int iters, int mode, long long* __restrict__ out,
+                                                               const double2* __restrict__ stream_buf,
+                                                               long long stream_elems) {
   extern __shared__ __align__(1024) unsigned char smem[];
   __shared__ __align__(8) uint64_t bar;
   __shared__ uint32_t slot;
   __shared__ int abort_flag;
   constexpr int S = 6;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // uniform: the MMA loop issues on the uniform datapath
   unsigned char* sW = smem;
   unsigned char* sX = smem + S * ot::W_PLANE;
   for (int i = tid; i < (S * ot::W_PLANE + 2 * S * ot::X_PLANE) / 4; i += OT_THREADS)
@@ -676,22 +730,29 @@ __global__ void __launch_bounds__(OT_THREADS, 1) k_ot_mma_rate(int iters, int mo
   asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
   const uint32_t tmem = slot;
   const bool same = mode & 1, opmajor = mode & 2, one_lane = mode & 4, no_idle = mode & 8, wide = mode & 16;
+  const bool no_mma = mode & 1024;
   long long t0 = 0;
   if (warp == OT_PW + OT_EW) {
-    if (lane == 0) {
+    if (no_mma) {
+      t0 = clock64();
+      if (lane == 0) ot_mbar_arrive(&bar);
+    } else {   // whole warp, one elected lane issues (the kernel's own issue path)
       const uint32_t IDESC = wide ? ot_idesc(ot::WROWS, 128) : ot_idesc(ot::WROWS, ot::ROWS);
       const uint64_t w_base = ot_desc(ot_smem_u32(sW), ot::W_LBO, ot::SBO);
       const uint64_t x_base = ot_desc(ot_smem_u32(sX), wide ? 2 * ot::X_LBO : ot::X_LBO, ot::SBO);
-      const uint32_t w_lo = (uint32_t)w_base, w_hi = (uint32_t)(w_base >> 32);
-      const uint32_t x_lo = (uint32_t)x_base, x_hi = (uint32_t)(x_base >> 32);
       const int ncol = wide ? 128 : 64;
       auto mma = [&](int g, int wp, int xp, int ks, uint32_t acc) {
         if (same) wp = xp = ks = 0;
         if (wide) xp >>= 1;
-        ot_umma_i8(tmem + (uint32_t)((wide ? (g & 3) : g) * ncol),
-                   w_lo + (uint32_t)((wp * ot::W_PLANE + ks * 2 * ot::W_LBO) >> 4), w_hi,
-                   x_lo + (uint32_t)((xp * (wide ? 2 : 1) * ot::X_PLANE + ks * 2 * (wide ? 2 : 1) * ot::X_LBO) >> 4),
-                   x_hi, IDESC, acc);
+        if (TS) {
+          ot_umma_i8_ts_elect(tmem + (uint32_t)((g & 3) * ncol), tmem + 384u + (uint32_t)((wp & 3) * 32 + ks * 8),
+                              x_base + (uint64_t)((xp * ot::X_PLANE + ks * 2 * ot::X_LBO) >> 4), IDESC, acc);
+          return;
+        }
+        ot_umma_i8_elect(tmem + (uint32_t)((wide ? (g & 3) : g) * ncol),
+                         w_base + (uint64_t)((wp * ot::W_PLANE + ks * 2 * ot::W_LBO) >> 4),
+                         x_base + (uint64_t)((xp * (wide ? 2 : 1) * ot::X_PLANE + ks * 2 * (wide ? 2 : 1) * ot::X_LBO) >> 4),
+                         IDESC, acc);
       };
       t0 = clock64();
       for (int it = 0; it < iters; ++it) {
@@ -707,8 +768,22 @@ __global__ void __launch_bounds__(OT_THREADS, 1) k_ot_mma_rate(int iters, int mo
               for (int xp = 0; xp + wp < S; ++xp) mma(wp + xp, wp, xp, ks, (uint32_t)(it > 0 || ks > 0 || wp > 0));
         }
       }
-      ot_commit(&bar);
+      ot_commit_elect(&bar);
     }
+  } else if ((mode & 512) && warp < OT_PW) {
+    // the producers' load stream beside the MMA stream
+    const long long a0 = clock64();
+    double acc = 0;
+    for (int it = 0; it < iters; ++it) {
+      const long long base = (((long long)it * gridDim.x + blockIdx.x) * 4096) % (stream_elems - 4096);
+      double2 v[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = stream_buf[base + i * 256 + tid];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) acc += v[i].x + v[i].y;
+    }
+    if (acc == 12345.0) out[400] = 1;
+    if (tid == 0) out[148 + blockIdx.x] = clock64() - a0;
   } else if (mode & (32 | 64 | 128)) {
     // contention probe: the other 16 warps run an arithmetic loop beside the MMA stream
     // (32: DFMA, 64: FFMA, 128: IMAD; 8 independent chains, 4096 iterations) and report their
@@ -959,7 +1034,9 @@ static bool g_ozaki_t_ready = false;
 static bool g_ozaki_t_launched = false;   // any k_ozaki_t launch in this process (see ozaki_t_check_watchdog)
 
 void init_kernels_ozaki_t() {
-  cudaError_t e[4];
+  cudaError_t e[5];
+  e[4] = cudaFuncSetAttribute(k_ozaki_t<double, false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              OtSmem<6>::kTotal);
   e[0] = cudaFuncSetAttribute(k_ozaki_t<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, OtSmem<6>::kTotal);
   e[1] = cudaFuncSetAttribute(k_ozaki_t<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, OtSmem<4>::kTotal);
   e[2] = cudaFuncSetAttribute(k_ozaki_t<double, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -987,6 +1064,9 @@ void run_zgemm_ozaki_t(const Launch& L, const FusedParams& fp, const void* A, co
   if (L.elem_size == 16) {
     if (trace)
       k_ozaki_t<double, true><<<grid, OT_THREADS, OtSmem<6>::kTotal, L.stream>>>(
+          (const double2*)A, (const double2*)B, (double2*)C, fq);
+    else if (L.opt && L.opt->ozaki_tsw == 2)   // W planes 0..3 in tensor memory (TS form of the MMA)
+      k_ozaki_t<double, false, 4><<<grid, OT_THREADS, OtSmem<6>::kTotal, L.stream>>>(
           (const double2*)A, (const double2*)B, (double2*)C, fq);
     else
       k_ozaki_t<double><<<grid, OT_THREADS, OtSmem<6>::kTotal, L.stream>>>(
@@ -1137,23 +1217,38 @@ double run_ozaki_t_microbench(const Launch& L, const std::string& what) {
   if (what.rfind("ozaki_t_rate_", 0) == 0) {   // SM clocks per MMA, mean over the SMs
     const int mode = std::atoi(what.c_str() + 13), iters = 200;
     const int smem = 6 * ot::W_PLANE + 2 * 6 * ot::X_PLANE;
-    PQ_CUDA(cudaFuncSetAttribute(k_ot_mma_rate, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    PQ_CUDA(cudaFuncSetAttribute(k_ot_mma_rate<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    PQ_CUDA(cudaFuncSetAttribute(k_ot_mma_rate<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     long long* d = nullptr;
     PQ_CUDA(cudaMalloc(&d, 512 * sizeof(long long)));
     PQ_CUDA(cudaMemsetAsync(d, 0, 512 * sizeof(long long), L.stream));
     std::vector<long long> h(512);
     const int grid = L.num_sms < 148 ? L.num_sms : 148;
-    for (int rep = 0; rep < 2; ++rep) k_ot_mma_rate<<<grid, OT_THREADS, smem, L.stream>>>(iters, mode, d);
+    double2* buf = nullptr;
+    const long long elems = (mode & 512) ? (1ll << 26) : 0;   // 1 GiB
+    if (elems) {
+      PQ_CUDA(cudaMalloc(&buf, elems * sizeof(double2)));
+      PQ_CUDA(cudaMemsetAsync(buf, 0, elems * sizeof(double2), L.stream));
+    }
+    for (int rep = 0; rep < 2; ++rep) {
+      if (mode & 256)
+        k_ot_mma_rate<true><<<grid, OT_THREADS, smem, L.stream>>>(iters, mode, d, buf, elems);
+      else
+        k_ot_mma_rate<false><<<grid, OT_THREADS, smem, L.stream>>>(iters, mode, d, buf, elems);
+    }
     cudaError_t e = cudaMemcpyAsync(h.data(), d, h.size() * sizeof(long long), cudaMemcpyDeviceToHost, L.stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(L.stream);
     cudaFree(d);
+    if (buf) cudaFree(buf);
     PQ_CUDA(e);
     double sum = 0, side = 0;
     for (int b = 0; b < grid; ++b) {
       sum += (double)h[b];
       side += (double)h[148 + b];
     }
-    if (mode & (32 | 64 | 128))   // clocks per warp-level arithmetic instruction of the side loop (16 warps)
+    if (mode & 512)   // clocks per 64 KB batch of the load stream
+      std::fprintf(stderr, "ozaki_t_rate mode %d: load stream %.0f clk per 64 KB batch\n", mode, side / grid / iters);
+    else if (mode & (32 | 64 | 128))   // clocks per warp-level arithmetic instruction of the side loop (16 warps)
       std::fprintf(stderr, "ozaki_t_rate mode %d: side loop %.2f clk per warp instruction per SMSP\n", mode,
                    side / grid / (4096.0 * 8.0 * 4.0));
     return sum / grid / (double(iters) * 84.0);

@@ -66,6 +66,32 @@ def test_forced_int8_contraction_matches_oracle(case, dtype, opt, groups, tol):
     b.close()
 
 
+@pytest.mark.parametrize("case", range(len(SHAPES)))
+def test_int8_w_planes_in_tensor_memory(case):
+    """Option ``ozaki_tsw = 2``: digit planes 0..3 of W live in tensor memory and their MMAs use the
+    TS form of tcgen05.mma (A operand from TMEM); no accumulator is double-buffered then.  The
+    integer arithmetic is the same, so the result must be IDENTICAL to the default kernel's."""
+    ad, ai, bd, bi = SHAPES[case]
+    rng = np.random.default_rng(100 + case)
+    A = np.asarray(rng.standard_normal(ad) + 1j * rng.standard_normal(ad), order="F")
+    B = np.asarray(rng.standard_normal(bd) + 1j * rng.standard_normal(bd), order="F")
+    out = []
+    for tsw in (0, 2):
+        b = B200(np.complex128, zgemm_ozaki=6, fused=0, ozaki_tsw=tsw)
+        for rep in range(2):      # the second launch re-uses tensor memory a first one has written
+            b.save_tensor_data("A", A)
+            b.save_tensor_data("B", B)
+            b.profile_enable(True)
+            b.contract_tensors("A", ai, "B", bi, "C")
+            prof = b.profile_read()
+        if case == 0:
+            assert "gemm_int8" in prof, prof
+        out.append(np.asarray(b.load_tensor_data("C")).copy())
+        assert b.microbench("ozaki_t_debug") == 0
+        b.close()
+    assert np.array_equal(out[0], out[1])
+
+
 def test_forced_int8_rejects_other_group_counts():
     from picoquant_jl_b200.host.b200_backend import B200Error
     b = B200()

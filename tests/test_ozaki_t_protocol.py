@@ -4,7 +4,8 @@ warps, the tensor core as an in-order asynchronous agent; barriers ``full[s]`` (
 ``empty[s]`` (tcgen05.commit), ``done[b][g]`` (tcgen05.commit), ``freed[b][g]`` (count 8), two X
 stages.  Accumulators: ComplexF32 (4 groups) all double-buffered; ComplexF64 (6 groups) groups
 4 and 5 double-buffered and issued first, groups 0..3 single-buffered (``ot_dbuf`` /
-``ot_issue_order`` in the kernel).
+``ot_issue_order`` in the kernel); the variant with W planes in tensor memory (``WT = 4``)
+double-buffers nothing and issues the groups in natural order.
 
 The wait / arrive sequence of every role is restated with the kernel's own parity arithmetic
 and run under random interleavings.  Checked: no deadlock; a producer never rewrites a stage
@@ -39,8 +40,12 @@ class MBar:
         return (self.phase & 1) != (parity & 1)
 
 
+WT = 0   # digit planes of W held in tensor memory (ComplexF64 variant k_ozaki_t<double, false, 4>):
+         # the spare columns are taken, no group is double-buffered, groups in natural order
+
+
 def dbuf(G, g):
-    return G == 4 or g >= 4
+    return G == 4 or (WT == 0 and g >= 4)
 
 
 def buf_use(t, G, g):
@@ -48,7 +53,7 @@ def buf_use(t, G, g):
 
 
 def issue_order(G):
-    return list(range(4)) if G == 4 else [5, 4, 0, 1, 2, 3]
+    return list(range(G)) if (G == 4 or WT > 0) else [5, 4, 0, 1, 2, 3]
 
 
 NSUB = 8   # sub-chunks of 4 tile rows per epilogue warp
@@ -171,6 +176,14 @@ def run(seed, tiles, G, broken=None):
 def test_protocol_random_interleavings(G):
     for seed in range(60):
         run(seed, tiles=1 + seed % 7, G=G)
+
+
+def test_protocol_w_planes_in_tensor_memory(monkeypatch):
+    """The variant without double-buffered accumulators (option ozaki_tsw = 2)."""
+    import sys
+    monkeypatch.setattr(sys.modules[__name__], "WT", 4)
+    for seed in range(60):
+        run(seed, tiles=1 + seed % 7, G=6)
 
 
 @pytest.mark.parametrize("broken", ["no_empty_wait", "no_freed_wait", "full_parity", "done_parity"])
