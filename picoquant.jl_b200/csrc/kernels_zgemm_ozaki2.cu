@@ -696,9 +696,11 @@ k_ozaki_t(const typename OtVec<Real>::type* __restrict__ A, const typename OtVec
 // (TS form; accumulators 0..3 only, W in columns 384..511), 512 = the eight producer warps stream
 // 64 KB batches from global memory beside the MMA stream like the kernel's producers (16 loads of
 // 16 bytes per thread, one batch in flight; their clocks per batch in out[148 + block]),
-// 1024 = no MMAs at all (the load stream alone).
+// 1024 = no MMAs at all (the load stream alone), 2048 = N = 32: two half-tile MMAs per X plane and
+// k-step (the reported clocks are per PAIR, i.e. per 64 rows as in the other modes).  TS and N = 32
+// are template parameters: a run-time branch around the MMA costs the uniform-datapath issue path.
 // ---------------------------------------------------------------------------
-template <bool TS>
+template <bool TS, bool NARROW>
 __global__ void __launch_bounds__(OT_THREADS, 1) k_ot_mma_rate(int iters, int mode, long long* __restrict__ out,
                                                                const double2* __restrict__ stream_buf,
                                                                long long stream_elems) {
@@ -731,13 +733,14 @@ __global__ void __launch_bounds__(OT_THREADS, 1) k_ot_mma_rate(int iters, int mo
   const uint32_t tmem = slot;
   const bool same = mode & 1, opmajor = mode & 2, one_lane = mode & 4, no_idle = mode & 8, wide = mode & 16;
   const bool no_mma = mode & 1024;
+  constexpr bool narrow = NARROW;   // mode 2048: N = 32 MMAs (half tiles), two per X plane and k-step
   long long t0 = 0;
   if (warp == OT_PW + OT_EW) {
     if (no_mma) {
       t0 = clock64();
       if (lane == 0) ot_mbar_arrive(&bar);
     } else {   // whole warp, one elected lane issues (the kernel's own issue path)
-      const uint32_t IDESC = wide ? ot_idesc(ot::WROWS, 128) : ot_idesc(ot::WROWS, ot::ROWS);
+      const uint32_t IDESC = wide ? ot_idesc(ot::WROWS, 128) : narrow ? ot_idesc(ot::WROWS, 32) : ot_idesc(ot::WROWS, ot::ROWS);
       const uint64_t w_base = ot_desc(ot_smem_u32(sW), ot::W_LBO, ot::SBO);
       const uint64_t x_base = ot_desc(ot_smem_u32(sX), wide ? 2 * ot::X_LBO : ot::X_LBO, ot::SBO);
       const int ncol = wide ? 128 : 64;
@@ -745,8 +748,23 @@ __global__ void __launch_bounds__(OT_THREADS, 1) k_ot_mma_rate(int iters, int mo
         if (same) wp = xp = ks = 0;
         if (wide) xp >>= 1;
         if (TS) {
+          if constexpr (NARROW) {   // two half-tile MMAs (rows 0..31 / 32..63 of the plane) into two 192-column accumulator sets
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+              ot_umma_i8_ts_elect(tmem + (uint32_t)(h * 192 + g * 32), tmem + 384u + (uint32_t)((wp & 3) * 32 + ks * 8),
+                                  x_base + (uint64_t)((xp * ot::X_PLANE + ks * 2 * ot::X_LBO + h * 512) >> 4), IDESC, acc);
+            return;
+          }
           ot_umma_i8_ts_elect(tmem + (uint32_t)((g & 3) * ncol), tmem + 384u + (uint32_t)((wp & 3) * 32 + ks * 8),
                               x_base + (uint64_t)((xp * ot::X_PLANE + ks * 2 * ot::X_LBO) >> 4), IDESC, acc);
+          return;
+        }
+        if constexpr (NARROW) {
+#pragma unroll
+          for (int h = 0; h < 2; ++h)
+            ot_umma_i8_elect(tmem + (uint32_t)(h * 192 + g * 32),
+                             w_base + (uint64_t)((wp * ot::W_PLANE + ks * 2 * ot::W_LBO) >> 4),
+                             x_base + (uint64_t)((xp * ot::X_PLANE + ks * 2 * ot::X_LBO + h * 512) >> 4), IDESC, acc);
           return;
         }
         ot_umma_i8_elect(tmem + (uint32_t)((wide ? (g & 3) : g) * ncol),
@@ -1217,8 +1235,9 @@ double run_ozaki_t_microbench(const Launch& L, const std::string& what) {
   if (what.rfind("ozaki_t_rate_", 0) == 0) {   // SM clocks per MMA, mean over the SMs
     const int mode = std::atoi(what.c_str() + 13), iters = 200;
     const int smem = 6 * ot::W_PLANE + 2 * 6 * ot::X_PLANE;
-    PQ_CUDA(cudaFuncSetAttribute(k_ot_mma_rate<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    PQ_CUDA(cudaFuncSetAttribute(k_ot_mma_rate<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    auto kern = (mode & 2048) ? ((mode & 256) ? k_ot_mma_rate<true, true> : k_ot_mma_rate<false, true>)
+                              : ((mode & 256) ? k_ot_mma_rate<true, false> : k_ot_mma_rate<false, false>);
+    PQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     long long* d = nullptr;
     PQ_CUDA(cudaMalloc(&d, 512 * sizeof(long long)));
     PQ_CUDA(cudaMemsetAsync(d, 0, 512 * sizeof(long long), L.stream));
@@ -1230,12 +1249,7 @@ double run_ozaki_t_microbench(const Launch& L, const std::string& what) {
       PQ_CUDA(cudaMalloc(&buf, elems * sizeof(double2)));
       PQ_CUDA(cudaMemsetAsync(buf, 0, elems * sizeof(double2), L.stream));
     }
-    for (int rep = 0; rep < 2; ++rep) {
-      if (mode & 256)
-        k_ot_mma_rate<true><<<grid, OT_THREADS, smem, L.stream>>>(iters, mode, d, buf, elems);
-      else
-        k_ot_mma_rate<false><<<grid, OT_THREADS, smem, L.stream>>>(iters, mode, d, buf, elems);
-    }
+    for (int rep = 0; rep < 2; ++rep) kern<<<grid, OT_THREADS, smem, L.stream>>>(iters, mode, d, buf, elems);
     cudaError_t e = cudaMemcpyAsync(h.data(), d, h.size() * sizeof(long long), cudaMemcpyDeviceToHost, L.stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(L.stream);
     cudaFree(d);

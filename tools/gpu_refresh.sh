@@ -49,7 +49,7 @@ timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_cg
 # 5. per-shape probes: the INT8 kernel against the other path, the MMA / TMEM / FP64 rate probes
 timeout 600 python tools/ozaki_t_probe.py > $OUT/ozaki_t_probe_$TAG.log 2>&1
 cp $OUT/ozaki_t_probe.json $OUT/ozaki_t_probe_$TAG.json
-timeout 120 python tools/ozaki_t_rate.py 0 1 2 4 8 16 32 64 256 512 768 1536 > $OUT/ozaki_t_rate_$TAG.log 2>&1
+timeout 120 python tools/ozaki_t_rate.py 0 1 2 4 8 16 32 64 256 512 768 1536 2048 2304 2560 2816 > $OUT/ozaki_t_rate_$TAG.log 2>&1
 timeout 120 python tools/ozaki_t_ldtm.py > $OUT/ozaki_t_ldtm_$TAG.log 2>&1
 timeout 300 python tools/slice_breakdown.py > $OUT/slice_breakdown_${TAG}_c128.txt 2>&1
 timeout 300 python tools/slice_breakdown.py c64 > $OUT/slice_breakdown_${TAG}_c64.txt 2>&1
