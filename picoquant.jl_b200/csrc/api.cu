@@ -2,6 +2,7 @@
 // (reference: src/backends/interactive.jl).  See include/pq_b200.h for the contract
 // of every entry point and the reference line it replaces.
 #include <cstring>
+#include <thread>
 #include <complex>
 
 #include "handle.h"
@@ -148,6 +149,10 @@ extern "C" int pq_destroy(pq_handle* h) {
   if (h->stage_host) cudaFreeHost(h->stage_host);
   if (h->stage_dev) cudaFree(h->stage_dev);
   if (h->stage_ev) cudaEventDestroy(h->stage_ev);
+  for (int i = 0; i < 2; ++i) {
+    if (h->d2h_stage[i]) cudaFreeHost(h->d2h_stage[i]);
+    if (h->d2h_ev[i]) cudaEventDestroy(h->d2h_ev[i]);
+  }
   cudaStreamSynchronize(h->stream);
   cudaStreamDestroy(h->stream);
   delete h;
@@ -328,6 +333,43 @@ extern "C" int pq_tensor_info(pq_handle* h, const char* label, int* rank, int64_
   return PQ_OK;
 }
 
+// Device -> pageable host memory for large tensors (a 2^26-element state vector is 1 GiB).  A
+// plain cudaMemcpy into pageable memory goes through the driver's own bounce buffer, one chunk
+// at a time, and pays the first-touch page faults of a freshly allocated destination inside the
+// copy (measured: ~3.4 GB/s).  Here two pinned blocks alternate: while the DMA engine fills one,
+// a few host threads copy the other into the destination.
+static void d2h_pipelined(pq_handle* h, unsigned char* dst, const unsigned char* src, size_t bytes) {
+  constexpr size_t CHUNK = size_t(32) << 20;
+  constexpr int THREADS = 4;
+  for (int i = 0; i < 2; ++i) {
+    if (!h->d2h_stage[i]) PQ_CUDA(cudaMallocHost(&h->d2h_stage[i], CHUNK));
+    if (!h->d2h_ev[i]) PQ_CUDA(cudaEventCreateWithFlags(&h->d2h_ev[i], cudaEventDisableTiming));
+  }
+  const size_t chunks = (bytes + CHUNK - 1) / CHUNK;
+  auto issue = [&](size_t c) {
+    const size_t off = c * CHUNK, len = std::min(CHUNK, bytes - off);
+    PQ_CUDA(cudaMemcpyAsync(h->d2h_stage[c & 1], src + off, len, cudaMemcpyDeviceToHost, h->stream));
+    PQ_CUDA(cudaEventRecord(h->d2h_ev[c & 1], h->stream));
+  };
+  issue(0);
+  for (size_t c = 0; c < chunks; ++c) {
+    PQ_CUDA(cudaEventSynchronize(h->d2h_ev[c & 1]));
+    if (c + 1 < chunks) issue(c + 1);   // the other block: its previous contents were copied out last turn
+    const size_t off = c * CHUNK, len = std::min(CHUNK, bytes - off);
+    const unsigned char* s = h->d2h_stage[c & 1];
+    const size_t part = (len / THREADS + 4095) & ~size_t(4095);
+    std::thread workers[THREADS - 1];
+    int started = 0;
+    for (int t = 1; t < THREADS; ++t) {
+      const size_t b = size_t(t) * part;
+      if (b >= len) break;
+      workers[started++] = std::thread([=] { std::memcpy(dst + off + b, s + b, std::min(part, len - b)); });
+    }
+    std::memcpy(dst + off, s, std::min(part, len));
+    for (int t = 0; t < started; ++t) workers[t].join();
+  }
+}
+
 extern "C" int pq_load_tensor(pq_handle* h, const char* label, void* host_out, int host_dtype) {
   if (!h) return PQ_ERR_INVALID;
   PQ_TRY(h)
@@ -339,7 +381,10 @@ extern "C" int pq_load_tensor(pq_handle* h, const char* label, void* host_out, i
   int64_t n = t.numel();
   bool direct = (h->dtype == PQ_C128 && host_dtype == PQ_HOST_C128) ||
                 (h->dtype == PQ_C64 && host_dtype == PQ_HOST_C64);
-  if (direct) {
+  if (direct && size_t(n) * h->elem_size >= (size_t(64) << 20)) {
+    d2h_pipelined(h, (unsigned char*)host_out, (const unsigned char*)t.buf->ptr, size_t(n) * h->elem_size);
+    PQ_CUDA(cudaStreamSynchronize(h->stream));
+  } else if (direct) {
     PQ_CUDA(cudaMemcpyAsync(host_out, t.buf->ptr, size_t(n) * h->elem_size, cudaMemcpyDeviceToHost,
                             h->stream));
     PQ_CUDA(cudaStreamSynchronize(h->stream));

@@ -57,6 +57,9 @@ struct pq_handle {
   unsigned char* stage_dev = nullptr;
   size_t stage_cap = 0;
   cudaEvent_t stage_ev = nullptr;
+  // pq_load_tensor of large tensors: two pinned bounce blocks + their copy-done events
+  unsigned char* d2h_stage[2] = {nullptr, nullptr};
+  cudaEvent_t d2h_ev[2] = {nullptr, nullptr};
   bool stage_busy = false;
 
   pq::Launch launch_ctx();

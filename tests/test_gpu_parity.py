@@ -341,6 +341,24 @@ def test_fused_ttgt_zgemm_shapes(cfg):
         assert rel_l2(got, ref) < 1e-10, (ad, ai, rel_l2(got, ref))
 
 
+@pytest.mark.parametrize("dtype", [np.complex128, np.complex64])
+def test_large_tensor_round_trip(dtype):
+    """load_tensor_data of tensors >= 64 MiB goes through the pinned two-block pipeline
+    (pq_load_tensor -> d2h_pipelined): whole chunks, a ragged last chunk, bit-exact."""
+    rng = np.random.default_rng(77)
+    b = B200(dtype)
+    item = np.dtype(dtype).itemsize
+    for n in ((64 << 20) // item, (100 << 20) // item + 12345):
+        x = rng.standard_normal(n).astype(np.float32).astype(dtype)
+        x.imag = np.arange(n, dtype=np.float32) % 251
+        b.save_tensor_data("big", x)
+        got = np.asarray(b.load_tensor_data("big"))
+        assert got.shape == (n,) and got.dtype == dtype
+        assert np.array_equal(got, x)
+        b.delete_tensor("big")
+    b.close()
+
+
 @pytest.mark.parametrize("thin", [0, 1, 2, 3])
 def test_thin_n_zgemm(thin):
     """ComplexF64 steps with one short open bond on the small side (N <= 16, K <= 64):
