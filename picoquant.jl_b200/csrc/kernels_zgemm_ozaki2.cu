@@ -49,7 +49,7 @@ constexpr int OT_EW = 8;                                // epilogue warps
 constexpr int OT_THREADS = (OT_PW + OT_EW + 1) * 32;    // + the MMA warp
 constexpr int OT_NST = 2;                               // X stages
 constexpr int OT_SLOTS = 4;                             // row-scale ring (tiles in flight P -> E)
-constexpr int OT_NBAR = 2 * OT_NST + 2 * 8 + 2 * 8;
+constexpr int OT_NBAR = 2 * OT_NST + 2 * 8 + 2 * 8 + 1;   // full, empty, done, freed, wready
 
 template <class Real> struct OtVec;
 template <> struct OtVec<double> { using type = double2; };
@@ -81,7 +81,7 @@ __device__ __forceinline__ void ot_mbar_arrive(uint64_t* bar) {
 // one it was and raises a CTA-wide abort flag, so a protocol mistake ends as a finished kernel
 // with a diagnosis (pq_microbench "ozaki_t_debug"), not as a hung GPU.
 //   g_ot_debug = {flag, wait id, tile, group, block, warp, -, -}
-//   wait ids: 1 full (MMA), 2 freed (MMA), 3 done (epilogue), 4 empty (producers)
+//   wait ids: 1 full (MMA), 2 freed (MMA), 3 done (epilogue), 4 empty (producers), 5 wready (MMA)
 __device__ int g_ot_debug[8];
 __device__ long long g_ot_trace[32 * 32];   // block 0: [tile < 32][event]
 __device__ long long g_ot_block_ns[2 * 160];   // TR: globaltimer at the start / end of every block
@@ -351,7 +351,8 @@ k_ozaki_t(const typename OtVec<Real>::type* __restrict__ A, const typename OtVec
   uint64_t* empty = full + OT_NST;
   uint64_t* done = empty + OT_NST;
   uint64_t* freed = done + 16;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(freed + 16);
+  uint64_t* wready = freed + 16;   // W (and its copy in tensor memory) is complete (count 8: the epilogue warps)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wready + 1);
   volatile int* abort_flag = reinterpret_cast<volatile int*>(tmem_slot + 1);
 
   // (the shuffle makes the warp index provably warp-uniform: the role branches below are then
@@ -381,6 +382,7 @@ k_ozaki_t(const typename OtVec<Real>::type* __restrict__ A, const typename OtVec
       ot_mbar_init(&done[g], 1);
       ot_mbar_init(&freed[g], OT_EW);
     }
+    ot_mbar_init(wready, OT_EW);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   if (warp == 0) {
@@ -395,9 +397,14 @@ k_ozaki_t(const typename OtVec<Real>::type* __restrict__ A, const typename OtVec
   asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
 
-  // ---- W: B gathered, scaled per column, sliced, once per CTA (the producer warps) ----
-  if (warp < OT_PW) {
-    const int n = warp * 8 + (lane & 7), c = lane >> 3;
+  // ---- W: B gathered, scaled per column, sliced, once per CTA -- by the EPILOGUE warps, which
+  // have nothing to drain yet, while the producers already fetch and slice the first tile (the
+  // set-up used to cost every launch 3-4 us in front of the pipeline; a slice has 25 launches).
+  // The MMA warp waits for `wready` before its first MMA; the epilogue warps meet at a named
+  // barrier of their own (colS is theirs to read).
+  if (warp >= OT_PW && warp < OT_PW + OT_EW) {
+    const int ew = warp - OT_PW;
+    const int n = ew * 8 + (lane & 7), c = lane >> 3;
     const bool on = c < KC;
     const long long rb = n < N ? map_offset(p.nB, n) : -1;
     Real xr[16], xi[16];
@@ -418,29 +425,30 @@ k_ozaki_t(const typename OtVec<Real>::type* __restrict__ A, const typename OtVec
     if (on) ot::w_item<Real>(sW, n, c, KC, xr, xi, Tr::slice_scale(eb));
     if (c == 0) colS[n] = eb;
     asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
-  }
-  __syncthreads();
-  if constexpr (WT > 0) {
-    // digit planes 0..WT-1 of W into tensor memory: lane = W row, 8 columns = the 32 digits of one
-    // k-step (two 16-byte chunks of the row).  Epilogue warp w writes the lanes of its quadrant.
-    if (warp >= OT_PW && warp < OT_PW + 4) {
-      const int r = 32 * (warp & 3) + lane;
+    if constexpr (WT > 0) {
+      // digit planes 0..WT-1 of W into tensor memory: lane = W row, 8 columns = the 32 digits of
+      // one k-step (two 16-byte chunks of the row).  Epilogue warp w < 4 writes the lanes of
+      // quadrant w once every epilogue warp has stored its rows.
+      asm volatile("bar.sync 1, %0;\n" ::"n"(OT_EW * 32) : "memory");
+      if (ew < 4) {
+        const int r = 32 * ew + lane;
 #pragma unroll
-      for (int wp = 0; wp < WT; ++wp)
+        for (int wp = 0; wp < WT; ++wp)
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks) {
-          const uint4 lo = *reinterpret_cast<const uint4*>(sW + wp * ot::W_PLANE + oz::plane_off(ot::WROWS, r, 2 * ks));
-          const uint4 hi = *reinterpret_cast<const uint4*>(sW + wp * ot::W_PLANE + oz::plane_off(ot::WROWS, r, 2 * ks + 1));
-          asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n" ::"r"(
-                           tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + ot_w_col(wp, ks)),
-                       "r"(lo.x), "r"(lo.y), "r"(lo.z), "r"(lo.w), "r"(hi.x), "r"(hi.y), "r"(hi.z), "r"(hi.w)
-                       : "memory");
-        }
-      asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
+          for (int ks = 0; ks < 4; ++ks) {
+            const uint4 lo = *reinterpret_cast<const uint4*>(sW + wp * ot::W_PLANE + oz::plane_off(ot::WROWS, r, 2 * ks));
+            const uint4 hi = *reinterpret_cast<const uint4*>(sW + wp * ot::W_PLANE + oz::plane_off(ot::WROWS, r, 2 * ks + 1));
+            asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n" ::"r"(
+                             tmem_base + ((uint32_t)(32 * ew) << 16) + ot_w_col(wp, ks)),
+                         "r"(lo.x), "r"(lo.y), "r"(lo.z), "r"(lo.w), "r"(hi.x), "r"(hi.y), "r"(hi.z), "r"(hi.w)
+                         : "memory");
+          }
+        asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
     }
-    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
-    __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    asm volatile("bar.sync 1, %0;\n" ::"n"(OT_EW * 32) : "memory");
+    if (lane == 0) ot_mbar_arrive(wready);
   }
 
   if (warp < OT_PW) {
@@ -527,6 +535,8 @@ k_ozaki_t(const typename OtVec<Real>::type* __restrict__ A, const typename OtVec
     const uint64_t w_base = ot_desc(ot_smem_u32(sW), ot::W_LBO, ot::SBO);
     const uint64_t x_base = ot_desc(ot_smem_u32(sX), ot::X_LBO, ot::SBO);
     uint32_t t = 0;
+    ot_wait(wready, 0u, abort_flag, 5, 0, -1);
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
     for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++t) {
       const uint32_t stage = t & 1u;
       ot_wait(&full[stage], (t >> 1) & 1u, abort_flag, 1, (int)t, -1);

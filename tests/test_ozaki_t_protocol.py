@@ -1,8 +1,8 @@
 """Model check of the mbarrier protocol of the second-generation INT8 kernel
 (csrc/kernels_zgemm_ozaki2.cu, k_ozaki_t): 8 producer warps, one MMA-issuing thread, 8 epilogue
 warps, the tensor core as an in-order asynchronous agent; barriers ``full[s]`` (count 8),
-``empty[s]`` (tcgen05.commit), ``done[b][g]`` (tcgen05.commit), ``freed[b][g]`` (count 8), two X
-stages.  Accumulators: ComplexF32 (4 groups) all double-buffered; ComplexF64 (6 groups) groups
+``empty[s]`` (tcgen05.commit), ``done[b][g]`` (tcgen05.commit), ``freed[b][g]`` (count 8),
+``wready`` (count 8: the epilogue warps have built the resident operand W), two X stages.  Accumulators: ComplexF32 (4 groups) all double-buffered; ComplexF64 (6 groups) groups
 4 and 5 double-buffered and issued first, groups 0..3 single-buffered (``ot_dbuf`` /
 ``ot_issue_order`` in the kernel); the variant with W planes in tensor memory (``WT = 4``)
 double-buffers nothing and issues the groups in natural order.
@@ -70,6 +70,8 @@ def producer(st, tiles, broken):
 
 
 def mma_thread(st, tiles, G, broken):
+    if broken != "no_wready_wait":
+        yield ("wait", st["wready"], 0)
     for t in range(tiles):
         stage = t & 1
         yield ("wait", st["full"][stage], ((t >> 1) & 1) if broken != "full_parity" else (t & 1))
@@ -83,6 +85,11 @@ def mma_thread(st, tiles, G, broken):
 
 
 def epilogue(st, tiles, G, broken):
+    # the epilogue warps build W (the resident operand) while the producers fetch the first tile
+    for _ in range(12):          # gather, slice, store: longer than a producer's first tile
+        yield ("setup_step",)
+    yield ("setup",)
+    yield ("arrive", st["wready"])
     for t in range(tiles):
         for sc in range(NSUB):
             for g in range(G):
@@ -100,7 +107,8 @@ def run(seed, tiles, G, broken=None):
     rng = random.Random(seed)
     st = {"full": [MBar(NP_) for _ in range(NST)], "empty": [MBar(1) for _ in range(NST)],
           "done": [[MBar(1) for _ in range(G)] for _ in range(NB)],
-          "freed": [[MBar(NE) for _ in range(G)] for _ in range(NB)]}
+          "freed": [[MBar(NE) for _ in range(G)] for _ in range(NB)],
+          "wready": MBar(NE)}
     agents = {("p", w): producer(st, tiles, broken) for w in range(NP_)}
     agents["mma"] = mma_thread(st, tiles, G, broken)
     agents.update({("e", w): epilogue(st, tiles, G, broken) for w in range(NE)})
@@ -110,6 +118,7 @@ def run(seed, tiles, G, broken=None):
     issued = set()                # (t, g) issued
     written = {}                  # tile -> producer warps that have written it
     reads = {}                    # (t, g) -> number of (warp, cb) reads done
+    w_rows = [0]                  # epilogue warps that have stored their rows of W
     live = set(agents)
     while live or queue:
         choices = [k for k in live]
@@ -148,8 +157,13 @@ def run(seed, tiles, G, broken=None):
                     for g in range(G):
                         assert (t - NST, g) in completed, ("stage rewritten while in use", t, g)
                 written[t] = written.get(t, 0) + 1
+            elif act[0] == "setup_step":
+                pass
+            elif act[0] == "setup":
+                w_rows[0] += 1
             elif act[0] == "issue":
                 _, t, g, stage, buf = act
+                assert w_rows[0] == NE, ("MMA issued before W is complete", t)
                 assert written.get(t, 0) == NP_, ("MMA issued before the planes are complete", t)
                 prev = t - (2 if dbuf(G, g) else 1)
                 if prev >= 0:
@@ -186,7 +200,7 @@ def test_protocol_w_planes_in_tensor_memory(monkeypatch):
         run(seed, tiles=1 + seed % 7, G=6)
 
 
-@pytest.mark.parametrize("broken", ["no_empty_wait", "no_freed_wait", "full_parity", "done_parity"])
+@pytest.mark.parametrize("broken", ["no_empty_wait", "no_freed_wait", "full_parity", "done_parity", "no_wready_wait"])
 def test_broken_protocols_are_caught(broken):
     caught = 0
     for seed in range(40):
