@@ -234,6 +234,9 @@ int pq_timer_end(pq_handle* h, double* ms);
  *                   on DMMA / K1 + tcgen05 3xTF32
  *   "zgemm_ozaki"   6 forces every eligible ComplexF64 step (K <= 64, N <= 64) onto k_ozaki_t
  *   "cgemm_ozaki"   4 forces every eligible ComplexF32 step onto k_ozaki_t (gather fused, no K1 pass)
+ *   "ozaki_tsw"     2: the ComplexF64 k_ozaki_t keeps digit planes 0..3 of its resident operand in tensor
+ *                   memory (TS form of tcgen05.mma) instead of double-buffering two accumulator groups;
+ *                   bit-identical results, measured equal or slower, kept for A/B runs
  *   "zgemm_kfirst"  1 row-first gather order only
  *   "zgemm_stagger" ns of start delay per resident-CTA slot in the first wave (tile-per-CTA ZGEMM)
  * Every alternative computes the same contraction; the tests run them against each other. */
