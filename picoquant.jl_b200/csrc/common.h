@@ -178,6 +178,7 @@ struct ContractPlan {
   size_t tempA_bytes = 0, tempB_bytes = 0, ws_bytes = 0;
   bool fused_gemm = false;             // gather straight from A and B inside the GEMM
   int dot_blocks = 0;
+  int dot_split = 0;                   // > 0: k = k_low + j * 2^dot_split, k_low = the thread (k_contract_dot, power-of-two extents)
 };
 
 ContractPlan lower_contract(const std::vector<int64_t>& a_dims, const std::vector<int32_t>& a_idx,

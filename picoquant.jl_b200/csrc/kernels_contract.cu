@@ -450,6 +450,7 @@ struct DotParams {
   IdxMap mA, kA, nB, kB;
   int M, N;
   long long K;
+  int split;   // > 0 (M = N = 1, power-of-two extents, 2^split threads): k = thread + j * 2^split
 };
 
 // MNT = compile-time bound on M*N (1, 4 or 16), U = independent k-iterations in flight per
@@ -480,7 +481,30 @@ k_contract_dot(const typename C2<R>::type* __restrict__ A,
   }
   const long long stride = (long long)gridDim.x * blockDim.x;
   long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (MNT == 1) {
+  if (MNT == 1 && p.split > 0) {
+    // offset(k_low + j 2^s) = offset(k_low) + offset(j 2^s): one index-map walk per thread, the
+    // j part from a table (<= 64 entries per operand)
+    __shared__ long long tabA[64], tabB[64];
+    const int J = (int)(p.K >> p.split);
+    if (threadIdx.x < J) {
+      tabA[threadIdx.x] = map_offset(p.kA, (long long)threadIdx.x << p.split);
+      tabB[threadIdx.x] = map_offset(p.kB, (long long)threadIdx.x << p.split);
+    }
+    __syncthreads();
+    const V* a0 = A + map_offset(p.kA, k) + offA[0];
+    const V* b0 = B + map_offset(p.kB, k) + offB[0];
+    for (int j = 0; j < J; j += 8) {
+      V a[8], b[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        a[u] = a0[tabA[j + u]];
+        b[u] = b0[tabB[j + u]];
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) cfma<V, R>(acc[0], a[u], b[u]);
+    }
+    k = p.K;   // nothing left for the generic loops
+  } else if (MNT == 1) {
     const long long oa = offA[0], ob = offB[0];
     for (; k + (U - 1) * stride < p.K; k += U * stride) {
       V a[U], b[U];
@@ -682,6 +706,7 @@ static void run_contract_t(const Launch& L, const ContractPlan& p, const void* A
       dp.M = (int)p.M;
       dp.N = (int)p.N;
       dp.K = p.K;
+      dp.split = p.dot_split;
       L.begin(KC_CONTRACT_DOT, bytes, flops);
       if (p.M * p.N == 1)
         k_contract_dot<R, 1, 4><<<p.dot_blocks, 256, 0, L.stream>>>((const V*)A, (const V*)B, (V*)ws, dp);
