@@ -903,7 +903,7 @@ static void launch_thin(const Launch& L, const FusedParams& fp, const void* A, c
   }
 }
 
-constexpr int SK_NG = 2, SK_S = 2;   // measured: four groups / deeper rings are not faster
+constexpr int SK_NG = 2, SK_S = 2;   // measured: four groups / deeper rings are not faster (six stages at K = 8: 72 vs 67 us)
 
 template <int TBN, bool AKF>
 static void init_skinny() {
