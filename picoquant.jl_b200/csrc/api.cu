@@ -748,6 +748,7 @@ extern "C" int pq_set_option(pq_handle* h, const char* key, int value) {
   else if (k == "zgemm_cfg") h->opt.zgemm_cfg = value;
   else if (k == "zgemm_thin") h->opt.zgemm_thin = value;
   else if (k == "ozaki_tsw") h->opt.ozaki_tsw = value;
+  else if (k == "small_tc") h->opt.small_tc = value;
   else if (k == "zgemm_kfirst") h->opt.zgemm_kfirst = value;
   else {
     h->last_error = "unknown option: " + k;

@@ -187,6 +187,150 @@ k_contract_small_c64x4(const float2* __restrict__ big, const float2* __restrict_
   }
 }
 
+// ComplexF32, small operand on the right with a short open bond (S <= 8) over 16 < K <= 64, the
+// big operand with a CONTRACTED axis fastest (the sweep's N = 8 steps: the boundary absorbs a
+// site tensor whose bond bits sit at the lowest addresses).  One row per thread makes every lane
+// of a load touch its own 128-byte line (k_contract_small: 70 us = 2.1 TB/s on R = 2^18, S = 8,
+// K = 64; an FP32-FMA variant with lanes over k re-read the small operand from shared memory
+// for every row block and was slower still).  Here a warp owns 16 rows per step and multiplies
+// on the legacy tensor path, mma.sync.m16n8k8.tf32 with 3xTF32 splitting (hi * hi + hi * lo +
+// lo * hi, 12 MMAs per 8 k's for the four real products): the A fragment IS the load layout --
+// lane (g, t) holds rows g, g + 8 and k = 8 s + t, 8 s + t + 4, so a quarter warp reads 2 rows x
+// 32 contiguous bytes -- and all loads of a step are issued before the first MMA.
+__device__ __forceinline__ float2 tcs_load(const float2* ptr, bool pred) {
+  float2 v;
+  asm volatile(
+      "{\n .reg .pred q;\n setp.ne.b32 q, %3, 0;\n mov.f32 %0, 0f00000000;\n mov.f32 %1, 0f00000000;\n"
+      " @q ld.global.nc.v2.f32 {%0, %1}, [%2];\n}\n"
+      : "=f"(v.x), "=f"(v.y)
+      : "l"(ptr), "r"((int)pred));
+  return v;
+}
+__device__ __forceinline__ uint32_t tcs_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ void tcs_mma(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+      "{%0, %1, %2, %3};\n"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+template <int KS>   // K <= 8 KS
+__global__ void __launch_bounds__(256, 2)
+k_contract_small_c64tc(const float2* __restrict__ big, const float2* __restrict__ small,
+                       float2* __restrict__ out, const SmallParams p) {
+  constexpr int KP = 8 * KS;
+  // the small operand, split and signed once per CTA: [variant][k][n], variants Br_hi, Br_lo,
+  // Bi_hi, Bi_lo, -Bi_hi, -Bi_lo (TF32 bit patterns)
+  __shared__ uint32_t Q[6][KP][8];
+  __shared__ int koff[KP];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  for (int i = tid; i < KP * 8; i += 256) {
+    const int k = i >> 3, n = i & 7;
+    float2 v = make_float2(0.f, 0.f);
+    if (k < p.K && n < p.S) v = small[map_offset(p.ksmall, k) + map_offset(p.ssmall, n)];
+    const uint32_t rh = tcs_tf32(v.x), ih = tcs_tf32(v.y);
+    const uint32_t rl = tcs_tf32(v.x - __uint_as_float(rh)), il = tcs_tf32(v.y - __uint_as_float(ih));
+    Q[0][k][n] = rh;
+    Q[1][k][n] = rl;
+    Q[2][k][n] = ih;
+    Q[3][k][n] = il;
+    Q[4][k][n] = ih ^ 0x80000000u;
+    Q[5][k][n] = il ^ 0x80000000u;
+  }
+  for (int k = tid; k < KP; k += 256) koff[k] = k < p.K ? (int)map_offset(p.kbig, k) : -1;
+  __syncthreads();
+  int ko[2 * KS];   // k = 8 s + t, 8 s + t + 4
+#pragma unroll
+  for (int s2 = 0; s2 < KS; ++s2) {
+    ko[2 * s2] = koff[8 * s2 + t];
+    ko[2 * s2 + 1] = koff[8 * s2 + t + 4];
+  }
+  const long long blocks = (p.R + 15) / 16, stride = (long long)gridDim.x * 8;
+  for (long long blk = (long long)blockIdx.x * 8 + warp; blk < blocks; blk += stride) {
+    const long long r0 = blk * 16 + g, r1 = r0 + 8;
+    const bool v0 = r0 < p.R, v1 = r1 < p.R;
+    const float2* row0 = big + (v0 ? map_offset(p.rmap, r0) : 0);
+    const float2* row1 = big + (v1 ? map_offset(p.rmap, r1) : 0);
+    float2 a[KS][4];   // fragment order: (g, t), (g + 8, t), (g, t + 4), (g + 8, t + 4)
+#pragma unroll
+    for (int s2 = 0; s2 < KS; ++s2) {
+      a[s2][0] = tcs_load(row0 + ko[2 * s2], v0 && ko[2 * s2] >= 0);
+      a[s2][1] = tcs_load(row1 + ko[2 * s2], v1 && ko[2 * s2] >= 0);
+      a[s2][2] = tcs_load(row0 + ko[2 * s2 + 1], v0 && ko[2 * s2 + 1] >= 0);
+      a[s2][3] = tcs_load(row1 + ko[2 * s2 + 1], v1 && ko[2 * s2 + 1] >= 0);
+    }
+    float cr[4] = {0.f, 0.f, 0.f, 0.f}, ci[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int s2 = 0; s2 < KS; ++s2) {
+      uint32_t rh[4], rl[4], ih[4], il[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        rh[j] = tcs_tf32(a[s2][j].x);
+        ih[j] = tcs_tf32(a[s2][j].y);
+        rl[j] = tcs_tf32(a[s2][j].x - __uint_as_float(rh[j]));
+        il[j] = tcs_tf32(a[s2][j].y - __uint_as_float(ih[j]));
+      }
+      uint32_t b[6][2];
+#pragma unroll
+      for (int v = 0; v < 6; ++v) {
+        b[v][0] = Q[v][8 * s2 + t][g];
+        b[v][1] = Q[v][8 * s2 + t + 4][g];
+      }
+      // small terms first
+      tcs_mma(cr, rl, b[0][0], b[0][1]);   // Ar_lo Br_hi
+      tcs_mma(cr, rh, b[1][0], b[1][1]);   // Ar_hi Br_lo
+      tcs_mma(cr, il, b[4][0], b[4][1]);   // Ai_lo (-Bi_hi)
+      tcs_mma(cr, ih, b[5][0], b[5][1]);   // Ai_hi (-Bi_lo)
+      tcs_mma(ci, rl, b[2][0], b[2][1]);   // Ar_lo Bi_hi
+      tcs_mma(ci, rh, b[3][0], b[3][1]);   // Ar_hi Bi_lo
+      tcs_mma(ci, il, b[0][0], b[0][1]);   // Ai_lo Br_hi
+      tcs_mma(ci, ih, b[1][0], b[1][1]);   // Ai_hi Br_lo
+      tcs_mma(cr, rh, b[0][0], b[0][1]);   // Ar_hi Br_hi
+      tcs_mma(cr, ih, b[4][0], b[4][1]);   // Ai_hi (-Bi_hi)
+      tcs_mma(ci, rh, b[2][0], b[2][1]);   // Ar_hi Bi_hi
+      tcs_mma(ci, ih, b[0][0], b[0][1]);   // Ai_hi Br_hi
+    }
+    // C fragment: (row g, cols 2 t, 2 t + 1), (row g + 8, cols 2 t, 2 t + 1)
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int n = 2 * t + j;
+      if (n < p.S) {
+        if (v0) out[r0 * p.out_rs + n * p.out_ss] = make_float2(cr[j], ci[j]);
+        if (v1) out[r1 * p.out_rs + n * p.out_ss] = make_float2(cr[2 + j], ci[2 + j]);
+      }
+    }
+  }
+}
+
+static int64_t map_min_stride(const IdxMap& m) {
+  int64_t best = INT64_MAX;
+  for (int d = 0; d < m.nd; ++d) best = m.str[d] < best ? m.str[d] : best;
+  return best;
+}
+
+// (see the kernel: ComplexF32, S <= 8, 16 < K <= 64, many rows, contracted axis fastest)
+static bool small_c64tc_ok(const SmallParams& p) {
+  return p.S > 4 && p.S <= 8 && p.K > 16 && p.K <= 64 && p.R >= 4096 && p.kbig.nd > 0 && p.rmap.nd > 0 &&
+         map_min_stride(p.kbig) < map_min_stride(p.rmap);
+}
+
+static void launch_small_c64tc(const Launch& L, const SmallParams& p, const void* big, const void* small,
+                               void* out) {
+  const unsigned grid = (unsigned)(2 * L.num_sms);
+  const float2 *b = (const float2*)big, *s = (const float2*)small;
+  float2* o = (float2*)out;
+  if (p.K <= 32)
+    k_contract_small_c64tc<4><<<grid, 256, 0, L.stream>>>(b, s, o, p);
+  else
+    k_contract_small_c64tc<8><<<grid, 256, 0, L.stream>>>(b, s, o, p);
+}
+
 template <int NS>
 static void launch_small_c64x4(const Launch& L, const SmallParams& p, const void* big,
                                const void* small, void* out) {
@@ -250,6 +394,10 @@ static bool small_vec4_ok(const SmallParams& p) {
 template <typename R>
 static void launch_small(const Launch& L, const SmallParams& p, const void* big, const void* small,
                          void* out) {
+  if (sizeof(R) == 4 && small_c64tc_ok(p) && !(L.opt && L.opt->small_tc == 1)) {
+    launch_small_c64tc(L, p, big, small, out);
+    return;
+  }
   if (sizeof(R) == 4 && small_vec4_ok(p) && ((uintptr_t)big % 32 == 0) && ((uintptr_t)out % 32 == 0) &&
       p.R >= (1 << 16)) {
     if (p.S <= 1)

@@ -359,6 +359,39 @@ def test_large_tensor_round_trip(dtype):
     b.close()
 
 
+@pytest.mark.parametrize("tc", [0, 1])
+def test_c64_small_operand_contracted_axis_fastest(tc):
+    """ComplexF32 small-operand steps whose big operand has a contracted axis fastest and whose
+    small operand keeps a short open bond (5..8) over 16 < K <= 64: k_contract_small_c64tc
+    (16 rows per warp, mma.sync.m16n8k8.tf32 with 3xTF32 splitting, fragments loaded straight
+    from the un-permuted operand; option small_tc = 1 switches it off).  Small operand on either
+    side, ragged rows / bond / K."""
+    rng = np.random.default_rng(83 + tc)
+    b = B200(np.complex64, small_tc=tc, ozaki_auto=0)
+    shapes = [
+        ((8, 5000, 8), [1, -1, 2], (8, 8, 8), [1, 2, -2]),          # K = 64, S = 8
+        ((4, 4100, 8), [1, -1, 2], (4, 8, 6), [1, 2, -2]),          # K = 32, S = 6
+        ((7, 4099, 5), [1, -1, 2], (7, 5, 5), [1, 2, -2]),          # K = 35, S = 5, everything ragged
+        ((2,) * 18, [1, 2, 3] + [-(i + 1) for i in range(12)] + [4, 5, 6],
+         (2,) * 9, [1, 2, 3, 4, 5, 6, -13, -14, -15]),              # bits, K = 64, S = 8, 2^12 rows
+        ((8, 8, 8), [-1, 1, 2], (8, 4500, 8), [1, -2, 2]),          # small operand on the LEFT
+    ]
+    for ad, ai, bd, bi in shapes:
+        A = rand_tensor(rng, tuple(ad), np.complex64)
+        B = rand_tensor(rng, tuple(bd), np.complex64)
+        b.save_tensor_data("A", A)
+        b.save_tensor_data("B", B)
+        b.profile_enable(True)
+        b.contract_tensors("A", ai, "B", bi, "C")
+        prof = b.profile_read()
+        b.profile_enable(False)
+        assert set(prof) == {"contract_small"}, (ad, prof)
+        got = b.load_tensor_data("C")
+        ref = layer1.contract_tensors((A.astype(np.complex128), B.astype(np.complex128)), (ai, bi))
+        assert got.shape == ref.shape
+        assert rel_l2(got, ref) < 2e-6, (tc, ad, ai, rel_l2(got, ref))
+
+
 @pytest.mark.parametrize("thin", [0, 1, 2, 3])
 def test_thin_n_zgemm(thin):
     """ComplexF64 steps with one short open bond on the small side (N <= 16, K <= 64):
