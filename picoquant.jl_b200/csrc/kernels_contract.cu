@@ -219,19 +219,20 @@ __device__ __forceinline__ void tcs_mma(float (&c)[4], const uint32_t (&a)[4], u
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-template <int KS>   // K <= 8 KS
+template <int KS, int NB>   // K <= 8 KS, S <= 8 NB
 __global__ void __launch_bounds__(256, 2)
 k_contract_small_c64tc(const float2* __restrict__ big, const float2* __restrict__ small,
                        float2* __restrict__ out, const SmallParams p) {
-  constexpr int KP = 8 * KS;
+  constexpr int KP = 8 * KS, NP = 8 * NB;
+  constexpr int QP = NB > 1 ? NP + 8 : NP;   // pitch = 8 (mod 32) words: conflict-free fragment reads
   // the small operand, split and signed once per CTA: [variant][k][n], variants Br_hi, Br_lo,
   // Bi_hi, Bi_lo, -Bi_hi, -Bi_lo (TF32 bit patterns)
-  __shared__ uint32_t Q[6][KP][8];
+  __shared__ uint32_t Q[6][KP][QP];
   __shared__ int koff[KP];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
-  for (int i = tid; i < KP * 8; i += 256) {
-    const int k = i >> 3, n = i & 7;
+  for (int i = tid; i < KP * NP; i += 256) {
+    const int k = i / NP, n = i % NP;
     float2 v = make_float2(0.f, 0.f);
     if (k < p.K && n < p.S) v = small[map_offset(p.ksmall, k) + map_offset(p.ssmall, n)];
     const uint32_t rh = tcs_tf32(v.x), ih = tcs_tf32(v.y);
@@ -265,7 +266,11 @@ k_contract_small_c64tc(const float2* __restrict__ big, const float2* __restrict_
       a[s2][2] = tcs_load(row0 + ko[2 * s2 + 1], v0 && ko[2 * s2 + 1] >= 0);
       a[s2][3] = tcs_load(row1 + ko[2 * s2 + 1], v1 && ko[2 * s2 + 1] >= 0);
     }
-    float cr[4] = {0.f, 0.f, 0.f, 0.f}, ci[4] = {0.f, 0.f, 0.f, 0.f};
+    float cr[NB][4], ci[NB][4];
+#pragma unroll
+    for (int y = 0; y < NB; ++y)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) cr[y][j] = ci[y][j] = 0.f;
 #pragma unroll
     for (int s2 = 0; s2 < KS; ++s2) {
       uint32_t rh[4], rl[4], ih[4], il[4];
@@ -276,35 +281,40 @@ k_contract_small_c64tc(const float2* __restrict__ big, const float2* __restrict_
         rl[j] = tcs_tf32(a[s2][j].x - __uint_as_float(rh[j]));
         il[j] = tcs_tf32(a[s2][j].y - __uint_as_float(ih[j]));
       }
-      uint32_t b[6][2];
 #pragma unroll
-      for (int v = 0; v < 6; ++v) {
-        b[v][0] = Q[v][8 * s2 + t][g];
-        b[v][1] = Q[v][8 * s2 + t + 4][g];
-      }
-      // small terms first
-      tcs_mma(cr, rl, b[0][0], b[0][1]);   // Ar_lo Br_hi
-      tcs_mma(cr, rh, b[1][0], b[1][1]);   // Ar_hi Br_lo
-      tcs_mma(cr, il, b[4][0], b[4][1]);   // Ai_lo (-Bi_hi)
-      tcs_mma(cr, ih, b[5][0], b[5][1]);   // Ai_hi (-Bi_lo)
-      tcs_mma(ci, rl, b[2][0], b[2][1]);   // Ar_lo Bi_hi
-      tcs_mma(ci, rh, b[3][0], b[3][1]);   // Ar_hi Bi_lo
-      tcs_mma(ci, il, b[0][0], b[0][1]);   // Ai_lo Br_hi
-      tcs_mma(ci, ih, b[1][0], b[1][1]);   // Ai_hi Br_lo
-      tcs_mma(cr, rh, b[0][0], b[0][1]);   // Ar_hi Br_hi
-      tcs_mma(cr, ih, b[4][0], b[4][1]);   // Ai_hi (-Bi_hi)
-      tcs_mma(ci, rh, b[2][0], b[2][1]);   // Ar_hi Bi_hi
-      tcs_mma(ci, ih, b[0][0], b[0][1]);   // Ai_hi Br_hi
-    }
-    // C fragment: (row g, cols 2 t, 2 t + 1), (row g + 8, cols 2 t, 2 t + 1)
+      for (int y = 0; y < NB; ++y) {
+        uint32_t b[6][2];
 #pragma unroll
-    for (int j = 0; j < 2; ++j) {
-      const int n = 2 * t + j;
-      if (n < p.S) {
-        if (v0) out[r0 * p.out_rs + n * p.out_ss] = make_float2(cr[j], ci[j]);
-        if (v1) out[r1 * p.out_rs + n * p.out_ss] = make_float2(cr[2 + j], ci[2 + j]);
+        for (int v = 0; v < 6; ++v) {
+          b[v][0] = Q[v][8 * s2 + t][8 * y + g];
+          b[v][1] = Q[v][8 * s2 + t + 4][8 * y + g];
+        }
+        // small terms first
+        tcs_mma(cr[y], rl, b[0][0], b[0][1]);   // Ar_lo Br_hi
+        tcs_mma(cr[y], rh, b[1][0], b[1][1]);   // Ar_hi Br_lo
+        tcs_mma(cr[y], il, b[4][0], b[4][1]);   // Ai_lo (-Bi_hi)
+        tcs_mma(cr[y], ih, b[5][0], b[5][1]);   // Ai_hi (-Bi_lo)
+        tcs_mma(ci[y], rl, b[2][0], b[2][1]);   // Ar_lo Bi_hi
+        tcs_mma(ci[y], rh, b[3][0], b[3][1]);   // Ar_hi Bi_lo
+        tcs_mma(ci[y], il, b[0][0], b[0][1]);   // Ai_lo Br_hi
+        tcs_mma(ci[y], ih, b[1][0], b[1][1]);   // Ai_hi Br_lo
+        tcs_mma(cr[y], rh, b[0][0], b[0][1]);   // Ar_hi Br_hi
+        tcs_mma(cr[y], ih, b[4][0], b[4][1]);   // Ai_hi (-Bi_hi)
+        tcs_mma(ci[y], rh, b[2][0], b[2][1]);   // Ar_hi Bi_hi
+        tcs_mma(ci[y], ih, b[0][0], b[0][1]);   // Ai_hi Br_hi
       }
     }
+    // C fragment: (row g, cols 2 t, 2 t + 1), (row g + 8, cols 2 t, 2 t + 1) of every n block
+#pragma unroll
+    for (int y = 0; y < NB; ++y)
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int n = 8 * y + 2 * t + j;
+        if (n < p.S) {
+          if (v0) out[r0 * p.out_rs + n * p.out_ss] = make_float2(cr[y][j], ci[y][j]);
+          if (v1) out[r1 * p.out_rs + n * p.out_ss] = make_float2(cr[y][2 + j], ci[y][2 + j]);
+        }
+      }
   }
 }
 
@@ -314,10 +324,14 @@ static int64_t map_min_stride(const IdxMap& m) {
   return best;
 }
 
-// (see the kernel: ComplexF32, S <= 8, 16 < K <= 64, many rows, contracted axis fastest)
+// ComplexF32, many rows, and either a short bond over a longer contraction with a contracted
+// axis fastest in the big operand (S <= 8, 16 < K <= 64), or a short contraction with up to 64
+// open on the small side (K <= 16, 16 < S <= 64: output-bound; lower.cpp sends those here
+// instead of to the INT8 kernel)
 static bool small_c64tc_ok(const SmallParams& p) {
-  return p.S > 4 && p.S <= 8 && p.K > 16 && p.K <= 64 && p.R >= 4096 && p.kbig.nd > 0 && p.rmap.nd > 0 &&
-         map_min_stride(p.kbig) < map_min_stride(p.rmap);
+  if (p.R < 4096 || p.kbig.nd < 1 || p.rmap.nd < 1) return false;
+  if (p.S > 16 && p.S <= 64 && p.K <= 16) return true;
+  return p.S > 4 && p.S <= 8 && p.K > 16 && p.K <= 64 && map_min_stride(p.kbig) < map_min_stride(p.rmap);
 }
 
 static void launch_small_c64tc(const Launch& L, const SmallParams& p, const void* big, const void* small,
@@ -325,10 +339,19 @@ static void launch_small_c64tc(const Launch& L, const SmallParams& p, const void
   const unsigned grid = (unsigned)(2 * L.num_sms);
   const float2 *b = (const float2*)big, *s = (const float2*)small;
   float2* o = (float2*)out;
-  if (p.K <= 32)
-    k_contract_small_c64tc<4><<<grid, 256, 0, L.stream>>>(b, s, o, p);
-  else
-    k_contract_small_c64tc<8><<<grid, 256, 0, L.stream>>>(b, s, o, p);
+  if (p.S > 8) {
+    if (p.K <= 8) {
+      if (p.S <= 32) k_contract_small_c64tc<1, 4><<<grid, 256, 0, L.stream>>>(b, s, o, p);
+      else k_contract_small_c64tc<1, 8><<<grid, 256, 0, L.stream>>>(b, s, o, p);
+    } else {
+      if (p.S <= 32) k_contract_small_c64tc<2, 4><<<grid, 256, 0, L.stream>>>(b, s, o, p);
+      else k_contract_small_c64tc<2, 8><<<grid, 256, 0, L.stream>>>(b, s, o, p);
+    }
+  } else if (p.K <= 32) {
+    k_contract_small_c64tc<4, 1><<<grid, 256, 0, L.stream>>>(b, s, o, p);
+  } else {
+    k_contract_small_c64tc<8, 1><<<grid, 256, 0, L.stream>>>(b, s, o, p);
+  }
 }
 
 template <int NS>
@@ -398,6 +421,7 @@ static void launch_small(const Launch& L, const SmallParams& p, const void* big,
     launch_small_c64tc(L, p, big, small, out);
     return;
   }
+  PQ_REQUIRE(p.S <= 16, PQ_ERR_UNSUPPORTED, "small-operand kernel: more than 16 open elements on the small side");
   if (sizeof(R) == 4 && small_vec4_ok(p) && ((uintptr_t)big % 32 == 0) && ((uintptr_t)out % 32 == 0) &&
       p.R >= (1 << 16)) {
     if (p.S <= 1)

@@ -269,6 +269,15 @@ ContractPlan lower_contract(const std::vector<int64_t>& a_dims, const std::vecto
     P.kind = CK_SMALL_RIGHT;
   } else if (fused_ok && M <= 16 && K <= 256 && M * K <= SMALL_Q) {
     P.kind = CK_SMALL_LEFT;
+  } else if (fused_ok && elem_size == 8 && opt.small_tc == 0 && opt.cgemm_ozaki == 0 && K <= 16 && N <= 64 &&
+             M >= 4096) {
+    // c64, short contraction, up to 64 open on the small side: output-bound; the small-operand
+    // tensor-core kernel (k_contract_small_c64tc) writes C at the speed the INT8 kernel's
+    // epilogue cannot (58 us for 151 MB at K = 8)
+    P.kind = CK_SMALL_RIGHT;
+  } else if (fused_ok && elem_size == 8 && opt.small_tc == 0 && opt.cgemm_ozaki == 0 && K <= 16 && M <= 64 &&
+             N >= 4096) {
+    P.kind = CK_SMALL_LEFT;
   } else if (fused_ok && M * N <= 16 && K >= 512) {
     P.kind = CK_DOT;
   } else if (M * N * K <= 65536 || (M * N <= 64 && K <= 4096)) {

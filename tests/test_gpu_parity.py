@@ -362,10 +362,11 @@ def test_large_tensor_round_trip(dtype):
 @pytest.mark.parametrize("tc", [0, 1])
 def test_c64_small_operand_contracted_axis_fastest(tc):
     """ComplexF32 small-operand steps whose big operand has a contracted axis fastest and whose
-    small operand keeps a short open bond (5..8) over 16 < K <= 64: k_contract_small_c64tc
-    (16 rows per warp, mma.sync.m16n8k8.tf32 with 3xTF32 splitting, fragments loaded straight
-    from the un-permuted operand; option small_tc = 1 switches it off).  Small operand on either
-    side, ragged rows / bond / K."""
+    small operand keeps a short open bond (5..8) over 16 < K <= 64, and short contractions
+    (K <= 16) with up to 64 open on the small side: k_contract_small_c64tc (16 rows per warp,
+    mma.sync.m16n8k8.tf32 with 3xTF32 splitting, fragments loaded straight from the un-permuted
+    operand; option small_tc = 1 switches it off: thread-per-row kernel / INT8 kernel / K1 + K3
+    instead).  Small operand on either side, ragged rows / bond / K."""
     rng = np.random.default_rng(83 + tc)
     b = B200(np.complex64, small_tc=tc, ozaki_auto=0)
     shapes = [
@@ -375,6 +376,13 @@ def test_c64_small_operand_contracted_axis_fastest(tc):
         ((2,) * 18, [1, 2, 3] + [-(i + 1) for i in range(12)] + [4, 5, 6],
          (2,) * 9, [1, 2, 3, 4, 5, 6, -13, -14, -15]),              # bits, K = 64, S = 8, 2^12 rows
         ((8, 8, 8), [-1, 1, 2], (8, 4500, 8), [1, -2, 2]),          # small operand on the LEFT
+        # short contraction, up to 64 open on the small side (output-bound steps)
+        ((2 ** 16, 8), [-1, 1], (8, 64), [1, -2]),                  # K = 8, S = 64, rows fastest
+        ((8, 2 ** 15), [1, -1], (8, 64), [1, -2]),                  # K = 8, S = 64, contracted axis fastest
+        ((2, 5000, 8), [1, -1, 2], (2, 8, 32), [1, 2, -2]),         # K = 16, S = 32
+        ((5, 4099), [1, -1], (5, 40), [1, -2]),                     # K = 5, S = 40, ragged
+        ((3, 11, 4), [1, -1, 2], (4, 3, 6000), [2, 1, -2]),         # small (S = 11 .. K = 12) on the left: plain small kernel
+        ((3, 33, 4), [1, -1, 2], (4, 3, 6000), [2, 1, -2]),         # S = 33 on the left, K = 12
     ]
     for ad, ai, bd, bi in shapes:
         A = rand_tensor(rng, tuple(ad), np.complex64)
@@ -385,7 +393,8 @@ def test_c64_small_operand_contracted_axis_fastest(tc):
         b.contract_tensors("A", ai, "B", bi, "C")
         prof = b.profile_read()
         b.profile_enable(False)
-        assert set(prof) == {"contract_small"}, (ad, prof)
+        if tc == 0:
+            assert set(prof) == {"contract_small"}, (ad, prof)
         got = b.load_tensor_data("C")
         ref = layer1.contract_tensors((A.astype(np.complex128), B.astype(np.complex128)), (ai, bi))
         assert got.shape == ref.shape
@@ -508,7 +517,7 @@ def test_default_policy_int8_kernel(dtype):
          (2,) * 11, [6, 5, 4, 3, 2, 1] + [-(20 + i) for i in range(5)], True),
         ((40017, 35), [-1, 1], (35, 33), [1, -2], True),          # ragged everything, odd M
         ((7, 5, 38000), [1, 2, -1], (5, 17, 7), [2, -2, 1], not c128),   # K = 35 first, N = 17: c64 only
-        ((3, 50000), [1, -1], (3, 64), [1, -2], not c128),        # K = 3: HBM-bound, DMMA kernel in c128
+        ((3, 50000), [1, -1], (3, 64), [1, -2], False),           # K = 3: output-bound; DMMA kernel (c128) / small-operand tensor-core kernel (c64)
         ((2000, 64), [-1, 1], (64, 64), [1, -2], False),          # M < 4096: outside the envelope
     ]
     for ad, ai, bd, bi, int8 in cases:
