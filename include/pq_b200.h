@@ -223,8 +223,9 @@ int pq_timer_end(pq_handle* h, double* ms);
  *   "zgemm_skinny"  1 disables the persistent skinny ZGEMM
  *   "zgemm_thin"    ComplexF64 steps with N <= 16 and K <= 64: default k_zgemm_thin (DMMA fragments
  *                   loaded straight from the un-permuted operand) when a contracted axis is the
- *                   fastest axis of A, else the 128x8 tiled kernel; 1 always tiled, 2 / 3 always
- *                   k_zgemm_thin with k-first / rows-first loads
+ *                   fastest axis of A, else the 128x8 tiled kernel; the same kernel takes K <= 8
+ *                   with 16 < N <= 64 (output-bound).  1 never, 2 / 3 always on N <= 16 with
+ *                   k-first / rows-first loads, 4 as default plus K <= 16 on the wide shapes
  *   "zgemm_3m"      1 four DMMAs per complex product instead of three (3M)
  *   "ozaki_auto"    default 1: GEMM-shaped steps with K <= 64, N <= 64 and M >= 4096 run on the INT8
  *                   tensor-core kernel k_ozaki_t (tcgen05.mma kind::i8, Ozaki-scheme slicing into

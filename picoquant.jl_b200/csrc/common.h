@@ -121,7 +121,7 @@ struct Options {
   int zgemm_kfirst = 0;  // 1: always use the row-first gather order in the fused ZGEMM (A/B check)
   int small_tc = 0;    // 1 disables k_contract_small_c64tc (ComplexF32 small-operand steps with a contracted axis fastest, 3xTF32 mma.sync)
   int ozaki_tsw = 0;   // k_ozaki_t<double>: 2 = digit planes 0..3 of W in tensor memory (TS form of the MMA)
-  int zgemm_thin = 0;  // N <= 16, K <= 64 steps: 0 auto (k_zgemm_thin when a contracted axis is the fastest of A), 1 off (tiled 128x8), 2 / 3 force k_zgemm_thin, k-first / rows-first loads
+  int zgemm_thin = 0;  // N <= 16, K <= 64 steps: 0 auto (k_zgemm_thin when a contracted axis is the fastest of A, or K <= 8 with 16 < N <= 64), 1 off (tiled 128x8 / skinny), 2 / 3 force k_zgemm_thin on N <= 16, k-first / rows-first loads, 4 also K <= 16 with 16 < N <= 64
   int zgemm_cfg = 0;  // fused ZGEMM: 0 auto, 1 = 64x64 (2 CTAs/SM), 2 = 64x32 (4 CTAs/SM), 3 = 128x8, 4 = 64x32 3M, 7 = persistent skinny where eligible
   int zgemm_3m = 0;       // persistent skinny ZGEMM: 0 = 3M (three DMMAs per complex product), 1 = 4M
   int zgemm_skinny = 0;   // persistent skinny fused ZGEMM: 0 auto, 1 off

@@ -519,7 +519,8 @@ __global__ void __launch_bounds__(256, 2)
 k_zgemm_thin(const double2* __restrict__ A, const double2* __restrict__ B,
              double2* __restrict__ C, const FusedParams p) {
   constexpr int KP = 4 * KS, NP = 8 * NB;
-  __shared__ __align__(16) double2 sB[KP][NP];
+  // (pitch = 2 (mod 8) double2: the four k rows a quarter warp reads fall into different banks)
+  __shared__ __align__(16) double2 sB[KP][NP + 2];
   __shared__ int koffA[KP];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int frow = lane >> 2, fk = lane & 3;                     // fragment order
@@ -894,7 +895,15 @@ static void launch_thin(const Launch& L, const FusedParams& fp, const void* A, c
   const unsigned grid = (unsigned)(2 * L.num_sms);
   const double2 *a = (const double2*)A, *b = (const double2*)B;
   double2* c = (double2*)C;
-  if (fp.K <= 32) {
+  if (fp.N > 16) {   // short contraction, up to 64 columns: K <= 16
+    if (fp.K <= 8) {
+      if (fp.N <= 32) k_zgemm_thin<2, 4, KF><<<grid, 256, 0, L.stream>>>(a, b, c, fp);
+      else k_zgemm_thin<2, 8, KF><<<grid, 256, 0, L.stream>>>(a, b, c, fp);
+    } else {
+      if (fp.N <= 32) k_zgemm_thin<4, 4, KF><<<grid, 256, 0, L.stream>>>(a, b, c, fp);
+      else k_zgemm_thin<4, 8, KF><<<grid, 256, 0, L.stream>>>(a, b, c, fp);
+    }
+  } else if (fp.K <= 32) {
     if (fp.N <= 8) k_zgemm_thin<8, 1, KF><<<grid, 256, 0, L.stream>>>(a, b, c, fp);
     else k_zgemm_thin<8, 2, KF><<<grid, 256, 0, L.stream>>>(a, b, c, fp);
   } else {
@@ -1010,14 +1019,21 @@ void run_zgemm_fused(const Launch& L, const ContractPlan& cp, const void* A, con
   // (k_zgemm_thin, 58 us against 93 us of the tiled kernel on M = 2^18, N = 8, K = 64); with an
   // open axis fastest the tiled kernel's row-first gather already touches one line per quarter
   // warp and stays ahead (58 vs 61 us).  Options: an explicit zgemm_cfg or zgemm_thin = 1 keep
-  // the tiled kernel, zgemm_thin = 2 / 3 force k_zgemm_thin with the k-first / rows-first order.
+  // the tiled / skinny kernels, zgemm_thin = 2 / 3 force k_zgemm_thin with the k-first /
+  // rows-first order on N <= 16.
   {
     const int thin = L.opt ? L.opt->zgemm_thin : 0;
-    PQ_REQUIRE(thin >= 0 && thin <= 3, PQ_ERR_INVALID, "zgemm_thin must be 0..3");
+    PQ_REQUIRE(thin >= 0 && thin <= 4, PQ_ERR_INVALID, "zgemm_thin must be 0..4");
     const bool k_fastest = min_stride(cp.kA) < min_stride(cp.mA);
-    if ((L.opt ? L.opt->zgemm_cfg : 0) == 0 && cp.N <= 16 && cp.K <= 64 &&
-        (thin >= 2 || (thin == 0 && k_fastest))) {
-      const bool kf = thin == 2 || (thin == 0 && k_fastest);
+    // short contraction with a wide small side (16 < N <= 64, output-bound): the same kernel with
+    // up to eight 8-column blocks; ncu durations against the persistent skinny kernel at M = 2^18,
+    // K = 8: N = 64 63.8 vs 68.3 us (75.8 when a contracted axis is fastest), N = 32 35.9 vs 42.3;
+    // K = 16: 91.3 vs 91.4, left to the skinny kernel (option zgemm_thin = 4 forces K <= 16)
+    const bool wide = cp.N > 16 && cp.N <= 64 && cp.M >= 4096 &&
+                      ((thin == 0 && cp.K <= 8) || (thin == 4 && cp.K <= 16));
+    if ((L.opt ? L.opt->zgemm_cfg : 0) == 0 && ((cp.N <= 16 && cp.K <= 64 &&
+        (thin == 2 || thin == 3 || (thin == 0 && k_fastest))) || wide)) {
+      const bool kf = thin == 2 || ((thin == 0 || thin == 4) && k_fastest);
       L.begin(KC_GEMM_TENSOR, bytes, flops);
       if (kf)
         launch_thin<true>(L, fp, A, B, C);

@@ -401,12 +401,12 @@ def test_c64_small_operand_contracted_axis_fastest(tc):
         assert rel_l2(got, ref) < 2e-6, (tc, ad, ai, rel_l2(got, ref))
 
 
-@pytest.mark.parametrize("thin", [0, 1, 2, 3])
+@pytest.mark.parametrize("thin", [0, 1, 2, 3, 4])
 def test_thin_n_zgemm(thin):
     """ComplexF64 steps with one short open bond on the small side (N <= 16, K <= 64):
     k_zgemm_thin (DMMA fragments loaded straight from the un-permuted operand; option zgemm_thin
     2 / 3 force its k-first / rows-first load order, 0 is the policy, 1 the tiled kernel it
-    replaced).  Contracted axes lowest / highest / scattered in A, N = 8 and 16, K = 32 and 64,
+    replaced, 4 extends the wide short-contraction case to K <= 16).  Contracted axes lowest / highest / scattered in A, N = 8 and 16, K = 32 and 64,
     ragged M, N and K, more 8-row steps than resident warps."""
     rng = np.random.default_rng(61 + thin)
     b = B200(np.complex128, zgemm_thin=thin, ozaki_auto=0)
@@ -431,6 +431,11 @@ def test_thin_n_zgemm(thin):
         ((4099, 37), [-1, 1], (37, 11), [1, -2]),                 # ragged M, N, K (rows fastest)
         ((53, 5001), [1, -1], (53, 13), [1, -2]),                 # ragged, contracted axis fastest
         ((8, 4100, 8), [1, -1, 2], (8, 8, 9), [2, 1, -2]),        # two contracted axes around the open one
+        # short contraction, wide small side (policy: K <= 8; option 4: K <= 16)
+        case(19, [16, 17, 18], 6),               # M = 2^16, N = 64, K = 8, contracted axes highest
+        case(19, [0, 1, 2], 5),                  # N = 32, contracted axes lowest
+        ((4099, 7), [-1, 1], (7, 37), [1, -2]),                   # ragged
+        ((13, 5001), [1, -1], (13, 50), [1, -2]),                 # K = 13 first
     ]
     for ad, ai, bd, bi in shapes:
         A = rand_tensor(rng, tuple(ad), np.complex128)
