@@ -569,6 +569,42 @@ static void test_ozaki_lowering() {
         "c64 with cgemm_ozaki: fused gather");
   P = lower_contract(ad, ai, bd, bi, 16, opt);
   CHECK(P.kind == CK_GEMM && P.fused_gemm, "c128 unaffected by cgemm_ozaki");
+  {   // c64, short contraction (K = 8) with 64 open on the small side: output-bound, the small-operand
+      // tensor-core kernel (S > 16 is its territory only) -- unless it is switched off or the INT8
+      // kernel is forced; c128 keeps the GEMM path (DMMA thin / skinny kernels); the dot split
+    std::vector<int64_t> aw(19, 2), bw(9, 2);
+    std::vector<int32_t> aiw, biw;
+    int ow = 0, kw = 0;
+    for (int i = 0; i < 19; ++i) {
+      if (i >= 16) aiw.push_back(++kw);
+      else aiw.push_back(-(++ow));
+    }
+    for (int i = 1; i <= 3; ++i) biw.push_back(i);
+    for (int j = 0; j < 6; ++j) biw.push_back(-(ow + 1 + j));
+    Options ow0;
+    ContractPlan W = lower_contract(aw, aiw, bw, biw, 8, ow0);
+    CHECK(W.kind == CK_SMALL_RIGHT && W.M == (1 << 16) && W.N == 64 && W.K == 8, "c64 K = 8, N = 64: small-operand tensor-core kernel");
+    ow0.small_tc = 1;
+    W = lower_contract(aw, aiw, bw, biw, 8, ow0);
+    CHECK(W.kind == CK_GEMM && W.fused_gemm, "c64 K = 8, N = 64 with small_tc = 1: INT8 kernel");
+    Options ow1;
+    ow1.cgemm_ozaki = 4;
+    W = lower_contract(aw, aiw, bw, biw, 8, ow1);
+    CHECK(W.kind == CK_GEMM && W.fused_gemm, "c64 K = 8, N = 64 with cgemm_ozaki forced: INT8 kernel");
+    Options ow2;
+    W = lower_contract(aw, aiw, bw, biw, 16, ow2);
+    CHECK(W.kind == CK_GEMM, "c128 K = 8, N = 64: GEMM path");
+    // inner product over 2^21 elements with power-of-two extents: 2^18 threads, 8 values of j each
+    std::vector<int64_t> dv(21, 2);
+    std::vector<int32_t> di;
+    for (int i = 1; i <= 21; ++i) di.push_back(i);
+    ContractPlan D = lower_contract(dv, di, dv, di, 16, ow2);
+    CHECK(D.kind == CK_DOT && D.dot_split == 18 && D.dot_blocks == 1024, "dot over 2^21: offset split");
+    std::vector<int64_t> d3 = {3, 7, 1000};
+    std::vector<int32_t> d3i = {1, 2, 3};
+    D = lower_contract(d3, d3i, d3, d3i, 16, ow2);
+    CHECK(D.kind == CK_DOT && D.dot_split == 0, "dot over non-power-of-two extents: generic loop");
+  }
   std::printf("ozaki lowering: ok\n");
 }
 
